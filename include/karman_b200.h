@@ -1,0 +1,191 @@
+/*
+ * karman_b200.h -- C ABI of libkarman_b200.so (hand-written sm_100a CUDA kernels).
+ *
+ * The reference (houkensjtu/karman_taichi) has no FFI: its device boundary is
+ * Python -> Taichi JIT (every @ti.kernel call, every field[None] access, every
+ * reduce() return value).  This header is the boundary a Taichi-free host binds in its
+ * place; each entry point cites the reference @ti.kernel / method it replaces
+ * (file:line under the reference root).  The Python mirror of the reference classes
+ * (karman_taichi_b200/{cgsolver,bicgsolver,simple,karman}.py) calls exactly these
+ * symbols through ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - All array arguments are DEVICE pointers unless the name ends in _host.
+ *  - A "field" is a (NX, pitch) row-major plane of reals (double for KT_F64, float
+ *    for KT_F32); logical shape (NX, NY), NY <= pitch, pitch % 16 == 0 (f64) or
+ *    % 32 == 0 (f32) so every row starts 128-byte aligned.  Pad columns
+ *    [NY, pitch) must be zero in every field and stay zero.
+ *  - A "coef" array is 5 consecutive planes (ap, aw, ae, an, as), plane stride
+ *    NX*pitch: the SoA form of the reference's coef[i,j,0..4] (cgsolver.py:59-60;
+ *    aw multiplies x[i-1,j], ae x[i+1,j], an x[i,j+1], as x[i,j-1]).
+ *  - Every function returns 0 on success, <0 on CUDA/argument error (message via
+ *    kt_last_error()).  Numerical breakdown is NOT an error: it is reported in
+ *    *status (KT_STATUS_*), so the host can mirror the reference's print/break/raise.
+ *  - Calls are asynchronous on the handle's stream unless they return a value to the
+ *    host (kt_dot, kt_*_solve, kt_relax_uv, kt_mdiv_max ...), which synchronise that
+ *    stream.  A handle is not thread-safe; one handle per (device, geometry).
+ *  - Ownership: the caller owns every field/coef buffer.  The handle owns only its
+ *    workspace (block partial sums, device scalars, pinned mirrors, events).
+ */
+#ifndef KARMAN_B200_H
+#define KARMAN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kt_handle_s* kt_handle_t;
+
+enum { KT_F64 = 0, KT_F32 = 1 };
+
+/* solver exit status (bicgsolver.py:96-98,108,118,130; karman_taichi.py:386-389,446-454) */
+enum {
+  KT_STATUS_CONVERGED = 0,
+  KT_STATUS_MAX_ITER = 1,
+  KT_STATUS_RHO_ZERO = 2,       /* '>>> BICG failed at first place...' */
+  KT_STATUS_ALPHA_DIV_ZERO = 3, /* (r_tld, Ap) == 0 or (p, Ap) == 0: reference raises ZeroDivisionError */
+  KT_STATUS_OMEGA_DIV_ZERO = 4, /* (t, t) == 0: reference raises ZeroDivisionError */
+  KT_STATUS_NON_FINITE = 5,
+  KT_STATUS_OMEGA_ZERO = 6      /* karman_taichi.py:451-454 */
+};
+
+/* kt_bicgstab_solve flags */
+enum {
+  KT_FLAG_WARM_START = 1,       /* r0 = b - A x0 (karman_taichi.py:360-371) instead of x0 = 0 */
+  KT_FLAG_OMEGA_ZERO_BREAK = 2  /* karman_taichi.py:451-454 */
+};
+
+/* ---- library / handle ------------------------------------------------------------- */
+int kt_version(void);
+const char* kt_last_error(void);
+/* recommended row pitch (elements) for a logical row length NY */
+int kt_pitch_for(int NY, int dtype);
+/* geometry = the (NX, NY) of the fields this handle operates on; stream = cudaStream_t
+ * (NULL = legacy default stream).  Replaces ti.init + the SNode allocation of
+ * cgsolver.py:17-26 (workspace only -- fields stay with the caller). */
+int kt_create(int device, int NX, int NY, int pitch, int dtype, void* stream, kt_handle_t* out);
+int kt_destroy(kt_handle_t h);
+int kt_set_stream(kt_handle_t h, void* stream);
+int kt_sync(kt_handle_t h);
+/* Restrict SpMV / vector updates / dots to rows [row_lo, row_hi) of the local plane (x-slab
+ * ownership; rows outside are halo rows that are read but never written or summed).
+ * Default [0, NX).  No reference counterpart (the reference is single-address-space). */
+int kt_set_rows(kt_handle_t h, int row_lo, int row_hi);
+/* number of kernels launched through this handle so far (bench.py: gpu_launches) */
+long long kt_launch_count(kt_handle_t h);
+
+/* ---- host <-> device staging (reference: field.from_numpy / to_numpy) ---------------------- */
+/* dense (NX, NY) host array -> pitched device field, and back */
+int kt_upload_field(kt_handle_t h, void* dst, const void* src_host);
+int kt_download_field(kt_handle_t h, void* dst_host, const void* src);
+/* reference layout coef[i][j][k] (AoS, k fastest) on host -> 5 pitched device planes.
+ * staging = device scratch of NX*NY*5 reals. */
+int kt_upload_coef(kt_handle_t h, void* dst_soa, const void* src_host_aos, void* staging);
+int kt_download_coef(kt_handle_t h, void* dst_host_aos, const void* src_soa, void* staging);
+/* device-side AoS (NX,NY,5) dense <-> SoA pitched conversion */
+int kt_coef_aos_to_soa(kt_handle_t h, void* dst_soa, const void* src_aos);
+int kt_coef_soa_to_aos(kt_handle_t h, void* dst_aos, const void* src_soa);
+
+/* ---- Krylov building blocks (one per reference kernel; for unit parity) --------------------- */
+/* y = A x.  cgsolver.py:56-66 (compute_Ap, compute_Ax), bicgsolver.py:65-76 (compute_As, compute_Ap) */
+int kt_spmv(kt_handle_t h, const void* coef, const void* x, void* y);
+/* y = A x and *dot_host = (q, y) in one pass (fused compute_Ap + reduce: cgsolver.py:94-95,
+ * bicgsolver.py:106-107).  q may equal x. */
+int kt_spmv_dot(kt_handle_t h, const void* coef, const void* x, void* y, const void* q, double* dot_host);
+/* s = r - alpha*v ; t = A s ; dots_host[0] = (t,s), dots_host[1] = (t,t)
+ * (fused update_s + compute_As + copy + 2 reduce: bicgsolver.py:110-117) */
+int kt_bicg_s_t(kt_handle_t h, const void* coef, const void* r, const void* v, double alpha,
+                void* s, void* t, double* dots_host);
+/* sum over the owned rows of p*q.  cgsolver.py:49-54 (reduce).  Deterministic: fixed grid,
+ * fixed-order two-stage (warp shuffle -> block -> ordered final) summation. */
+int kt_dot(kt_handle_t h, const void* p, const void* q, double* out_host);
+int kt_copy(kt_handle_t h, void* dst, const void* src);          /* bicgsolver.py:38-41 */
+int kt_fill(kt_handle_t h, void* dst, double value);
+/* y = y + a*x      cgsolver.py:68-76 (update_x; update_r with a = -alpha) */
+int kt_axpy(kt_handle_t h, void* y, double a, const void* x);
+/* out = x + a*y    cgsolver.py:78-81 (update_p; out may alias y) */
+int kt_xpay(kt_handle_t h, void* out, const void* x, double a, const void* y);
+/* out = x - a*y    bicgsolver.py:60-63 (update_s), :83-86 (update_r) */
+int kt_xmay(kt_handle_t h, void* out, const void* x, double a, const void* y);
+/* p = r + beta*(p - omega*v)          bicgsolver.py:43-46 (update_p) */
+int kt_bicg_update_p(kt_handle_t h, void* p, const void* r, const void* v, double beta, double omega);
+/* x = x + (alpha*p + omega*s)         bicgsolver.py:78-81 (update_x) */
+int kt_bicg_update_x(kt_handle_t h, void* x, const void* p, const void* s, double alpha, double omega);
+/* fused: x += alpha*p + omega*s ; r = s - omega*t ; dots_host = {(r,r), (r,r_tld)}
+ * (update_x + update_r + 2 reduce: bicgsolver.py:120-123,95) */
+int kt_bicg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* s, const void* t,
+               const void* r_tld, double alpha, double omega, double* dots_host);
+/* fused: x += alpha*p ; r -= alpha*Ap ; *dot_host = (r,r)   (cgsolver.py:98-101) */
+int kt_cg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* Ap, double alpha, double* dot_host);
+
+/* ---- device-resident solvers ---------------------------------------------------------- */
+typedef struct {
+  void* r;      /* residual                                   (cgsolver.py:18) */
+  void* p;      /* search direction                           (cgsolver.py:19) */
+  void* Ap;     /* A p  (BiCGSTAB's v)                        (cgsolver.py:20) */
+  void* r_tld;  /* BiCGSTAB shadow residual; NULL => alias b when x0 = 0 (bicgsolver.py:9) */
+  void* s;      /* BiCGSTAB s                                 (bicgsolver.py:11) */
+  void* t;      /* BiCGSTAB t = A s (reference Ashat/t)       (bicgsolver.py:13-14) */
+  double* history; /* DEVICE array or NULL: sqrt(rTr) per iteration (cgsolver.py:88,111) */
+  long history_cap;
+} kt_krylov_ws;
+
+/* CGSolver.solve (cgsolver.py:83-114): x0 = 0, stop sqrt(rTr) < sqrt(rTr0)*eps, at most
+ * max_iter loop bodies.  *iters = loop bodies executed.  *rel_res = sqrt(rTr/rTr0). */
+int kt_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws,
+                double eps, long max_iter, long* iters, double* rel_res, int* status);
+/* BICGSolver.solve (bicgsolver.py:88-135) when Minv == NULL and flags == 0: unpreconditioned,
+ * x0 = 0, r_tld = b.  With Minv (= 1/M plane) and KT_FLAG_WARM_START|KT_FLAG_OMEGA_ZERO_BREAK:
+ * the monolith's Jacobi right-preconditioned kernel (karman_taichi.py:342-456). */
+int kt_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const void* Minv,
+                      const kt_krylov_ws* ws, double eps, long max_iter, int flags,
+                      long* iters, double* rel_res, int* status);
+/* Fixed-iteration throughput variants used by bench.py: run exactly n_iter iterations with
+ * the convergence test disabled (eps = 0); *ms = device time (CUDA events on the handle's stream). */
+int kt_bicgstab_bench(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws,
+                      long n_iter, float* ms);
+int kt_cg_bench(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws,
+                long n_iter, float* ms);
+/* Reference-facing end-to-end call with HOST buffers in the reference layout
+ * (coef[i][j][k] AoS, dense (NX,NY) b and x): uploads, solves, downloads x.
+ * dev_* are caller-owned device buffers: coef_soa (5 planes), staging (NX*NY*5 dense), b, x. */
+int kt_bicgstab_solve_host(kt_handle_t h, const void* coef_host_aos, const void* b_host, void* x_host,
+                           void* dev_coef_soa, void* dev_staging, void* dev_b, void* dev_x,
+                           const kt_krylov_ws* ws, double eps, long max_iter,
+                           long* iters, double* rel_res, int* status);
+
+/* ---- SIMPLE (cavity) kernels: simple.py / bicgsimp.py -------------------------------------- */
+typedef struct {
+  int nx, ny;               /* cells */
+  double dx, dy, dt, rho, mu;
+  double alpha_p, alpha_u, alpha_m;
+  double bc_w[2], bc_e[2], bc_n[2], bc_s[2]; /* {normal, tangential}  (simple.py:39) */
+  int pin_p;                /* 1: bicgsimp.py:146-151 pin at (1,1); 0: simple.py:165-170 */
+  int east_wall_bug;        /* 1: simple.py:215 adds aw instead of ae */
+  int pitch_u, pitch_v, pitch_p; /* row pitches of the (nx+3,ny+2), (nx+2,ny+3), (nx+2,ny+2) planes */
+} kt_simple_params;
+
+/* compute_coef_u + compute_coef_v (bicgsimp.py:79-112) */
+int kt_assemble_uv(kt_handle_t h, const kt_simple_params* P, const void* u, const void* v, const void* p,
+                   const void* u0, const void* v0, void* coef_u, void* b_u, void* coef_v, void* b_v);
+/* set_bc (bicgsimp.py:153-197); also writes u[1,:], u[nx+1,:], v[:,1], v[:,ny+1] */
+int kt_set_bc_cavity(kt_handle_t h, const kt_simple_params* P, void* u, void* v,
+                     void* coef_u, void* b_u, void* coef_v, void* b_v);
+/* compute_coef_p (bicgsimp.py:124-151): mdiv, b_p, coef_p (+ pin) */
+int kt_assemble_p(kt_handle_t h, const kt_simple_params* P, const void* u, const void* v,
+                  const void* coef_u, const void* coef_v, void* coef_p, void* b_p, void* mdiv);
+/* update_velocity (bicgsimp.py:212-225): *residual_host = sqrt(max|du|^2 + max|dv|^2) */
+int kt_relax_uv(kt_handle_t h, const kt_simple_params* P, void* u, void* v, const void* u_mid,
+                const void* v_mid, double* residual_host);
+/* correct_pressure + correct_velocity (bicgsimp.py:232-244) in one pass.  p == NULL skips the
+ * pressure update; u == v == NULL skips the velocity update (the reference's two separate kernels). */
+int kt_correct_puv(kt_handle_t h, const kt_simple_params* P, void* p, void* u, void* v, const void* pcor,
+                   const void* coef_u, const void* coef_v);
+/* compute_mdiv (bicgsimp.py:114-122): *max_host = max |mdiv| */
+int kt_mdiv_max(kt_handle_t h, const kt_simple_params* P, const void* u, const void* v, void* mdiv,
+                double* max_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KARMAN_B200_H */

@@ -1,0 +1,122 @@
+"""ctypes binding of libkarman_b200.so (the C ABI in ``include/karman_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or a CUDA device is not usable, the
+calls raise.  The library is built in-tree by ``karman_taichi_b200.build`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libkarman_b200.so')
+
+KT_F64, KT_F32 = 0, 1
+
+STATUS_CONVERGED = 0
+STATUS_MAX_ITER = 1
+STATUS_RHO_ZERO = 2
+STATUS_ALPHA_DIV_ZERO = 3
+STATUS_OMEGA_DIV_ZERO = 4
+STATUS_NON_FINITE = 5
+STATUS_OMEGA_ZERO = 6
+
+FLAG_WARM_START = 1
+FLAG_OMEGA_ZERO_BREAK = 2
+
+
+class KtError(RuntimeError):
+    pass
+
+
+class KrylovWs(C.Structure):
+    """``kt_krylov_ws``"""
+    _fields_ = [('r', C.c_void_p), ('p', C.c_void_p), ('Ap', C.c_void_p), ('r_tld', C.c_void_p),
+                ('s', C.c_void_p), ('t', C.c_void_p), ('history', C.c_void_p), ('history_cap', C.c_long)]
+
+
+class SimpleParams(C.Structure):
+    """``kt_simple_params``"""
+    _fields_ = [('nx', C.c_int), ('ny', C.c_int),
+                ('dx', C.c_double), ('dy', C.c_double), ('dt', C.c_double), ('rho', C.c_double), ('mu', C.c_double),
+                ('alpha_p', C.c_double), ('alpha_u', C.c_double), ('alpha_m', C.c_double),
+                ('bc_w', C.c_double * 2), ('bc_e', C.c_double * 2), ('bc_n', C.c_double * 2), ('bc_s', C.c_double * 2),
+                ('pin_p', C.c_int), ('east_wall_bug', C.c_int),
+                ('pitch_u', C.c_int), ('pitch_v', C.c_int), ('pitch_p', C.c_int)]
+
+
+_P, _I, _D, _L = C.c_void_p, C.c_int, C.c_double, C.c_long
+_PD, _PL, _PI, _PF = C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_int), C.POINTER(C.c_float)
+_WS, _SP = C.POINTER(KrylovWs), C.POINTER(SimpleParams)
+
+# name -> (restype, argtypes); every symbol include/karman_b200.h declares
+SIGNATURES = {
+    'kt_version': (_I, []),
+    'kt_last_error': (C.c_char_p, []),
+    'kt_pitch_for': (_I, [_I, _I]),
+    'kt_create': (_I, [_I, _I, _I, _I, _I, _P, C.POINTER(_P)]),
+    'kt_destroy': (_I, [_P]),
+    'kt_set_stream': (_I, [_P, _P]),
+    'kt_sync': (_I, [_P]),
+    'kt_set_rows': (_I, [_P, _I, _I]),
+    'kt_launch_count': (C.c_longlong, [_P]),
+    'kt_upload_field': (_I, [_P, _P, _P]),
+    'kt_download_field': (_I, [_P, _P, _P]),
+    'kt_upload_coef': (_I, [_P, _P, _P, _P]),
+    'kt_download_coef': (_I, [_P, _P, _P, _P]),
+    'kt_coef_aos_to_soa': (_I, [_P, _P, _P]),
+    'kt_coef_soa_to_aos': (_I, [_P, _P, _P]),
+    'kt_spmv': (_I, [_P, _P, _P, _P]),
+    'kt_spmv_dot': (_I, [_P, _P, _P, _P, _P, _PD]),
+    'kt_bicg_s_t': (_I, [_P, _P, _P, _P, _D, _P, _P, _PD]),
+    'kt_dot': (_I, [_P, _P, _P, _PD]),
+    'kt_copy': (_I, [_P, _P, _P]),
+    'kt_fill': (_I, [_P, _P, _D]),
+    'kt_axpy': (_I, [_P, _P, _D, _P]),
+    'kt_xpay': (_I, [_P, _P, _P, _D, _P]),
+    'kt_xmay': (_I, [_P, _P, _P, _D, _P]),
+    'kt_bicg_update_p': (_I, [_P, _P, _P, _P, _D, _D]),
+    'kt_bicg_update_x': (_I, [_P, _P, _P, _P, _D, _D]),
+    'kt_bicg_xr': (_I, [_P, _P, _P, _P, _P, _P, _P, _D, _D, _PD]),
+    'kt_cg_xr': (_I, [_P, _P, _P, _P, _P, _D, _PD]),
+    'kt_cg_solve': (_I, [_P, _P, _P, _P, _WS, _D, _L, _PL, _PD, _PI]),
+    'kt_bicgstab_solve': (_I, [_P, _P, _P, _P, _P, _WS, _D, _L, _I, _PL, _PD, _PI]),
+    'kt_bicgstab_bench': (_I, [_P, _P, _P, _P, _WS, _L, _PF]),
+    'kt_cg_bench': (_I, [_P, _P, _P, _P, _WS, _L, _PF]),
+    'kt_bicgstab_solve_host': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _WS, _D, _L, _PL, _PD, _PI]),
+    'kt_assemble_uv': (_I, [_P, _SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'kt_set_bc_cavity': (_I, [_P, _SP, _P, _P, _P, _P, _P, _P]),
+    'kt_assemble_p': (_I, [_P, _SP, _P, _P, _P, _P, _P, _P, _P]),
+    'kt_relax_uv': (_I, [_P, _SP, _P, _P, _P, _P, _PD]),
+    'kt_correct_puv': (_I, [_P, _SP, _P, _P, _P, _P, _P, _P]),
+    'kt_mdiv_max': (_I, [_P, _SP, _P, _P, _P, _PD]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library and declare every prototype.  Raises ``KtError`` if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KtError(f'{LIB_PATH} is missing: build it with `python -m karman_taichi_b200.build` '
+                      '(there is no CPU fallback)')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().kt_last_error().decode('utf-8', 'replace')
+        raise KtError(f'libkarman_b200 call failed (rc={rc}): {msg}')
+
+
+def pitch_for(ny, dtype_code=KT_F64):
+    q = 16 if dtype_code == KT_F64 else 32
+    return (ny + q - 1) // q * q

@@ -1,0 +1,184 @@
+// kt_api.cu -- handle lifetime, error reporting, host<->device staging and layout conversion.
+#include <mutex>
+#include <string>
+#include "kt_handle.h"
+
+namespace kt {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in `" + what + "` at " + file + ":" + std::to_string(line);
+  return -1;
+}
+
+// dense AoS (NX, NY, 5) <-> 5 pitched planes.  One thread per (i, j); the AoS side is staged through shared
+// memory so both sides are coalesced.
+template <typename T, bool TO_SOA>
+__global__ void __launch_bounds__(256) k_coef_layout(T* soa, T* aos, int NX, int NY, int pitch) {
+  __shared__ T tile[256 * 5];
+  const int i = blockIdx.y;
+  const int jb = blockIdx.x * 256;
+  const int nj = min(256, NY - jb);
+  const size_t plane = (size_t)NX * pitch;
+  T* a = aos + ((size_t)i * NY + jb) * 5;
+  if (TO_SOA) {
+    for (int e = threadIdx.x; e < nj * 5; e += 256) tile[e] = a[e];
+    __syncthreads();
+    if ((int)threadIdx.x < nj)
+      for (int k = 0; k < 5; ++k) soa[k * plane + (size_t)i * pitch + jb + threadIdx.x] = tile[threadIdx.x * 5 + k];
+  } else {
+    if ((int)threadIdx.x < nj)
+      for (int k = 0; k < 5; ++k) tile[threadIdx.x * 5 + k] = soa[k * plane + (size_t)i * pitch + jb + threadIdx.x];
+    __syncthreads();
+    for (int e = threadIdx.x; e < nj * 5; e += 256) a[e] = tile[e];
+  }
+}
+
+template <typename T, bool TO_SOA>
+static int coef_layout(kt_handle_s* h, void* soa, void* aos) {
+  dim3 grid((h->NY + 255) / 256, h->NX);
+  k_coef_layout<T, TO_SOA><<<grid, 256, 0, h->stream>>>((T*)soa, (T*)aos, h->NX, h->NY, h->pitch);
+  KT_LAUNCH_CHECK(h);
+  return 0;
+}
+
+static size_t esize(const kt_handle_s* h) { return h->dtype == KT_F64 ? 8 : 4; }
+
+}  // namespace kt
+
+using namespace kt;
+
+extern "C" {
+
+int kt_version(void) { return 100; }
+
+const char* kt_last_error(void) { return g_err.c_str(); }
+
+int kt_pitch_for(int NY, int dtype) {
+  const int q = (dtype == KT_F64) ? 16 : 32;  // 128-byte rows
+  return (NY + q - 1) / q * q;
+}
+
+int kt_create(int device, int NX, int NY, int pitch, int dtype, void* stream, kt_handle_t* out) {
+  KT_CHECK_ARG(out, "kt_create: out is null");
+  KT_CHECK_ARG(dtype == KT_F64 || dtype == KT_F32, "kt_create: dtype must be KT_F64 or KT_F32");
+  KT_CHECK_ARG(NX > 0 && NY > 0, "kt_create: NX, NY must be positive");
+  KT_CHECK_ARG(pitch >= NY && pitch % ((dtype == KT_F64) ? 16 : 32) == 0, "kt_create: pitch must be >= NY and a multiple of 128 bytes");
+  int ndev = 0;
+  KT_CUDA(cudaGetDeviceCount(&ndev));
+  KT_CHECK_ARG(device >= 0 && device < ndev, "kt_create: no such CUDA device");
+  KT_CUDA(cudaSetDevice(device));
+  kt_handle_s* h = new kt_handle_s();
+  h->device = device; h->NX = NX; h->NY = NY; h->pitch = pitch; h->dtype = dtype;
+  h->row_lo = 0; h->row_hi = NX;
+  h->stream = (cudaStream_t)stream;
+  cudaDeviceProp prop;
+  KT_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
+  h->max_blocks = h->num_sms * 8;
+  KT_CUDA(cudaMalloc(&h->partials, sizeof(double) * KT_MAX_DOTS * h->max_blocks));
+  KT_CUDA(cudaMalloc(&h->ticket, sizeof(unsigned int)));
+  KT_CUDA(cudaMemset(h->ticket, 0, sizeof(unsigned int)));
+  KT_CUDA(cudaMalloc(&h->sc, sizeof(Scalars)));
+  KT_CUDA(cudaMemset(h->sc, 0, sizeof(Scalars)));
+  KT_CUDA(cudaMallocHost(&h->sc_host, 2 * sizeof(Scalars)));
+  KT_CUDA(cudaMalloc(&h->red_out, 4 * sizeof(double)));
+  KT_CUDA(cudaMallocHost(&h->red_host, 4 * sizeof(double)));
+  for (int k = 0; k < 2; ++k) KT_CUDA(cudaEventCreateWithFlags(&h->ev[k], cudaEventDisableTiming));
+  KT_CUDA(cudaEventCreate(&h->t0));
+  KT_CUDA(cudaEventCreate(&h->t1));
+  *out = h;
+  return 0;
+}
+
+int kt_destroy(kt_handle_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->partials); cudaFree(h->ticket); cudaFree(h->sc); cudaFreeHost(h->sc_host);
+  cudaFree(h->red_out); cudaFreeHost(h->red_host);
+  for (int k = 0; k < 2; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+  if (h->t0) cudaEventDestroy(h->t0);
+  if (h->t1) cudaEventDestroy(h->t1);
+  delete h;
+  return 0;
+}
+
+int kt_set_stream(kt_handle_t h, void* stream) {
+  KT_CHECK_ARG(h, "kt_set_stream: null handle");
+  h->stream = (cudaStream_t)stream;
+  return 0;
+}
+
+int kt_sync(kt_handle_t h) {
+  KT_CHECK_ARG(h, "kt_sync: null handle");
+  KT_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int kt_set_rows(kt_handle_t h, int row_lo, int row_hi) {
+  KT_CHECK_ARG(h, "kt_set_rows: null handle");
+  KT_CHECK_ARG(0 <= row_lo && row_lo <= row_hi && row_hi <= h->NX, "kt_set_rows: need 0 <= row_lo <= row_hi <= NX");
+  h->row_lo = row_lo; h->row_hi = row_hi;
+  return 0;
+}
+
+long long kt_launch_count(kt_handle_t h) { return h ? h->launches : 0; }
+
+int kt_upload_field(kt_handle_t h, void* dst, const void* src_host) {
+  KT_CHECK_ARG(h && dst && src_host, "kt_upload_field: null argument");
+  const size_t es = esize(h);
+  KT_CUDA(cudaMemcpy2DAsync(dst, h->pitch * es, src_host, h->NY * es, h->NY * es, h->NX, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int kt_download_field(kt_handle_t h, void* dst_host, const void* src) {
+  KT_CHECK_ARG(h && dst_host && src, "kt_download_field: null argument");
+  const size_t es = esize(h);
+  KT_CUDA(cudaMemcpy2DAsync(dst_host, h->NY * es, src, h->pitch * es, h->NY * es, h->NX, cudaMemcpyDeviceToHost, h->stream));
+  KT_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int kt_coef_aos_to_soa(kt_handle_t h, void* dst_soa, const void* src_aos) {
+  KT_CHECK_ARG(h && dst_soa && src_aos, "kt_coef_aos_to_soa: null argument");
+  return h->dtype == KT_F64 ? coef_layout<double, true>(h, dst_soa, (void*)src_aos) : coef_layout<float, true>(h, dst_soa, (void*)src_aos);
+}
+
+int kt_coef_soa_to_aos(kt_handle_t h, void* dst_aos, const void* src_soa) {
+  KT_CHECK_ARG(h && dst_aos && src_soa, "kt_coef_soa_to_aos: null argument");
+  return h->dtype == KT_F64 ? coef_layout<double, false>(h, (void*)src_soa, dst_aos) : coef_layout<float, false>(h, (void*)src_soa, dst_aos);
+}
+
+int kt_upload_coef(kt_handle_t h, void* dst_soa, const void* src_host_aos, void* staging) {
+  KT_CHECK_ARG(h && dst_soa && src_host_aos && staging, "kt_upload_coef: null argument");
+  const size_t bytes = (size_t)h->NX * h->NY * 5 * esize(h);
+  KT_CUDA(cudaMemcpyAsync(staging, src_host_aos, bytes, cudaMemcpyHostToDevice, h->stream));
+  return kt_coef_aos_to_soa(h, dst_soa, staging);
+}
+
+int kt_download_coef(kt_handle_t h, void* dst_host_aos, const void* src_soa, void* staging) {
+  KT_CHECK_ARG(h && dst_host_aos && src_soa && staging, "kt_download_coef: null argument");
+  int rc = kt_coef_soa_to_aos(h, staging, src_soa);
+  if (rc) return rc;
+  const size_t bytes = (size_t)h->NX * h->NY * 5 * esize(h);
+  KT_CUDA(cudaMemcpyAsync(dst_host_aos, staging, bytes, cudaMemcpyDeviceToHost, h->stream));
+  KT_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int kt_bicgstab_solve_host(kt_handle_t h, const void* coef_host_aos, const void* b_host, void* x_host, void* dev_coef_soa,
+                           void* dev_staging, void* dev_b, void* dev_x, const kt_krylov_ws* ws, double eps, long max_iter,
+                           long* iters, double* rel_res, int* status) {
+  KT_CHECK_ARG(h && coef_host_aos && b_host && x_host && dev_coef_soa && dev_staging && dev_b && dev_x && ws,
+               "kt_bicgstab_solve_host: null argument");
+  int rc = kt_upload_coef(h, dev_coef_soa, coef_host_aos, dev_staging);
+  if (rc) return rc;
+  rc = kt_upload_field(h, dev_b, b_host);
+  if (rc) return rc;
+  rc = kt_bicgstab_solve(h, dev_coef_soa, dev_b, dev_x, nullptr, ws, eps, max_iter, 0, iters, rel_res, status);
+  if (rc) return rc;
+  return kt_download_field(h, x_host, dev_x);
+}
+
+}  // extern "C"

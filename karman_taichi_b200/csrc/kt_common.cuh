@@ -1,0 +1,232 @@
+// kt_common.cuh -- shared device helpers for libkarman_b200 (sm_100a).
+//
+// Design notes (DESIGN.md has the full story):
+//  * Every field is a pitched (NX, pitch) plane, pitch a multiple of 128 B, so each thread can move
+//    one 16-byte vector (double2 / float4) per array per row with fully coalesced, aligned accesses.
+//  * Streaming operands (coefficients, vectors read once) use ld.global.nc.L1::no_allocate; the
+//    stencil operand uses plain cached loads so row i+-1 / edge re-reads hit L1/L2.
+//  * Inner products are deterministic: per-thread sequential accumulation over a statically assigned
+//    tile list -> warp shuffle tree -> fixed-order sum over warps in shared memory -> one partial per
+//    block -> the LAST block to finish (threadfence + ticket) sums the partials in index order and runs
+//    the scalar algebra of the Krylov step.  No floating-point atomics anywhere.
+//  * The library is compiled with -fmad=false: element-wise results are bit-identical to the NumPy
+//    oracle (which cannot contract to FMA); the kernels are HBM-bound so this costs nothing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define KT_WARP 32
+#define KT_MAX_DOTS 2
+
+namespace kt {
+
+template <typename T> struct VT;
+template <> struct VT<double> { static constexpr int V = 2; };
+template <> struct VT<float>  { static constexpr int V = 4; };
+
+// One 16-byte vector of reals.
+template <typename T> struct __align__(16) Pack { T a[VT<T>::V]; };
+
+template <typename T> __device__ __forceinline__ Pack<T> pack_zero() {
+  Pack<T> p;
+#pragma unroll
+  for (int k = 0; k < VT<T>::V; ++k) p.a[k] = T(0);
+  return p;
+}
+
+// ---- 16-byte global loads / stores ---------------------------------------------------------
+__device__ __forceinline__ Pack<double> ld_stream(const double* p) {
+  Pack<double> r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ Pack<float> ld_stream(const float* p) {
+  Pack<float> r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]) : "l"(p));
+  return r;
+}
+// cached (L1-allocating) load for the stencil operand; not .nc because some kernels read a plane that an
+// earlier kernel of the same stream wrote (coherent across launches either way) -- plain ld.global.
+__device__ __forceinline__ Pack<double> ld_cached(const double* p) {
+  Pack<double> r;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ Pack<float> ld_cached(const float* p) {
+  Pack<float> r;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_vec(double* p, const Pack<double>& v) {
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.a[0]), "d"(v.a[1]) : "memory");
+}
+__device__ __forceinline__ void st_vec(float* p, const Pack<float>& v) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.a[0]), "f"(v.a[1]), "f"(v.a[2]), "f"(v.a[3])
+               : "memory");
+}
+
+// ---- warp shuffles for double/float ------------------------------------------------------
+template <typename T> __device__ __forceinline__ T shfl_up1(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+template <typename T> __device__ __forceinline__ T shfl_down1(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Device-resident Krylov scalars.  Lives in the handle's workspace; mirrored to pinned host memory
+// when the host polls.  All in double regardless of the field dtype.
+struct Scalars {
+  double rho, rho_1, alpha, beta, omega;  // bicgsolver.py:15-18 / cgsolver.py:22-23
+  double rTr0, rTr, old_rTr;              // initial / current / previous residual norms squared
+  double dot0, dot1;                      // last finalised raw sums (unit entry points, multi-GPU)
+  double eps;
+  long long iter;                         // completed loop bodies
+  long long max_iter;
+  int status;
+  int done;                               // every kernel of the solve returns at once when set
+  int first;                              // 1 until the first p-update has run (p = r: bicgsolver.py:99-100)
+  int flags;
+};
+
+// Kinds of scalar algebra run by the finalising block.
+enum Fin {
+  FIN_NONE = 0,     // just publish dot0/dot1
+  FIN_BICG_INIT,    // after K0: rTr0, rho
+  FIN_BICG_ALPHA,   // after v = A p_hat: alpha = rho / (r_tld, v)
+  FIN_BICG_OMEGA,   // after t = A s_hat: omega = (t,s)/(t,t)
+  FIN_BICG_END,     // after x/r update: convergence, rho, beta
+  FIN_CG_INIT,
+  FIN_CG_ALPHA,
+  FIN_CG_END
+};
+
+struct ReduceWs {
+  double* partials;        // [KT_MAX_DOTS][max_blocks]
+  unsigned int* ticket;    // one counter, reset by the finalising block
+  int max_blocks;
+  Scalars* sc;
+  double* history;         // device, may be null
+  long long history_cap;
+};
+
+__device__ __forceinline__ void scalar_algebra(int fin, Scalars* sc, double d0, double d1, double* history,
+                                               long long history_cap) {
+  sc->dot0 = d0;
+  sc->dot1 = d1;
+  switch (fin) {
+    case FIN_BICG_INIT: {
+      // bicgsolver.py:90 initial_rTr; :95 rho = (r, r_tld), and r_tld == r at this point in both the
+      // class version (r = r_tld = b) and the monolith (r_tld = r = b - A x0), so rho == rTr0 exactly.
+      sc->rTr0 = d0;
+      sc->rTr = d0;
+      sc->rho = d0;
+      if (history && history_cap > 0) history[0] = sqrt(d0);
+      if (sc->max_iter <= 0) { sc->status = 1; sc->done = 1; }
+      else if (d0 == 0.0) { sc->status = 2; sc->done = 1; }  // :96-98
+      break;
+    }
+    case FIN_BICG_ALPHA: {
+      if (d0 == 0.0) { sc->status = 3; sc->done = 1; }        // :108 ZeroDivisionError
+      else sc->alpha = sc->rho / d0;
+      break;
+    }
+    case FIN_BICG_OMEGA: {
+      if (d1 == 0.0 && !(sc->flags & 2)) { sc->status = 4; sc->done = 1; }  // :118 ZeroDivisionError
+      else sc->omega = d0 / d1;   // monolith (flag 2): Taichi f64 division, may yield nan/inf
+      break;
+    }
+    case FIN_BICG_END: {
+      // d0 = (r,r), d1 = (r, r_tld)
+      sc->rTr = d0;
+      sc->iter += 1;
+      if (history && sc->iter < history_cap) history[sc->iter] = sqrt(d0);
+      double ratio = d0 / sc->rTr0;
+      if (sqrt(ratio) < sc->eps) { sc->status = 0; sc->done = 1; break; }   // :130
+      if ((sc->flags & 2) && sc->omega == 0.0) { sc->status = 6; sc->done = 1; break; }  // karman_taichi.py:451
+      if (!isfinite(d0)) { sc->status = 5; sc->done = 1; break; }
+      if (sc->iter >= sc->max_iter) { sc->status = 1; sc->done = 1; break; }
+      sc->rho_1 = sc->rho;                                      // :135
+      sc->rho = d1;                                             // :95 of the next body
+      if (d1 == 0.0) { sc->status = 2; sc->done = 1; break; }   // :96-98
+      if (!(sc->flags & 2) && sc->omega == 0.0) { sc->status = 4; sc->done = 1; break; }  // :102 alpha/omega raises
+      sc->beta = (sc->rho / sc->rho_1) * (sc->alpha / sc->omega);  // :102
+      break;
+    }
+    case FIN_CG_INIT: {
+      sc->rTr0 = d0; sc->rTr = d0; sc->old_rTr = d0;            // cgsolver.py:85,89
+      if (history && history_cap > 0) history[0] = sqrt(d0);
+      if (sc->max_iter <= 0) { sc->status = 1; sc->done = 1; }
+      break;
+    }
+    case FIN_CG_ALPHA: {
+      if (d0 == 0.0) { sc->status = 3; sc->done = 1; }          // :96 ZeroDivisionError
+      else sc->alpha = sc->old_rTr / d0;
+      break;
+    }
+    case FIN_CG_END: {
+      sc->rTr = d0;
+      sc->iter += 1;
+      if (sqrt(d0) < sqrt(sc->rTr0) * sc->eps) { sc->status = 0; sc->done = 1; break; }  // :102
+      if (!isfinite(d0)) { sc->status = 5; sc->done = 1; break; }
+      sc->beta = d0 / sc->old_rTr;                              // :107
+      sc->old_rTr = d0;                                         // :110
+      if (history && sc->iter < history_cap) history[sc->iter] = sqrt(d0);  // :111
+      if (sc->iter >= sc->max_iter) { sc->status = 1; sc->done = 1; }
+      break;
+    }
+    default: break;
+  }
+}
+
+// Block-level deterministic reduction of up to two running sums + last-block finalisation.
+// Must be called by every thread of every block of the grid (blockDim.x multiple of 32, <= 1024).
+template <int NDOT>
+__device__ __forceinline__ void block_reduce_finalize(double a0, double a1, const ReduceWs& ws, int fin) {
+  __shared__ double sm[KT_MAX_DOTS][32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  a0 = warp_sum(a0);
+  if (NDOT > 1) a1 = warp_sum(a1);
+  if (lane == 0) { sm[0][wid] = a0; if (NDOT > 1) sm[1][wid] = a1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int w = 0; w < nw; ++w) { s0 += sm[0][w]; if (NDOT > 1) s1 += sm[1][w]; }
+    ws.partials[blockIdx.x] = s0;
+    if (NDOT > 1) ws.partials[ws.max_blocks + blockIdx.x] = s1;
+    __threadfence();
+    unsigned int t = atomicAdd(ws.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // fixed-order final sum: thread k owns partials k, k+B, k+2B ...; then the same tree as above.
+  double f0 = 0.0, f1 = 0.0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+    f0 += __ldcg(ws.partials + b);
+    if (NDOT > 1) f1 += __ldcg(ws.partials + ws.max_blocks + b);
+  }
+  f0 = warp_sum(f0);
+  if (NDOT > 1) f1 = warp_sum(f1);
+  __syncthreads();
+  if (lane == 0) { sm[0][wid] = f0; if (NDOT > 1) sm[1][wid] = f1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int w = 0; w < nw; ++w) { s0 += sm[0][w]; if (NDOT > 1) s1 += sm[1][w]; }
+    *ws.ticket = 0u;
+    scalar_algebra(fin, ws.sc, s0, s1, ws.history, ws.history_cap);
+  }
+}
+
+}  // namespace kt

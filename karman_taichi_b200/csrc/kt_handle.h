@@ -1,0 +1,48 @@
+// kt_handle.h -- host-side handle shared by the .cu translation units of libkarman_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include "kt_common.cuh"
+#include "../../include/karman_b200.h"
+
+struct kt_handle_s {
+  int device = 0;
+  int NX = 0, NY = 0, pitch = 0, dtype = KT_F64;
+  int row_lo = 0, row_hi = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  // workspace (owned)
+  double* partials = nullptr;        // [KT_MAX_DOTS][max_blocks]
+  unsigned int* ticket = nullptr;
+  int max_blocks = 0;
+  kt::Scalars* sc = nullptr;         // device
+  kt::Scalars* sc_host = nullptr;    // pinned, 2 slots (double-buffered polling)
+  double* red_out = nullptr;         // device scratch for max-reductions [4]
+  double* red_host = nullptr;        // pinned [4]
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  long long launches = 0;            // kernels launched through this handle (bench: gpu_launches)
+};
+
+namespace kt {
+void set_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+}  // namespace kt
+
+#define KT_CUDA(expr)                                                   \
+  do {                                                                  \
+    cudaError_t _e = (expr);                                            \
+    if (_e != cudaSuccess) return kt::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define KT_CHECK_ARG(cond, msg)                      \
+  do {                                               \
+    if (!(cond)) { kt::set_error(std::string("argument error: ") + msg); return -2; } \
+  } while (0)
+
+#define KT_LAUNCH_CHECK(h)                           \
+  do {                                               \
+    (h)->launches++;                                 \
+    cudaError_t _e = cudaGetLastError();             \
+    if (_e != cudaSuccess) return kt::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+  } while (0)

@@ -1,0 +1,686 @@
+// kt_krylov.cu -- matrix-free 5-point CG / BiCGSTAB for sm_100a.
+//
+// Replaces the Taichi kernels of cgsolver.py:31-81 and bicgsolver.py:21-86 (one launch per vector
+// op, one host sync per inner product) and the serial mega-kernel karman_taichi.py:342-456 with
+// three (BiCGSTAB: four) fused HBM-streaming kernels per iteration whose scalars never leave the
+// device:
+//
+//   BiCGSTAB (28 N words / iteration, 31 N with the Jacobi plane):
+//     K1 k_bicg_p      p = r + beta (p - omega v)                         4 N   bicgsolver.py:99-103
+//     K2 k_stencil     v = A p^, (r~, v)           -> alpha               8 N   :104-108
+//     K3 k_stencil     s = r - alpha v, t = A s^, (t,s), (t,t) -> omega   9 N   :110-118
+//     K4 k_bicg_xr     x += alpha p^ + omega s^, r = s - omega t,
+//                      (r,r), (r,r~)               -> test, rho, beta     7 N   :120-135,95-102
+//   CG (16 N words / iteration):
+//     C1 k_stencil     Ap = A p, (p, Ap)           -> alpha               7 N   cgsolver.py:94-96
+//     C2 k_cg_xr       x += alpha p, r -= alpha Ap, (r,r) -> test, beta   6 N   :98-107
+//     C3 k_cg_p        p = r + beta p                                     3 N   :109
+//
+// The stencil kernel marches each warp down a (TI rows x 32 vectors) tile keeping rows i-1, i, i+1 of
+// the operand in registers (one load per element), gets the j+-1 neighbours by warp shuffle (edge lanes
+// re-load one scalar, an L1/L2 hit), streams the five coefficient planes with 16-byte no-allocate
+// loads, and accumulates the fused inner products in double.
+#include <algorithm>
+#include <cstring>
+#include "kt_handle.h"
+
+namespace kt {
+
+// ---------------------------------------------------------------------------------------------
+// stencil kernel
+// ---------------------------------------------------------------------------------------------
+enum { SRC_X = 0, SRC_S = 1 };
+enum { EPI_Y = 0, EPI_DOT_Q = 1, EPI_DOT_SRC = 2, EPI_ST = 3, EPI_RESID = 4 };
+
+template <typename T> struct StencilArgs {
+  const T* c[5];     // ap, aw, ae, an, as planes
+  const T* x;        // SRC_X operand            | SRC_S: r
+  const T* v;        //                          | SRC_S: v   (s = r - alpha v)
+  const T* minv;     // PRE: Jacobi 1/M plane
+  const T* q;        // EPI_DOT_Q: external dot vector; EPI_RESID: b
+  T* y;              // A*src  (EPI_RESID: r = b - A*src)
+  T* s_out;          // EPI_ST: s ; EPI_RESID: r_tld copy (may be null)
+  int NX, pitch, row_lo, row_hi, TI, nCC;
+  long long nTiles;
+  double alpha_imm;
+  int alpha_from_sc;
+  int check_done;
+  int fin;
+  ReduceWs ws;
+};
+
+template <typename T, int SRC, bool PRE>
+struct SrcRow {
+  // vector of the stencil operand at (i, j0..j0+V-1); also returns the un-preconditioned value (s or x)
+  static __device__ __forceinline__ void load(const StencilArgs<T>& A, int i, int j0, bool act, T alpha,
+                                              Pack<T>& hat, Pack<T>& raw) {
+    constexpr int V = VT<T>::V;
+    if (!act || i < 0 || i >= A.NX) { hat = pack_zero<T>(); raw = hat; return; }
+    const size_t o = (size_t)i * A.pitch + j0;
+    if (SRC == SRC_X) {
+      raw = ld_cached(A.x + o);
+    } else {
+      Pack<T> r = ld_cached(A.x + o), v = ld_cached(A.v + o);
+#pragma unroll
+      for (int k = 0; k < V; ++k) raw.a[k] = r.a[k] - alpha * v.a[k];
+    }
+    if (PRE) {
+      Pack<T> m = ld_cached(A.minv + o);
+#pragma unroll
+      for (int k = 0; k < V; ++k) hat.a[k] = m.a[k] * raw.a[k];
+    } else {
+      hat = raw;
+    }
+  }
+  // scalar of the (preconditioned) operand at (i, j); j may be out of [0, pitch)
+  static __device__ __forceinline__ T scalar(const StencilArgs<T>& A, int i, int j, T alpha) {
+    if (j < 0 || j >= A.pitch || i < 0 || i >= A.NX) return T(0);
+    const size_t o = (size_t)i * A.pitch + j;
+    T raw;
+    if (SRC == SRC_X) raw = A.x[o];
+    else raw = A.x[o] - alpha * A.v[o];
+    if (PRE) raw = A.minv[o] * raw;
+    return raw;
+  }
+};
+
+template <typename T, int SRC, bool PRE, int EPI>
+__global__ void __launch_bounds__(256) k_stencil(const StencilArgs<T> A) {
+  constexpr int V = VT<T>::V;
+  if (A.check_done && A.ws.sc->done) return;
+  const T alpha = (SRC == SRC_S) ? T(A.alpha_from_sc ? A.ws.sc->alpha : A.alpha_imm) : T(0);
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const long long gwarp = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * wpb;
+  double acc0 = 0.0, acc1 = 0.0;
+
+  for (long long tile = gwarp; tile < A.nTiles; tile += nwarps) {
+    const int rchunk = (int)(tile / A.nCC), cc = (int)(tile - (long long)rchunk * A.nCC);
+    const int i0 = A.row_lo + rchunk * A.TI;
+    const int i1 = min(i0 + A.TI, A.row_hi);
+    const int j0 = (cc * 32 + lane) * V;
+    const bool act = j0 < A.pitch;
+    Pack<T> xw, xc, xe;        // (preconditioned) operand rows i-1, i, i+1
+    Pack<T> raw_c, raw_e;      // un-preconditioned operand (s or x) rows i, i+1
+    SrcRow<T, SRC, PRE>::load(A, i0 - 1, j0, act, alpha, xw, raw_c);
+    SrcRow<T, SRC, PRE>::load(A, i0, j0, act, alpha, xc, raw_c);
+#pragma unroll 2
+    for (int i = i0; i < i1; ++i) {
+      const size_t o = (size_t)i * A.pitch + j0;
+      Pack<T> c0, c1, c2, c3, c4, qv;
+      if (act) {
+        c0 = ld_stream(A.c[0] + o); c1 = ld_stream(A.c[1] + o); c2 = ld_stream(A.c[2] + o);
+        c3 = ld_stream(A.c[3] + o); c4 = ld_stream(A.c[4] + o);
+        if (EPI == EPI_DOT_Q || EPI == EPI_RESID) qv = ld_stream(A.q + o);
+      } else {
+        c0 = c1 = c2 = c3 = c4 = qv = pack_zero<T>();
+      }
+      SrcRow<T, SRC, PRE>::load(A, i + 1, j0, act, alpha, xe, raw_e);
+      // j-1 / j+V neighbours of the centre row
+      T xs = shfl_up1(xc.a[V - 1]);
+      T xn = shfl_down1(xc.a[0]);
+      if (lane == 0) xs = SrcRow<T, SRC, PRE>::scalar(A, i, j0 - 1, alpha);
+      if (lane == 31) xn = SrcRow<T, SRC, PRE>::scalar(A, i, j0 + V, alpha);
+      Pack<T> y;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const T north = (k < V - 1) ? xc.a[k + 1 < V ? k + 1 : k] : xn;
+        const T south = (k > 0) ? xc.a[k > 0 ? k - 1 : 0] : xs;
+        // cgsolver.py:59-60 left-to-right: ap*x + aw*x[i-1] + ae*x[i+1] + an*x[j+1] + as*x[j-1]
+        T acc = c0.a[k] * xc.a[k];
+        acc = acc + c1.a[k] * xw.a[k];
+        acc = acc + c2.a[k] * xe.a[k];
+        acc = acc + c3.a[k] * north;
+        acc = acc + c4.a[k] * south;
+        y.a[k] = acc;
+      }
+      if (act) {
+        if (EPI == EPI_RESID) {
+          Pack<T> r;
+#pragma unroll
+          for (int k = 0; k < V; ++k) { r.a[k] = qv.a[k] - y.a[k]; acc0 += (double)r.a[k] * (double)r.a[k]; }
+          st_vec(A.y + o, r);
+          if (A.s_out) st_vec(A.s_out + o, r);
+        } else {
+          st_vec(A.y + o, y);
+          if (EPI == EPI_ST) st_vec(A.s_out + o, raw_c);
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            if (EPI == EPI_DOT_Q) acc0 += (double)qv.a[k] * (double)y.a[k];
+            if (EPI == EPI_DOT_SRC) acc0 += (double)raw_c.a[k] * (double)y.a[k];
+            if (EPI == EPI_ST) { acc0 += (double)y.a[k] * (double)raw_c.a[k]; acc1 += (double)y.a[k] * (double)y.a[k]; }
+          }
+        }
+      }
+      xw = xc; xc = xe; raw_c = raw_e;
+    }
+  }
+  if (EPI == EPI_Y) return;
+  if (EPI == EPI_ST) block_reduce_finalize<2>(acc0, acc1, A.ws, A.fin);
+  else block_reduce_finalize<1>(acc0, acc1, A.ws, A.fin);
+}
+
+// ---------------------------------------------------------------------------------------------
+// element-wise kernels (flat over the owned rows; 16-byte vectors; static grid-stride assignment)
+// ---------------------------------------------------------------------------------------------
+struct EwGeom { long long v_lo, v_hi; };   // vector-index range [row_lo*pitch/V, row_hi*pitch/V)
+
+enum { EW_COPY, EW_FILL, EW_AXPY, EW_XPAY, EW_XMAY, EW_BICG_P, EW_BICG_X };
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(256) k_ew(EwGeom g, T* out, const T* x, const T* y, const T* z, double a_, double b_) {
+  constexpr int V = VT<T>::V;
+  const T a = T(a_), b = T(b_);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
+    const size_t o = (size_t)vi * V;
+    Pack<T> r;
+    if (OP == EW_COPY) r = ld_stream(x + o);
+    if (OP == EW_FILL) { for (int k = 0; k < V; ++k) r.a[k] = a; }
+    if (OP == EW_AXPY) { Pack<T> yy = ld_stream(out + o), xx = ld_stream(x + o);
+      for (int k = 0; k < V; ++k) r.a[k] = yy.a[k] + a * xx.a[k]; }
+    if (OP == EW_XPAY) { Pack<T> xx = ld_stream(x + o), yy = ld_stream(y + o);
+      for (int k = 0; k < V; ++k) r.a[k] = xx.a[k] + a * yy.a[k]; }
+    if (OP == EW_XMAY) { Pack<T> xx = ld_stream(x + o), yy = ld_stream(y + o);
+      for (int k = 0; k < V; ++k) r.a[k] = xx.a[k] - a * yy.a[k]; }
+    if (OP == EW_BICG_P) { Pack<T> rr = ld_stream(x + o), pp = ld_stream(out + o), vv = ld_stream(y + o);
+      for (int k = 0; k < V; ++k) r.a[k] = rr.a[k] + a * (pp.a[k] - b * vv.a[k]); }          // bicgsolver.py:46
+    if (OP == EW_BICG_X) { Pack<T> xx = ld_stream(out + o), pp = ld_stream(x + o), ss = ld_stream(y + o);
+      for (int k = 0; k < V; ++k) r.a[k] = xx.a[k] + (a * pp.a[k] + b * ss.a[k]); }          // bicgsolver.py:81
+    st_vec(out + o, r);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_dot(EwGeom g, const T* p, const T* q, ReduceWs ws) {
+  constexpr int V = VT<T>::V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
+    const size_t o = (size_t)vi * V;
+    Pack<T> a = ld_stream(p + o), b = ld_stream(q + o);
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc += (double)a.a[k] * (double)b.a[k];
+  }
+  block_reduce_finalize<1>(acc, 0.0, ws, FIN_NONE);
+}
+
+// K0: r = b, (r_tld = b), x = 0, [p = r for CG]; dot (r,r).   bicgsolver.py:21-36 / cgsolver.py:31-39,90
+template <typename T, bool CG>
+__global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_tld, T* x, T* p, ReduceWs ws, int fin) {
+  constexpr int V = VT<T>::V;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
+    const size_t o = (size_t)vi * V;
+    Pack<T> bb = ld_stream(b + o);
+    st_vec(r + o, bb);
+    if (r_tld) st_vec(r_tld + o, bb);
+    if (CG) st_vec(p + o, bb);
+    st_vec(x + o, pack_zero<T>());
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc += (double)bb.a[k] * (double)bb.a[k];
+  }
+  block_reduce_finalize<1>(acc, 0.0, ws, fin);
+}
+
+// K1: p = r + beta (p - omega v); first iteration p = r (bicgsolver.py:99-103)
+template <typename T>
+__global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, const T* v, const Scalars* sc) {
+  constexpr int V = VT<T>::V;
+  if (sc->done) return;
+  const bool first = sc->iter == 0;
+  const T beta = T(sc->beta), omega = T(sc->omega);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
+    const size_t o = (size_t)vi * V;
+    Pack<T> rr = ld_stream(r + o), out;
+    if (first) {
+      out = rr;
+    } else {
+      Pack<T> pp = ld_stream(p + o), vv = ld_stream(v + o);
+#pragma unroll
+      for (int k = 0; k < V; ++k) out.a[k] = rr.a[k] + beta * (pp.a[k] - omega * vv.a[k]);
+    }
+    st_vec(p + o, out);
+  }
+}
+
+// K4: x += alpha p^ + omega s^ ; r = s - omega t ; dots (r,r), (r,r_tld)   (bicgsolver.py:120-123, 95)
+template <typename T, bool PRE>
+__global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* p, const T* s, const T* t,
+                                                 const T* r_tld, const T* minv, double alpha_imm, double omega_imm,
+                                                 int from_sc, ReduceWs ws, int fin) {
+  constexpr int V = VT<T>::V;
+  if (from_sc && ws.sc->done) return;
+  const T alpha = T(from_sc ? ws.sc->alpha : alpha_imm), omega = T(from_sc ? ws.sc->omega : omega_imm);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double a0 = 0.0, a1 = 0.0;
+  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
+    const size_t o = (size_t)vi * V;
+    Pack<T> xx = ld_stream(x + o), pp = ld_stream(p + o), ss = ld_stream(s + o), tt = ld_stream(t + o),
+            rt = ld_stream(r_tld + o), rn;
+    Pack<T> ph = pp, sh = ss;
+    if (PRE) {
+      Pack<T> m = ld_stream(minv + o);
+#pragma unroll
+      for (int k = 0; k < V; ++k) { ph.a[k] = m.a[k] * pp.a[k]; sh.a[k] = m.a[k] * ss.a[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      xx.a[k] = xx.a[k] + (alpha * ph.a[k] + omega * sh.a[k]);
+      rn.a[k] = ss.a[k] - omega * tt.a[k];
+      a0 += (double)rn.a[k] * (double)rn.a[k];
+      a1 += (double)rn.a[k] * (double)rt.a[k];
+    }
+    st_vec(x + o, xx);
+    st_vec(r + o, rn);
+  }
+  block_reduce_finalize<2>(a0, a1, ws, fin);
+}
+
+// C2: x += alpha p ; r -= alpha Ap ; dot (r,r)   (cgsolver.py:98-101)
+template <typename T>
+__global__ void __launch_bounds__(256) k_cg_xr(EwGeom g, T* x, T* r, const T* p, const T* Ap, double alpha_imm,
+                                               int from_sc, ReduceWs ws, int fin) {
+  constexpr int V = VT<T>::V;
+  if (from_sc && ws.sc->done) return;
+  const T alpha = T(from_sc ? ws.sc->alpha : alpha_imm);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double a0 = 0.0;
+  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
+    const size_t o = (size_t)vi * V;
+    Pack<T> xx = ld_stream(x + o), rr = ld_stream(r + o), pp = ld_stream(p + o), aa = ld_stream(Ap + o);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      xx.a[k] = xx.a[k] + alpha * pp.a[k];
+      rr.a[k] = rr.a[k] - alpha * aa.a[k];
+      a0 += (double)rr.a[k] * (double)rr.a[k];
+    }
+    st_vec(x + o, xx);
+    st_vec(r + o, rr);
+  }
+  block_reduce_finalize<1>(a0, 0.0, ws, fin);
+}
+
+// C3: p = r + beta p   (cgsolver.py:78-81)
+template <typename T>
+__global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const Scalars* sc) {
+  constexpr int V = VT<T>::V;
+  if (sc->done) return;
+  const T beta = T(sc->beta);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
+    const size_t o = (size_t)vi * V;
+    Pack<T> rr = ld_stream(r + o), pp = ld_stream(p + o);
+#pragma unroll
+    for (int k = 0; k < V; ++k) pp.a[k] = rr.a[k] + beta * pp.a[k];
+    st_vec(p + o, pp);
+  }
+}
+
+__global__ void k_sc_reset(Scalars* sc, double eps, long long max_iter, int flags) {
+  sc->rho = 0.0; sc->rho_1 = 1.0; sc->alpha = 1.0; sc->beta = 1.0; sc->omega = 1.0;  // bicgsolver.py:32-36
+  sc->rTr0 = sc->rTr = sc->old_rTr = 0.0; sc->dot0 = sc->dot1 = 0.0;
+  sc->eps = eps; sc->iter = 0; sc->max_iter = max_iter; sc->status = 1; sc->done = 0; sc->first = 1; sc->flags = flags;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+  int V, TI, nCC, grid_st, grid_ew;
+  long long nTiles;
+  EwGeom g;
+};
+
+static Plan make_plan(const kt_handle_s* h) {
+  Plan P;
+  P.V = (h->dtype == KT_F64) ? 2 : 4;
+  const int rows = h->row_hi - h->row_lo;
+  P.nCC = (h->pitch / P.V + 31) / 32;
+  const long long target_warps = (long long)h->num_sms * 32;       // 8 blocks x 8 warps... per SM upper bound
+  int TI = 64;
+  while (TI > 4 && (long long)((rows + TI - 1) / TI) * P.nCC < 4 * target_warps) TI >>= 1;
+  P.TI = TI;
+  P.nTiles = (long long)((rows + TI - 1) / TI) * P.nCC;
+  long long blocks_needed = (P.nTiles + 7) / 8;
+  P.grid_st = (int)std::max<long long>(1, std::min<long long>(blocks_needed, (long long)h->num_sms * 8));
+  P.g.v_lo = (long long)h->row_lo * h->pitch / P.V;
+  P.g.v_hi = (long long)h->row_hi * h->pitch / P.V;
+  long long nvec = P.g.v_hi - P.g.v_lo;
+  P.grid_ew = (int)std::max<long long>(1, std::min<long long>((nvec + 255) / 256, (long long)h->num_sms * 8));
+  return P;
+}
+
+static ReduceWs make_ws(kt_handle_s* h, double* history = nullptr, long long cap = 0) {
+  ReduceWs ws;
+  ws.partials = h->partials; ws.ticket = h->ticket; ws.max_blocks = h->max_blocks; ws.sc = h->sc;
+  ws.history = history; ws.history_cap = cap;
+  return ws;
+}
+
+template <typename T>
+static StencilArgs<T> stencil_args(kt_handle_s* h, const Plan& P, const void* coef) {
+  StencilArgs<T> A;
+  memset(&A, 0, sizeof(A));
+  const size_t plane = (size_t)h->NX * h->pitch;
+  for (int k = 0; k < 5; ++k) A.c[k] = (const T*)coef + k * plane;
+  A.NX = h->NX; A.pitch = h->pitch; A.row_lo = h->row_lo; A.row_hi = h->row_hi;
+  A.TI = P.TI; A.nCC = P.nCC; A.nTiles = P.nTiles;
+  A.ws = make_ws(h);
+  return A;
+}
+
+template <typename T, int SRC, bool PRE, int EPI>
+static int launch_stencil(kt_handle_s* h, const Plan& P, const StencilArgs<T>& A) {
+  k_stencil<T, SRC, PRE, EPI><<<P.grid_st, 256, 0, h->stream>>>(A);
+  KT_LAUNCH_CHECK(h);
+  return 0;
+}
+
+static int read_dots(kt_handle_s* h, double* out, int n) {
+  KT_CUDA(cudaMemcpyAsync(h->sc_host, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+  KT_CUDA(cudaStreamSynchronize(h->stream));
+  out[0] = h->sc_host->dot0;
+  if (n > 1) out[1] = h->sc_host->dot1;
+  return 0;
+}
+
+// ---- unit entry points --------------------------------------------------------------------------
+template <typename T>
+static int t_spmv(kt_handle_s* h, const void* coef, const void* x, void* y, const void* q, double* dot_host) {
+  Plan P = make_plan(h);
+  StencilArgs<T> A = stencil_args<T>(h, P, coef);
+  A.x = (const T*)x; A.y = (T*)y; A.q = (const T*)q; A.fin = FIN_NONE;
+  if (!q) return launch_stencil<T, SRC_X, false, EPI_Y>(h, P, A);
+  int rc = launch_stencil<T, SRC_X, false, EPI_DOT_Q>(h, P, A);
+  if (rc) return rc;
+  return read_dots(h, dot_host, 1);
+}
+
+template <typename T>
+static int t_bicg_s_t(kt_handle_s* h, const void* coef, const void* r, const void* v, double alpha, void* s, void* t,
+                      double* dots_host) {
+  Plan P = make_plan(h);
+  StencilArgs<T> A = stencil_args<T>(h, P, coef);
+  A.x = (const T*)r; A.v = (const T*)v; A.y = (T*)t; A.s_out = (T*)s; A.alpha_imm = alpha; A.fin = FIN_NONE;
+  int rc = launch_stencil<T, SRC_S, false, EPI_ST>(h, P, A);
+  if (rc) return rc;
+  return read_dots(h, dots_host, 2);
+}
+
+template <typename T, int OP>
+static int t_ew(kt_handle_s* h, void* out, const void* x, const void* y, const void* z, double a, double b) {
+  Plan P = make_plan(h);
+  k_ew<T, OP><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (T*)out, (const T*)x, (const T*)y, (const T*)z, a, b);
+  KT_LAUNCH_CHECK(h);
+  return 0;
+}
+
+template <typename T>
+static int t_dot(kt_handle_s* h, const void* p, const void* q, double* out_host) {
+  Plan P = make_plan(h);
+  k_dot<T><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (const T*)p, (const T*)q, make_ws(h));
+  KT_LAUNCH_CHECK(h);
+  return read_dots(h, out_host, 1);
+}
+
+// ---- solvers ------------------------------------------------------------------------------------
+static int sc_reset(kt_handle_s* h, double eps, long long max_iter, int flags) {
+  k_sc_reset<<<1, 1, 0, h->stream>>>(h->sc, eps, max_iter, flags);
+  KT_LAUNCH_CHECK(h);
+  return 0;
+}
+
+// Poll loop shared by both solvers: enqueue `chunk` iterations at a time; the device-side `done` flag makes
+// every later kernel a no-op, so the host may notice convergence late without changing the result.
+template <typename EnqueueIter>
+static int run_chunks(kt_handle_s* h, long long max_iter, EnqueueIter&& enqueue_iter) {
+  const int chunk = 16;
+  long long enq = 0;
+  int slot = 0;
+  bool pending[2] = {false, false};
+  for (;;) {
+    long long n = std::min<long long>(chunk, std::max<long long>(1, max_iter - enq));
+    for (long long k = 0; k < n; ++k) { int rc = enqueue_iter(); if (rc) return rc; }
+    enq += n;
+    KT_CUDA(cudaMemcpyAsync(h->sc_host + slot, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+    KT_CUDA(cudaEventRecord(h->ev[slot], h->stream));
+    pending[slot] = true;
+    const int other = slot ^ 1;
+    if (pending[other]) {
+      KT_CUDA(cudaEventSynchronize(h->ev[other]));
+      pending[other] = false;
+      if (h->sc_host[other].done) break;
+    }
+    slot = other;
+  }
+  KT_CUDA(cudaStreamSynchronize(h->stream));
+  KT_CUDA(cudaMemcpy(h->sc_host, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+template <typename T>
+static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* w,
+                      double eps, long long max_iter, int flags, long* iters, double* rel_res, int* status,
+                      bool fixed_iters) {
+  Plan P = make_plan(h);
+  const bool pre = Minv != nullptr;
+  const bool warm = (flags & KT_FLAG_WARM_START) != 0;
+  T* r = (T*)w->r; T* p = (T*)w->p; T* v = (T*)w->Ap; T* s = (T*)w->s; T* t = (T*)w->t;
+  T* r_tld = (T*)w->r_tld;
+  KT_CHECK_ARG(r && p && v && s && t, "kt_krylov_ws: r, p, Ap, s, t are required for BiCGSTAB");
+  KT_CHECK_ARG(!(warm && !r_tld), "warm start needs a separate r_tld plane");
+  const T* r_tld_c = r_tld ? r_tld : (const T*)b;     // x0 = 0  =>  r_tld == b exactly (bicgsolver.py:25-26)
+  int rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, flags);
+  if (rc) return rc;
+  ReduceWs ws = make_ws(h, w->history, w->history_cap);
+  // K0
+  if (warm) {
+    StencilArgs<T> A = stencil_args<T>(h, P, coef);
+    A.ws = ws; A.x = (const T*)x; A.q = (const T*)b; A.y = r; A.s_out = r_tld; A.fin = FIN_BICG_INIT;
+    rc = launch_stencil<T, SRC_X, false, EPI_RESID>(h, P, A);
+    if (rc) return rc;
+  } else {
+    k_init<T, false><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (const T*)b, r, r_tld, (T*)x, nullptr, ws, FIN_BICG_INIT);
+    KT_LAUNCH_CHECK(h);
+  }
+  StencilArgs<T> A2 = stencil_args<T>(h, P, coef);
+  A2.ws = ws; A2.x = p; A2.minv = (const T*)Minv; A2.q = r_tld_c; A2.y = v; A2.check_done = 1; A2.fin = FIN_BICG_ALPHA;
+  StencilArgs<T> A3 = stencil_args<T>(h, P, coef);
+  A3.ws = ws; A3.x = r; A3.v = v; A3.minv = (const T*)Minv; A3.y = t; A3.s_out = s; A3.alpha_from_sc = 1;
+  A3.check_done = 1; A3.fin = FIN_BICG_OMEGA;
+  auto iter = [&]() -> int {
+    k_bicg_p<T><<<P.grid_ew, 256, 0, h->stream>>>(P.g, p, r, v, h->sc);
+    KT_LAUNCH_CHECK(h);
+    int e = pre ? launch_stencil<T, SRC_X, true, EPI_DOT_Q>(h, P, A2) : launch_stencil<T, SRC_X, false, EPI_DOT_Q>(h, P, A2);
+    if (e) return e;
+    e = pre ? launch_stencil<T, SRC_S, true, EPI_ST>(h, P, A3) : launch_stencil<T, SRC_S, false, EPI_ST>(h, P, A3);
+    if (e) return e;
+    if (pre) k_bicg_xr<T, true><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END);
+    else k_bicg_xr<T, false><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END);
+    KT_LAUNCH_CHECK(h);
+    return 0;
+  };
+  rc = run_chunks(h, max_iter, iter);
+  if (rc) return rc;
+  const Scalars& S = *h->sc_host;
+  if (iters) *iters = (long)S.iter;
+  if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
+  if (status) *status = S.status;
+  return 0;
+}
+
+template <typename T>
+static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const kt_krylov_ws* w, double eps,
+                long long max_iter, long* iters, double* rel_res, int* status, bool fixed_iters) {
+  Plan P = make_plan(h);
+  T* r = (T*)w->r; T* p = (T*)w->p; T* Ap = (T*)w->Ap;
+  KT_CHECK_ARG(r && p && Ap, "kt_krylov_ws: r, p, Ap are required for CG");
+  int rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0);
+  if (rc) return rc;
+  ReduceWs ws = make_ws(h, w->history, w->history_cap);
+  k_init<T, true><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (const T*)b, r, nullptr, (T*)x, p, ws, FIN_CG_INIT);
+  KT_LAUNCH_CHECK(h);
+  StencilArgs<T> A1 = stencil_args<T>(h, P, coef);
+  A1.ws = ws; A1.x = p; A1.y = Ap; A1.check_done = 1; A1.fin = FIN_CG_ALPHA;
+  auto iter = [&]() -> int {
+    int e = launch_stencil<T, SRC_X, false, EPI_DOT_SRC>(h, P, A1);
+    if (e) return e;
+    k_cg_xr<T><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws, FIN_CG_END);
+    KT_LAUNCH_CHECK(h);
+    k_cg_p<T><<<P.grid_ew, 256, 0, h->stream>>>(P.g, p, r, h->sc);
+    KT_LAUNCH_CHECK(h);
+    return 0;
+  };
+  rc = run_chunks(h, max_iter, iter);
+  if (rc) return rc;
+  const Scalars& S = *h->sc_host;
+  if (iters) *iters = (long)S.iter;
+  if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
+  if (status) *status = S.status;
+  return 0;
+}
+
+}  // namespace kt
+
+using namespace kt;
+
+#define KT_DISPATCH(h, call_d, call_f) ((h)->dtype == KT_F64 ? (call_d) : (call_f))
+
+extern "C" {
+
+int kt_spmv(kt_handle_t h, const void* coef, const void* x, void* y) {
+  KT_CHECK_ARG(h && coef && x && y, "kt_spmv: null argument");
+  KT_CHECK_ARG(x != y, "kt_spmv: x and y must not alias");
+  return KT_DISPATCH(h, t_spmv<double>(h, coef, x, y, nullptr, nullptr), t_spmv<float>(h, coef, x, y, nullptr, nullptr));
+}
+
+int kt_spmv_dot(kt_handle_t h, const void* coef, const void* x, void* y, const void* q, double* dot_host) {
+  KT_CHECK_ARG(h && coef && x && y && q && dot_host, "kt_spmv_dot: null argument");
+  KT_CHECK_ARG(x != y, "kt_spmv_dot: x and y must not alias");
+  return KT_DISPATCH(h, t_spmv<double>(h, coef, x, y, q, dot_host), t_spmv<float>(h, coef, x, y, q, dot_host));
+}
+
+int kt_bicg_s_t(kt_handle_t h, const void* coef, const void* r, const void* v, double alpha, void* s, void* t,
+                double* dots_host) {
+  KT_CHECK_ARG(h && coef && r && v && s && t && dots_host, "kt_bicg_s_t: null argument");
+  return KT_DISPATCH(h, t_bicg_s_t<double>(h, coef, r, v, alpha, s, t, dots_host),
+                     t_bicg_s_t<float>(h, coef, r, v, alpha, s, t, dots_host));
+}
+
+int kt_dot(kt_handle_t h, const void* p, const void* q, double* out_host) {
+  KT_CHECK_ARG(h && p && q && out_host, "kt_dot: null argument");
+  return KT_DISPATCH(h, t_dot<double>(h, p, q, out_host), t_dot<float>(h, p, q, out_host));
+}
+
+int kt_copy(kt_handle_t h, void* dst, const void* src) {
+  KT_CHECK_ARG(h && dst && src, "kt_copy: null argument");
+  return KT_DISPATCH(h, (t_ew<double, EW_COPY>(h, dst, src, nullptr, nullptr, 0, 0)),
+                     (t_ew<float, EW_COPY>(h, dst, src, nullptr, nullptr, 0, 0)));
+}
+int kt_fill(kt_handle_t h, void* dst, double value) {
+  KT_CHECK_ARG(h && dst, "kt_fill: null argument");
+  return KT_DISPATCH(h, (t_ew<double, EW_FILL>(h, dst, nullptr, nullptr, nullptr, value, 0)),
+                     (t_ew<float, EW_FILL>(h, dst, nullptr, nullptr, nullptr, value, 0)));
+}
+int kt_axpy(kt_handle_t h, void* y, double a, const void* x) {
+  KT_CHECK_ARG(h && y && x, "kt_axpy: null argument");
+  return KT_DISPATCH(h, (t_ew<double, EW_AXPY>(h, y, x, nullptr, nullptr, a, 0)),
+                     (t_ew<float, EW_AXPY>(h, y, x, nullptr, nullptr, a, 0)));
+}
+int kt_xpay(kt_handle_t h, void* out, const void* x, double a, const void* y) {
+  KT_CHECK_ARG(h && out && x && y, "kt_xpay: null argument");
+  return KT_DISPATCH(h, (t_ew<double, EW_XPAY>(h, out, x, y, nullptr, a, 0)),
+                     (t_ew<float, EW_XPAY>(h, out, x, y, nullptr, a, 0)));
+}
+int kt_xmay(kt_handle_t h, void* out, const void* x, double a, const void* y) {
+  KT_CHECK_ARG(h && out && x && y, "kt_xmay: null argument");
+  return KT_DISPATCH(h, (t_ew<double, EW_XMAY>(h, out, x, y, nullptr, a, 0)),
+                     (t_ew<float, EW_XMAY>(h, out, x, y, nullptr, a, 0)));
+}
+int kt_bicg_update_p(kt_handle_t h, void* p, const void* r, const void* v, double beta, double omega) {
+  KT_CHECK_ARG(h && p && r && v, "kt_bicg_update_p: null argument");
+  return KT_DISPATCH(h, (t_ew<double, EW_BICG_P>(h, p, r, v, nullptr, beta, omega)),
+                     (t_ew<float, EW_BICG_P>(h, p, r, v, nullptr, beta, omega)));
+}
+int kt_bicg_update_x(kt_handle_t h, void* x, const void* p, const void* s, double alpha, double omega) {
+  KT_CHECK_ARG(h && x && p && s, "kt_bicg_update_x: null argument");
+  return KT_DISPATCH(h, (t_ew<double, EW_BICG_X>(h, x, p, s, nullptr, alpha, omega)),
+                     (t_ew<float, EW_BICG_X>(h, x, p, s, nullptr, alpha, omega)));
+}
+
+int kt_bicg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* s, const void* t, const void* r_tld,
+               double alpha, double omega, double* dots_host) {
+  KT_CHECK_ARG(h && x && r && p && s && t && r_tld && dots_host, "kt_bicg_xr: null argument");
+  Plan P = make_plan(h);
+  ReduceWs ws = make_ws(h);
+  if (h->dtype == KT_F64)
+    k_bicg_xr<double, false><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)s,
+                                                              (const double*)t, (const double*)r_tld, nullptr, alpha, omega, 0, ws, FIN_NONE);
+  else
+    k_bicg_xr<float, false><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)s,
+                                                             (const float*)t, (const float*)r_tld, nullptr, alpha, omega, 0, ws, FIN_NONE);
+  KT_LAUNCH_CHECK(h);
+  return read_dots(h, dots_host, 2);
+}
+
+int kt_cg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* Ap, double alpha, double* dot_host) {
+  KT_CHECK_ARG(h && x && r && p && Ap && dot_host, "kt_cg_xr: null argument");
+  Plan P = make_plan(h);
+  ReduceWs ws = make_ws(h);
+  if (h->dtype == KT_F64)
+    k_cg_xr<double><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)Ap, alpha, 0, ws, FIN_NONE);
+  else
+    k_cg_xr<float><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)Ap, alpha, 0, ws, FIN_NONE);
+  KT_LAUNCH_CHECK(h);
+  return read_dots(h, dot_host, 1);
+}
+
+int kt_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, double eps, long max_iter,
+                long* iters, double* rel_res, int* status) {
+  KT_CHECK_ARG(h && coef && b && x && ws, "kt_cg_solve: null argument");
+  return KT_DISPATCH(h, t_cg<double>(h, coef, b, x, ws, eps, max_iter, iters, rel_res, status, false),
+                     t_cg<float>(h, coef, b, x, ws, eps, max_iter, iters, rel_res, status, false));
+}
+
+int kt_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* ws,
+                      double eps, long max_iter, int flags, long* iters, double* rel_res, int* status) {
+  KT_CHECK_ARG(h && coef && b && x && ws, "kt_bicgstab_solve: null argument");
+  return KT_DISPATCH(h, t_bicgstab<double>(h, coef, b, x, Minv, ws, eps, max_iter, flags, iters, rel_res, status, false),
+                     t_bicgstab<float>(h, coef, b, x, Minv, ws, eps, max_iter, flags, iters, rel_res, status, false));
+}
+
+static int timed(kt_handle_t h, float* ms, int rc_before) { (void)h; (void)ms; return rc_before; }
+
+int kt_bicgstab_bench(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, long n_iter, float* ms) {
+  KT_CHECK_ARG(h && coef && b && x && ws && ms, "kt_bicgstab_bench: null argument");
+  KT_CUDA(cudaEventRecord(h->t0, h->stream));
+  long it = 0; int st = 0; double rr = 0;
+  int rc = KT_DISPATCH(h, t_bicgstab<double>(h, coef, b, x, nullptr, ws, 0.0, n_iter, 0, &it, &rr, &st, true),
+                       t_bicgstab<float>(h, coef, b, x, nullptr, ws, 0.0, n_iter, 0, &it, &rr, &st, true));
+  if (rc) return rc;
+  KT_CUDA(cudaEventRecord(h->t1, h->stream));
+  KT_CUDA(cudaEventSynchronize(h->t1));
+  KT_CUDA(cudaEventElapsedTime(ms, h->t0, h->t1));
+  if (it != n_iter) { set_error("kt_bicgstab_bench: solver stopped early (status " + std::to_string(st) + ")"); return -3; }
+  return timed(h, ms, 0);
+}
+
+int kt_cg_bench(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, long n_iter, float* ms) {
+  KT_CHECK_ARG(h && coef && b && x && ws && ms, "kt_cg_bench: null argument");
+  KT_CUDA(cudaEventRecord(h->t0, h->stream));
+  long it = 0; int st = 0; double rr = 0;
+  int rc = KT_DISPATCH(h, t_cg<double>(h, coef, b, x, ws, 0.0, n_iter, &it, &rr, &st, true),
+                       t_cg<float>(h, coef, b, x, ws, 0.0, n_iter, &it, &rr, &st, true));
+  if (rc) return rc;
+  KT_CUDA(cudaEventRecord(h->t1, h->stream));
+  KT_CUDA(cudaEventSynchronize(h->t1));
+  KT_CUDA(cudaEventElapsedTime(ms, h->t0, h->t1));
+  if (it != n_iter) { set_error("kt_cg_bench: solver stopped early (status " + std::to_string(st) + ")"); return -3; }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+"""CPU oracle for the karman_taichi hot path -- TEST INFRASTRUCTURE ONLY.
+
+This package is a CPU restatement (NumPy, plus a small C/OpenMP port under
+``oracle/c``) of the reference's arithmetic for the SIMPLE / BiCGSTAB / CG path.
+It is the checker the CUDA path is compared against; it is never the product.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import or execute anything under ``oracle/``.
+``karman_taichi_b200`` never imports it.
+
+How the oracle is pinned: Taichi 0.9.0 cannot be installed in this
+image (no wheel for Python 3.12, no network), so the reference itself cannot be run
+here.  The reference keeps no golden vectors, no expected iteration counts and no
+field snapshots.  What it does hold is re-expressed in ``tests/``:
+
+* ``data/ghia1982.dat`` (Ghia et al. 1982 centreline profiles, compared at
+  ``bicgsimp.py:291-304``)              -> ``tests/golden/ghia1982_re100.json``
+* ``np.allclose`` against ``np.linalg.solve`` on a random 5-diagonal system
+  (``debug/ti_bicg_test.py:45-98``)     -> ``tests/test_oracle_krylov.py``
+* ``np.allclose(Ax, b)`` after CG (``benchmark/2dcg.py:129-132``)
+* residual / convergence-history comparison against SciPy BiCGSTAB and a sparse
+  direct solve (``benchmark/cg_to_sparse/test_cg_sparse.py:38-41``,
+  ``validation.py:26-45``)
+
+Every function cites the reference file:line it follows.
+"""

@@ -1,0 +1,265 @@
+"""GPU parity: CUDA Krylov kernels (through the C ABI / host classes) vs the CPU oracle.
+
+Bars (north_star): element-wise / SpMV results bit-exact (the library is built -fmad=false and keeps the
+reference's operation order); inner products to rounding (different summation order, rtol 1e-13);
+iteration counts within +-1; solutions within relative L2 1e-8 (f64) / 1e-4 (f32).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import krylov
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def make(cuda, coef, b, cls):
+    import karman_taichi_b200 as kt
+    fc = kt.Field(coef.shape, coef.dtype, cuda).from_numpy(coef)
+    fb = kt.Field(b.shape, b.dtype, cuda).from_numpy(b)
+    fx = kt.Field(b.shape, b.dtype, cuda)
+    return cls(fc, fb, fx)
+
+
+SHAPES = [(5, 7), (37, 53), (130, 130), (66, 323), (258, 1030), (1026, 514)]
+
+
+@pytest.mark.parametrize('shape', SHAPES)
+def test_field_roundtrip_and_layout(cuda, shape):
+    import karman_taichi_b200 as kt
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal(shape)
+    c = rng.standard_normal(shape + (5,))
+    fa = kt.Field(shape, np.float64, cuda).from_numpy(a)
+    fc = kt.Field(shape + (5,), np.float64, cuda).from_numpy(c)
+    np.testing.assert_array_equal(fa.to_numpy(), a)
+    np.testing.assert_array_equal(fc.to_numpy(), c)
+    assert fa.pitch % 16 == 0 and fa.pitch >= shape[1]
+    assert float(fa.data[:, shape[1]:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize('shape', SHAPES)
+def test_spmv_bit_exact(cuda, shape):
+    import karman_taichi_b200 as kt
+    rng = np.random.default_rng(2)
+    coef = rng.standard_normal(shape + (5,))          # bare array: exercises the out-of-range = 0 rule too
+    x = rng.standard_normal(shape)
+    s = make(cuda, coef, np.zeros(shape), kt.CGSolver)
+    s.p.from_numpy(x)
+    s.compute_Ap()
+    np.testing.assert_array_equal(s.Ap.to_numpy(), krylov.spmv(coef, x))
+    s.x.from_numpy(x)
+    s.compute_Ax()
+    np.testing.assert_array_equal(s.Ax.to_numpy(), krylov.spmv(coef, x))
+
+
+@pytest.mark.parametrize('shape', SHAPES)
+def test_reduce_and_vector_updates(cuda, shape):
+    import karman_taichi_b200 as kt
+    rng = np.random.default_rng(3)
+    coef = rng.standard_normal(shape + (5,))
+    b = rng.standard_normal(shape)
+    s = make(cuda, coef, b, kt.BICGSolver)
+    p, q = rng.standard_normal(shape), rng.standard_normal(shape)
+    s.p.from_numpy(p)
+    s.s.from_numpy(q)
+    d = s.reduce(s.p, s.s)
+    assert d == pytest.approx(float(np.sum(p * q)), rel=1e-13, abs=1e-13 * np.abs(p * q).sum())
+    # deterministic: same bits on a second call
+    assert s.reduce(s.p, s.s) == d
+    # BiCG vector ops, bit-exact against the reference expressions
+    r, v, t = rng.standard_normal(shape), rng.standard_normal(shape), rng.standard_normal(shape)
+    x0 = rng.standard_normal(shape)
+    s.r.from_numpy(r); s.Ap.from_numpy(v); s.t.from_numpy(t); s.x.from_numpy(x0)
+    s.alpha[None], s.beta[None], s.omega[None] = 0.37, -1.21, 0.83
+    s.update_p()
+    np.testing.assert_array_equal(s.p.to_numpy(), r + (-1.21) * (p - 0.83 * v))
+    s.update_s()
+    np.testing.assert_array_equal(s.s.to_numpy(), r - 0.37 * v)
+    pn, sn = s.p.to_numpy(), s.s.to_numpy()
+    s.update_x()
+    np.testing.assert_array_equal(s.x.to_numpy(), x0 + (0.37 * pn + 0.83 * sn))
+    s.update_r()
+    np.testing.assert_array_equal(s.r.to_numpy(), sn - 0.83 * t)
+    # CG vector ops
+    c = make(cuda, coef, b, kt.CGSolver)
+    c.p.from_numpy(p); c.r.from_numpy(r); c.Ap.from_numpy(v); c.x.from_numpy(x0)
+    c.alpha[None], c.beta[None] = 0.61, 0.29
+    c.update_x()
+    np.testing.assert_array_equal(c.x.to_numpy(), x0 + 0.61 * p)
+    c.update_r()
+    np.testing.assert_array_equal(c.r.to_numpy(), r - 0.61 * v)
+    rn = c.r.to_numpy()
+    c.update_p()
+    np.testing.assert_array_equal(c.p.to_numpy(), rn + 0.29 * p)
+
+
+@pytest.mark.parametrize('shape', [(37, 53), (258, 1030)])
+def test_fused_kernels_match_unfused(cuda, shape):
+    """kt_spmv_dot / kt_bicg_s_t / kt_bicg_xr / kt_cg_xr against the oracle expressions."""
+    import karman_taichi_b200 as kt
+    from karman_taichi_b200 import _lib
+    from karman_taichi_b200.cgsolver import _p
+    rng = np.random.default_rng(4)
+    coef = rng.standard_normal(shape + (5,))
+    s = make(cuda, coef, rng.standard_normal(shape), kt.BICGSolver)
+    L, h = s._lib, s._h
+    r, v, p, x0 = (rng.standard_normal(shape) for _ in range(4))
+    s.r.from_numpy(r); s.Ap.from_numpy(v); s.p.from_numpy(p); s.x.from_numpy(x0)
+    # v' = A p, (b, v')
+    out = (C.c_double * 2)()
+    tmp = kt.Field(shape, np.float64, cuda)
+    _lib.check(L.kt_spmv_dot(h, _p(s.coef), _p(s.p), _p(tmp), _p(s.b), out))
+    Ap = krylov.spmv(coef, p)
+    np.testing.assert_array_equal(tmp.to_numpy(), Ap)
+    assert out[0] == pytest.approx(float(np.sum(s.b.to_numpy() * Ap)), rel=1e-12)
+    # s = r - alpha v, t = A s, (t,s), (t,t)
+    alpha, omega = 0.43, 0.77
+    _lib.check(L.kt_bicg_s_t(h, _p(s.coef), _p(s.r), _p(s.Ap), alpha, _p(s.s), _p(s.t), out))
+    s_ref = r - alpha * v
+    t_ref = krylov.spmv(coef, s_ref)
+    np.testing.assert_array_equal(s.s.to_numpy(), s_ref)
+    np.testing.assert_array_equal(s.t.to_numpy(), t_ref)
+    assert out[0] == pytest.approx(float(np.sum(t_ref * s_ref)), rel=1e-12)
+    assert out[1] == pytest.approx(float(np.sum(t_ref * t_ref)), rel=1e-12)
+    # x += alpha p + omega s ; r = s - omega t ; (r,r), (r,b)
+    _lib.check(L.kt_bicg_xr(h, _p(s.x), _p(s.r), _p(s.p), _p(s.s), _p(s.t), _p(s.b), alpha, omega, out))
+    r_new = s_ref - omega * t_ref
+    np.testing.assert_array_equal(s.x.to_numpy(), x0 + (alpha * p + omega * s_ref))
+    np.testing.assert_array_equal(s.r.to_numpy(), r_new)
+    assert out[0] == pytest.approx(float(np.sum(r_new * r_new)), rel=1e-12)
+    assert out[1] == pytest.approx(float(np.sum(r_new * s.b.to_numpy())), rel=1e-12, abs=1e-9)
+    # CG fused x/r
+    s.x.from_numpy(x0); s.r.from_numpy(r)
+    _lib.check(L.kt_cg_xr(h, _p(s.x), _p(s.r), _p(s.p), _p(s.Ap), alpha, out))
+    np.testing.assert_array_equal(s.x.to_numpy(), x0 + alpha * p)
+    np.testing.assert_array_equal(s.r.to_numpy(), r - alpha * v)
+
+
+CASES = [('poisson', 64, 0.0, 1e-6), ('poisson', 128, 0.1, 1e-10), ('poisson', 512, 0.1, 1e-12),
+         ('random', 37, 53, 1e-10), ('random', 128, 128, 1e-8), ('random', 300, 1026, 1e-8)]
+
+
+def system(kind, a, b):
+    if kind == 'poisson':
+        return krylov.poisson_sin_system(a, b)
+    return krylov.random_dd_system(a, b, seed=0)
+
+
+@pytest.mark.parametrize('kind,a,b,eps', CASES)
+def test_bicgstab_solve_parity(cuda, kind, a, b, eps):
+    import karman_taichi_b200 as kt
+    coef, rhs = system(kind, a, b)
+    x_ref, it_ref, st_ref = krylov.bicgstab_solve(coef, rhs, eps=eps)
+    s = make(cuda, coef, rhs, kt.BICGSolver)
+    s.solve(eps=eps, quiet=True)
+    assert s.status == st_ref == 0
+    assert abs(s.iterations - it_ref) <= 1
+    assert rel_l2(s.x.to_numpy(), x_ref) < 1e-8
+    # size-independent property: the returned x really solves the system to the requested tolerance
+    res = krylov.spmv(coef, s.x.to_numpy()) - rhs
+    assert np.linalg.norm(res) <= 1.01 * eps * np.linalg.norm(rhs) + 1e-13 * np.linalg.norm(rhs)
+    # ghost ring untouched
+    assert np.all(s.x.to_numpy()[0, :] == 0) and np.all(s.x.to_numpy()[:, 0] == 0)
+
+
+@pytest.mark.parametrize('kind,a,b,eps', [c for c in CASES if c[0] == 'poisson'])
+def test_cg_solve_parity(cuda, kind, a, b, eps):
+    import karman_taichi_b200 as kt
+    coef, rhs = system(kind, a, b)
+    hist_ref = []
+    x_ref, it_ref, st_ref = krylov.cg_solve(coef, rhs, eps=eps, history=hist_ref)
+    s = make(cuda, coef, rhs, kt.CGSolver)
+    s.solve(eps=eps, quiet=True)
+    assert s.status == st_ref == 0
+    assert abs(s.iterations - it_ref) <= 1
+    assert rel_l2(s.x.to_numpy(), x_ref) < 1e-8
+    # convergence history parity (cgsolver.py:88,111): same strings up to the last common entry
+    m = min(len(hist_ref), len(s.history)) - 1
+    got = np.array([float(h) for h in s.history[:m]])
+    ref = np.array([float(h) for h in hist_ref[:m]])
+    np.testing.assert_allclose(got, ref, rtol=1e-5)
+
+
+def test_bicgstab_f32(cuda):
+    import karman_taichi_b200 as kt
+    coef, rhs = krylov.poisson_sin_system(128, 0.1)
+    x_ref, it_ref, _ = krylov.bicgstab_solve(coef, rhs, eps=1e-5)
+    s = make(cuda, coef.astype(np.float32), rhs.astype(np.float32), kt.BICGSolver)
+    s.solve(eps=1e-5, quiet=True)
+    assert s.status == 0
+    assert abs(s.iterations - it_ref) <= 2
+    assert rel_l2(s.x.to_numpy().astype(np.float64), x_ref) < 1e-4
+
+
+def test_bicgstab_rho_zero_and_zero_division(cuda, capsys):
+    import karman_taichi_b200 as kt
+    coef, rhs = krylov.poisson_sin_system(16, 0.1)
+    s = make(cuda, coef, np.zeros_like(rhs), kt.BICGSolver)
+    s.solve()
+    assert s.status == 2 and s.iterations == 0
+    assert '>>> BICG failed at first place...' in capsys.readouterr().out     # bicgsolver.py:97
+    assert np.all(s.x.to_numpy() == 0.0)
+    c = make(cuda, coef, np.zeros_like(rhs), kt.CGSolver)
+    with pytest.raises(ZeroDivisionError):                                    # cgsolver.py:96
+        c.solve()
+    # singular operator: A = 0 -> (r_tld, Ap) == 0 -> ZeroDivisionError (bicgsolver.py:108)
+    z = make(cuda, np.zeros_like(coef), rhs, kt.BICGSolver)
+    with pytest.raises(ZeroDivisionError):
+        z.solve()
+
+
+def test_max_iter_status(cuda):
+    import karman_taichi_b200 as kt
+    coef, rhs = krylov.poisson_sin_system(64, 0.0)
+    s = make(cuda, coef, rhs, kt.BICGSolver)
+    s.max_steps = 7
+    s.solve(eps=1e-30)
+    assert s.status == 1 and s.iterations == 7
+    x_ref, it, st = krylov.bicgstab_solve(coef, rhs, eps=1e-30, max_iter=7)
+    assert rel_l2(s.x.to_numpy(), x_ref) < 1e-10
+
+
+def test_jacobi_warm_start_variant(cuda):
+    """Monolith solver (karman_taichi.py:342-456): Jacobi M, warm start, omega == 0 break."""
+    import karman_taichi_b200 as kt
+    coef, rhs = krylov.random_dd_system(66, 323, seed=7)
+    rng = np.random.default_rng(8)
+    M = coef[:, :, 0] * (1.0 + 0.1 * rng.random(rhs.shape))   # M != diag(A) on purpose
+    x0 = np.zeros_like(rhs)
+    x0[1:-1, 1:-1] = rng.standard_normal((66, 323))
+    x_ref, it_ref, st_ref = krylov.jacobi_bicgstab(coef, M, rhs, x0, eps=1e-8)
+    s = make(cuda, coef, rhs, kt.BICGSolver)
+    with np.errstate(divide='ignore'):
+        minv = np.where(M != 0.0, 1.0 / np.where(M != 0.0, M, 1.0), 0.0)
+    s.Minv = kt.Field(rhs.shape, np.float64, cuda).from_numpy(minv)
+    s.warm_start = True
+    s.omega_zero_break = True
+    s.max_steps = 100 * 66 * 323
+    s.x.from_numpy(x0)
+    s.solve(eps=1e-8)
+    assert s.status == st_ref == 0
+    assert abs(s.iterations - it_ref) <= 1
+    assert rel_l2(s.x.to_numpy(), x_ref) < 1e-8
+
+
+def test_large_roundtrip_property(cuda):
+    """Full-size property check (4098^2, config 3): solve, then verify ||A x - b|| on the device result."""
+    import karman_taichi_b200 as kt
+    n = 4096
+    coef, rhs = krylov.poisson_sin_system(n, 0.1)
+    s = make(cuda, coef, rhs, kt.BICGSolver)
+    s.solve(eps=1e-8)
+    assert s.status == 0 and s.iterations < 200
+    x = s.x.to_numpy()
+    res = krylov.spmv(coef, x) - rhs
+    assert np.linalg.norm(res) <= 1.01e-8 * np.linalg.norm(rhs)
+    c = make(cuda, coef, rhs, kt.CGSolver)
+    c.solve(eps=1e-8)
+    assert c.status == 0
+    assert rel_l2(c.x.to_numpy(), x) < 1e-7
