@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libkarman_b200.so')
+# KT_LIB_PATH: development override to load a tuning variant of the same library (tools/variants.py)
+LIB_PATH = os.environ.get('KT_LIB_PATH') or os.path.join(HERE, 'libkarman_b200.so')
 
 KT_F64, KT_F32 = 0, 1
 

@@ -41,12 +41,13 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False, extra_flags=()):
-    """Compile every .cu into one shared library next to this file.  Returns the path."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile every .cu into one shared library next to this file.  Returns the path.
+    ``out`` + ``extra_flags`` (-D...) build a tuning variant elsewhere (tools/variants.py)."""
+    if out is None and not force and not needs_build():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ['-o', LIB] + srcs
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ['-o', out or LIB] + srcs
     if verbose:
         print(' '.join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -55,7 +56,7 @@ def build(force=False, verbose=False, extra_flags=()):
         raise RuntimeError('nvcc failed building libkarman_b200.so')
     if verbose and (res.stdout or res.stderr):
         print(res.stdout + res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == '__main__':

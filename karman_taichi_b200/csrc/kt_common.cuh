@@ -35,28 +35,48 @@ template <typename T> __device__ __forceinline__ Pack<T> pack_zero() {
 }
 
 // ---- 16-byte global loads / stores ---------------------------------------------------------
+// The load asms are deliberately NOT volatile: they are pure functions of the address as far as the
+// compiler is concerned, so an unrolled loop can batch the loads of several rows / strides ahead of the
+// (volatile, memory-clobbering) stores -- that is where the memory-level parallelism comes from.  Every
+// kernel reads an address at most once before (possibly) overwriting it with a value that depends on
+// that read, so no load can be legally or usefully moved across a store to the same address.
+//   ld_stream : read-only operand, streamed once      -> ld.global.nc.L1::no_allocate
+//   ld_rw     : operand this kernel also writes        -> ld.global.L1::no_allocate (no .nc)
+//   ld_cached : stencil operand, re-read by neighbours -> ld.global (L1 allocating)
+#ifndef KT_EW_UNROLL
+#define KT_EW_UNROLL 4
+#endif
 __device__ __forceinline__ Pack<double> ld_stream(const double* p) {
   Pack<double> r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
   return r;
 }
 __device__ __forceinline__ Pack<float> ld_stream(const float* p) {
   Pack<float> r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]) : "l"(p));
   return r;
 }
-// cached (L1-allocating) load for the stencil operand; not .nc because some kernels read a plane that an
-// earlier kernel of the same stream wrote (coherent across launches either way) -- plain ld.global.
+__device__ __forceinline__ Pack<double> ld_rw(const double* p) {
+  Pack<double> r;
+  asm("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ Pack<float> ld_rw(const float* p) {
+  Pack<float> r;
+  asm("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ Pack<double> ld_cached(const double* p) {
   Pack<double> r;
-  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
+  asm("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
   return r;
 }
 __device__ __forceinline__ Pack<float> ld_cached(const float* p) {
   Pack<float> r;
-  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]) : "l"(p));
+  asm("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]) : "l"(p));
   return r;
 }
 __device__ __forceinline__ void st_vec(double* p, const Pack<double>& v) {

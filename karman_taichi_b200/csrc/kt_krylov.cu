@@ -21,6 +21,7 @@
 // re-load one scalar, an L1/L2 hit), streams the five coefficient planes with 16-byte no-allocate
 // loads, and accumulates the fused inner products in double.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "kt_handle.h"
 
@@ -84,8 +85,17 @@ struct SrcRow {
   }
 };
 
+#ifndef KT_STENCIL_MINB
+#define KT_STENCIL_MINB 1
+#endif
+#ifndef KT_STENCIL_UNROLL
+#define KT_STENCIL_UNROLL 2
+#endif
+constexpr int kStencilUnroll = KT_STENCIL_UNROLL;   // rows of loads the compiler may batch ahead
+constexpr int kEwUnroll = KT_EW_UNROLL;             // strides of loads batched ahead in element-wise kernels
+
 template <typename T, int SRC, bool PRE, int EPI>
-__global__ void __launch_bounds__(256) k_stencil(const StencilArgs<T> A) {
+__global__ void __launch_bounds__(256, KT_STENCIL_MINB) k_stencil(const StencilArgs<T> A) {
   constexpr int V = VT<T>::V;
   if (A.check_done && A.ws.sc->done) return;
   const T alpha = (SRC == SRC_S) ? T(A.alpha_from_sc ? A.ws.sc->alpha : A.alpha_imm) : T(0);
@@ -105,7 +115,7 @@ __global__ void __launch_bounds__(256) k_stencil(const StencilArgs<T> A) {
     Pack<T> raw_c, raw_e;      // un-preconditioned operand (s or x) rows i, i+1
     SrcRow<T, SRC, PRE>::load(A, i0 - 1, j0, act, alpha, xw, raw_c);
     SrcRow<T, SRC, PRE>::load(A, i0, j0, act, alpha, xc, raw_c);
-#pragma unroll 2
+#pragma unroll kStencilUnroll
     for (int i = i0; i < i1; ++i) {
       const size_t o = (size_t)i * A.pitch + j0;
       Pack<T> c0, c1, c2, c3, c4, qv;
@@ -168,40 +178,60 @@ struct EwGeom { long long v_lo, v_hi; };   // vector-index range [row_lo*pitch/V
 
 enum { EW_COPY, EW_FILL, EW_AXPY, EW_XPAY, EW_XMAY, EW_BICG_P, EW_BICG_X };
 
+// Every element-wise kernel walks its statically assigned vectors in batches of U strides: the U x (arrays)
+// 16-byte loads of a batch are issued back to back before the first dependent instruction, so each thread
+// keeps U x arrays x 16 B in flight (explicit batching -- ptxas will not hoist a possibly-aliasing load above a
+// store on its own).  KT_EW_FOR(u, vi) iterates the batch; out-of-range strides are predicated off.
+#define KT_EW_OUTER(U)                                                                                     \
+  const long long stride = (long long)gridDim.x * blockDim.x;                                              \
+  for (long long vb = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vb < g.v_hi; vb += stride * (U))
+#define KT_EW_FOR(U, u, o)                                                  \
+  _Pragma("unroll") for (int u = 0; u < (U); ++u)                           \
+    if (const size_t o = (size_t)(vb + u * stride) * V; vb + u * stride < g.v_hi)
+
 template <typename T, int OP>
 __global__ void __launch_bounds__(256) k_ew(EwGeom g, T* out, const T* x, const T* y, const T* z, double a_, double b_) {
   constexpr int V = VT<T>::V;
+  constexpr int U = kEwUnroll;
   const T a = T(a_), b = T(b_);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
-    const size_t o = (size_t)vi * V;
-    Pack<T> r;
-    if (OP == EW_COPY) r = ld_stream(x + o);
-    if (OP == EW_FILL) { for (int k = 0; k < V; ++k) r.a[k] = a; }
-    if (OP == EW_AXPY) { Pack<T> yy = ld_stream(out + o), xx = ld_stream(x + o);
-      for (int k = 0; k < V; ++k) r.a[k] = yy.a[k] + a * xx.a[k]; }
-    if (OP == EW_XPAY) { Pack<T> xx = ld_stream(x + o), yy = ld_stream(y + o);
-      for (int k = 0; k < V; ++k) r.a[k] = xx.a[k] + a * yy.a[k]; }
-    if (OP == EW_XMAY) { Pack<T> xx = ld_stream(x + o), yy = ld_stream(y + o);
-      for (int k = 0; k < V; ++k) r.a[k] = xx.a[k] - a * yy.a[k]; }
-    if (OP == EW_BICG_P) { Pack<T> rr = ld_stream(x + o), pp = ld_stream(out + o), vv = ld_stream(y + o);
-      for (int k = 0; k < V; ++k) r.a[k] = rr.a[k] + a * (pp.a[k] - b * vv.a[k]); }          // bicgsolver.py:46
-    if (OP == EW_BICG_X) { Pack<T> xx = ld_stream(out + o), pp = ld_stream(x + o), ss = ld_stream(y + o);
-      for (int k = 0; k < V; ++k) r.a[k] = xx.a[k] + (a * pp.a[k] + b * ss.a[k]); }          // bicgsolver.py:81
-    st_vec(out + o, r);
+  KT_EW_OUTER(U) {
+    Pack<T> p0[U], p1[U], p2[U];
+    KT_EW_FOR(U, u, o) {
+      if (OP == EW_COPY) p0[u] = ld_stream(x + o);
+      if (OP == EW_AXPY) { p0[u] = ld_rw(out + o); p1[u] = ld_stream(x + o); }
+      if (OP == EW_XPAY || OP == EW_XMAY) { p0[u] = ld_rw(x + o); p1[u] = ld_rw(y + o); }
+      if (OP == EW_BICG_P) { p0[u] = ld_stream(x + o); p1[u] = ld_rw(out + o); p2[u] = ld_stream(y + o); }
+      if (OP == EW_BICG_X) { p0[u] = ld_rw(out + o); p1[u] = ld_stream(x + o); p2[u] = ld_stream(y + o); }
+    }
+    KT_EW_FOR(U, u, o) {
+      Pack<T> r;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        if (OP == EW_COPY) r.a[k] = p0[u].a[k];
+        if (OP == EW_FILL) r.a[k] = a;
+        if (OP == EW_AXPY) r.a[k] = p0[u].a[k] + a * p1[u].a[k];                             // cgsolver.py:71,76
+        if (OP == EW_XPAY) r.a[k] = p0[u].a[k] + a * p1[u].a[k];                             // cgsolver.py:81
+        if (OP == EW_XMAY) r.a[k] = p0[u].a[k] - a * p1[u].a[k];                             // bicgsolver.py:63,86
+        if (OP == EW_BICG_P) r.a[k] = p0[u].a[k] + a * (p1[u].a[k] - b * p2[u].a[k]);        // bicgsolver.py:46
+        if (OP == EW_BICG_X) r.a[k] = p0[u].a[k] + (a * p1[u].a[k] + b * p2[u].a[k]);        // bicgsolver.py:81
+      }
+      st_vec(out + o, r);
+    }
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_dot(EwGeom g, const T* p, const T* q, ReduceWs ws) {
   constexpr int V = VT<T>::V;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int U = kEwUnroll;
   double acc = 0.0;
-  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
-    const size_t o = (size_t)vi * V;
-    Pack<T> a = ld_stream(p + o), b = ld_stream(q + o);
+  KT_EW_OUTER(U) {
+    Pack<T> a[U], b[U];
+    KT_EW_FOR(U, u, o) { a[u] = ld_stream(p + o); b[u] = ld_stream(q + o); }
+    KT_EW_FOR(U, u, o) {
 #pragma unroll
-    for (int k = 0; k < V; ++k) acc += (double)a.a[k] * (double)b.a[k];
+      for (int k = 0; k < V; ++k) acc += (double)a[u].a[k] * (double)b[u].a[k];
+    }
   }
   block_reduce_finalize<1>(acc, 0.0, ws, FIN_NONE);
 }
@@ -210,17 +240,19 @@ __global__ void __launch_bounds__(256) k_dot(EwGeom g, const T* p, const T* q, R
 template <typename T, bool CG>
 __global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_tld, T* x, T* p, ReduceWs ws, int fin) {
   constexpr int V = VT<T>::V;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int U = kEwUnroll;
   double acc = 0.0;
-  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
-    const size_t o = (size_t)vi * V;
-    Pack<T> bb = ld_stream(b + o);
-    st_vec(r + o, bb);
-    if (r_tld) st_vec(r_tld + o, bb);
-    if (CG) st_vec(p + o, bb);
-    st_vec(x + o, pack_zero<T>());
+  KT_EW_OUTER(U) {
+    Pack<T> bb[U];
+    KT_EW_FOR(U, u, o) bb[u] = ld_stream(b + o);
+    KT_EW_FOR(U, u, o) {
+      st_vec(r + o, bb[u]);
+      if (r_tld) st_vec(r_tld + o, bb[u]);
+      if (CG) st_vec(p + o, bb[u]);
+      st_vec(x + o, pack_zero<T>());
 #pragma unroll
-    for (int k = 0; k < V; ++k) acc += (double)bb.a[k] * (double)bb.a[k];
+      for (int k = 0; k < V; ++k) acc += (double)bb[u].a[k] * (double)bb[u].a[k];
+    }
   }
   block_reduce_finalize<1>(acc, 0.0, ws, fin);
 }
@@ -229,21 +261,24 @@ __global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_t
 template <typename T>
 __global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, const T* v, const Scalars* sc) {
   constexpr int V = VT<T>::V;
+  constexpr int U = kEwUnroll;
   if (sc->done) return;
   const bool first = sc->iter == 0;
   const T beta = T(sc->beta), omega = T(sc->omega);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
-    const size_t o = (size_t)vi * V;
-    Pack<T> rr = ld_stream(r + o), out;
-    if (first) {
-      out = rr;
-    } else {
-      Pack<T> pp = ld_stream(p + o), vv = ld_stream(v + o);
-#pragma unroll
-      for (int k = 0; k < V; ++k) out.a[k] = rr.a[k] + beta * (pp.a[k] - omega * vv.a[k]);
+  KT_EW_OUTER(U) {
+    Pack<T> rr[U], pp[U], vv[U];
+    KT_EW_FOR(U, u, o) {
+      rr[u] = ld_stream(r + o);
+      if (!first) { pp[u] = ld_rw(p + o); vv[u] = ld_stream(v + o); }
     }
-    st_vec(p + o, out);
+    KT_EW_FOR(U, u, o) {
+      Pack<T> out = rr[u];
+      if (!first) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) out.a[k] = rr[u].a[k] + beta * (pp[u].a[k] - omega * vv[u].a[k]);
+      }
+      st_vec(p + o, out);
+    }
   }
 }
 
@@ -253,29 +288,31 @@ __global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* 
                                                  const T* r_tld, const T* minv, double alpha_imm, double omega_imm,
                                                  int from_sc, ReduceWs ws, int fin) {
   constexpr int V = VT<T>::V;
+  constexpr int U = (kEwUnroll > 2) ? 2 : kEwUnroll;     // 5-6 operand planes: 2 strides already keep ~190 B in flight
   if (from_sc && ws.sc->done) return;
   const T alpha = T(from_sc ? ws.sc->alpha : alpha_imm), omega = T(from_sc ? ws.sc->omega : omega_imm);
-  const long long stride = (long long)gridDim.x * blockDim.x;
   double a0 = 0.0, a1 = 0.0;
-  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
-    const size_t o = (size_t)vi * V;
-    Pack<T> xx = ld_stream(x + o), pp = ld_stream(p + o), ss = ld_stream(s + o), tt = ld_stream(t + o),
-            rt = ld_stream(r_tld + o), rn;
-    Pack<T> ph = pp, sh = ss;
-    if (PRE) {
-      Pack<T> m = ld_stream(minv + o);
-#pragma unroll
-      for (int k = 0; k < V; ++k) { ph.a[k] = m.a[k] * pp.a[k]; sh.a[k] = m.a[k] * ss.a[k]; }
+  KT_EW_OUTER(U) {
+    Pack<T> xx[U], pp[U], ss[U], tt[U], rt[U], mm[U];
+    KT_EW_FOR(U, u, o) {
+      xx[u] = ld_rw(x + o); pp[u] = ld_stream(p + o); ss[u] = ld_stream(s + o); tt[u] = ld_stream(t + o);
+      rt[u] = ld_stream(r_tld + o);
+      if (PRE) mm[u] = ld_stream(minv + o);
     }
+    KT_EW_FOR(U, u, o) {
+      Pack<T> rn;
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      xx.a[k] = xx.a[k] + (alpha * ph.a[k] + omega * sh.a[k]);
-      rn.a[k] = ss.a[k] - omega * tt.a[k];
-      a0 += (double)rn.a[k] * (double)rn.a[k];
-      a1 += (double)rn.a[k] * (double)rt.a[k];
+      for (int k = 0; k < V; ++k) {
+        const T ph = PRE ? mm[u].a[k] * pp[u].a[k] : pp[u].a[k];
+        const T sh = PRE ? mm[u].a[k] * ss[u].a[k] : ss[u].a[k];
+        xx[u].a[k] = xx[u].a[k] + (alpha * ph + omega * sh);
+        rn.a[k] = ss[u].a[k] - omega * tt[u].a[k];
+        a0 += (double)rn.a[k] * (double)rn.a[k];
+        a1 += (double)rn.a[k] * (double)rt[u].a[k];
+      }
+      st_vec(x + o, xx[u]);
+      st_vec(r + o, rn);
     }
-    st_vec(x + o, xx);
-    st_vec(r + o, rn);
   }
   block_reduce_finalize<2>(a0, a1, ws, fin);
 }
@@ -285,21 +322,23 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_cg_xr(EwGeom g, T* x, T* r, const T* p, const T* Ap, double alpha_imm,
                                                int from_sc, ReduceWs ws, int fin) {
   constexpr int V = VT<T>::V;
+  constexpr int U = (kEwUnroll > 2) ? 2 : kEwUnroll;
   if (from_sc && ws.sc->done) return;
   const T alpha = T(from_sc ? ws.sc->alpha : alpha_imm);
-  const long long stride = (long long)gridDim.x * blockDim.x;
   double a0 = 0.0;
-  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
-    const size_t o = (size_t)vi * V;
-    Pack<T> xx = ld_stream(x + o), rr = ld_stream(r + o), pp = ld_stream(p + o), aa = ld_stream(Ap + o);
+  KT_EW_OUTER(U) {
+    Pack<T> xx[U], rr[U], pp[U], aa[U];
+    KT_EW_FOR(U, u, o) { xx[u] = ld_rw(x + o); rr[u] = ld_rw(r + o); pp[u] = ld_stream(p + o); aa[u] = ld_stream(Ap + o); }
+    KT_EW_FOR(U, u, o) {
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      xx.a[k] = xx.a[k] + alpha * pp.a[k];
-      rr.a[k] = rr.a[k] - alpha * aa.a[k];
-      a0 += (double)rr.a[k] * (double)rr.a[k];
+      for (int k = 0; k < V; ++k) {
+        xx[u].a[k] = xx[u].a[k] + alpha * pp[u].a[k];
+        rr[u].a[k] = rr[u].a[k] - alpha * aa[u].a[k];
+        a0 += (double)rr[u].a[k] * (double)rr[u].a[k];
+      }
+      st_vec(x + o, xx[u]);
+      st_vec(r + o, rr[u]);
     }
-    st_vec(x + o, xx);
-    st_vec(r + o, rr);
   }
   block_reduce_finalize<1>(a0, 0.0, ws, fin);
 }
@@ -308,15 +347,17 @@ __global__ void __launch_bounds__(256) k_cg_xr(EwGeom g, T* x, T* r, const T* p,
 template <typename T>
 __global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const Scalars* sc) {
   constexpr int V = VT<T>::V;
+  constexpr int U = kEwUnroll;
   if (sc->done) return;
   const T beta = T(sc->beta);
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long vi = g.v_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < g.v_hi; vi += stride) {
-    const size_t o = (size_t)vi * V;
-    Pack<T> rr = ld_stream(r + o), pp = ld_stream(p + o);
+  KT_EW_OUTER(U) {
+    Pack<T> rr[U], pp[U];
+    KT_EW_FOR(U, u, o) { rr[u] = ld_stream(r + o); pp[u] = ld_rw(p + o); }
+    KT_EW_FOR(U, u, o) {
 #pragma unroll
-    for (int k = 0; k < V; ++k) pp.a[k] = rr.a[k] + beta * pp.a[k];
-    st_vec(p + o, pp);
+      for (int k = 0; k < V; ++k) pp[u].a[k] = rr[u].a[k] + beta * pp[u].a[k];
+      st_vec(p + o, pp[u]);
+    }
   }
 }
 
@@ -330,27 +371,55 @@ __global__ void k_sc_reset(Scalars* sc, double eps, long long max_iter, int flag
 // host side
 // ---------------------------------------------------------------------------------------------
 struct Plan {
-  int V, TI, nCC, grid_st, grid_ew;
-  long long nTiles;
+  int V, TI, nCC;
+  long long nTiles, st_blocks, ew_blocks;   // blocks that would give every warp / thread exactly one unit
   EwGeom g;
 };
+
+// Resident blocks per SM of a kernel (256 threads, no dynamic smem), cached per kernel.  Grids are sized
+// num_SMs x this, i.e. exactly one wave of co-resident blocks that stride statically over the work: no tail
+// wave, and a grid (hence a summation order) that depends only on the problem geometry and the device.
+template <typename K>
+static int resident_blocks(K kernel) {
+  static int cached = 0;   // one instantiation of this template per kernel type
+  if (!cached) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, 0) != cudaSuccess || nb < 1) nb = 1;
+    if (nb > 8) nb = 8;
+    cached = nb;
+  }
+  return cached;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+template <typename K>
+static int grid_for(const kt_handle_s* h, K kernel, long long blocks_wanted) {
+  static int waves = env_int("KT_GRID_WAVES", 1);    // development knob
+  long long cap = (long long)h->num_sms * resident_blocks(kernel) * waves;
+  if (cap > h->max_blocks) cap = h->max_blocks;
+  return (int)std::max<long long>(1, std::min<long long>(blocks_wanted, cap));
+}
 
 static Plan make_plan(const kt_handle_s* h) {
   Plan P;
   P.V = (h->dtype == KT_F64) ? 2 : 4;
   const int rows = h->row_hi - h->row_lo;
   P.nCC = (h->pitch / P.V + 31) / 32;
-  const long long target_warps = (long long)h->num_sms * 32;       // 8 blocks x 8 warps... per SM upper bound
+  const long long target_warps = (long long)h->num_sms * 32;       // ~resident warps of a stencil kernel
+  static int ti_env = env_int("KT_TI", 0);
   int TI = 64;
-  while (TI > 4 && (long long)((rows + TI - 1) / TI) * P.nCC < 4 * target_warps) TI >>= 1;
+  while (TI > 4 && (long long)((rows + TI - 1) / TI) * P.nCC < 8 * target_warps) TI >>= 1;
+  if (ti_env > 0) TI = ti_env;
   P.TI = TI;
   P.nTiles = (long long)((rows + TI - 1) / TI) * P.nCC;
-  long long blocks_needed = (P.nTiles + 7) / 8;
-  P.grid_st = (int)std::max<long long>(1, std::min<long long>(blocks_needed, (long long)h->num_sms * 8));
+  P.st_blocks = (P.nTiles + 7) / 8;
   P.g.v_lo = (long long)h->row_lo * h->pitch / P.V;
   P.g.v_hi = (long long)h->row_hi * h->pitch / P.V;
-  long long nvec = P.g.v_hi - P.g.v_lo;
-  P.grid_ew = (int)std::max<long long>(1, std::min<long long>((nvec + 255) / 256, (long long)h->num_sms * 8));
+  P.ew_blocks = (P.g.v_hi - P.g.v_lo + 255) / 256;
   return P;
 }
 
@@ -375,7 +444,8 @@ static StencilArgs<T> stencil_args(kt_handle_s* h, const Plan& P, const void* co
 
 template <typename T, int SRC, bool PRE, int EPI>
 static int launch_stencil(kt_handle_s* h, const Plan& P, const StencilArgs<T>& A) {
-  k_stencil<T, SRC, PRE, EPI><<<P.grid_st, 256, 0, h->stream>>>(A);
+  auto kern = k_stencil<T, SRC, PRE, EPI>;
+  kern<<<grid_for(h, kern, P.st_blocks), 256, 0, h->stream>>>(A);
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -414,7 +484,7 @@ static int t_bicg_s_t(kt_handle_s* h, const void* coef, const void* r, const voi
 template <typename T, int OP>
 static int t_ew(kt_handle_s* h, void* out, const void* x, const void* y, const void* z, double a, double b) {
   Plan P = make_plan(h);
-  k_ew<T, OP><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (T*)out, (const T*)x, (const T*)y, (const T*)z, a, b);
+  k_ew<T, OP><<<grid_for(h, k_ew<T, OP>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)out, (const T*)x, (const T*)y, (const T*)z, a, b);
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -422,7 +492,7 @@ static int t_ew(kt_handle_s* h, void* out, const void* x, const void* y, const v
 template <typename T>
 static int t_dot(kt_handle_s* h, const void* p, const void* q, double* out_host) {
   Plan P = make_plan(h);
-  k_dot<T><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (const T*)p, (const T*)q, make_ws(h));
+  k_dot<T><<<grid_for(h, k_dot<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (const T*)p, (const T*)q, make_ws(h));
   KT_LAUNCH_CHECK(h);
   return read_dots(h, out_host, 1);
 }
@@ -484,7 +554,7 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
     rc = launch_stencil<T, SRC_X, false, EPI_RESID>(h, P, A);
     if (rc) return rc;
   } else {
-    k_init<T, false><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (const T*)b, r, r_tld, (T*)x, nullptr, ws, FIN_BICG_INIT);
+    k_init<T, false><<<grid_for(h, k_init<T, false>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (const T*)b, r, r_tld, (T*)x, nullptr, ws, FIN_BICG_INIT);
     KT_LAUNCH_CHECK(h);
   }
   StencilArgs<T> A2 = stencil_args<T>(h, P, coef);
@@ -493,14 +563,14 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
   A3.ws = ws; A3.x = r; A3.v = v; A3.minv = (const T*)Minv; A3.y = t; A3.s_out = s; A3.alpha_from_sc = 1;
   A3.check_done = 1; A3.fin = FIN_BICG_OMEGA;
   auto iter = [&]() -> int {
-    k_bicg_p<T><<<P.grid_ew, 256, 0, h->stream>>>(P.g, p, r, v, h->sc);
+    k_bicg_p<T><<<grid_for(h, k_bicg_p<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, p, r, v, h->sc);
     KT_LAUNCH_CHECK(h);
     int e = pre ? launch_stencil<T, SRC_X, true, EPI_DOT_Q>(h, P, A2) : launch_stencil<T, SRC_X, false, EPI_DOT_Q>(h, P, A2);
     if (e) return e;
     e = pre ? launch_stencil<T, SRC_S, true, EPI_ST>(h, P, A3) : launch_stencil<T, SRC_S, false, EPI_ST>(h, P, A3);
     if (e) return e;
-    if (pre) k_bicg_xr<T, true><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END);
-    else k_bicg_xr<T, false><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END);
+    if (pre) k_bicg_xr<T, true><<<grid_for(h, k_bicg_xr<T, true>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END);
+    else k_bicg_xr<T, false><<<grid_for(h, k_bicg_xr<T, false>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END);
     KT_LAUNCH_CHECK(h);
     return 0;
   };
@@ -522,16 +592,16 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
   int rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0);
   if (rc) return rc;
   ReduceWs ws = make_ws(h, w->history, w->history_cap);
-  k_init<T, true><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (const T*)b, r, nullptr, (T*)x, p, ws, FIN_CG_INIT);
+  k_init<T, true><<<grid_for(h, k_init<T, true>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (const T*)b, r, nullptr, (T*)x, p, ws, FIN_CG_INIT);
   KT_LAUNCH_CHECK(h);
   StencilArgs<T> A1 = stencil_args<T>(h, P, coef);
   A1.ws = ws; A1.x = p; A1.y = Ap; A1.check_done = 1; A1.fin = FIN_CG_ALPHA;
   auto iter = [&]() -> int {
     int e = launch_stencil<T, SRC_X, false, EPI_DOT_SRC>(h, P, A1);
     if (e) return e;
-    k_cg_xr<T><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws, FIN_CG_END);
+    k_cg_xr<T><<<grid_for(h, k_cg_xr<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws, FIN_CG_END);
     KT_LAUNCH_CHECK(h);
-    k_cg_p<T><<<P.grid_ew, 256, 0, h->stream>>>(P.g, p, r, h->sc);
+    k_cg_p<T><<<grid_for(h, k_cg_p<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, p, r, h->sc);
     KT_LAUNCH_CHECK(h);
     return 0;
   };
@@ -618,10 +688,10 @@ int kt_bicg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* s, co
   Plan P = make_plan(h);
   ReduceWs ws = make_ws(h);
   if (h->dtype == KT_F64)
-    k_bicg_xr<double, false><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)s,
+    k_bicg_xr<double, false><<<grid_for(h, k_bicg_xr<double, false>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)s,
                                                               (const double*)t, (const double*)r_tld, nullptr, alpha, omega, 0, ws, FIN_NONE);
   else
-    k_bicg_xr<float, false><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)s,
+    k_bicg_xr<float, false><<<grid_for(h, k_bicg_xr<float, false>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)s,
                                                              (const float*)t, (const float*)r_tld, nullptr, alpha, omega, 0, ws, FIN_NONE);
   KT_LAUNCH_CHECK(h);
   return read_dots(h, dots_host, 2);
@@ -632,9 +702,9 @@ int kt_cg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* Ap, dou
   Plan P = make_plan(h);
   ReduceWs ws = make_ws(h);
   if (h->dtype == KT_F64)
-    k_cg_xr<double><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)Ap, alpha, 0, ws, FIN_NONE);
+    k_cg_xr<double><<<grid_for(h, k_cg_xr<double>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)Ap, alpha, 0, ws, FIN_NONE);
   else
-    k_cg_xr<float><<<P.grid_ew, 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)Ap, alpha, 0, ws, FIN_NONE);
+    k_cg_xr<float><<<grid_for(h, k_cg_xr<float>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)Ap, alpha, 0, ws, FIN_NONE);
   KT_LAUNCH_CHECK(h);
   return read_dots(h, dot_host, 1);
 }

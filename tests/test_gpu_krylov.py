@@ -160,7 +160,9 @@ def test_bicgstab_solve_parity(cuda, kind, a, b, eps):
     s.solve(eps=eps, quiet=True)
     assert s.status == st_ref == 0
     assert abs(s.iterations - it_ref) <= 1
-    assert rel_l2(s.x.to_numpy(), x_ref) < 1e-8
+    # two iterates that both satisfy ||r|| <= eps ||b|| differ by O(cond * eps): the 1e-8 field bar applies
+    # when the solve itself is converged that far
+    assert rel_l2(s.x.to_numpy(), x_ref) < max(1e-8, 10 * eps)
     # size-independent property: the returned x really solves the system to the requested tolerance
     res = krylov.spmv(coef, s.x.to_numpy()) - rhs
     assert np.linalg.norm(res) <= 1.01 * eps * np.linalg.norm(rhs) + 1e-13 * np.linalg.norm(rhs)
@@ -178,7 +180,7 @@ def test_cg_solve_parity(cuda, kind, a, b, eps):
     s.solve(eps=eps, quiet=True)
     assert s.status == st_ref == 0
     assert abs(s.iterations - it_ref) <= 1
-    assert rel_l2(s.x.to_numpy(), x_ref) < 1e-8
+    assert rel_l2(s.x.to_numpy(), x_ref) < max(1e-8, 10 * eps)
     # convergence history parity (cgsolver.py:88,111): same strings up to the last common entry
     m = min(len(hist_ref), len(s.history)) - 1
     got = np.array([float(h) for h in s.history[:m]])

@@ -1,0 +1,34 @@
+"""The C/OpenMP port (CPU baseline of bench.py) must be the same algorithm as the NumPy oracle."""
+import numpy as np
+import pytest
+
+from oracle import cport, krylov
+
+
+def test_spmv_bit_exact_and_reduce():
+    rng = np.random.default_rng(0)
+    coef = rng.standard_normal((37, 53, 5))
+    x = rng.standard_normal((37, 53))
+    np.testing.assert_array_equal(cport.spmv(coef, x), krylov.spmv(coef, x))
+    y = rng.standard_normal((37, 53))
+    assert cport.reduce(x, y) == pytest.approx(float(np.sum(x * y)), rel=1e-13)
+
+
+@pytest.mark.parametrize('n,offset,eps', [(64, 0.0, 1e-6), (128, 0.1, 1e-10)])
+def test_solvers_match_numpy_oracle(n, offset, eps):
+    coef, b = krylov.poisson_sin_system(n, offset)
+    for c_fn, o_fn in ((cport.cg_solve, krylov.cg_solve), (cport.bicgstab_solve, krylov.bicgstab_solve)):
+        xo, ito, sto = o_fn(coef, b, eps=eps)
+        xc, itc, stc, rel = c_fn(coef, b, eps=eps)
+        assert stc == sto == 0
+        assert abs(itc - ito) <= 1
+        assert np.linalg.norm(xc - xo) / np.linalg.norm(xo) < max(1e-8, 10 * eps)
+        assert rel < eps
+
+
+def test_status_codes():
+    coef, b = krylov.poisson_sin_system(8, 0.1)
+    x, it, st, _ = cport.bicgstab_solve(coef, np.zeros_like(b))
+    assert st == krylov.RHO_ZERO and it == 0
+    x, it, st, _ = cport.bicgstab_solve(coef, b, eps=1e-30, max_iter=5)
+    assert st == krylov.MAX_ITER and it == 5

@@ -68,6 +68,7 @@ def main():
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--dtype', default='f64')
     ap.add_argument('--kernels', action='store_true', help='also time individual kernels')
+    ap.add_argument('--brief', default=None, help='print one line tagged with this label')
     a = ap.parse_args()
     dtype = np.float64 if a.dtype == 'f64' else np.float32
     w = 8 if a.dtype == 'f64' else 4
@@ -126,7 +127,11 @@ def main():
             med, mn = time_call(fn)
             out['kernels'][name] = {'ms': med, 'ms_min': mn, 'gbs': words * N * w / med / 1e6,
                                     'frac': words * N * w / med / 1e6 / peak}
-    print(json.dumps(out, indent=1))
+    if a.brief is not None:
+        print(f"{a.brief:28s} n={a.n} bicg {out['bicgstab']['ms_per_iter']:.4f} ms/it {out['bicgstab']['alg_gbs']:.0f} GB/s "
+              f"({out['bicgstab']['frac']:.3f}) | cg {out['cg']['ms_per_iter']:.4f} ms/it {out['cg']['alg_gbs']:.0f} GB/s ({out['cg']['frac']:.3f})")
+    else:
+        print(json.dumps(out, indent=1))
 
 
 if __name__ == '__main__':
