@@ -154,6 +154,29 @@ int kt_bicgstab_solve_host(kt_handle_t h, const void* coef_host_aos, const void*
                            const kt_krylov_ws* ws, double eps, long max_iter,
                            long* iters, double* rel_res, int* status);
 
+/* ---- x-slab (multi-GPU) BiCGSTAB phases -------------------------------------------------------
+ * No reference counterpart (the reference is single-process).  The plane is this rank's slab: owned rows
+ * [row_lo, row_hi) (kt_set_rows) plus one halo row on each interior side that the host fills from the neighbour
+ * rank before a phase that reads it (phase 2 reads p, phase 3 reads r and v with halos).  Each phase launches the
+ * same kernel the single-GPU solver uses, but only publishes the LOCAL inner products into dots_dev[0..1]; the
+ * host all-reduces dots_dev over the ranks and kt_dist_scalar runs the step's scalar algebra (KT_FIN_*) on every
+ * rank from the identical reduced sums.  phase: 0 init (a0=b; o0=r, o1=x, o2=r_tld or NULL), 1 p-update (a0=r, a1=v;
+ * o0=p), 2 v=Ap (a0=p, a1=r_tld; o0=v), 3 s,t (a0=r, a1=v; o0=s, o1=t), 4 x,r (a0=p, a1=s, a2=t; o0=x, o1=r, o2=r_tld). */
+enum { KT_FIN_NONE = 0, KT_FIN_BICG_INIT = 1, KT_FIN_BICG_ALPHA = 2, KT_FIN_BICG_OMEGA = 3, KT_FIN_BICG_END = 4,
+       KT_FIN_CG_INIT = 5, KT_FIN_CG_ALPHA = 6, KT_FIN_CG_END = 7 };
+int kt_dist_begin(kt_handle_t h, double eps, long max_iter, int flags);
+int kt_dist_bicg_phase(kt_handle_t h, int phase, const void* coef, const void* a0, const void* a1, const void* a2,
+                       void* o0, void* o1, void* o2, double* dots_dev);
+int kt_dist_scalar(kt_handle_t h, int fin, const double* dots_dev, double* history_dev, long history_cap);
+int kt_dist_poll(kt_handle_t h, int* done, long* iters, int* status, double* rel_res);
+
+/* ---- per-kernel device timing (bench.py roofline) ----------------------------------------------
+ * Between kt_prof_begin and kt_prof_end every launch of the solver kernels is bracketed by a CUDA event pair on
+ * the handle's stream; kt_prof_end returns the summed duration and launch count per kernel class
+ * (0 bicg p-update, 1 bicg v=Ap+dot, 2 bicg s,t+2 dots, 3 bicg x,r+2 dots, 4 cg Ap+dot, 5 cg x,r+dot, 6 cg p). */
+int kt_prof_begin(kt_handle_t h, int max_launches);
+int kt_prof_end(kt_handle_t h, double* total_ms, long* count, int n_classes);
+
 /* ---- SIMPLE (cavity) kernels: simple.py / bicgsimp.py -------------------------------------- */
 typedef struct {
   int nx, ny;               /* cells */

@@ -85,6 +85,12 @@ SIGNATURES = {
     'kt_bicgstab_bench': (_I, [_P, _P, _P, _P, _WS, _L, _PF]),
     'kt_cg_bench': (_I, [_P, _P, _P, _P, _WS, _L, _PF]),
     'kt_bicgstab_solve_host': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _WS, _D, _L, _PL, _PD, _PI]),
+    'kt_dist_begin': (_I, [_P, _D, _L, _I]),
+    'kt_dist_bicg_phase': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'kt_dist_scalar': (_I, [_P, _I, _P, _P, _L]),
+    'kt_dist_poll': (_I, [_P, _PI, _PL, _PI, _PD]),
+    'kt_prof_begin': (_I, [_P, _I]),
+    'kt_prof_end': (_I, [_P, _PD, _PL, _I]),
     'kt_assemble_uv': (_I, [_P, _SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'kt_set_bc_cavity': (_I, [_P, _SP, _P, _P, _P, _P, _P, _P]),
     'kt_assemble_p': (_I, [_P, _SP, _P, _P, _P, _P, _P, _P, _P]),

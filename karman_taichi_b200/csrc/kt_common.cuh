@@ -35,47 +35,54 @@ template <typename T> __device__ __forceinline__ Pack<T> pack_zero() {
 }
 
 // ---- 16-byte global loads / stores ---------------------------------------------------------
-// The load asms are deliberately NOT volatile: they are pure functions of the address as far as the
-// compiler is concerned, so an unrolled loop can batch the loads of several rows / strides ahead of the
-// (volatile, memory-clobbering) stores -- that is where the memory-level parallelism comes from.  Every
-// kernel reads an address at most once before (possibly) overwriting it with a value that depends on
-// that read, so no load can be legally or usefully moved across a store to the same address.
+// Memory-level parallelism is explicit: every kernel issues all the loads of a batch (U strides of an
+// element-wise kernel, W column chunks x one row of the stencil kernel) back to back before the first
+// dependent instruction.  The asms are volatile (KT_LD_VOLATILE=0 makes them plain asm for experiments), so
+// the issue order is exactly the program order.
 //   ld_stream : read-only operand, streamed once      -> ld.global.nc.L1::no_allocate
 //   ld_rw     : operand this kernel also writes        -> ld.global.L1::no_allocate (no .nc)
 //   ld_cached : stencil operand, re-read by neighbours -> ld.global (L1 allocating)
+#ifndef KT_LD_VOLATILE
+#define KT_LD_VOLATILE 1
+#endif
+#if KT_LD_VOLATILE
+#define KT_ASM asm volatile
+#else
+#define KT_ASM asm
+#endif
 #ifndef KT_EW_UNROLL
 #define KT_EW_UNROLL 4
 #endif
 __device__ __forceinline__ Pack<double> ld_stream(const double* p) {
   Pack<double> r;
-  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
+  KT_ASM("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
   return r;
 }
 __device__ __forceinline__ Pack<float> ld_stream(const float* p) {
   Pack<float> r;
-  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+  KT_ASM("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
       : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]) : "l"(p));
   return r;
 }
 __device__ __forceinline__ Pack<double> ld_rw(const double* p) {
   Pack<double> r;
-  asm("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
+  KT_ASM("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
   return r;
 }
 __device__ __forceinline__ Pack<float> ld_rw(const float* p) {
   Pack<float> r;
-  asm("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+  KT_ASM("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
       : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]) : "l"(p));
   return r;
 }
 __device__ __forceinline__ Pack<double> ld_cached(const double* p) {
   Pack<double> r;
-  asm("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
+  KT_ASM("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p));
   return r;
 }
 __device__ __forceinline__ Pack<float> ld_cached(const float* p) {
   Pack<float> r;
-  asm("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+  KT_ASM("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
       : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]) : "l"(p));
   return r;
 }
@@ -136,6 +143,8 @@ struct ReduceWs {
   Scalars* sc;
   double* history;         // device, may be null
   long long history_cap;
+  double* dots_out;        // device, may be null: raw finalised sums also land here (x-slab mode: the
+                           // buffer that is all-reduced across ranks before kt_dist_scalar runs the algebra)
 };
 
 __device__ __forceinline__ void scalar_algebra(int fin, Scalars* sc, double d0, double d1, double* history,
@@ -245,6 +254,7 @@ __device__ __forceinline__ void block_reduce_finalize(double a0, double a1, cons
     double s0 = 0.0, s1 = 0.0;
     for (int w = 0; w < nw; ++w) { s0 += sm[0][w]; if (NDOT > 1) s1 += sm[1][w]; }
     *ws.ticket = 0u;
+    if (ws.dots_out) { ws.dots_out[0] = s0; if (NDOT > 1) ws.dots_out[1] = s1; }
     scalar_algebra(fin, ws.sc, s0, s1, ws.history, ws.history_cap);
   }
 }

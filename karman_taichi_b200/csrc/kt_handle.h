@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <string>
+#include <vector>
 #include "kt_common.cuh"
 #include "../../include/karman_b200.h"
 
@@ -22,7 +23,30 @@ struct kt_handle_s {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   long long launches = 0;            // kernels launched through this handle (bench: gpu_launches)
+  // optional per-kernel-class device timing (bench.py roofline): events bracket every launch of a class
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;  // pairs (begin, end)
+  std::vector<int> prof_cls;         // class id per pair
+  size_t prof_used = 0;
 };
+
+// kernel classes for kt_prof_*
+enum { KT_K_BICG_P = 0, KT_K_BICG_V = 1, KT_K_BICG_ST = 2, KT_K_BICG_XR = 3, KT_K_CG_AP = 4, KT_K_CG_XR = 5, KT_K_CG_P = 6,
+       KT_K_INIT = 7, KT_K_NCLASS = 8 };
+
+namespace kt {
+struct ProfScope {   // records an event pair around a launch when profiling is on
+  kt_handle_s* h; int idx;
+  ProfScope(kt_handle_s* h_, int cls) : h(h_), idx(-1) {
+    if (h->prof_on && h->prof_used + 2 <= h->prof_ev.size()) {
+      idx = (int)h->prof_used; h->prof_used += 2; h->prof_cls[idx / 2] = cls;
+      cudaEventRecord(h->prof_ev[idx], h->stream);
+    }
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof_ev[idx + 1], h->stream); }
+};
+}  // namespace kt
+
 
 namespace kt {
 void set_error(const std::string& s);

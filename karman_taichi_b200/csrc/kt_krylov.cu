@@ -89,14 +89,20 @@ struct SrcRow {
 #define KT_STENCIL_MINB 1
 #endif
 #ifndef KT_STENCIL_UNROLL
-#define KT_STENCIL_UNROLL 2
+#define KT_STENCIL_UNROLL 1
 #endif
 constexpr int kStencilUnroll = KT_STENCIL_UNROLL;   // rows of loads the compiler may batch ahead
 constexpr int kEwUnroll = KT_EW_UNROLL;             // strides of loads batched ahead in element-wise kernels
 
+#ifndef KT_STENCIL_W
+#define KT_STENCIL_W 2
+#endif
+constexpr int kStencilW = KT_STENCIL_W;   // column chunks (32 vectors each) a warp processes side by side
+
 template <typename T, int SRC, bool PRE, int EPI>
 __global__ void __launch_bounds__(256, KT_STENCIL_MINB) k_stencil(const StencilArgs<T> A) {
   constexpr int V = VT<T>::V;
+  constexpr int W = kStencilW;
   if (A.check_done && A.ws.sc->done) return;
   const T alpha = (SRC == SRC_S) ? T(A.alpha_from_sc ? A.ws.sc->alpha : A.alpha_imm) : T(0);
   const int lane = threadIdx.x & 31;
@@ -109,61 +115,85 @@ __global__ void __launch_bounds__(256, KT_STENCIL_MINB) k_stencil(const StencilA
     const int rchunk = (int)(tile / A.nCC), cc = (int)(tile - (long long)rchunk * A.nCC);
     const int i0 = A.row_lo + rchunk * A.TI;
     const int i1 = min(i0 + A.TI, A.row_hi);
-    const int j0 = (cc * 32 + lane) * V;
-    const bool act = j0 < A.pitch;
-    Pack<T> xw, xc, xe;        // (preconditioned) operand rows i-1, i, i+1
-    Pack<T> raw_c, raw_e;      // un-preconditioned operand (s or x) rows i, i+1
-    SrcRow<T, SRC, PRE>::load(A, i0 - 1, j0, act, alpha, xw, raw_c);
-    SrcRow<T, SRC, PRE>::load(A, i0, j0, act, alpha, xc, raw_c);
+    int j0[W];
+    bool act[W];
+    Pack<T> xw[W], xc[W], xe[W];   // (preconditioned) operand rows i-1, i, i+1
+    Pack<T> raw_c[W], raw_e[W];    // un-preconditioned operand (s or x) rows i, i+1
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      j0[w] = ((cc * W + w) * 32 + lane) * V;
+      act[w] = j0[w] < A.pitch;
+      SrcRow<T, SRC, PRE>::load(A, i0 - 1, j0[w], act[w], alpha, xw[w], raw_c[w]);
+      SrcRow<T, SRC, PRE>::load(A, i0, j0[w], act[w], alpha, xc[w], raw_c[w]);
+    }
 #pragma unroll kStencilUnroll
     for (int i = i0; i < i1; ++i) {
-      const size_t o = (size_t)i * A.pitch + j0;
-      Pack<T> c0, c1, c2, c3, c4, qv;
-      if (act) {
-        c0 = ld_stream(A.c[0] + o); c1 = ld_stream(A.c[1] + o); c2 = ld_stream(A.c[2] + o);
-        c3 = ld_stream(A.c[3] + o); c4 = ld_stream(A.c[4] + o);
-        if (EPI == EPI_DOT_Q || EPI == EPI_RESID) qv = ld_stream(A.q + o);
-      } else {
-        c0 = c1 = c2 = c3 = c4 = qv = pack_zero<T>();
-      }
-      SrcRow<T, SRC, PRE>::load(A, i + 1, j0, act, alpha, xe, raw_e);
-      // j-1 / j+V neighbours of the centre row
-      T xs = shfl_up1(xc.a[V - 1]);
-      T xn = shfl_down1(xc.a[0]);
-      if (lane == 0) xs = SrcRow<T, SRC, PRE>::scalar(A, i, j0 - 1, alpha);
-      if (lane == 31) xn = SrcRow<T, SRC, PRE>::scalar(A, i, j0 + V, alpha);
-      Pack<T> y;
+      // ---- issue every load of this row step: W x (5 coefficient planes [+ q] + operand row i+1)
+      Pack<T> c[W][5], qv[W];
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        const T north = (k < V - 1) ? xc.a[k + 1 < V ? k + 1 : k] : xn;
-        const T south = (k > 0) ? xc.a[k > 0 ? k - 1 : 0] : xs;
-        // cgsolver.py:59-60 left-to-right: ap*x + aw*x[i-1] + ae*x[i+1] + an*x[j+1] + as*x[j-1]
-        T acc = c0.a[k] * xc.a[k];
-        acc = acc + c1.a[k] * xw.a[k];
-        acc = acc + c2.a[k] * xe.a[k];
-        acc = acc + c3.a[k] * north;
-        acc = acc + c4.a[k] * south;
-        y.a[k] = acc;
-      }
-      if (act) {
-        if (EPI == EPI_RESID) {
-          Pack<T> r;
+      for (int w = 0; w < W; ++w) {
+        const size_t o = (size_t)i * A.pitch + j0[w];
+        if (act[w]) {
 #pragma unroll
-          for (int k = 0; k < V; ++k) { r.a[k] = qv.a[k] - y.a[k]; acc0 += (double)r.a[k] * (double)r.a[k]; }
-          st_vec(A.y + o, r);
-          if (A.s_out) st_vec(A.s_out + o, r);
+          for (int k = 0; k < 5; ++k) c[w][k] = ld_stream(A.c[k] + o);
+          if (EPI == EPI_DOT_Q || EPI == EPI_RESID) qv[w] = ld_stream(A.q + o);
         } else {
-          st_vec(A.y + o, y);
-          if (EPI == EPI_ST) st_vec(A.s_out + o, raw_c);
 #pragma unroll
-          for (int k = 0; k < V; ++k) {
-            if (EPI == EPI_DOT_Q) acc0 += (double)qv.a[k] * (double)y.a[k];
-            if (EPI == EPI_DOT_SRC) acc0 += (double)raw_c.a[k] * (double)y.a[k];
-            if (EPI == EPI_ST) { acc0 += (double)y.a[k] * (double)raw_c.a[k]; acc1 += (double)y.a[k] * (double)y.a[k]; }
-          }
+          for (int k = 0; k < 5; ++k) c[w][k] = pack_zero<T>();
+          qv[w] = pack_zero<T>();
         }
       }
-      xw = xc; xc = xe; raw_c = raw_e;
+#pragma unroll
+      for (int w = 0; w < W; ++w) SrcRow<T, SRC, PRE>::load(A, i + 1, j0[w], act[w], alpha, xe[w], raw_e[w]);
+      // ---- j-1 / j+V neighbours of the centre row: warp shuffles; only the two outer edge lanes reload
+      T xs[W], xn[W];
+#pragma unroll
+      for (int w = 0; w < W; ++w) { xs[w] = shfl_up1(xc[w].a[V - 1]); xn[w] = shfl_down1(xc[w].a[0]); }
+#pragma unroll
+      for (int w = 1; w < W; ++w) {
+        const T from_prev = __shfl_sync(0xffffffffu, xc[w - 1].a[V - 1], 31);
+        const T from_next = __shfl_sync(0xffffffffu, xc[w].a[0], 0);
+        if (lane == 0) xs[w] = from_prev;
+        if (lane == 31) xn[w - 1] = from_next;
+      }
+      if (lane == 0) xs[0] = SrcRow<T, SRC, PRE>::scalar(A, i, j0[0] - 1, alpha);
+      if (lane == 31) xn[W - 1] = SrcRow<T, SRC, PRE>::scalar(A, i, j0[W - 1] + V, alpha);
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const size_t o = (size_t)i * A.pitch + j0[w];
+        Pack<T> y;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const T north = (k < V - 1) ? xc[w].a[k + 1 < V ? k + 1 : k] : xn[w];
+          const T south = (k > 0) ? xc[w].a[k > 0 ? k - 1 : 0] : xs[w];
+          // cgsolver.py:59-60 left-to-right: ap*x + aw*x[i-1] + ae*x[i+1] + an*x[j+1] + as*x[j-1]
+          T acc = c[w][0].a[k] * xc[w].a[k];
+          acc = acc + c[w][1].a[k] * xw[w].a[k];
+          acc = acc + c[w][2].a[k] * xe[w].a[k];
+          acc = acc + c[w][3].a[k] * north;
+          acc = acc + c[w][4].a[k] * south;
+          y.a[k] = acc;
+        }
+        if (act[w]) {
+          if (EPI == EPI_RESID) {
+            Pack<T> r;
+#pragma unroll
+            for (int k = 0; k < V; ++k) { r.a[k] = qv[w].a[k] - y.a[k]; acc0 += (double)r.a[k] * (double)r.a[k]; }
+            st_vec(A.y + o, r);
+            if (A.s_out) st_vec(A.s_out + o, r);
+          } else {
+            st_vec(A.y + o, y);
+            if (EPI == EPI_ST) st_vec(A.s_out + o, raw_c[w]);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+              if (EPI == EPI_DOT_Q) acc0 += (double)qv[w].a[k] * (double)y.a[k];
+              if (EPI == EPI_DOT_SRC) acc0 += (double)raw_c[w].a[k] * (double)y.a[k];
+              if (EPI == EPI_ST) { acc0 += (double)y.a[k] * (double)raw_c[w].a[k]; acc1 += (double)y.a[k] * (double)y.a[k]; }
+            }
+          }
+        }
+        xw[w] = xc[w]; xc[w] = xe[w]; raw_c[w] = raw_e[w];
+      }
     }
   }
   if (EPI == EPI_Y) return;
@@ -408,7 +438,7 @@ static Plan make_plan(const kt_handle_s* h) {
   Plan P;
   P.V = (h->dtype == KT_F64) ? 2 : 4;
   const int rows = h->row_hi - h->row_lo;
-  P.nCC = (h->pitch / P.V + 31) / 32;
+  P.nCC = (h->pitch / P.V + 32 * kStencilW - 1) / (32 * kStencilW);
   const long long target_warps = (long long)h->num_sms * 32;       // ~resident warps of a stencil kernel
   static int ti_env = env_int("KT_TI", 0);
   int TI = 64;
@@ -423,10 +453,10 @@ static Plan make_plan(const kt_handle_s* h) {
   return P;
 }
 
-static ReduceWs make_ws(kt_handle_s* h, double* history = nullptr, long long cap = 0) {
+static ReduceWs make_ws(kt_handle_s* h, double* history = nullptr, long long cap = 0, double* dots_out = nullptr) {
   ReduceWs ws;
   ws.partials = h->partials; ws.ticket = h->ticket; ws.max_blocks = h->max_blocks; ws.sc = h->sc;
-  ws.history = history; ws.history_cap = cap;
+  ws.history = history; ws.history_cap = cap; ws.dots_out = dots_out;
   return ws;
 }
 
@@ -512,8 +542,8 @@ static int run_chunks(kt_handle_s* h, long long max_iter, EnqueueIter&& enqueue_
   long long enq = 0;
   int slot = 0;
   bool pending[2] = {false, false};
-  for (;;) {
-    long long n = std::min<long long>(chunk, std::max<long long>(1, max_iter - enq));
+  while (enq < max_iter) {   // iteration max_iter always sets `done`, so nothing beyond it is ever needed
+    long long n = std::min<long long>(chunk, max_iter - enq);
     for (long long k = 0; k < n; ++k) { int rc = enqueue_iter(); if (rc) return rc; }
     enq += n;
     KT_CUDA(cudaMemcpyAsync(h->sc_host + slot, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
@@ -563,12 +593,23 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
   A3.ws = ws; A3.x = r; A3.v = v; A3.minv = (const T*)Minv; A3.y = t; A3.s_out = s; A3.alpha_from_sc = 1;
   A3.check_done = 1; A3.fin = FIN_BICG_OMEGA;
   auto iter = [&]() -> int {
-    k_bicg_p<T><<<grid_for(h, k_bicg_p<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, p, r, v, h->sc);
+    {
+      ProfScope ps(h, KT_K_BICG_P);
+      k_bicg_p<T><<<grid_for(h, k_bicg_p<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, p, r, v, h->sc);
+    }
     KT_LAUNCH_CHECK(h);
-    int e = pre ? launch_stencil<T, SRC_X, true, EPI_DOT_Q>(h, P, A2) : launch_stencil<T, SRC_X, false, EPI_DOT_Q>(h, P, A2);
+    int e;
+    {
+      ProfScope ps(h, KT_K_BICG_V);
+      e = pre ? launch_stencil<T, SRC_X, true, EPI_DOT_Q>(h, P, A2) : launch_stencil<T, SRC_X, false, EPI_DOT_Q>(h, P, A2);
+    }
     if (e) return e;
-    e = pre ? launch_stencil<T, SRC_S, true, EPI_ST>(h, P, A3) : launch_stencil<T, SRC_S, false, EPI_ST>(h, P, A3);
+    {
+      ProfScope ps(h, KT_K_BICG_ST);
+      e = pre ? launch_stencil<T, SRC_S, true, EPI_ST>(h, P, A3) : launch_stencil<T, SRC_S, false, EPI_ST>(h, P, A3);
+    }
     if (e) return e;
+    ProfScope ps(h, KT_K_BICG_XR);
     if (pre) k_bicg_xr<T, true><<<grid_for(h, k_bicg_xr<T, true>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END);
     else k_bicg_xr<T, false><<<grid_for(h, k_bicg_xr<T, false>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END);
     KT_LAUNCH_CHECK(h);
@@ -597,11 +638,21 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
   StencilArgs<T> A1 = stencil_args<T>(h, P, coef);
   A1.ws = ws; A1.x = p; A1.y = Ap; A1.check_done = 1; A1.fin = FIN_CG_ALPHA;
   auto iter = [&]() -> int {
-    int e = launch_stencil<T, SRC_X, false, EPI_DOT_SRC>(h, P, A1);
+    int e;
+    {
+      ProfScope ps(h, KT_K_CG_AP);
+      e = launch_stencil<T, SRC_X, false, EPI_DOT_SRC>(h, P, A1);
+    }
     if (e) return e;
-    k_cg_xr<T><<<grid_for(h, k_cg_xr<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws, FIN_CG_END);
+    {
+      ProfScope ps(h, KT_K_CG_XR);
+      k_cg_xr<T><<<grid_for(h, k_cg_xr<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws, FIN_CG_END);
+    }
     KT_LAUNCH_CHECK(h);
-    k_cg_p<T><<<grid_for(h, k_cg_p<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, p, r, h->sc);
+    {
+      ProfScope ps(h, KT_K_CG_P);
+      k_cg_p<T><<<grid_for(h, k_cg_p<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, p, r, h->sc);
+    }
     KT_LAUNCH_CHECK(h);
     return 0;
   };
@@ -611,6 +662,51 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
   if (iters) *iters = (long)S.iter;
   if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
   if (status) *status = S.status;
+  return 0;
+}
+
+
+// ---- x-slab (multi-GPU) phases: the same kernels, but the last block only publishes the LOCAL sums into a
+// caller-owned device buffer; the host all-reduces that buffer across ranks (NCCL) and kt_dist_scalar then runs
+// the scalar algebra on every rank from the identical reduced values.
+__global__ void k_scalar_step(Scalars* sc, int fin, const double* dots, double* history, long long cap) {
+  if (sc->done) return;
+  scalar_algebra(fin, sc, dots[0], dots[1], history, cap);
+}
+
+template <typename T>
+static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void* a0, const void* a1, const void* a2,
+                        void* o0, void* o1, void* o2, double* dots_dev) {
+  Plan P = make_plan(h);
+  ReduceWs ws = make_ws(h, nullptr, 0, dots_dev);
+  switch (phase) {
+    case 0: {   // init: r = b (a0), x = 0 (o1), r (o0), r_tld (o2, may be null); local (r,r)
+      k_init<T, false><<<grid_for(h, k_init<T, false>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (const T*)a0, (T*)o0, (T*)o2, (T*)o1, nullptr, ws, FIN_NONE);
+      break;
+    }
+    case 1: {   // p (o0) = r (a0) + beta (p - omega v (a1))
+      k_bicg_p<T><<<grid_for(h, k_bicg_p<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)o0, (const T*)a0, (const T*)a1, h->sc);
+      break;
+    }
+    case 2: {   // v (o0) = A p (a0); local (r_tld (a1), v)
+      StencilArgs<T> A = stencil_args<T>(h, P, coef);
+      A.ws = ws; A.x = (const T*)a0; A.q = (const T*)a1; A.y = (T*)o0; A.check_done = 1; A.fin = FIN_NONE;
+      return launch_stencil<T, SRC_X, false, EPI_DOT_Q>(h, P, A);
+    }
+    case 3: {   // s (o0) = r (a0) - alpha v (a1); t (o1) = A s; local (t,s), (t,t)
+      StencilArgs<T> A = stencil_args<T>(h, P, coef);
+      A.ws = ws; A.x = (const T*)a0; A.v = (const T*)a1; A.y = (T*)o1; A.s_out = (T*)o0; A.alpha_from_sc = 1; A.check_done = 1;
+      A.fin = FIN_NONE;
+      return launch_stencil<T, SRC_S, false, EPI_ST>(h, P, A);
+    }
+    case 4: {   // x (o0) += alpha p (a0) + omega s (a1); r (o1) = s - omega t (a2); local (r,r), (r, r_tld (o2))
+      k_bicg_xr<T, false><<<grid_for(h, k_bicg_xr<T, false>, P.ew_blocks), 256, 0, h->stream>>>(
+          P.g, (T*)o0, (T*)o1, (const T*)a0, (const T*)a1, (const T*)a2, (const T*)o2, nullptr, 0, 0, 1, ws, FIN_NONE);
+      break;
+    }
+    default: set_error("kt_dist_bicg_phase: unknown phase"); return -2;
+  }
+  KT_LAUNCH_CHECK(h);
   return 0;
 }
 
@@ -723,7 +819,65 @@ int kt_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, c
                      t_bicgstab<float>(h, coef, b, x, Minv, ws, eps, max_iter, flags, iters, rel_res, status, false));
 }
 
-static int timed(kt_handle_t h, float* ms, int rc_before) { (void)h; (void)ms; return rc_before; }
+
+int kt_dist_begin(kt_handle_t h, double eps, long max_iter, int flags) {
+  KT_CHECK_ARG(h, "kt_dist_begin: null handle");
+  return sc_reset(h, eps, max_iter, flags);
+}
+
+int kt_dist_bicg_phase(kt_handle_t h, int phase, const void* coef, const void* a0, const void* a1, const void* a2, void* o0,
+                       void* o1, void* o2, double* dots_dev) {
+  KT_CHECK_ARG(h, "kt_dist_bicg_phase: null handle");
+  return KT_DISPATCH(h, t_dist_phase<double>(h, phase, coef, a0, a1, a2, o0, o1, o2, dots_dev),
+                     t_dist_phase<float>(h, phase, coef, a0, a1, a2, o0, o1, o2, dots_dev));
+}
+
+int kt_dist_scalar(kt_handle_t h, int fin, const double* dots_dev, double* history_dev, long history_cap) {
+  KT_CHECK_ARG(h && dots_dev, "kt_dist_scalar: null argument");
+  k_scalar_step<<<1, 1, 0, h->stream>>>(h->sc, fin, dots_dev, history_dev, history_cap);
+  KT_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int kt_dist_poll(kt_handle_t h, int* done, long* iters, int* status, double* rel_res) {
+  KT_CHECK_ARG(h, "kt_dist_poll: null handle");
+  KT_CUDA(cudaMemcpyAsync(h->sc_host, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+  KT_CUDA(cudaStreamSynchronize(h->stream));
+  const Scalars& S = *h->sc_host;
+  if (done) *done = S.done;
+  if (iters) *iters = (long)S.iter;
+  if (status) *status = S.status;
+  if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
+  return 0;
+}
+
+int kt_prof_begin(kt_handle_t h, int max_launches) {
+  KT_CHECK_ARG(h && max_launches > 0, "kt_prof_begin: bad argument");
+  while ((int)h->prof_ev.size() < 2 * max_launches) {
+    cudaEvent_t e;
+    KT_CUDA(cudaEventCreate(&e));
+    h->prof_ev.push_back(e);
+  }
+  h->prof_cls.assign(h->prof_ev.size() / 2, -1);
+  h->prof_used = 0;
+  h->prof_on = true;
+  return 0;
+}
+
+int kt_prof_end(kt_handle_t h, double* total_ms, long* count, int n_classes) {
+  KT_CHECK_ARG(h && total_ms && count && n_classes > 0, "kt_prof_end: bad argument");
+  h->prof_on = false;
+  KT_CUDA(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < n_classes; ++c) { total_ms[c] = 0.0; count[c] = 0; }
+  for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    float ms = 0.f;
+    KT_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]));
+    const int c = h->prof_cls[i / 2];
+    if (c >= 0 && c < n_classes) { total_ms[c] += ms; count[c] += 1; }
+  }
+  h->prof_used = 0;
+  return 0;
+}
 
 int kt_bicgstab_bench(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, long n_iter, float* ms) {
   KT_CHECK_ARG(h && coef && b && x && ws && ms, "kt_bicgstab_bench: null argument");
@@ -736,7 +890,7 @@ int kt_bicgstab_bench(kt_handle_t h, const void* coef, const void* b, void* x, c
   KT_CUDA(cudaEventSynchronize(h->t1));
   KT_CUDA(cudaEventElapsedTime(ms, h->t0, h->t1));
   if (it != n_iter) { set_error("kt_bicgstab_bench: solver stopped early (status " + std::to_string(st) + ")"); return -3; }
-  return timed(h, ms, 0);
+  return 0;
 }
 
 int kt_cg_bench(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, long n_iter, float* ms) {

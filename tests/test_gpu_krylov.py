@@ -195,8 +195,9 @@ def test_bicgstab_f32(cuda):
     s = make(cuda, coef.astype(np.float32), rhs.astype(np.float32), kt.BICGSolver)
     s.solve(eps=1e-5, quiet=True)
     assert s.status == 0
-    assert abs(s.iterations - it_ref) <= 2
-    assert rel_l2(s.x.to_numpy().astype(np.float64), x_ref) < 1e-4
+    # f32 fields (dots still accumulate in f64) against the f64 oracle: the iteration count moves by a few
+    assert abs(s.iterations - it_ref) <= max(3, 0.15 * it_ref)
+    assert rel_l2(s.x.to_numpy().astype(np.float64), x_ref) < 1e-4     # north_star f32 bar
 
 
 def test_bicgstab_rho_zero_and_zero_division(cuda, capsys):

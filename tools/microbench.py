@@ -109,7 +109,7 @@ def main():
     out['cg'] = {'ms_per_iter': per_it, 'mcell_iters_per_s': cells / per_it / 1e3,
                  'alg_gbs': 16 * N * w / per_it / 1e6, 'frac': 16 * N * w / per_it / 1e6 / peak}
 
-    if a.kernels:
+    if a.kernels or a.brief is not None:
         d2 = (C.c_double * 2)()
         kern = {
             'copy(2N)': (2, lambda: _lib.check(L.kt_copy(h, _p(s.t), _p(s.s)))),
@@ -129,7 +129,9 @@ def main():
                                     'frac': words * N * w / med / 1e6 / peak}
     if a.brief is not None:
         print(f"{a.brief:28s} n={a.n} bicg {out['bicgstab']['ms_per_iter']:.4f} ms/it {out['bicgstab']['alg_gbs']:.0f} GB/s "
-              f"({out['bicgstab']['frac']:.3f}) | cg {out['cg']['ms_per_iter']:.4f} ms/it {out['cg']['alg_gbs']:.0f} GB/s ({out['cg']['frac']:.3f})")
+              f"({out['bicgstab']['frac']:.3f}) | cg {out['cg']['ms_per_iter']:.4f} ms/it {out['cg']['alg_gbs']:.0f} GB/s ({out['cg']['frac']:.3f})"
+              + ' | ' + ' '.join(f"{k.split('(')[0]} {v['ms']:.3f}" for k, v in out['kernels'].items()
+                                 if k.split('(')[0] in ('bicg_update_p', 'spmv_dot', 'bicg_s_t', 'bicg_xr')))
     else:
         print(json.dumps(out, indent=1))
 

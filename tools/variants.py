@@ -5,15 +5,13 @@ sys.path.insert(0, ROOT)
 from karman_taichi_b200 import build
 
 VARIANTS = {
-    'base': [],
-    'minb3': ['-DKT_STENCIL_MINB=3'],
-    'minb4': ['-DKT_STENCIL_MINB=4'],
-    'su1': ['-DKT_STENCIL_UNROLL=1'],
-    'su1_minb4': ['-DKT_STENCIL_UNROLL=1', '-DKT_STENCIL_MINB=4'],
-    'su4': ['-DKT_STENCIL_UNROLL=4'],
-    'ew2': ['-DKT_EW_UNROLL=2'],
-    'ew1': ['-DKT_EW_UNROLL=1'],
-    'ew8': ['-DKT_EW_UNROLL=8'],
+    'w1': ['-DKT_STENCIL_W=1'],
+    'w1_minb4': ['-DKT_STENCIL_W=1', '-DKT_STENCIL_MINB=4'],
+    'w1_su2': ['-DKT_STENCIL_W=1', '-DKT_STENCIL_UNROLL=2'],
+    'w2': ['-DKT_STENCIL_W=2'],
+    'w2_minb2': ['-DKT_STENCIL_W=2', '-DKT_STENCIL_MINB=2'],
+    'w2_minb3': ['-DKT_STENCIL_W=2', '-DKT_STENCIL_MINB=3'],
+    'w2_nv': ['-DKT_STENCIL_W=2', '-DKT_LD_VOLATILE=0'],
 }
 if __name__ == '__main__':
     d = os.path.join(ROOT, 'gpurun_variants')
