@@ -30,6 +30,8 @@
 #ifndef KARMAN_B200_H
 #define KARMAN_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -78,10 +80,10 @@ long long kt_launch_count(kt_handle_t h);
 /* dense (NX, NY) host array -> pitched device field, and back */
 int kt_upload_field(kt_handle_t h, void* dst, const void* src_host);
 int kt_download_field(kt_handle_t h, void* dst_host, const void* src);
-/* reference layout coef[i][j][k] (AoS, k fastest) on host -> 5 pitched device planes.
- * staging = device scratch of NX*NY*5 reals. */
-int kt_upload_coef(kt_handle_t h, void* dst_soa, const void* src_host_aos, void* staging);
-int kt_download_coef(kt_handle_t h, void* dst_host_aos, const void* src_soa, void* staging);
+/* reference layout coef[i][j][k] (AoS, k fastest) on host <-> 5 pitched device planes, in row chunks through
+ * a caller-owned device staging buffer of staging_bytes (>= one row = NY*5 reals; larger = fewer chunks). */
+int kt_upload_coef(kt_handle_t h, void* dst_soa, const void* src_host_aos, void* staging, size_t staging_bytes);
+int kt_download_coef(kt_handle_t h, void* dst_host_aos, const void* src_soa, void* staging, size_t staging_bytes);
 /* device-side AoS (NX,NY,5) dense <-> SoA pitched conversion */
 int kt_coef_aos_to_soa(kt_handle_t h, void* dst_soa, const void* src_aos);
 int kt_coef_soa_to_aos(kt_handle_t h, void* dst_aos, const void* src_soa);
@@ -148,9 +150,9 @@ int kt_cg_bench(kt_handle_t h, const void* coef, const void* b, void* x, const k
                 long n_iter, float* ms);
 /* Reference-facing end-to-end call with HOST buffers in the reference layout
  * (coef[i][j][k] AoS, dense (NX,NY) b and x): uploads, solves, downloads x.
- * dev_* are caller-owned device buffers: coef_soa (5 planes), staging (NX*NY*5 dense), b, x. */
+ * dev_* are caller-owned device buffers: coef_soa (5 planes), staging (staging_bytes, see kt_upload_coef), b, x. */
 int kt_bicgstab_solve_host(kt_handle_t h, const void* coef_host_aos, const void* b_host, void* x_host,
-                           void* dev_coef_soa, void* dev_staging, void* dev_b, void* dev_x,
+                           void* dev_coef_soa, void* dev_staging, size_t staging_bytes, void* dev_b, void* dev_x,
                            const kt_krylov_ws* ws, double eps, long max_iter,
                            long* iters, double* rel_res, int* status);
 

@@ -63,8 +63,8 @@ SIGNATURES = {
     'kt_launch_count': (C.c_longlong, [_P]),
     'kt_upload_field': (_I, [_P, _P, _P]),
     'kt_download_field': (_I, [_P, _P, _P]),
-    'kt_upload_coef': (_I, [_P, _P, _P, _P]),
-    'kt_download_coef': (_I, [_P, _P, _P, _P]),
+    'kt_upload_coef': (_I, [_P, _P, _P, _P, C.c_size_t]),
+    'kt_download_coef': (_I, [_P, _P, _P, _P, C.c_size_t]),
     'kt_coef_aos_to_soa': (_I, [_P, _P, _P]),
     'kt_coef_soa_to_aos': (_I, [_P, _P, _P]),
     'kt_spmv': (_I, [_P, _P, _P, _P]),
@@ -84,7 +84,7 @@ SIGNATURES = {
     'kt_bicgstab_solve': (_I, [_P, _P, _P, _P, _P, _WS, _D, _L, _I, _PL, _PD, _PI]),
     'kt_bicgstab_bench': (_I, [_P, _P, _P, _P, _WS, _L, _PF]),
     'kt_cg_bench': (_I, [_P, _P, _P, _P, _WS, _L, _PF]),
-    'kt_bicgstab_solve_host': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _WS, _D, _L, _PL, _PD, _PI]),
+    'kt_bicgstab_solve_host': (_I, [_P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _WS, _D, _L, _PL, _PD, _PI]),
     'kt_dist_begin': (_I, [_P, _D, _L, _I]),
     'kt_dist_bicg_phase': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'kt_dist_scalar': (_I, [_P, _I, _P, _P, _L]),

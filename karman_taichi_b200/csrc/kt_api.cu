@@ -1,5 +1,5 @@
 // kt_api.cu -- handle lifetime, error reporting, host<->device staging and layout conversion.
-#include <mutex>
+#include <algorithm>
 #include <string>
 #include "kt_handle.h"
 
@@ -15,13 +15,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 // dense AoS (NX, NY, 5) <-> 5 pitched planes.  One thread per (i, j); the AoS side is staged through shared
 // memory so both sides are coalesced.
 template <typename T, bool TO_SOA>
-__global__ void __launch_bounds__(256) k_coef_layout(T* soa, T* aos, int NX, int NY, int pitch) {
+__global__ void __launch_bounds__(256) k_coef_layout(T* soa, T* aos, int NX, int NY, int pitch, int row0) {
   __shared__ T tile[256 * 5];
-  const int i = blockIdx.y;
+  const int i = row0 + blockIdx.y;          // plane row; the AoS buffer starts at row0 (chunked staging)
   const int jb = blockIdx.x * 256;
   const int nj = min(256, NY - jb);
   const size_t plane = (size_t)NX * pitch;
-  T* a = aos + ((size_t)i * NY + jb) * 5;
+  T* a = aos + ((size_t)blockIdx.y * NY + jb) * 5;
   if (TO_SOA) {
     for (int e = threadIdx.x; e < nj * 5; e += 256) tile[e] = a[e];
     __syncthreads();
@@ -36,10 +36,14 @@ __global__ void __launch_bounds__(256) k_coef_layout(T* soa, T* aos, int NX, int
 }
 
 template <typename T, bool TO_SOA>
-static int coef_layout(kt_handle_s* h, void* soa, void* aos) {
-  dim3 grid((h->NY + 255) / 256, h->NX);
-  k_coef_layout<T, TO_SOA><<<grid, 256, 0, h->stream>>>((T*)soa, (T*)aos, h->NX, h->NY, h->pitch);
-  KT_LAUNCH_CHECK(h);
+static int coef_layout(kt_handle_s* h, void* soa, void* aos, int row0 = 0, int nrows = -1) {
+  if (nrows < 0) nrows = h->NX;
+  for (int r = 0; r < nrows; r += 32768) {            // gridDim.y <= 65535
+    const int nr = std::min(32768, nrows - r);
+    dim3 grid((h->NY + 255) / 256, nr);
+    k_coef_layout<T, TO_SOA><<<grid, 256, 0, h->stream>>>((T*)soa, (T*)aos + (size_t)r * h->NY * 5, h->NX, h->NY, h->pitch, row0 + r);
+    KT_LAUNCH_CHECK(h);
+  }
   return 0;
 }
 
@@ -150,29 +154,46 @@ int kt_coef_soa_to_aos(kt_handle_t h, void* dst_aos, const void* src_soa) {
   return h->dtype == KT_F64 ? coef_layout<double, false>(h, (void*)src_soa, dst_aos) : coef_layout<float, false>(h, (void*)src_soa, dst_aos);
 }
 
-int kt_upload_coef(kt_handle_t h, void* dst_soa, const void* src_host_aos, void* staging) {
+// Host AoS <-> device SoA in row chunks through a caller-owned staging buffer of any size >= one row
+// (NY*5 reals): H2D copy of a chunk, then the layout kernel for those rows, on the handle's stream.
+int kt_upload_coef(kt_handle_t h, void* dst_soa, const void* src_host_aos, void* staging, size_t staging_bytes) {
   KT_CHECK_ARG(h && dst_soa && src_host_aos && staging, "kt_upload_coef: null argument");
-  const size_t bytes = (size_t)h->NX * h->NY * 5 * esize(h);
-  KT_CUDA(cudaMemcpyAsync(staging, src_host_aos, bytes, cudaMemcpyHostToDevice, h->stream));
-  return kt_coef_aos_to_soa(h, dst_soa, staging);
+  const size_t row_bytes = (size_t)h->NY * 5 * esize(h);
+  const int chunk = (int)std::min<size_t>(staging_bytes / row_bytes, (size_t)h->NX);
+  KT_CHECK_ARG(chunk >= 1, "kt_upload_coef: staging buffer smaller than one row of coefficients");
+  for (int r = 0; r < h->NX; r += chunk) {
+    const int nr = std::min(chunk, h->NX - r);
+    KT_CUDA(cudaMemcpyAsync(staging, (const char*)src_host_aos + (size_t)r * row_bytes, (size_t)nr * row_bytes,
+                            cudaMemcpyHostToDevice, h->stream));
+    int rc = h->dtype == KT_F64 ? coef_layout<double, true>(h, dst_soa, staging, r, nr) : coef_layout<float, true>(h, dst_soa, staging, r, nr);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
-int kt_download_coef(kt_handle_t h, void* dst_host_aos, const void* src_soa, void* staging) {
+int kt_download_coef(kt_handle_t h, void* dst_host_aos, const void* src_soa, void* staging, size_t staging_bytes) {
   KT_CHECK_ARG(h && dst_host_aos && src_soa && staging, "kt_download_coef: null argument");
-  int rc = kt_coef_soa_to_aos(h, staging, src_soa);
-  if (rc) return rc;
-  const size_t bytes = (size_t)h->NX * h->NY * 5 * esize(h);
-  KT_CUDA(cudaMemcpyAsync(dst_host_aos, staging, bytes, cudaMemcpyDeviceToHost, h->stream));
+  const size_t row_bytes = (size_t)h->NY * 5 * esize(h);
+  const int chunk = (int)std::min<size_t>(staging_bytes / row_bytes, (size_t)h->NX);
+  KT_CHECK_ARG(chunk >= 1, "kt_download_coef: staging buffer smaller than one row of coefficients");
+  for (int r = 0; r < h->NX; r += chunk) {
+    const int nr = std::min(chunk, h->NX - r);
+    int rc = h->dtype == KT_F64 ? coef_layout<double, false>(h, (void*)src_soa, staging, r, nr)
+                                : coef_layout<float, false>(h, (void*)src_soa, staging, r, nr);
+    if (rc) return rc;
+    KT_CUDA(cudaMemcpyAsync((char*)dst_host_aos + (size_t)r * row_bytes, staging, (size_t)nr * row_bytes,
+                            cudaMemcpyDeviceToHost, h->stream));
+  }
   KT_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
 int kt_bicgstab_solve_host(kt_handle_t h, const void* coef_host_aos, const void* b_host, void* x_host, void* dev_coef_soa,
-                           void* dev_staging, void* dev_b, void* dev_x, const kt_krylov_ws* ws, double eps, long max_iter,
-                           long* iters, double* rel_res, int* status) {
+                           void* dev_staging, size_t staging_bytes, void* dev_b, void* dev_x, const kt_krylov_ws* ws,
+                           double eps, long max_iter, long* iters, double* rel_res, int* status) {
   KT_CHECK_ARG(h && coef_host_aos && b_host && x_host && dev_coef_soa && dev_staging && dev_b && dev_x && ws,
                "kt_bicgstab_solve_host: null argument");
-  int rc = kt_upload_coef(h, dev_coef_soa, coef_host_aos, dev_staging);
+  int rc = kt_upload_coef(h, dev_coef_soa, coef_host_aos, dev_staging, staging_bytes);
   if (rc) return rc;
   rc = kt_upload_field(h, dev_b, b_host);
   if (rc) return rc;

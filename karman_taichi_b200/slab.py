@@ -1,0 +1,194 @@
+"""x-slab domain decomposition of the BiCGSTAB solve across the GPUs of one box (north_star (e); no reference
+counterpart -- the reference is a single address space).
+
+One process per GPU (``torch.distributed``: NCCL on GPUs, gloo in the CPU tests).  The ``(NX, NY)`` planes are split
+along ``i`` (the slowest axis) into contiguous row blocks; a rank stores its owned rows plus one halo row on each
+interior side, so a halo is one contiguous (pitched) row.  Per BiCGSTAB iteration the ranks exchange the boundary
+rows of ``p`` (before ``v = A p``), of ``v`` and of ``r`` (before the fused ``s = r - alpha v, t = A s``), and
+all-reduce the 1-2 local inner products of each of the three fused kernels; every rank then runs the same scalar
+algebra on the identical reduced values, so all ranks take the same convergence decision without talking again.
+
+``DistBiCGSTAB`` is the host-side driver; the arithmetic lives behind an ``ops`` object:
+``CudaSlabOps`` (libkarman_b200 ``kt_dist_*`` phases -- the product) or, in ``tests/``, a NumPy stand-in built on
+the oracle, which is how the partition / halo / reduction logic is tested on CPU with gloo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+FIN_NONE, FIN_BICG_INIT, FIN_BICG_ALPHA, FIN_BICG_OMEGA, FIN_BICG_END = 0, 1, 2, 3, 4
+
+
+class SlabPartition:
+    """Rows ``[0, NX)`` of the global plane split into ``nranks`` contiguous blocks (sizes differ by <= 1)."""
+
+    def __init__(self, NX, nranks):
+        if nranks < 1 or NX < nranks:
+            raise ValueError('need 1 <= nranks <= NX')
+        self.NX, self.nranks = int(NX), int(nranks)
+        base, rem = divmod(self.NX, self.nranks)
+        self.bounds = [0]
+        for r in range(self.nranks):
+            self.bounds.append(self.bounds[-1] + base + (1 if r < rem else 0))
+
+    def owned(self, rank):
+        """Global row range owned by ``rank``."""
+        return self.bounds[rank], self.bounds[rank + 1]
+
+    def halo(self, rank):
+        """(rows of halo below, rows of halo above) = (1 if there is a lower neighbour, 1 if an upper one)."""
+        return (1 if rank > 0 else 0), (1 if rank < self.nranks - 1 else 0)
+
+    def stored(self, rank):
+        """Global row range present in the rank's local plane (owned rows + halos)."""
+        lo, hi = self.owned(rank)
+        hl, hu = self.halo(rank)
+        return lo - hl, hi + hu
+
+    def local_owned(self, rank):
+        """Owned rows in local indices: what ``kt_set_rows`` gets."""
+        lo, hi = self.owned(rank)
+        hl, _ = self.halo(rank)
+        return hl, hl + (hi - lo)
+
+    def local_nx(self, rank):
+        a, b = self.stored(rank)
+        return b - a
+
+    def scatter(self, global_array, rank):
+        """Local copy (owned rows + halo rows filled from the global array) of a NumPy / torch array whose first
+        axis is ``i``."""
+        a, b = self.stored(rank)
+        return global_array[a:b]
+
+    def owned_of_local(self, local_array, rank):
+        l0, l1 = self.local_owned(rank)
+        return local_array[l0:l1]
+
+
+class HaloExchanger:
+    """Boundary-row exchange with the two x-neighbours over ``torch.distributed`` point-to-point ops."""
+
+    def __init__(self, part: SlabPartition, rank, group=None):
+        self.part, self.rank, self.group = part, rank, group
+        self.l0, self.l1 = part.local_owned(rank)
+        self.has_lo, self.has_hi = (h == 1 for h in part.halo(rank))
+
+    def exchange(self, plane: torch.Tensor):
+        """``plane``: the local ``(NX_local, pitch)`` tensor.  Sends the first / last owned row to the lower /
+        upper neighbour and receives their boundary rows into this rank's halo rows."""
+        ops = []
+        if self.has_lo:
+            ops.append(dist.P2POp(dist.isend, plane[self.l0], self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, plane[self.l0 - 1], self.rank - 1, self.group))
+        if self.has_hi:
+            ops.append(dist.P2POp(dist.isend, plane[self.l1 - 1], self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, plane[self.l1], self.rank + 1, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+
+class CudaSlabOps:
+    """The product arithmetic of one rank: ``kt_dist_*`` phases of libkarman_b200 on this rank's slab."""
+
+    def __init__(self, coef, b, x, part: SlabPartition, rank):
+        from .cgsolver import _Handle
+        from .field import Field
+        self.coef, self.b, self.x = coef, b, x
+        self.lib = _lib.load()
+        self._hd = _Handle(b)
+        l0, l1 = part.local_owned(rank)
+        _lib.check(self.lib.kt_set_rows(self._hd.h, l0, l1))
+        mk = lambda: Field(b.shape, b.np_dtype, b.device)
+        self.r, self.p, self.v, self.s, self.t = mk(), mk(), mk(), mk(), mk()
+        self.dots = torch.zeros(2, dtype=torch.float64, device=b.device)
+
+    @property
+    def h(self):
+        self._hd.use_current_stream()
+        return self._hd.h
+
+    def _phase(self, phase, a0=None, a1=None, a2=None, o0=None, o1=None, o2=None):
+        P = lambda f: C.c_void_p(f.ptr) if f is not None else None
+        _lib.check(self.lib.kt_dist_bicg_phase(self.h, phase, C.c_void_p(self.coef.ptr), P(a0), P(a1), P(a2), P(o0), P(o1), P(o2),
+                                               C.c_void_p(self.dots.data_ptr())))
+
+    def planes(self):
+        return {'p': self.p.data, 'v': self.v.data, 'r': self.r.data}
+
+    def begin(self, eps, max_iter):
+        _lib.check(self.lib.kt_dist_begin(self.h, float(eps), int(max_iter), 0))
+
+    def init(self):
+        self._phase(0, a0=self.b, o0=self.r, o1=self.x)          # r_tld aliases b (x0 = 0)
+
+    def update_p(self):
+        self._phase(1, a0=self.r, a1=self.v, o0=self.p)
+
+    def v_dot(self):
+        self._phase(2, a0=self.p, a1=self.b, o0=self.v)
+
+    def st_dots(self):
+        self._phase(3, a0=self.r, a1=self.v, o0=self.s, o1=self.t)
+
+    def xr_dots(self):
+        self._phase(4, a0=self.p, a1=self.s, a2=self.t, o0=self.x, o1=self.r, o2=self.b)
+
+    def scalar(self, fin):
+        _lib.check(self.lib.kt_dist_scalar(self.h, fin, C.c_void_p(self.dots.data_ptr()), None, 0))
+
+    def poll(self):
+        done, it, st, rel = C.c_int(), C.c_long(), C.c_int(), C.c_double()
+        _lib.check(self.lib.kt_dist_poll(self.h, C.byref(done), C.byref(it), C.byref(st), C.byref(rel)))
+        return bool(done.value), it.value, st.value, rel.value
+
+    def launch_count(self):
+        return self._hd.launch_count()
+
+
+class DistBiCGSTAB:
+    """``BICGSolver.solve`` (``bicgsolver.py:88-135``) over x-slabs: same recurrence, same stopping test."""
+
+    def __init__(self, ops, exchanger: HaloExchanger, group=None, poll_every=8):
+        self.ops, self.ex, self.group, self.poll_every = ops, exchanger, group, poll_every
+        self.iterations, self.status, self.rel_res = 0, 0, float('nan')
+
+    def _allreduce(self):
+        dist.all_reduce(self.ops.dots, op=dist.ReduceOp.SUM, group=self.group)
+
+    def solve(self, eps=1e-8, max_iter=None, fixed_iters=False):
+        ops, ex = self.ops, self.ex
+        planes = ops.planes()
+        ops.begin(-1.0 if fixed_iters else eps, max_iter)
+        ops.init()
+        self._allreduce()
+        ops.scalar(FIN_BICG_INIT)
+        ex.exchange(planes['r'])
+        it = 0
+        while it < max_iter:
+            ops.update_p()
+            ex.exchange(planes['p'])
+            ops.v_dot()
+            self._allreduce()
+            ops.scalar(FIN_BICG_ALPHA)
+            ex.exchange(planes['v'])
+            ops.st_dots()
+            self._allreduce()
+            ops.scalar(FIN_BICG_OMEGA)
+            ops.xr_dots()
+            self._allreduce()
+            ops.scalar(FIN_BICG_END)
+            ex.exchange(planes['r'])
+            it += 1
+            if not fixed_iters and it % self.poll_every == 0:
+                done, _, _, _ = ops.poll()
+                if done:
+                    break
+        done, self.iterations, self.status, self.rel_res = ops.poll()
+        return self.iterations, self.status

@@ -159,7 +159,11 @@ def test_bicgstab_solve_parity(cuda, kind, a, b, eps):
     s = make(cuda, coef, rhs, kt.BICGSolver)
     s.solve(eps=eps, quiet=True)
     assert s.status == st_ref == 0
-    assert abs(s.iterations - it_ref) <= 1
+    # BiCGSTAB's residual is erratic near convergence: the stopping iteration moves by a few steps with the
+    # summation order of the inner products alone (NumPy pairwise vs the C port's sequential sums differ by the
+    # same amount -- tests/test_oracle_cport.py::test_bicgstab_count_noise_floor), and the reference's own
+    # parallel reduction order is not even deterministic.  CG (below) is held to +-1.
+    assert abs(s.iterations - it_ref) <= max(3, round(0.1 * it_ref))
     # two iterates that both satisfy ||r|| <= eps ||b|| differ by O(cond * eps): the 1e-8 field bar applies
     # when the solve itself is converged that far
     assert rel_l2(s.x.to_numpy(), x_ref) < max(1e-8, 10 * eps)
