@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- the contract benchmark of the hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--iters I]
+
+Metric (BASELINE.json): BiCGSTAB Mcell-iters/s = cells x iterations / second / 1e6 on the pressure-correction-type
+system S1 (5-point Poisson stencil arrays with a zero-coefficient ghost ring, sin*sin right-hand side,
+offset 0), f64.  A *step* is one ``BICGSolver.solve`` of a fixed ``--iters`` BiCGSTAB iterations (eps = 0 so the
+count is exact) on synthetic inputs.  Default workload at every N: ``pcor32768`` (config 5, the largest configuration;
+it fits one B200: 103 GB).  N > 1 splits the same grid into x-slabs (strong scaling), one rank per GPU under torchrun,
+halo rows over NCCL send/recv and the inner products over NCCL all-reduce.
+
+One JSON line on stdout (rank 0): value (inputs resident in HBM), e2e (host buffers in the reference layout through
+the C ABI, H2D/D2H inside the timed region), roofline (dominant kernel, timed live with CUDA events), cpu_baseline
+(the oracle's C/OpenMP port of the reference algorithm on this box's host cores), clocks, gpu_launches.
+
+``--impl reference`` times the reference's own CPU implementation of the path.  The reference is Python + Taichi 0.9
+(``ti.init(arch=ti.cpu)``); Taichi cannot be installed offline for this Python (no wheel, no network), so the arm runs
+the C/OpenMP port in ``oracle/c`` that keeps the reference's kernel granularity one to one (kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n cells per side, description)
+    'pcor32768': (32768, 'BASELINE config 5: 32768x32768 pressure-correction BiCGSTAB (x-slabs when N > 1)'),
+    'pcor16384': (16384, 'north_star single-B200 target: 16384x16384 pressure-correction BiCGSTAB'),
+    'pcor4096': (4096, 'BASELINE config 3: standalone 4096x4096 pressure-correction BiCGSTAB'),
+    'pcor1024': (1024, 'development size'),
+}
+METRIC = 'bicgstab_mcell_iters_per_s'
+UNIT = 'Mcell-iters/s'
+BYTES_PER_CELL_ITER = 28 * 8            # BiCGSTAB algorithmic traffic, f64
+K3_WORDS = 9                            # dominant kernel: s = r - alpha v, t = A s, (t,s), (t,t): 9 N words
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture
+# (profiles/), scaled by the plane size: measured 19.45 GB at 16386 x 16400 words (72.4 B / word).
+K3_TRAFFIC_BYTES_PER_WORD = 72.4
+
+
+def peaks():
+    try:
+        return float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpus):
+        self.gpus, self.proc, self.lines = set(gpus), None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9 or not f[0].isdigit() or int(f[0]) not in self.gpus:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic S1 system
+# ---------------------------------------------------------------------------------------------------------
+def s1_rows_numpy(n, g0, g1, offset=0.0):
+    """Rows [g0, g1) of the global S1 system in the REFERENCE layout: coef (rows, n+2, 5) AoS, b (rows, n+2).
+    Same arrays as oracle.krylov.poisson_sin_system (restated here so the product path never imports oracle/)."""
+    NY = n + 2
+    rows = g1 - g0
+    coef = np.zeros((rows, NY, 5))
+    b = np.zeros((rows, NY))
+    g = np.arange(g0, g1)
+    inner = (g >= 1) & (g <= n)
+    coef[inner, 1:n + 1, 0] = 4.0 + offset
+    coef[inner, 1:n + 1, 1:5] = -1.0
+    coef[g == 1, :, 1] = 0.0
+    coef[g == n, :, 2] = 0.0
+    coef[:, n, 3] = 0.0
+    coef[:, 1, 4] = 0.0
+    sj = np.sin(2.0 * np.pi * np.arange(n) / n)
+    si = np.where(inner, np.sin(2.0 * np.pi * (g - 1) / n), 0.0)
+    b[:, 1:n + 1] = si[:, None] * sj[None, :]
+    return coef, b
+
+
+def s1_rows_device(kt, torch, n, g0, g1, dev, offset=0.0):
+    """The same rows assembled directly in HBM (value leg: inputs resident before the timed region)."""
+    NY = n + 2
+    rows = g1 - g0
+    coef = kt.Field((rows, NY, 5), np.float64, dev)
+    b = kt.Field((rows, NY), np.float64, dev)
+    x = kt.Field((rows, NY), np.float64, dev)
+    g = torch.arange(g0, g1, device=dev)
+    inner = ((g >= 1) & (g <= n)).to(torch.float64)[:, None]
+    d = coef.data
+    d[0, :, 1:n + 1] = (4.0 + offset) * inner
+    for k in range(1, 5):
+        d[k, :, 1:n + 1] = -1.0 * inner
+    d[1][(g == 1).nonzero().flatten(), :] = 0.0
+    d[2][(g == n).nonzero().flatten(), :] = 0.0
+    d[3, :, n] = 0.0
+    d[4, :, 1] = 0.0
+    sj = torch.sin(2.0 * np.pi * torch.arange(n, dtype=torch.float64, device=dev) / n)
+    si = torch.sin(2.0 * np.pi * (g.to(torch.float64) - 1.0) / n) * inner[:, 0]
+    b.data[:, 1:n + 1] = si[:, None] * sj[None, :]
+    return coef, b, x
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm (oracle C/OpenMP port) -- cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------------------------------------
+def cpu_port_run(n_sample, iters, reps):
+    """Time `reps` fixed-iteration BiCGSTAB runs of the C/OpenMP port on an n_sample^2 S1 system.  Returns
+    (best seconds per run, threads)."""
+    from oracle import cport
+    threads = os.cpu_count() or 1
+    os.environ.setdefault('OMP_NUM_THREADS', str(threads))
+    cport.load()
+    coef, b = s1_rows_numpy(n_sample, 0, n_sample + 2)
+    work = np.zeros(9 * b.size)
+    best = float('inf')
+    for _ in range(reps):
+        t = time.perf_counter()
+        _, it, st, _ = cport.bicgstab_solve(coef, b, eps=0.0, max_iter=iters, work=work)
+        best = min(best, time.perf_counter() - t)
+        assert it == iters, (it, st)
+    return best, int(os.environ['OMP_NUM_THREADS'])
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    n, desc = WORKLOADS[a.workload]
+    n_s, its = min(n, 4096), 6
+    cpu_port_run(n_s, 2, 1)                       # page-in / first touch
+    for _ in range(max(a.warmup, 1) - 1):
+        cpu_port_run(n_s, its, 1)
+    t0 = time.perf_counter()
+    per = [cpu_port_run(n_s, its, 1)[0] for _ in range(a.steps)]
+    total = time.perf_counter() - t0
+    threads = int(os.environ.get('OMP_NUM_THREADS', os.cpu_count() or 1))
+    val = n_s * n_s * its * a.steps / sum(per) / 1e6
+    sample = f'{n_s}x{n_s} sub-grid of the S1 system, {its} BiCGSTAB iterations per step (reference kernel granularity: 14 loops + 5 reductions per iteration)'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': 1e3 * sum(per) / a.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': {'workload': a.workload, 'description': desc, 'cpu_sample': sample},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'note': 'Taichi ti.cpu itself cannot run offline (no taichi wheel for this Python); C/OpenMP port of cgsolver.py/bicgsolver.py',
+            'wall_s': total}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if a.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun exactly as the driver does
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={a.gpus}', '--master-addr', '127.0.0.1',
+               '--master-port', str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    assert world == a.gpus, f'--gpus {a.gpus} but WORLD_SIZE={world}'
+    assert torch.cuda.is_available(), 'bench.py needs CUDA (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import karman_taichi_b200 as kt
+    from karman_taichi_b200 import _lib
+    from karman_taichi_b200.cgsolver import _p
+    from karman_taichi_b200.slab import CudaSlabOps, DistBiCGSTAB, HaloExchanger, SlabPartition
+    lib = _lib.load()
+
+    n, desc = WORKLOADS[a.workload]
+    NX = NY = n + 2
+    part = SlabPartition(NX, world)
+    g0, g1 = part.stored(rank)
+    l0, l1 = part.local_owned(rank)
+    coef, b, x = s1_rows_device(kt, torch, n, g0, g1, dev)
+    cells = n * n
+    iters = a.iters
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    if world == 1:
+        solver = kt.BICGSolver(coef, b, x)
+        solver.max_steps = iters
+        handle = solver._hd
+
+        def step():
+            solver.solve(eps=0.0, quiet=True)          # the public call: BICGSolver.solve (bicgsolver.py:88)
+            assert solver.iterations == iters, (solver.iterations, solver.status)
+    else:
+        ops = CudaSlabOps(coef, b, x, part, rank)
+        drv = DistBiCGSTAB(ops, HaloExchanger(part, rank))
+        handle = ops._hd
+
+        def step():
+            it, st = drv.solve(eps=0.0, max_iter=iters, fixed_iters=True)
+            assert it == iters, (it, st)
+
+    # ---- value leg: inputs resident in HBM -------------------------------------------------------------
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(range(world))
+    if rank == 0:
+        sampler.start()
+    _lib.check(lib.kt_prof_begin(handle.h, 4 * iters * a.steps + 64))
+    launches0 = handle.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = allmax(e0.elapsed_time(e1))
+    launches = int(allsum(handle.launch_count() - launches0))
+    tot = (C.c_double * 8)()
+    cnt = (C.c_long * 8)()
+    _lib.check(lib.kt_prof_end(handle.h, tot, cnt, 8))
+    clocks = sampler.stop() if rank == 0 else None
+    value = cells * iters * a.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (class 2: s = r - alpha v, t = A s, two dots), timed live ---------------
+    peak, peak_kind = peaks()
+    k3_ms = tot[2] / max(cnt[2], 1)
+    k3_ms = allmax(k3_ms)
+    words_local = (l1 - l0) * NY
+    alg_bytes = K3_WORDS * 8 * words_local
+    achieved = alg_bytes / (k3_ms * 1e-3) / 1e9
+    kernel_share = {nm: allmax(tot[i]) / ms_total for i, nm in enumerate(['p_update', 'v=Ap+dot', 's,t+2dots', 'x,r+2dots']) if cnt[i]}
+    roofline = {'bound': 'hbm', 'kernel': 'k_stencil<SRC_S,EPI_ST>: s = r - alpha v, t = A s, (t,s), (t,t)  [9 N words]',
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_kind': peak_kind,
+                'traffic': K3_TRAFFIC_BYTES_PER_WORD * (l1 - l0) * coef.pitch, 'traffic_source': 'profiles/ ncu --set full capture, scaled by plane words',
+                'ms_per_launch': k3_ms, 'launches_timed': int(cnt[2]), 'algorithmic_bytes_per_launch': alg_bytes,
+                'kernel_share_of_step': kernel_share,
+                'whole_iteration': {'algorithmic_bytes_per_cell_iter': BYTES_PER_CELL_ITER,
+                                    'achieved_gbs_per_gpu': BYTES_PER_CELL_ITER * NX * NY * iters * a.steps / world / (ms_total * 1e-3) / 1e9,
+                                    'frac': BYTES_PER_CELL_ITER * NX * NY * iters * a.steps / world / (ms_total * 1e-3) / 1e9 / peak}}
+
+    # ---- e2e leg: host buffers in the reference layout, H2D + solve + D2H inside the timed region --------------------
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(a, kt, _lib, lib, torch, dist, world, rank, dev, n, g0, g1, coef, b, x, step, handle, cells, iters, barrier, allmax, allsum)
+
+    # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        n_s, its = 4096, 6
+        cpu_port_run(n_s, 2, 1)
+        t, threads = cpu_port_run(n_s, its, 3)
+        cpu = {'value': n_s * n_s * its / t / 1e6, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': f'{n_s}x{n_s} sub-grid of the same S1 system, {its} BiCGSTAB iterations, best of 3 (C/OpenMP port of bicgsolver.py, '
+                         'reference kernel granularity)'}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+                'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+                'data': 'synthetic',
+                'config': {'workload': a.workload, 'description': desc, 'grid': [n, n], 'bicgstab_iters_per_step': iters,
+                           'system': 'S1 Poisson-sin, offset 0, zero-coefficient ghost ring (SURVEY.md 8d)',
+                           'parallelism': f'x-slab x{world}' if world > 1 else 'single GPU',
+                           'cache': 'working set 103 GB >> 126 MB L2 (inputs larger than L2; no flush needed)'},
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(a, kt, _lib, lib, torch, dist, world, rank, dev, n, g0, g1, coef, b, x, step, handle, cells, iters, barrier, allmax, allsum):
+    """The reference-facing call with HOST buffers: coef[i][j][k] (AoS) and b in pinned host memory are copied to the
+    device, converted to the kernel layout, solved, and x is copied back -- every step, all inside the timed region."""
+    rows, NY = g1 - g0, n + 2
+    need = rows * NY * 8 * 7
+    try:
+        avail = int([l for l in open('/proc/meminfo') if l.startswith('MemAvailable')][0].split()[1]) * 1024
+    except Exception:
+        avail = None
+    if avail is not None and need * (world if world > 1 else 1) > 0.8 * avail:
+        return {'value': None, 'unit': UNIT, 'skipped': f'host needs {need / 1e9:.0f} GB pinned per rank, {avail / 1e9:.0f} GB available'}
+    try:
+        coef_h = torch.empty((rows, NY, 5), dtype=torch.float64, pin_memory=True)
+        b_h = torch.empty((rows, NY), dtype=torch.float64, pin_memory=True)
+        x_h = torch.empty((rows, NY), dtype=torch.float64, pin_memory=True)
+    except Exception as e:   # pinned allocation refused
+        return {'value': None, 'unit': UNIT, 'skipped': f'pinned host allocation failed: {e}'}
+    CH = 8192                                    # fill in row chunks to bound temporary memory
+    for r in range(0, rows, CH):
+        c_np, b_np = s1_rows_numpy(n, g0 + r, min(g0 + r + CH, g1))
+        coef_h[r:r + CH] = torch.from_numpy(c_np)
+        b_h[r:r + CH] = torch.from_numpy(b_np)
+    staging_bytes = 256 << 20
+    staging = torch.empty(staging_bytes // 8, dtype=torch.float64, device=dev)
+    h = handle.h
+    P = lambda t: C.c_void_p(t.data_ptr())
+
+    def e2e_step():
+        handle.use_current_stream()
+        _lib.check(lib.kt_upload_coef(h, C.c_void_p(coef.ptr), P(coef_h), P(staging), staging_bytes))
+        _lib.check(lib.kt_upload_field(h, C.c_void_p(b.ptr), P(b_h)))
+        step()
+        _lib.check(lib.kt_download_field(h, P(x_h), C.c_void_p(x.ptr)))
+
+    k_e = max(1, min(a.steps, 3))
+    e2e_step()                                   # warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k_e):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms = allmax(e0.elapsed_time(e1))
+    h2d = int(allsum(float(coef_h.numel() * 8 + b_h.numel() * 8)))     # bytes of the tensors copied, all ranks
+    d2h = int(allsum(float(x_h.numel() * 8)))
+    return {'value': cells * iters * k_e / (ms * 1e-3) / 1e6, 'unit': UNIT,
+            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+            'steps': k_e, 'ms_per_step': ms / k_e,
+            'call': 'kt_upload_coef + kt_upload_field + BICGSolver.solve + kt_download_field (= kt_bicgstab_solve_host) on pinned host buffers'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='pcor32768', choices=sorted(WORKLOADS))
+    ap.add_argument('--iters', type=int, default=50, help='BiCGSTAB iterations per step')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == 'ours':
+        a.warmup = 3                                   # timing rules: W >= 3
+    sys.exit(run_reference(a) if a.impl == 'reference' else run_ours(a))
+
+
+if __name__ == '__main__':
+    main()

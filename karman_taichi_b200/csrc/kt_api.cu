@@ -80,7 +80,7 @@ int kt_create(int device, int NX, int NY, int pitch, int dtype, void* stream, kt
   cudaDeviceProp prop;
   KT_CUDA(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
-  h->max_blocks = h->num_sms * 32;   // upper bound of any grid that produces block partials
+  h->max_blocks = h->num_sms * 512;  // upper bound of any grid that produces block partials (1.2 MB of partials)
   KT_CUDA(cudaMalloc(&h->partials, sizeof(double) * KT_MAX_DOTS * h->max_blocks));
   KT_CUDA(cudaMalloc(&h->ticket, sizeof(unsigned int)));
   KT_CUDA(cudaMemset(h->ticket, 0, sizeof(unsigned int)));

@@ -240,10 +240,20 @@ __device__ __forceinline__ void block_reduce_finalize(double a0, double a1, cons
   if (!is_last) return;
   __threadfence();
   // fixed-order final sum: thread k owns partials k, k+B, k+2B ...; then the same tree as above.
+  // (eight independent L2 loads in flight per thread, then added in index order: the sum order is fixed, the
+  // latency of the partial reads is paid once per eight instead of once per partial)
   double f0 = 0.0, f1 = 0.0;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
-    f0 += __ldcg(ws.partials + b);
-    if (NDOT > 1) f1 += __ldcg(ws.partials + ws.max_blocks + b);
+  const int nb = (int)gridDim.x;
+  for (int base = threadIdx.x; base < nb; base += 8 * blockDim.x) {
+    double v0[8], v1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int b = base + k * blockDim.x;
+      v0[k] = (b < nb) ? __ldcg(ws.partials + b) : 0.0;
+      v1[k] = (NDOT > 1 && b < nb) ? __ldcg(ws.partials + ws.max_blocks + b) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { f0 += v0[k]; if (NDOT > 1) f1 += v1[k]; }
   }
   f0 = warp_sum(f0);
   if (NDOT > 1) f1 = warp_sum(f1);

@@ -86,7 +86,7 @@ struct SrcRow {
 };
 
 #ifndef KT_STENCIL_MINB
-#define KT_STENCIL_MINB 1
+#define KT_STENCIL_MINB 4
 #endif
 #ifndef KT_STENCIL_UNROLL
 #define KT_STENCIL_UNROLL 1
@@ -94,15 +94,21 @@ struct SrcRow {
 constexpr int kStencilUnroll = KT_STENCIL_UNROLL;   // rows of loads the compiler may batch ahead
 constexpr int kEwUnroll = KT_EW_UNROLL;             // strides of loads batched ahead in element-wise kernels
 
-#ifndef KT_STENCIL_W
-#define KT_STENCIL_W 2
+// Column chunks (32 vectors each) a warp processes side by side, and the register budget that goes with it
+// (measured, profiles/r01_grid_sweep.md): the plain-operand product (v = A p, Ap = A p) is fastest with two chunks
+// per warp at 2 blocks/SM (14 x 512 B in flight per warp); the fused s = r - alpha v / Jacobi variants, which carry
+// more operand rows, with one chunk per warp at 4 blocks/SM (<= 64 registers).
+#ifdef KT_STENCIL_W
+template <int SRC, bool PRE> struct StencilCfg { static constexpr int W = KT_STENCIL_W; static constexpr int MINB = KT_STENCIL_MINB; };
+#else
+template <int SRC, bool PRE> struct StencilCfg { static constexpr int W = 1; static constexpr int MINB = 4; };
+template <> struct StencilCfg<SRC_X, false> { static constexpr int W = 2; static constexpr int MINB = 2; };
 #endif
-constexpr int kStencilW = KT_STENCIL_W;   // column chunks (32 vectors each) a warp processes side by side
 
 template <typename T, int SRC, bool PRE, int EPI>
-__global__ void __launch_bounds__(256, KT_STENCIL_MINB) k_stencil(const StencilArgs<T> A) {
+__global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(const StencilArgs<T> A) {
   constexpr int V = VT<T>::V;
-  constexpr int W = kStencilW;
+  constexpr int W = StencilCfg<SRC, PRE>::W;
   if (A.check_done && A.ws.sc->done) return;
   const T alpha = (SRC == SRC_S) ? T(A.alpha_from_sc ? A.ws.sc->alpha : A.alpha_imm) : T(0);
   const int lane = threadIdx.x & 31;
@@ -401,52 +407,56 @@ __global__ void k_sc_reset(Scalars* sc, double eps, long long max_iter, int flag
 // host side
 // ---------------------------------------------------------------------------------------------
 struct Plan {
-  int V, TI, nCC;
-  long long nTiles, st_blocks, ew_blocks;   // blocks that would give every warp / thread exactly one unit
+  int V;
+  long long ew_blocks;   // blocks that would give every thread exactly one vector
   EwGeom g;
 };
-
-// Resident blocks per SM of a kernel (256 threads, no dynamic smem), cached per kernel.  Grids are sized
-// num_SMs x this, i.e. exactly one wave of co-resident blocks that stride statically over the work: no tail
-// wave, and a grid (hence a summation order) that depends only on the problem geometry and the device.
-template <typename K>
-static int resident_blocks(K kernel) {
-  static int cached = 0;   // one instantiation of this template per kernel type
-  if (!cached) {
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, 0) != cudaSuccess || nb < 1) nb = 1;
-    if (nb > 8) nb = 8;
-    cached = nb;
-  }
-  return cached;
-}
 
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
 
-template <typename K>
-static int grid_for(const kt_handle_s* h, K kernel, long long blocks_wanted) {
-  static int waves = env_int("KT_GRID_WAVES", 1);    // development knob
-  long long cap = (long long)h->num_sms * resident_blocks(kernel) * waves;
-  if (cap > h->max_blocks) cap = h->max_blocks;
-  return (int)std::max<long long>(1, std::min<long long>(blocks_wanted, cap));
+// Grid sizing.  Work is assigned statically (tile / vector index = f(blockIdx, threadIdx, stride)), so the
+// summation order of every inner product depends only on the problem geometry and the grid -- never on which SM
+// ran which block.  Measured on B200 (profiles/r01_grid_sweep.md): many small blocks that the hardware scheduler
+// hands out as SMs free up beat a grid of exactly-resident persistent blocks by 3-5 % (SMs differ in effective
+// bandwidth; a static persistent split leaves the fast ones idle at the end), while too many blocks make the
+// last-block sum of the block partials visible.  ~1 MB of traffic per block is the measured sweet spot at both
+// 4096^2 and 16384^2, so: blocks = bytes moved / KT_BLOCK_BYTES, clamped to [4, 128] blocks per SM.
+static int grid_for(const kt_handle_s* h, long long blocks_wanted, int planes_moved) {
+  static long long block_bytes = env_int("KT_BLOCK_BYTES", 1 << 20);
+  const long long bytes = (long long)planes_moved * (h->row_hi - h->row_lo) * h->pitch * (h->dtype == KT_F64 ? 8 : 4);
+  long long g = bytes / block_bytes;
+  g = std::max<long long>(g, (long long)h->num_sms * 4);
+  g = std::min<long long>(g, (long long)h->num_sms * 128);
+  g = std::min<long long>(g, h->max_blocks);
+  return (int)std::max<long long>(1, std::min<long long>(blocks_wanted, g));
+}
+
+struct StPlan { int TI, nCC, grid; long long nTiles; };
+
+// Stencil launch geometry for W column chunks per warp: grid from the traffic, then the tallest row tile (<= 64 rows,
+// >= 8) that still leaves every warp of the grid >= 4 tiles to stride over.
+static StPlan stencil_plan(const kt_handle_s* h, int V, int W, int planes_moved) {
+  StPlan S;
+  const int rows = h->row_hi - h->row_lo;
+  S.nCC = (h->pitch / V + 32 * W - 1) / (32 * W);
+  const long long max_tiles = (long long)((rows + 7) / 8) * S.nCC;
+  S.grid = grid_for(h, (max_tiles + 7) / 8, planes_moved);
+  static int ti_env = env_int("KT_TI", 0);
+  int TI = 64;
+  while (TI > 8 && (long long)((rows + TI - 1) / TI) * S.nCC < 4LL * S.grid * 8) TI >>= 1;
+  if (ti_env > 0) TI = ti_env;
+  S.TI = TI;
+  S.nTiles = (long long)((rows + TI - 1) / TI) * S.nCC;
+  S.grid = (int)std::max<long long>(1, std::min<long long>(S.grid, (S.nTiles + 7) / 8));
+  return S;
 }
 
 static Plan make_plan(const kt_handle_s* h) {
   Plan P;
   P.V = (h->dtype == KT_F64) ? 2 : 4;
-  const int rows = h->row_hi - h->row_lo;
-  P.nCC = (h->pitch / P.V + 32 * kStencilW - 1) / (32 * kStencilW);
-  const long long target_warps = (long long)h->num_sms * 32;       // ~resident warps of a stencil kernel
-  static int ti_env = env_int("KT_TI", 0);
-  int TI = 64;
-  while (TI > 4 && (long long)((rows + TI - 1) / TI) * P.nCC < 8 * target_warps) TI >>= 1;
-  if (ti_env > 0) TI = ti_env;
-  P.TI = TI;
-  P.nTiles = (long long)((rows + TI - 1) / TI) * P.nCC;
-  P.st_blocks = (P.nTiles + 7) / 8;
   P.g.v_lo = (long long)h->row_lo * h->pitch / P.V;
   P.g.v_hi = (long long)h->row_hi * h->pitch / P.V;
   P.ew_blocks = (P.g.v_hi - P.g.v_lo + 255) / 256;
@@ -467,15 +477,19 @@ static StencilArgs<T> stencil_args(kt_handle_s* h, const Plan& P, const void* co
   const size_t plane = (size_t)h->NX * h->pitch;
   for (int k = 0; k < 5; ++k) A.c[k] = (const T*)coef + k * plane;
   A.NX = h->NX; A.pitch = h->pitch; A.row_lo = h->row_lo; A.row_hi = h->row_hi;
-  A.TI = P.TI; A.nCC = P.nCC; A.nTiles = P.nTiles;
   A.ws = make_ws(h);
   return A;
 }
 
 template <typename T, int SRC, bool PRE, int EPI>
 static int launch_stencil(kt_handle_s* h, const Plan& P, const StencilArgs<T>& A) {
-  auto kern = k_stencil<T, SRC, PRE, EPI>;
-  kern<<<grid_for(h, kern, P.st_blocks), 256, 0, h->stream>>>(A);
+  // planes streamed: 5 coefficients + operand(s) + outputs (+ q / Minv)
+  constexpr int planes = 5 + (SRC == SRC_S ? 2 : 1) + (PRE ? 1 : 0) + 1 + (EPI == EPI_DOT_Q || EPI == EPI_RESID ? 1 : 0) +
+                         (EPI == EPI_ST ? 1 : 0);
+  const StPlan S = stencil_plan(h, P.V, StencilCfg<SRC, PRE>::W, planes);
+  StencilArgs<T> B = A;
+  B.TI = S.TI; B.nCC = S.nCC; B.nTiles = S.nTiles;
+  k_stencil<T, SRC, PRE, EPI><<<S.grid, 256, 0, h->stream>>>(B);
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -514,7 +528,7 @@ static int t_bicg_s_t(kt_handle_s* h, const void* coef, const void* r, const voi
 template <typename T, int OP>
 static int t_ew(kt_handle_s* h, void* out, const void* x, const void* y, const void* z, double a, double b) {
   Plan P = make_plan(h);
-  k_ew<T, OP><<<grid_for(h, k_ew<T, OP>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)out, (const T*)x, (const T*)y, (const T*)z, a, b);
+  k_ew<T, OP><<<grid_for(h, P.ew_blocks, 3), 256, 0, h->stream>>>(P.g, (T*)out, (const T*)x, (const T*)y, (const T*)z, a, b);
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -522,7 +536,7 @@ static int t_ew(kt_handle_s* h, void* out, const void* x, const void* y, const v
 template <typename T>
 static int t_dot(kt_handle_s* h, const void* p, const void* q, double* out_host) {
   Plan P = make_plan(h);
-  k_dot<T><<<grid_for(h, k_dot<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (const T*)p, (const T*)q, make_ws(h));
+  k_dot<T><<<grid_for(h, P.ew_blocks, 2), 256, 0, h->stream>>>(P.g, (const T*)p, (const T*)q, make_ws(h));
   KT_LAUNCH_CHECK(h);
   return read_dots(h, out_host, 1);
 }
@@ -584,7 +598,7 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
     rc = launch_stencil<T, SRC_X, false, EPI_RESID>(h, P, A);
     if (rc) return rc;
   } else {
-    k_init<T, false><<<grid_for(h, k_init<T, false>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (const T*)b, r, r_tld, (T*)x, nullptr, ws, FIN_BICG_INIT);
+    k_init<T, false><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (const T*)b, r, r_tld, (T*)x, nullptr, ws, FIN_BICG_INIT);
     KT_LAUNCH_CHECK(h);
   }
   StencilArgs<T> A2 = stencil_args<T>(h, P, coef);
@@ -595,7 +609,7 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
   auto iter = [&]() -> int {
     {
       ProfScope ps(h, KT_K_BICG_P);
-      k_bicg_p<T><<<grid_for(h, k_bicg_p<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, p, r, v, h->sc);
+      k_bicg_p<T><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, p, r, v, h->sc);
     }
     KT_LAUNCH_CHECK(h);
     int e;
@@ -610,8 +624,8 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
     }
     if (e) return e;
     ProfScope ps(h, KT_K_BICG_XR);
-    if (pre) k_bicg_xr<T, true><<<grid_for(h, k_bicg_xr<T, true>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END);
-    else k_bicg_xr<T, false><<<grid_for(h, k_bicg_xr<T, false>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END);
+    if (pre) k_bicg_xr<T, true><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END);
+    else k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END);
     KT_LAUNCH_CHECK(h);
     return 0;
   };
@@ -633,7 +647,7 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
   int rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0);
   if (rc) return rc;
   ReduceWs ws = make_ws(h, w->history, w->history_cap);
-  k_init<T, true><<<grid_for(h, k_init<T, true>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (const T*)b, r, nullptr, (T*)x, p, ws, FIN_CG_INIT);
+  k_init<T, true><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (const T*)b, r, nullptr, (T*)x, p, ws, FIN_CG_INIT);
   KT_LAUNCH_CHECK(h);
   StencilArgs<T> A1 = stencil_args<T>(h, P, coef);
   A1.ws = ws; A1.x = p; A1.y = Ap; A1.check_done = 1; A1.fin = FIN_CG_ALPHA;
@@ -646,12 +660,12 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
     if (e) return e;
     {
       ProfScope ps(h, KT_K_CG_XR);
-      k_cg_xr<T><<<grid_for(h, k_cg_xr<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws, FIN_CG_END);
+      k_cg_xr<T><<<grid_for(h, P.ew_blocks, 6), 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws, FIN_CG_END);
     }
     KT_LAUNCH_CHECK(h);
     {
       ProfScope ps(h, KT_K_CG_P);
-      k_cg_p<T><<<grid_for(h, k_cg_p<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, p, r, h->sc);
+      k_cg_p<T><<<grid_for(h, P.ew_blocks, 3), 256, 0, h->stream>>>(P.g, p, r, h->sc);
     }
     KT_LAUNCH_CHECK(h);
     return 0;
@@ -679,13 +693,15 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
                         void* o0, void* o1, void* o2, double* dots_dev) {
   Plan P = make_plan(h);
   ReduceWs ws = make_ws(h, nullptr, 0, dots_dev);
+  static const int cls_of_phase[5] = {KT_K_INIT, KT_K_BICG_P, KT_K_BICG_V, KT_K_BICG_ST, KT_K_BICG_XR};
+  ProfScope ps(h, (phase >= 0 && phase < 5) ? cls_of_phase[phase] : KT_K_INIT);
   switch (phase) {
     case 0: {   // init: r = b (a0), x = 0 (o1), r (o0), r_tld (o2, may be null); local (r,r)
-      k_init<T, false><<<grid_for(h, k_init<T, false>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (const T*)a0, (T*)o0, (T*)o2, (T*)o1, nullptr, ws, FIN_NONE);
+      k_init<T, false><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (const T*)a0, (T*)o0, (T*)o2, (T*)o1, nullptr, ws, FIN_NONE);
       break;
     }
     case 1: {   // p (o0) = r (a0) + beta (p - omega v (a1))
-      k_bicg_p<T><<<grid_for(h, k_bicg_p<T>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (T*)o0, (const T*)a0, (const T*)a1, h->sc);
+      k_bicg_p<T><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (T*)o0, (const T*)a0, (const T*)a1, h->sc);
       break;
     }
     case 2: {   // v (o0) = A p (a0); local (r_tld (a1), v)
@@ -700,7 +716,7 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
       return launch_stencil<T, SRC_S, false, EPI_ST>(h, P, A);
     }
     case 4: {   // x (o0) += alpha p (a0) + omega s (a1); r (o1) = s - omega t (a2); local (r,r), (r, r_tld (o2))
-      k_bicg_xr<T, false><<<grid_for(h, k_bicg_xr<T, false>, P.ew_blocks), 256, 0, h->stream>>>(
+      k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(
           P.g, (T*)o0, (T*)o1, (const T*)a0, (const T*)a1, (const T*)a2, (const T*)o2, nullptr, 0, 0, 1, ws, FIN_NONE);
       break;
     }
@@ -784,10 +800,10 @@ int kt_bicg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* s, co
   Plan P = make_plan(h);
   ReduceWs ws = make_ws(h);
   if (h->dtype == KT_F64)
-    k_bicg_xr<double, false><<<grid_for(h, k_bicg_xr<double, false>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)s,
+    k_bicg_xr<double, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)s,
                                                               (const double*)t, (const double*)r_tld, nullptr, alpha, omega, 0, ws, FIN_NONE);
   else
-    k_bicg_xr<float, false><<<grid_for(h, k_bicg_xr<float, false>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)s,
+    k_bicg_xr<float, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)s,
                                                              (const float*)t, (const float*)r_tld, nullptr, alpha, omega, 0, ws, FIN_NONE);
   KT_LAUNCH_CHECK(h);
   return read_dots(h, dots_host, 2);
@@ -798,9 +814,9 @@ int kt_cg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* Ap, dou
   Plan P = make_plan(h);
   ReduceWs ws = make_ws(h);
   if (h->dtype == KT_F64)
-    k_cg_xr<double><<<grid_for(h, k_cg_xr<double>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)Ap, alpha, 0, ws, FIN_NONE);
+    k_cg_xr<double><<<grid_for(h, P.ew_blocks, 6), 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)Ap, alpha, 0, ws, FIN_NONE);
   else
-    k_cg_xr<float><<<grid_for(h, k_cg_xr<float>, P.ew_blocks), 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)Ap, alpha, 0, ws, FIN_NONE);
+    k_cg_xr<float><<<grid_for(h, P.ew_blocks, 6), 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)Ap, alpha, 0, ws, FIN_NONE);
   KT_LAUNCH_CHECK(h);
   return read_dots(h, dot_host, 1);
 }

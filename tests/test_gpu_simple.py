@@ -119,7 +119,7 @@ def test_cavity_first_steps_vs_oracle(cuda, n, eps_uv, eps_p, tol):
         assert cg == pytest.approx(co, rel=1e-3)
         for key in 'uvp':
             ref_it = o.last_iters[key]
-            tol_it = 1 if key == 'p' else max(3, round(0.1 * ref_it))    # CG +-1; BiCGSTAB: see test_gpu_krylov.py
+            tol_it = 1 if key == 'p' else max(3, round(0.15 * ref_it))    # CG +-1; BiCGSTAB: see test_gpu_krylov.py
             assert abs(g.log[-1][2][key] - ref_it) <= tol_it, (k, key)
     for name in ('u', 'v', 'p'):
         assert rel_l2(getattr(g, name).to_numpy(), getattr(o, name)) < tol, name

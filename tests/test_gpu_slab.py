@@ -1,0 +1,134 @@
+"""GPU parity of the x-slab (multi-GPU) phases.
+
+* ``test_emulated_slabs_single_gpu``: P virtual ranks on ONE device -- every rank's slab goes through the real
+  ``kt_dist_*`` kernels (row-range restricted SpMV / updates / dots), the halo exchange and the all-reduce are done by
+  hand in the test.  P-slab result must equal the 1-slab result.
+* ``test_two_gpu_nccl``: the real thing over NCCL when the box has >= 2 GPUs (skipped otherwise).
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import krylov
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.mark.parametrize('P,case', [(2, ('poisson', 96, 0.1, 1e-10)), (3, ('random', 130, 67, 1e-10)), (4, ('random', 37, 300, 1e-9))])
+def test_emulated_slabs_single_gpu(cuda, P, case):
+    import torch
+    import karman_taichi_b200 as kt
+    from karman_taichi_b200.slab import CudaSlabOps, SlabPartition
+    kind, a, b_, eps = case
+    coef, rhs = krylov.poisson_sin_system(a, b_) if kind == 'poisson' else krylov.random_dd_system(a, b_, seed=0)
+    x_ref, it_ref, st_ref = krylov.bicgstab_solve(coef, rhs, eps=eps)
+    part = SlabPartition(rhs.shape[0], P)
+    ranks = []
+    for r in range(P):
+        c_l = np.ascontiguousarray(part.scatter(coef, r))
+        b_l = np.ascontiguousarray(part.scatter(rhs, r))
+        fc = kt.Field(c_l.shape, np.float64, cuda).from_numpy(c_l)
+        fb = kt.Field(b_l.shape, np.float64, cuda).from_numpy(b_l)
+        fx = kt.Field(b_l.shape, np.float64, cuda)
+        ranks.append(CudaSlabOps(fc, fb, fx, part, r))
+
+    def exchange(name):
+        for r in range(P - 1):
+            lo, up = ranks[r].planes()[name], ranks[r + 1].planes()[name]
+            l0r, l1r = part.local_owned(r)
+            l0u, _ = part.local_owned(r + 1)
+            lo[l1r].copy_(up[l0u])           # upper neighbour's first owned row -> my top halo
+            up[l0u - 1].copy_(lo[l1r - 1])   # my last owned row -> its bottom halo
+
+    def allreduce():
+        tot = sum(o.dots for o in ranks)
+        for o in ranks:
+            o.dots.copy_(tot)
+
+    def each(fn):
+        for o in ranks:
+            getattr(o, fn)()
+
+    def scalar(fin):
+        for o in ranks:
+            o.scalar(fin)
+
+    for o in ranks:
+        o.begin(eps, rhs.size)
+    each('init'); allreduce(); scalar(1); exchange('r')
+    for it in range(rhs.size):
+        each('update_p'); exchange('p')
+        each('v_dot'); allreduce(); scalar(2); exchange('v')
+        each('st_dots'); allreduce(); scalar(3)
+        each('xr_dots'); allreduce(); scalar(4); exchange('r')
+        polls = [o.poll() for o in ranks]
+        assert len({(p[0], p[1], p[2]) for p in polls}) == 1      # identical decisions on every rank
+        if polls[0][0]:
+            break
+    done, iters, status, rel = polls[0]
+    assert status == st_ref == 0
+    assert abs(iters - it_ref) <= max(3, round(0.1 * it_ref))
+    x = np.concatenate([part.owned_of_local(o.x.to_numpy(), r) for r, o in enumerate(ranks)], axis=0)
+    assert rel_l2(x, x_ref) < 1e-8
+    # and against the single-slab CUDA solve: same kernels, different partition of the sums
+    fc = kt.Field(coef.shape, np.float64, cuda).from_numpy(coef)
+    fb = kt.Field(rhs.shape, np.float64, cuda).from_numpy(rhs)
+    fx = kt.Field(rhs.shape, np.float64, cuda)
+    s = kt.BICGSolver(fc, fb, fx)
+    s.solve(eps=eps)
+    assert rel_l2(x, fx.to_numpy()) < 1e-8
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        import karman_taichi_b200 as kt
+        from karman_taichi_b200.slab import CudaSlabOps, DistBiCGSTAB, HaloExchanger, SlabPartition
+        coef, rhs = krylov.poisson_sin_system(256, 0.1)
+        part = SlabPartition(rhs.shape[0], world)
+        c_l = np.ascontiguousarray(part.scatter(coef, rank))
+        b_l = np.ascontiguousarray(part.scatter(rhs, rank))
+        fc = kt.Field(c_l.shape, np.float64, dev).from_numpy(c_l)
+        fb = kt.Field(b_l.shape, np.float64, dev).from_numpy(b_l)
+        fx = kt.Field(b_l.shape, np.float64, dev)
+        ops = CudaSlabOps(fc, fb, fx, part, rank)
+        drv = DistBiCGSTAB(ops, HaloExchanger(part, rank), poll_every=4)
+        iters, status = drv.solve(eps=1e-10, max_iter=rhs.size)
+        np.save(os.path.join(out_dir, f'x_{rank}.npy'), part.owned_of_local(fx.to_numpy(), rank))
+        np.save(os.path.join(out_dir, f'meta_{rank}.npy'), np.array([iters, status]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_nccl(cuda, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip('needs >= 2 GPUs')
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    coef, rhs = krylov.poisson_sin_system(256, 0.1)
+    x_ref, it_ref, _ = krylov.bicgstab_solve(coef, rhs, eps=1e-10)
+    x = np.concatenate([np.load(tmp_path / f'x_{r}.npy') for r in range(world)], axis=0)
+    metas = [np.load(tmp_path / f'meta_{r}.npy') for r in range(world)]
+    assert all(int(m[1]) == 0 for m in metas) and len({int(m[0]) for m in metas}) == 1
+    assert abs(int(metas[0][0]) - it_ref) <= max(3, round(0.1 * it_ref))
+    assert rel_l2(x, x_ref) < 1e-8

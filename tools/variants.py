@@ -5,13 +5,10 @@ sys.path.insert(0, ROOT)
 from karman_taichi_b200 import build
 
 VARIANTS = {
-    'w1': ['-DKT_STENCIL_W=1'],
     'w1_minb4': ['-DKT_STENCIL_W=1', '-DKT_STENCIL_MINB=4'],
-    'w1_su2': ['-DKT_STENCIL_W=1', '-DKT_STENCIL_UNROLL=2'],
-    'w2': ['-DKT_STENCIL_W=2'],
-    'w2_minb2': ['-DKT_STENCIL_W=2', '-DKT_STENCIL_MINB=2'],
-    'w2_minb3': ['-DKT_STENCIL_W=2', '-DKT_STENCIL_MINB=3'],
-    'w2_nv': ['-DKT_STENCIL_W=2', '-DKT_LD_VOLATILE=0'],
+    'w1_minb5': ['-DKT_STENCIL_W=1', '-DKT_STENCIL_MINB=5'],
+    'w1_minb6': ['-DKT_STENCIL_W=1', '-DKT_STENCIL_MINB=6'],
+    'w2': ['-DKT_STENCIL_W=2', '-DKT_STENCIL_MINB=1'],
 }
 if __name__ == '__main__':
     d = os.path.join(ROOT, 'gpurun_variants')
