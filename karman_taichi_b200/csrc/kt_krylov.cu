@@ -422,10 +422,10 @@ static int env_int(const char* name, int dflt) {
 // ran which block.  Measured on B200 (profiles/r01_grid_sweep.md): many small blocks that the hardware scheduler
 // hands out as SMs free up beat a grid of exactly-resident persistent blocks by 3-5 % (SMs differ in effective
 // bandwidth; a static persistent split leaves the fast ones idle at the end), while too many blocks make the
-// last-block sum of the block partials visible.  ~1 MB of traffic per block is the measured sweet spot at both
-// 4096^2 and 16384^2, so: blocks = bytes moved / KT_BLOCK_BYTES, clamped to [4, 128] blocks per SM.
+// last-block sum of the block partials visible.  256-512 KB of traffic per block is the measured sweet spot at
+// both 4096^2 and 16384^2, so: blocks = bytes moved / KT_BLOCK_BYTES (512 KB), clamped to [4, 128] blocks per SM.
 static int grid_for(const kt_handle_s* h, long long blocks_wanted, int planes_moved) {
-  static long long block_bytes = env_int("KT_BLOCK_BYTES", 1 << 20);
+  static long long block_bytes = env_int("KT_BLOCK_BYTES", 1 << 19);
   const long long bytes = (long long)planes_moved * (h->row_hi - h->row_lo) * h->pitch * (h->dtype == KT_F64 ? 8 : 4);
   long long g = bytes / block_bytes;
   g = std::max<long long>(g, (long long)h->num_sms * 4);
