@@ -210,6 +210,36 @@ int kt_correct_puv(kt_handle_t h, const kt_simple_params* P, void* p, void* u, v
 int kt_mdiv_max(kt_handle_t h, const kt_simple_params* P, const void* u, const void* v, void* mdiv,
                 double* max_host);
 
+/* ---- channel + square-cell cylinder: the monolith karman_taichi.py in stencil form -------------------------------
+ * Unknowns: u[i,j] i in [1,nx+1], j in [1,ny] of the (nx+3, ny+2) plane; v[i,j] i in [1,nx], j in [1,ny+1] of
+ * (nx+2, ny+3); pcor[i,j] i in [1,nx], j in [1,ny] of (nx+2, ny+2).  ct: int32 (nx+2, ny+2) plane with pitch_p,
+ * 1 solid / -1 fluid (karman_taichi.py:143-150).  M_* = the reference's Mu/Mv/Mp diagonal planes, Minv_* = 1/M_*
+ * (what kt_bicgstab_solve takes). */
+typedef struct {
+  int nx, ny;
+  double dx, dy, dt, rho, mu, velo_rel, p_rel;
+  int cyl_cx, cyl_cy, cyl_r2;       /* (i-cx)^2 + (j-cy)^2 < r2 -> solid   (karman_taichi.py:148-149) */
+  int pitch_u, pitch_v, pitch_p;
+} kt_channel_params;
+
+/* init (karman_taichi.py:130-154) */
+int kt_channel_init(kt_handle_t h, const kt_channel_params* P, void* p, void* u, void* u0, void* v, void* v0, int* ct);
+/* fill_Au + fill_Av (karman_taichi.py:161-294) */
+int kt_channel_assemble_uv(kt_handle_t h, const kt_channel_params* P, const int* ct, const void* u, const void* v,
+                           const void* p, const void* u0, const void* v0, void* coef_u, void* b_u, void* M_u,
+                           void* Minv_u, void* coef_v, void* b_v, void* M_v, void* Minv_v);
+/* fill_Ap (karman_taichi.py:296-339) */
+int kt_channel_assemble_p(kt_handle_t h, const kt_channel_params* P, const int* ct, const void* u, const void* v,
+                          const void* coef_u, const void* coef_v, void* coef_p, void* b_p, void* M_p, void* Minv_p);
+/* xu_back + xv_back (karman_taichi.py:458-470): u += velo_rel (x_u - u), v likewise */
+int kt_channel_relax(kt_handle_t h, const kt_channel_params* P, void* u, void* v, const void* x_u, const void* x_v);
+/* correct_conserv (karman_taichi.py:585-614): scale u[nx+1,:] by sum u[1,:] / sum u[nx+1,:]; udiv (may be NULL);
+ * sums_host (may be NULL) receives {inlet sum, outlet sum before scaling, ratio} */
+int kt_outlet_scale(kt_handle_t h, const kt_channel_params* P, void* u, const void* v, void* udiv, double* sums_host);
+/* puv_correction (karman_taichi.py:506-542): returns max |pcor| */
+int kt_channel_correct(kt_handle_t h, const kt_channel_params* P, const int* ct, void* u, void* v, void* p,
+                       const void* pcor, const void* coef_u, const void* coef_v, double* pcor_max_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ from .field import Field, ScalarField
 from .cgsolver import CGSolver
 from .bicgsolver import BICGSolver
 from .simple import SIMPLESolver, lid_driven_cavity
+from .karman import KarmanSolver
 
-__all__ = ['Field', 'ScalarField', 'CGSolver', 'BICGSolver', 'SIMPLESolver', 'lid_driven_cavity', 'KtError']
+__all__ = ['Field', 'ScalarField', 'CGSolver', 'BICGSolver', 'SIMPLESolver', 'lid_driven_cavity', 'KarmanSolver', 'KtError']
 __version__ = '0.1.0'

@@ -36,6 +36,15 @@ class KrylovWs(C.Structure):
                 ('s', C.c_void_p), ('t', C.c_void_p), ('history', C.c_void_p), ('history_cap', C.c_long)]
 
 
+class ChannelParams(C.Structure):
+    """``kt_channel_params``"""
+    _fields_ = [('nx', C.c_int), ('ny', C.c_int),
+                ('dx', C.c_double), ('dy', C.c_double), ('dt', C.c_double), ('rho', C.c_double), ('mu', C.c_double),
+                ('velo_rel', C.c_double), ('p_rel', C.c_double),
+                ('cyl_cx', C.c_int), ('cyl_cy', C.c_int), ('cyl_r2', C.c_int),
+                ('pitch_u', C.c_int), ('pitch_v', C.c_int), ('pitch_p', C.c_int)]
+
+
 class SimpleParams(C.Structure):
     """``kt_simple_params``"""
     _fields_ = [('nx', C.c_int), ('ny', C.c_int),
@@ -48,7 +57,7 @@ class SimpleParams(C.Structure):
 
 _P, _I, _D, _L = C.c_void_p, C.c_int, C.c_double, C.c_long
 _PD, _PL, _PI, _PF = C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_int), C.POINTER(C.c_float)
-_WS, _SP = C.POINTER(KrylovWs), C.POINTER(SimpleParams)
+_WS, _SP, _CP = C.POINTER(KrylovWs), C.POINTER(SimpleParams), C.POINTER(ChannelParams)
 
 # name -> (restype, argtypes); every symbol include/karman_b200.h declares
 SIGNATURES = {
@@ -97,6 +106,12 @@ SIGNATURES = {
     'kt_relax_uv': (_I, [_P, _SP, _P, _P, _P, _P, _PD]),
     'kt_correct_puv': (_I, [_P, _SP, _P, _P, _P, _P, _P, _P]),
     'kt_mdiv_max': (_I, [_P, _SP, _P, _P, _P, _PD]),
+    'kt_channel_init': (_I, [_P, _CP, _P, _P, _P, _P, _P, _P]),
+    'kt_channel_assemble_uv': (_I, [_P, _CP] + [_P] * 14),
+    'kt_channel_assemble_p': (_I, [_P, _CP] + [_P] * 9),
+    'kt_channel_relax': (_I, [_P, _CP, _P, _P, _P, _P]),
+    'kt_outlet_scale': (_I, [_P, _CP, _P, _P, _P, _PD]),
+    'kt_channel_correct': (_I, [_P, _CP, _P, _P, _P, _P, _P, _P, _P, _PD]),
 }
 
 _lib = None

@@ -35,6 +35,7 @@ class BICGSolver(CGSolver):
         self.omega_zero_break = False
         self._r_tld_own = None
         self.max_steps = None
+        self.report_rho_zero = True   # bicgsolver.py:97 prints; the monolith only does with output=1 (karman_taichi.py:387)
 
     # -- reference kernels ---------------------------------------------------------------------
     def init(self):
@@ -108,7 +109,8 @@ class BICGSolver(CGSolver):
             for i in range(1, min(self.iterations, len(hist) - 1) + 1):
                 print('>>> Iter =', i, ' Residual =', hist[i])
         if st == _lib.STATUS_RHO_ZERO:
-            print('>>> BICG failed at first place...')           # bicgsolver.py:97
+            if self.report_rho_zero:
+                print('>>> BICG failed at first place...')           # bicgsolver.py:97
         elif st in (_lib.STATUS_ALPHA_DIV_ZERO, _lib.STATUS_OMEGA_DIV_ZERO):
             raise ZeroDivisionError('float division by zero')    # bicgsolver.py:102,108,118
         elif st == _lib.STATUS_CONVERGED and not quiet:

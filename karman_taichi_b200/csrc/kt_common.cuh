@@ -269,4 +269,39 @@ __device__ __forceinline__ void block_reduce_finalize(double a0, double a1, cons
   }
 }
 
+// block max -> partials[block] -> last block takes the max (order-independent, exact)
+__device__ __forceinline__ void block_max_finalize(double m0, double m1, double* partials, int max_blocks,
+                                                   unsigned int* ticket, double* out) {
+  __shared__ double sm[2][32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+  m0 = warp_max(m0); m1 = warp_max(m1);
+  if (lane == 0) { sm[0][wid] = m0; sm[1][wid] = m1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < nw; ++w) { a = fmax(a, sm[0][w]); b = fmax(b, sm[1][w]); }
+    partials[bid] = a; partials[max_blocks + bid] = b;
+    __threadfence();
+    is_last = (atomicAdd(ticket, 1u) == (unsigned)nblocks - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double a = 0.0, b = 0.0;
+  for (int k = threadIdx.x; k < nblocks; k += blockDim.x) { a = fmax(a, __ldcg(partials + k)); b = fmax(b, __ldcg(partials + max_blocks + k)); }
+  a = warp_max(a); b = warp_max(b);
+  __syncthreads();
+  if (lane == 0) { sm[0][wid] = a; sm[1][wid] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = 0.0; b = 0.0;
+    for (int w = 0; w < nw; ++w) { a = fmax(a, sm[0][w]); b = fmax(b, sm[1][w]); }
+    out[0] = a; out[1] = b;
+    *ticket = 0u;
+  }
+}
+
+
 }  // namespace kt
