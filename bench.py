@@ -44,10 +44,10 @@ WORKLOADS = {
 METRIC = 'bicgstab_mcell_iters_per_s'
 UNIT = 'Mcell-iters/s'
 BYTES_PER_CELL_ITER = 28 * 8            # BiCGSTAB algorithmic traffic, f64
-K3_WORDS = 9                            # dominant kernel: s = r - alpha v, t = A s, (t,s), (t,t): 9 N words
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture
-# (profiles/), scaled by the plane size: measured 19.45 GB at 16386 x 16400 words (72.4 B / word).
-K3_TRAFFIC_BYTES_PER_WORD = 72.4
+# dram__bytes_read.sum + dram__bytes_write.sum per launch and per plane word of each kernel come from the committed
+# ncu captures (profiles/r01_launch_list_summary.md, 16386 x 16400-word planes); the fused K1+K2 kernel's figure is
+# filled in once it has been captured (None = not measured yet).
+FUSED_TRAFFIC_BYTES_PER_WORD = None
 
 
 def peaks():
@@ -293,20 +293,30 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else None
     value = cells * iters * a.steps / (ms_total * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (class 2: s = r - alpha v, t = A s, two dots), timed live ---------------
+    # ---- roofline of the dominant kernel (largest share of the step), timed live with CUDA-event pairs ---------------
     peak, peak_kind = peaks()
-    k3_ms = tot[2] / max(cnt[2], 1)
-    k3_ms = allmax(k3_ms)
+    fused = cnt[0] == 0                       # BICGSolver.fuse_p_update: K1 folded into K2 (11 N instead of 4 N + 8 N)
+    classes = {0: ('p_update', 'k_bicg_p: p = r + beta (p - omega v)', 4, 29.9),
+               1: (('p_update+v=Ap+dot', 'k_stencil<SRC_P,EPI_DOT_Q_ST>: p = r + beta (p - omega v), v = A p, (r~, v)', 11, FUSED_TRAFFIC_BYTES_PER_WORD)
+                   if fused else ('v=Ap+dot', 'k_stencil<SRC_X,EPI_DOT_Q>: v = A p, (r~, v)', 8, 63.9)),
+               2: ('s,t+2dots', 'k_stencil<SRC_S,EPI_ST>: s = r - alpha v, t = A s, (t,s), (t,t)', 9, 72.8),
+               3: ('x,r+2dots', 'k_bicg_xr: x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 7, 55.8)}
+    tots = [allmax(tot[i]) for i in range(4)]
+    dom = max(range(4), key=lambda i: tots[i])
+    d_name, d_desc, d_words, d_traffic = classes[dom]
+    d_ms = tots[dom] / max(cnt[dom], 1)
     words_local = (l1 - l0) * NY
-    alg_bytes = K3_WORDS * 8 * words_local
-    achieved = alg_bytes / (k3_ms * 1e-3) / 1e9
-    kernel_share = {nm: allmax(tot[i]) / ms_total for i, nm in enumerate(['p_update', 'v=Ap+dot', 's,t+2dots', 'x,r+2dots']) if cnt[i]}
-    roofline = {'bound': 'hbm', 'kernel': 'k_stencil<SRC_S,EPI_ST>: s = r - alpha v, t = A s, (t,s), (t,t)  [9 N words]',
+    alg_bytes = d_words * 8 * words_local
+    achieved = alg_bytes / (d_ms * 1e-3) / 1e9
+    kernel_share = {classes[i][0]: tots[i] / ms_total for i in range(4) if cnt[i]}
+    iter_bytes = (27 if fused else 28) * 8
+    roofline = {'bound': 'hbm', 'kernel': f'{d_desc}  [{d_words} N words]',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_kind': peak_kind,
-                'traffic': K3_TRAFFIC_BYTES_PER_WORD * (l1 - l0) * coef.pitch, 'traffic_source': 'profiles/ ncu --set full capture, scaled by plane words',
-                'ms_per_launch': k3_ms, 'launches_timed': int(cnt[2]), 'algorithmic_bytes_per_launch': alg_bytes,
+                'traffic': (d_traffic * (l1 - l0) * coef.pitch) if d_traffic else None,
+                'traffic_source': 'profiles/r01_launch_list_summary.md (ncu dram__bytes_read+write per launch at 16384^2), scaled by plane words',
+                'ms_per_launch': d_ms, 'launches_timed': int(cnt[dom]), 'algorithmic_bytes_per_launch': alg_bytes,
                 'kernel_share_of_step': kernel_share,
-                'whole_iteration': {'algorithmic_bytes_per_cell_iter': BYTES_PER_CELL_ITER,
+                'whole_iteration': {'algorithmic_bytes_per_cell_iter': BYTES_PER_CELL_ITER, 'bytes_per_cell_iter_as_run': iter_bytes,
                                     'achieved_gbs_per_gpu': BYTES_PER_CELL_ITER * NX * NY * iters * a.steps / world / (ms_total * 1e-3) / 1e9,
                                     'frac': BYTES_PER_CELL_ITER * NX * NY * iters * a.steps / world / (ms_total * 1e-3) / 1e9 / peak}}
 

@@ -130,6 +130,8 @@ typedef struct {
   void* t;      /* BiCGSTAB t = A s (reference Ashat/t)       (bicgsolver.py:13-14) */
   double* history; /* DEVICE array or NULL: sqrt(rTr) per iteration (cgsolver.py:88,111) */
   long history_cap;
+  void* p2;     /* optional second p / Ap planes: when both are given BiCGSTAB fuses the p-update into the v = A p */
+  void* Ap2;    /* kernel (ping-pong buffers; 27 N instead of 28 N words per iteration).  NULL = unfused.          */
 } kt_krylov_ws;
 
 /* CGSolver.solve (cgsolver.py:83-114): x0 = 0, stop sqrt(rTr) < sqrt(rTr0)*eps, at most

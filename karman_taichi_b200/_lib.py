@@ -33,7 +33,8 @@ class KtError(RuntimeError):
 class KrylovWs(C.Structure):
     """``kt_krylov_ws``"""
     _fields_ = [('r', C.c_void_p), ('p', C.c_void_p), ('Ap', C.c_void_p), ('r_tld', C.c_void_p),
-                ('s', C.c_void_p), ('t', C.c_void_p), ('history', C.c_void_p), ('history_cap', C.c_long)]
+                ('s', C.c_void_p), ('t', C.c_void_p), ('history', C.c_void_p), ('history_cap', C.c_long),
+                ('p2', C.c_void_p), ('Ap2', C.c_void_p)]
 
 
 class ChannelParams(C.Structure):

@@ -35,6 +35,8 @@ class BICGSolver(CGSolver):
         self.omega_zero_break = False
         self._r_tld_own = None
         self.max_steps = None
+        self.fuse_p_update = True     # fused K1+K2 (needs two extra planes, allocated on first solve)
+        self._p2 = self._Ap2 = None
         self.report_rho_zero = True   # bicgsolver.py:97 prints; the monolith only does with output=1 (karman_taichi.py:387)
 
     # -- reference kernels ---------------------------------------------------------------------
@@ -97,7 +99,13 @@ class BICGSolver(CGSolver):
             r_tld = self._r_tld_own.ptr
         if self.omega_zero_break:
             flags |= _lib.FLAG_OMEGA_ZERO_BREAK
-        ws = self._ws(r_tld=r_tld, s=self.s.ptr, t=self.t.ptr)
+        p2 = ap2 = None
+        if self.fuse_p_update:
+            if self._p2 is None:
+                self._p2 = Field((self.NX, self.NY), self.real, self.coef.device)
+                self._Ap2 = Field((self.NX, self.NY), self.real, self.coef.device)
+            p2, ap2 = self._p2.ptr, self._Ap2.ptr
+        ws = self._ws(r_tld=r_tld, s=self.s.ptr, t=self.t.ptr, p2=p2, Ap2=ap2)
         iters, rel, status = C.c_long(), C.c_double(), C.c_int()
         steps = self.steps if self.max_steps is None else self.max_steps
         _lib.check(self._lib.kt_bicgstab_solve(self._h, _p(self.coef), _p(self.b), _p(self.x), _p(self.Minv), C.byref(ws),

@@ -100,7 +100,7 @@ class CGSolver:
     def _ws(self, **extra):
         hist = self._history_buffer()
         ws = _lib.KrylovWs(r=self.r.ptr, p=self.p.ptr, Ap=self.Ap.ptr, r_tld=None, s=None, t=None,
-                           history=hist.data_ptr(), history_cap=hist.numel())
+                           history=hist.data_ptr(), history_cap=hist.numel(), p2=None, Ap2=None)
         for k, v in extra.items():
             setattr(ws, k, v)
         return ws

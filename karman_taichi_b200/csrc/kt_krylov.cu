@@ -30,17 +30,18 @@ namespace kt {
 // ---------------------------------------------------------------------------------------------
 // stencil kernel
 // ---------------------------------------------------------------------------------------------
-enum { SRC_X = 0, SRC_S = 1 };
-enum { EPI_Y = 0, EPI_DOT_Q = 1, EPI_DOT_SRC = 2, EPI_ST = 3, EPI_RESID = 4 };
+enum { SRC_X = 0, SRC_S = 1, SRC_P = 2 };
+enum { EPI_Y = 0, EPI_DOT_Q = 1, EPI_DOT_SRC = 2, EPI_ST = 3, EPI_RESID = 4, EPI_DOT_Q_ST = 5 };
 
 template <typename T> struct StencilArgs {
   const T* c[5];     // ap, aw, ae, an, as planes
-  const T* x;        // SRC_X operand            | SRC_S: r
-  const T* v;        //                          | SRC_S: v   (s = r - alpha v)
+  const T* x;        // SRC_X operand            | SRC_S: r                      | SRC_P: r
+  const T* v;        //                          | SRC_S: v  (s = r - alpha v)   | SRC_P: p_old
+  const T* w;        //                          |                               | SRC_P: v_old  (p = r + beta (p_old - omega v_old))
   const T* minv;     // PRE: Jacobi 1/M plane
-  const T* q;        // EPI_DOT_Q: external dot vector; EPI_RESID: b
+  const T* q;        // EPI_DOT_Q / EPI_DOT_Q_ST: external dot vector; EPI_RESID: b
   T* y;              // A*src  (EPI_RESID: r = b - A*src)
-  T* s_out;          // EPI_ST: s ; EPI_RESID: r_tld copy (may be null)
+  T* s_out;          // EPI_ST: s ; EPI_DOT_Q_ST: p_new ; EPI_RESID: r_tld copy (may be null)
   int NX, pitch, row_lo, row_hi, TI, nCC;
   long long nTiles;
   double alpha_imm;
@@ -50,20 +51,30 @@ template <typename T> struct StencilArgs {
   ReduceWs ws;
 };
 
+// scalars of the on-the-fly operand: SRC_S: a = alpha; SRC_P: a = beta, b = omega, first = (iteration 0: p = r)
+template <typename T> struct SrcCoef { T a, b; bool first; };
+
 template <typename T, int SRC, bool PRE>
 struct SrcRow {
-  // vector of the stencil operand at (i, j0..j0+V-1); also returns the un-preconditioned value (s or x)
-  static __device__ __forceinline__ void load(const StencilArgs<T>& A, int i, int j0, bool act, T alpha,
+  // vector of the stencil operand at (i, j0..j0+V-1); also returns the un-preconditioned value (x, s or p)
+  static __device__ __forceinline__ void load(const StencilArgs<T>& A, int i, int j0, bool act, const SrcCoef<T>& K,
                                               Pack<T>& hat, Pack<T>& raw) {
     constexpr int V = VT<T>::V;
     if (!act || i < 0 || i >= A.NX) { hat = pack_zero<T>(); raw = hat; return; }
     const size_t o = (size_t)i * A.pitch + j0;
     if (SRC == SRC_X) {
       raw = ld_cached(A.x + o);
-    } else {
+    } else if (SRC == SRC_S) {
       Pack<T> r = ld_cached(A.x + o), v = ld_cached(A.v + o);
 #pragma unroll
-      for (int k = 0; k < V; ++k) raw.a[k] = r.a[k] - alpha * v.a[k];
+      for (int k = 0; k < V; ++k) raw.a[k] = r.a[k] - K.a * v.a[k];                     // bicgsolver.py:63
+    } else {
+      raw = ld_cached(A.x + o);
+      if (!K.first) {
+        Pack<T> pp = ld_cached(A.v + o), vv = ld_cached(A.w + o);
+#pragma unroll
+        for (int k = 0; k < V; ++k) raw.a[k] = raw.a[k] + K.a * (pp.a[k] - K.b * vv.a[k]);   // bicgsolver.py:46
+      }
     }
     if (PRE) {
       Pack<T> m = ld_cached(A.minv + o);
@@ -74,12 +85,13 @@ struct SrcRow {
     }
   }
   // scalar of the (preconditioned) operand at (i, j); j may be out of [0, pitch)
-  static __device__ __forceinline__ T scalar(const StencilArgs<T>& A, int i, int j, T alpha) {
+  static __device__ __forceinline__ T scalar(const StencilArgs<T>& A, int i, int j, const SrcCoef<T>& K) {
     if (j < 0 || j >= A.pitch || i < 0 || i >= A.NX) return T(0);
     const size_t o = (size_t)i * A.pitch + j;
     T raw;
     if (SRC == SRC_X) raw = A.x[o];
-    else raw = A.x[o] - alpha * A.v[o];
+    else if (SRC == SRC_S) raw = A.x[o] - K.a * A.v[o];
+    else { raw = A.x[o]; if (!K.first) raw = raw + K.a * (A.v[o] - K.b * A.w[o]); }
     if (PRE) raw = A.minv[o] * raw;
     return raw;
   }
@@ -103,6 +115,7 @@ template <int SRC, bool PRE> struct StencilCfg { static constexpr int W = KT_STE
 #else
 template <int SRC, bool PRE> struct StencilCfg { static constexpr int W = 1; static constexpr int MINB = 4; };
 template <> struct StencilCfg<SRC_X, false> { static constexpr int W = 2; static constexpr int MINB = 2; };
+template <bool PRE> struct StencilCfg<SRC_P, PRE> { static constexpr int W = 1; static constexpr int MINB = 3; };
 #endif
 
 template <typename T, int SRC, bool PRE, int EPI>
@@ -110,7 +123,10 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
   constexpr int V = VT<T>::V;
   constexpr int W = StencilCfg<SRC, PRE>::W;
   if (A.check_done && A.ws.sc->done) return;
-  const T alpha = (SRC == SRC_S) ? T(A.alpha_from_sc ? A.ws.sc->alpha : A.alpha_imm) : T(0);
+  SrcCoef<T> alpha;   // (named for its SRC_S role)
+  alpha.a = T(0); alpha.b = T(0); alpha.first = false;
+  if (SRC == SRC_S) alpha.a = T(A.alpha_from_sc ? A.ws.sc->alpha : A.alpha_imm);
+  if (SRC == SRC_P) { alpha.a = T(A.ws.sc->beta); alpha.b = T(A.ws.sc->omega); alpha.first = A.ws.sc->iter == 0; }
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const long long gwarp = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
@@ -142,7 +158,7 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
         if (act[w]) {
 #pragma unroll
           for (int k = 0; k < 5; ++k) c[w][k] = ld_stream(A.c[k] + o);
-          if (EPI == EPI_DOT_Q || EPI == EPI_RESID) qv[w] = ld_stream(A.q + o);
+          if (EPI == EPI_DOT_Q || EPI == EPI_DOT_Q_ST || EPI == EPI_RESID) qv[w] = ld_stream(A.q + o);
         } else {
 #pragma unroll
           for (int k = 0; k < 5; ++k) c[w][k] = pack_zero<T>();
@@ -189,10 +205,10 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
             if (A.s_out) st_vec(A.s_out + o, r);
           } else {
             st_vec(A.y + o, y);
-            if (EPI == EPI_ST) st_vec(A.s_out + o, raw_c[w]);
+            if (EPI == EPI_ST || EPI == EPI_DOT_Q_ST) st_vec(A.s_out + o, raw_c[w]);
 #pragma unroll
             for (int k = 0; k < V; ++k) {
-              if (EPI == EPI_DOT_Q) acc0 += (double)qv[w].a[k] * (double)y.a[k];
+              if (EPI == EPI_DOT_Q || EPI == EPI_DOT_Q_ST) acc0 += (double)qv[w].a[k] * (double)y.a[k];
               if (EPI == EPI_DOT_SRC) acc0 += (double)raw_c[w].a[k] * (double)y.a[k];
               if (EPI == EPI_ST) { acc0 += (double)y.a[k] * (double)raw_c[w].a[k]; acc1 += (double)y.a[k] * (double)y.a[k]; }
             }
@@ -484,8 +500,9 @@ static StencilArgs<T> stencil_args(kt_handle_s* h, const Plan& P, const void* co
 template <typename T, int SRC, bool PRE, int EPI>
 static int launch_stencil(kt_handle_s* h, const Plan& P, const StencilArgs<T>& A) {
   // planes streamed: 5 coefficients + operand(s) + outputs (+ q / Minv)
-  constexpr int planes = 5 + (SRC == SRC_S ? 2 : 1) + (PRE ? 1 : 0) + 1 + (EPI == EPI_DOT_Q || EPI == EPI_RESID ? 1 : 0) +
-                         (EPI == EPI_ST ? 1 : 0);
+  constexpr int planes = 5 + (SRC == SRC_S ? 2 : SRC == SRC_P ? 3 : 1) + (PRE ? 1 : 0) + 1 +
+                         (EPI == EPI_DOT_Q || EPI == EPI_DOT_Q_ST || EPI == EPI_RESID ? 1 : 0) +
+                         (EPI == EPI_ST || EPI == EPI_DOT_Q_ST ? 1 : 0);
   const StPlan S = stencil_plan(h, P.V, StencilCfg<SRC, PRE>::W, planes);
   StencilArgs<T> B = A;
   B.TI = S.TI; B.nCC = S.nCC; B.nTiles = S.nTiles;
@@ -601,31 +618,48 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
     k_init<T, false><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (const T*)b, r, r_tld, (T*)x, nullptr, ws, FIN_BICG_INIT);
     KT_LAUNCH_CHECK(h);
   }
+  // Fused K1+K2 (27 N words / iteration instead of 28 N) when the caller provides the second p / v planes: the
+  // p-update is recomputed on the fly for the three operand rows of v = A p^ (halo recompute), which needs p_old and
+  // v_old to stay intact while p_new / v_new are written -> ping-pong between (p, Ap) and (p2, Ap2).
+  T* pb[2] = {p, (T*)w->p2};
+  T* vb[2] = {v, (T*)w->Ap2};
+  const bool fused = pb[1] != nullptr && vb[1] != nullptr;
+  long long it_enq = 0;                       // parity of the iteration being enqueued selects the buffers
   StencilArgs<T> A2 = stencil_args<T>(h, P, coef);
-  A2.ws = ws; A2.x = p; A2.minv = (const T*)Minv; A2.q = r_tld_c; A2.y = v; A2.check_done = 1; A2.fin = FIN_BICG_ALPHA;
+  A2.ws = ws; A2.minv = (const T*)Minv; A2.q = r_tld_c; A2.check_done = 1; A2.fin = FIN_BICG_ALPHA;
   StencilArgs<T> A3 = stencil_args<T>(h, P, coef);
-  A3.ws = ws; A3.x = r; A3.v = v; A3.minv = (const T*)Minv; A3.y = t; A3.s_out = s; A3.alpha_from_sc = 1;
+  A3.ws = ws; A3.x = r; A3.minv = (const T*)Minv; A3.y = t; A3.s_out = s; A3.alpha_from_sc = 1;
   A3.check_done = 1; A3.fin = FIN_BICG_OMEGA;
   auto iter = [&]() -> int {
-    {
-      ProfScope ps(h, KT_K_BICG_P);
-      k_bicg_p<T><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, p, r, v, h->sc);
-    }
-    KT_LAUNCH_CHECK(h);
+    const int cur = fused ? (int)(it_enq & 1) : 0, prev = fused ? cur ^ 1 : 0;
+    ++it_enq;
+    T* p_new = pb[cur]; T* v_new = vb[cur];
     int e;
-    {
+    if (fused) {
       ProfScope ps(h, KT_K_BICG_V);
+      A2.x = r; A2.v = pb[prev]; A2.w = vb[prev]; A2.y = v_new; A2.s_out = p_new;
+      e = pre ? launch_stencil<T, SRC_P, true, EPI_DOT_Q_ST>(h, P, A2) : launch_stencil<T, SRC_P, false, EPI_DOT_Q_ST>(h, P, A2);
+      if (e) return e;
+    } else {
+      {
+        ProfScope ps(h, KT_K_BICG_P);
+        k_bicg_p<T><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, p_new, r, v_new, h->sc);
+      }
+      KT_LAUNCH_CHECK(h);
+      ProfScope ps(h, KT_K_BICG_V);
+      A2.x = p_new; A2.y = v_new;
       e = pre ? launch_stencil<T, SRC_X, true, EPI_DOT_Q>(h, P, A2) : launch_stencil<T, SRC_X, false, EPI_DOT_Q>(h, P, A2);
+      if (e) return e;
     }
-    if (e) return e;
     {
       ProfScope ps(h, KT_K_BICG_ST);
+      A3.v = v_new;
       e = pre ? launch_stencil<T, SRC_S, true, EPI_ST>(h, P, A3) : launch_stencil<T, SRC_S, false, EPI_ST>(h, P, A3);
     }
     if (e) return e;
     ProfScope ps(h, KT_K_BICG_XR);
-    if (pre) k_bicg_xr<T, true><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END);
-    else k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END);
+    if (pre) k_bicg_xr<T, true><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END);
+    else k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END);
     KT_LAUNCH_CHECK(h);
     return 0;
   };

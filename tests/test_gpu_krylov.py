@@ -151,12 +151,14 @@ def system(kind, a, b):
     return krylov.random_dd_system(a, b, seed=0)
 
 
+@pytest.mark.parametrize('fused', [True, False])
 @pytest.mark.parametrize('kind,a,b,eps', CASES)
-def test_bicgstab_solve_parity(cuda, kind, a, b, eps):
+def test_bicgstab_solve_parity(cuda, kind, a, b, eps, fused):
     import karman_taichi_b200 as kt
     coef, rhs = system(kind, a, b)
     x_ref, it_ref, st_ref = krylov.bicgstab_solve(coef, rhs, eps=eps)
     s = make(cuda, coef, rhs, kt.BICGSolver)
+    s.fuse_p_update = fused          # True: K1 folded into K2 (27 N words / iteration); False: four kernels (28 N)
     s.solve(eps=eps, quiet=True)
     assert s.status == st_ref == 0
     # BiCGSTAB's residual is erratic near convergence: the stopping iteration moves by a few steps with the
@@ -248,11 +250,13 @@ def test_jacobi_warm_start_variant(cuda):
     s.warm_start = True
     s.omega_zero_break = True
     s.max_steps = 100 * 66 * 323
-    s.x.from_numpy(x0)
-    s.solve(eps=1e-8)
-    assert s.status == st_ref == 0
-    assert abs(s.iterations - it_ref) <= 1
-    assert rel_l2(s.x.to_numpy(), x_ref) < 1e-8
+    for fused in (True, False):
+        s.fuse_p_update = fused
+        s.x.from_numpy(x0)
+        s.solve(eps=1e-8)
+        assert s.status == st_ref == 0
+        assert abs(s.iterations - it_ref) <= max(3, round(0.1 * it_ref))
+        assert rel_l2(s.x.to_numpy(), x_ref) < 1e-8
 
 
 def test_large_roundtrip_property(cuda):
