@@ -45,9 +45,8 @@ METRIC = 'bicgstab_mcell_iters_per_s'
 UNIT = 'Mcell-iters/s'
 BYTES_PER_CELL_ITER = 28 * 8            # BiCGSTAB algorithmic traffic, f64
 # dram__bytes_read.sum + dram__bytes_write.sum per launch and per plane word of each kernel come from the committed
-# ncu captures (profiles/r01_launch_list_summary.md, 16386 x 16400-word planes); the fused K1+K2 kernel's figure is
-# filled in once it has been captured (None = not measured yet).
-FUSED_TRAFFIC_BYTES_PER_WORD = None
+# ncu captures (profiles/r01_launch_list_summary.md, 16386 x 16400-word planes).
+FUSED_TRAFFIC_BYTES_PER_WORD = 86.9
 
 
 def peaks():

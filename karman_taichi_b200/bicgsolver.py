@@ -35,7 +35,10 @@ class BICGSolver(CGSolver):
         self.omega_zero_break = False
         self._r_tld_own = None
         self.max_steps = None
-        self.fuse_p_update = True     # fused K1+K2 (needs two extra planes, allocated on first solve)
+        # fused K1+K2 (27 N words / iteration, two extra planes).  Off by default: measured on B200 the 12-stream fused
+        # kernel streams at 6.0 TB/s vs 6.7-7.0 TB/s for K1 and K2 apart -- 9.29 vs 9.00 ms / iteration at 16384^2
+        # (profiles/r01_grid_sweep.md).  The persistent small-grid solver uses it (one grid barrier less).
+        self.fuse_p_update = False
         self._p2 = self._Ap2 = None
         self.report_rho_zero = True   # bicgsolver.py:97 prints; the monolith only does with output=1 (karman_taichi.py:387)
 
