@@ -129,6 +129,12 @@ int kt_set_rows(kt_handle_t h, int row_lo, int row_hi) {
 
 long long kt_launch_count(kt_handle_t h) { return h ? h->launches : 0; }
 
+int kt_set_cluster(kt_handle_t h, int enable) {
+  KT_CHECK_ARG(h, "kt_set_cluster: null handle");
+  h->allow_cluster = enable != 0;
+  return 0;
+}
+
 int kt_upload_field(kt_handle_t h, void* dst, const void* src_host) {
   KT_CHECK_ARG(h && dst && src_host, "kt_upload_field: null argument");
   const size_t es = esize(h);

@@ -23,6 +23,7 @@ struct kt_handle_s {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   long long launches = 0;            // kernels launched through this handle (bench: gpu_launches)
+  bool allow_cluster = true;         // small grids: whole solve inside one thread-block cluster (kt_cluster.cu)
   // optional per-kernel-class device timing (bench.py roofline): events bracket every launch of a class
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs (begin, end)
@@ -49,6 +50,11 @@ struct ProfScope {   // records an event pair around a launch when profiling is 
 
 
 namespace kt {
+// kt_cluster.cu: whole solve inside one thread-block cluster when every plane fits its shared memory.
+// Returns 1 = solved (h->sc_host holds the final scalars), 0 = does not fit / not schedulable, < 0 = error.
+template <typename T>
+int cluster_try_solve(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, void* r_out,
+                      double* history, long long hist_cap, double eps, long long max_iter, int flags, bool is_cg);
 void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 }  // namespace kt

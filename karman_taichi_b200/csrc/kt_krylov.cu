@@ -605,7 +605,16 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
   KT_CHECK_ARG(r && p && v && s && t, "kt_krylov_ws: r, p, Ap, s, t are required for BiCGSTAB");
   KT_CHECK_ARG(!(warm && !r_tld), "warm start needs a separate r_tld plane");
   const T* r_tld_c = r_tld ? r_tld : (const T*)b;     // x0 = 0  =>  r_tld == b exactly (bicgsolver.py:25-26)
-  int rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, flags);
+  int rc = cluster_try_solve<T>(h, coef, b, x, Minv, r, w->history, w->history_cap, fixed_iters ? -1.0 : eps, max_iter, flags, false);
+  if (rc < 0) return rc;
+  if (rc == 1) {       // small grid: solved inside one thread-block cluster (kt_cluster.cu)
+    const Scalars& S = *h->sc_host;
+    if (iters) *iters = (long)S.iter;
+    if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
+    if (status) *status = S.status;
+    return 0;
+  }
+  rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, flags);
   if (rc) return rc;
   ReduceWs ws = make_ws(h, w->history, w->history_cap);
   // K0
@@ -678,7 +687,16 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
   Plan P = make_plan(h);
   T* r = (T*)w->r; T* p = (T*)w->p; T* Ap = (T*)w->Ap;
   KT_CHECK_ARG(r && p && Ap, "kt_krylov_ws: r, p, Ap are required for CG");
-  int rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0);
+  int rc = cluster_try_solve<T>(h, coef, b, x, nullptr, r, w->history, w->history_cap, fixed_iters ? -1.0 : eps, max_iter, 0, true);
+  if (rc < 0) return rc;
+  if (rc == 1) {
+    const Scalars& S = *h->sc_host;
+    if (iters) *iters = (long)S.iter;
+    if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
+    if (status) *status = S.status;
+    return 0;
+  }
+  rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0);
   if (rc) return rc;
   ReduceWs ws = make_ws(h, w->history, w->history_cap);
   k_init<T, true><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (const T*)b, r, nullptr, (T*)x, p, ws, FIN_CG_INIT);

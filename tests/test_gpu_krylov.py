@@ -151,14 +151,18 @@ def system(kind, a, b):
     return krylov.random_dd_system(a, b, seed=0)
 
 
-@pytest.mark.parametrize('fused', [True, False])
+@pytest.mark.parametrize('path', ['cluster', 'stream', 'stream-fused'])
 @pytest.mark.parametrize('kind,a,b,eps', CASES)
-def test_bicgstab_solve_parity(cuda, kind, a, b, eps, fused):
+def test_bicgstab_solve_parity(cuda, kind, a, b, eps, path):
+    """Three device paths, one recurrence: 'cluster' = whole solve inside one thread-block cluster (taken only when
+    the planes fit its shared memory, else it falls through to 'stream'); 'stream' = four HBM-streaming kernels per
+    iteration (28 N words); 'stream-fused' = p-update folded into v = A p (27 N)."""
     import karman_taichi_b200 as kt
     coef, rhs = system(kind, a, b)
     x_ref, it_ref, st_ref = krylov.bicgstab_solve(coef, rhs, eps=eps)
     s = make(cuda, coef, rhs, kt.BICGSolver)
-    s.fuse_p_update = fused          # True: K1 folded into K2 (27 N words / iteration); False: four kernels (28 N)
+    s.cluster = path == 'cluster'
+    s.fuse_p_update = path == 'stream-fused'
     s.solve(eps=eps, quiet=True)
     assert s.status == st_ref == 0
     # BiCGSTAB's residual is erratic near convergence: the stopping iteration moves by a few steps with the
@@ -176,13 +180,15 @@ def test_bicgstab_solve_parity(cuda, kind, a, b, eps, fused):
     assert np.all(s.x.to_numpy()[0, :] == 0) and np.all(s.x.to_numpy()[:, 0] == 0)
 
 
+@pytest.mark.parametrize('cluster', [True, False])
 @pytest.mark.parametrize('kind,a,b,eps', [c for c in CASES if c[0] == 'poisson'])
-def test_cg_solve_parity(cuda, kind, a, b, eps):
+def test_cg_solve_parity(cuda, kind, a, b, eps, cluster):
     import karman_taichi_b200 as kt
     coef, rhs = system(kind, a, b)
     hist_ref = []
     x_ref, it_ref, st_ref = krylov.cg_solve(coef, rhs, eps=eps, history=hist_ref)
     s = make(cuda, coef, rhs, kt.CGSolver)
+    s.cluster = cluster
     s.solve(eps=eps, quiet=True)
     assert s.status == st_ref == 0
     assert abs(s.iterations - it_ref) <= 1
@@ -250,8 +256,8 @@ def test_jacobi_warm_start_variant(cuda):
     s.warm_start = True
     s.omega_zero_break = True
     s.max_steps = 100 * 66 * 323
-    for fused in (True, False):
-        s.fuse_p_update = fused
+    for cluster, fused in ((True, False), (False, True), (False, False)):
+        s.cluster, s.fuse_p_update = cluster, fused
         s.x.from_numpy(x0)
         s.solve(eps=1e-8)
         assert s.status == st_ref == 0
