@@ -12,6 +12,7 @@ from .cgsolver import CGSolver
 from .bicgsolver import BICGSolver
 from .simple import SIMPLESolver, lid_driven_cavity
 from .karman import KarmanSolver
+from .display import Display
 
-__all__ = ['Field', 'ScalarField', 'CGSolver', 'BICGSolver', 'SIMPLESolver', 'lid_driven_cavity', 'KarmanSolver', 'KtError']
+__all__ = ['Field', 'ScalarField', 'CGSolver', 'BICGSolver', 'SIMPLESolver', 'lid_driven_cavity', 'KarmanSolver', 'Display', 'KtError']
 __version__ = '0.1.0'

@@ -114,7 +114,7 @@ class BICGSolver(CGSolver):
         _lib.check(self._lib.kt_set_cluster(self._h, 1 if self.cluster else 0))
         _lib.check(self._lib.kt_bicgstab_solve(self._h, _p(self.coef), _p(self.b), _p(self.x), _p(self.Minv), C.byref(ws),
                                                float(eps), steps, flags, C.byref(iters), C.byref(rel), C.byref(status)))
-        hist = self._finish(iters, rel, status, quiet, None)
+        hist = self._finish(iters, rel, status, quiet, None, want_history=not quiet)   # history is commented out in the reference (:93,125)
         st = status.value
         if not quiet:
             print('>>> Initial residual =', hist[0] if len(hist) else float('nan'))

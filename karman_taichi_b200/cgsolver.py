@@ -64,7 +64,7 @@ class CGSolver:
         self.real = coef.np_dtype
         self.N_ext = 0
         self.steps = self.NX * self.NY      # cgsolver.py:14
-        self.history = []                   # cgsolver.py:15
+        self._history = []                  # cgsolver.py:15 (strings, or raw residual arrays formatted on first read)
         mk = lambda: Field((self.NX, self.NY), self.real, coef.device)
         self.r = mk()
         self.p = mk()
@@ -81,6 +81,24 @@ class CGSolver:
         self.rel_res = float('nan')
 
     # -- plumbing ---------------------------------------------------------------------------
+    @property
+    def history(self):
+        """``cgsolver.py:15,88,111``: list of ``f'{residual:e}\\n'`` strings.  Residual arrays coming back from the device
+        are kept raw and formatted here on first access (a SIMPLE run appends hundreds of entries per outer iteration)."""
+        if any(not isinstance(h, str) for h in self._history):
+            flat = []
+            for h in self._history:
+                if isinstance(h, str):
+                    flat.append(h)
+                else:
+                    flat.extend(f'{v:e}\n' for v in h)
+            self._history = flat
+        return self._history
+
+    @history.setter
+    def history(self, value):
+        self._history = list(value)
+
     @property
     def Ax(self):
         if self._Ax is None:
@@ -160,10 +178,11 @@ class CGSolver:
         return np.sqrt(self.reduce(self.r, self.r))
 
     # -- solve ---------------------------------------------------------------------------------
-    def _finish(self, iters, rel, status, quiet, converged_msg):
+    def _finish(self, iters, rel, status, quiet, converged_msg, want_history=True):
         self.iterations, self.rel_res, self.status = iters.value, rel.value, status.value
-        hist = self._hist_dev[:min(self.iterations + 1, self._hist_dev.numel())].cpu().numpy()
-        return hist
+        if not want_history:
+            return None
+        return self._hist_dev[:min(self.iterations + 1, self._hist_dev.numel())].cpu().numpy()
 
     def solve(self, eps=1e-8, quiet=True):
         """``cgsolver.py:83-114``"""
@@ -175,16 +194,15 @@ class CGSolver:
         hist = self._finish(iters, rel, status, quiet, None)
         if status.value == _lib.STATUS_ALPHA_DIV_ZERO:
             raise ZeroDivisionError('float division by zero')      # cgsolver.py:96 old_rTr / pAp
+        n_logged = self.iterations - (1 if status.value == _lib.STATUS_CONVERGED else 0)
+        n_logged = min(n_logged, len(hist) - 1)
+        self._history.append(hist[:n_logged + 1].copy())         # initial + one entry per non-final iteration (:88,111)
         if not quiet:
             print('>>> Initial residual =', hist[0] if len(hist) else float('nan'))
-        self.history.append(f'{hist[0]:e}\n')
-        n_logged = self.iterations - (1 if status.value == _lib.STATUS_CONVERGED else 0)
-        for i in range(1, min(n_logged, len(hist) - 1) + 1):
-            self.history.append(f'{hist[i]:e}\n')
-            if not quiet:
+            for i in range(1, n_logged + 1):
                 print(f'>>> Iter = {i:4}, Residual = {hist[i]:e}')
-        if status.value == _lib.STATUS_CONVERGED and not quiet:
-            print('>>> Conjugate Gradient method converged.')
+            if status.value == _lib.STATUS_CONVERGED:
+                print('>>> Conjugate Gradient method converged.')
 
     def save_history(self):
         """``cgsolver.py:116-119``"""

@@ -35,30 +35,39 @@ constexpr int CL_THREADS = 512;
 
 struct ClShared {           // per-CTA control block at the start of dynamic shared memory
   Scalars sc;
-  double part[3][2];        // block-partial sums of the three dot groups of an iteration
+  double part[3][2][16];    // [dot group][value][source rank]: every CTA PUSHES its block sums into all CTAs' slots
   double red[2][CL_THREADS / 32];
 };
 
-// fixed-order cluster-wide sum of up to two values: block reduce -> own slot -> cluster barrier -> every CTA sums the
-// slots of ranks 0..C-1 in order.  Returns the sums in d0/d1 (identical bits on every CTA and every thread).
+// fixed-order cluster-wide sum of up to two values.  Block reduce -> lanes 0..C-1 of warp 0 store the block sums into
+// slot [rank] of EVERY CTA (remote DSMEM stores, fire and forget) -> cluster barrier (release / acquire) -> every thread
+// sums its own CTA's C slots in rank order from local shared memory.  Identical bits on every CTA and thread; no remote
+// load sits on the critical path after the barrier.
 template <int NDOT>
-__device__ __forceinline__ void cluster_sum(cg::cluster_group& cl, ClShared* S, int group, double& d0, double& d1, int nranks) {
+__device__ __forceinline__ void cluster_sum(cg::cluster_group& cl, ClShared* S, int group, double& d0, double& d1, int nranks,
+                                            int rank) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   d0 = warp_sum(d0);
   if (NDOT > 1) d1 = warp_sum(d1);
   if (lane == 0) { S->red[0][wid] = d0; if (NDOT > 1) S->red[1][wid] = d1; }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (wid == 0) {
     double s0 = 0.0, s1 = 0.0;
-    for (int w = 0; w < CL_THREADS / 32; ++w) { s0 += S->red[0][w]; if (NDOT > 1) s1 += S->red[1][w]; }
-    S->part[group][0] = s0; S->part[group][1] = s1;
+    if (lane == 0)
+      for (int w = 0; w < CL_THREADS / 32; ++w) { s0 += S->red[0][w]; if (NDOT > 1) s1 += S->red[1][w]; }
+    s0 = __shfl_sync(0xffffffffu, s0, 0);
+    if (NDOT > 1) s1 = __shfl_sync(0xffffffffu, s1, 0);
+    if (lane < nranks) {
+      ClShared* R = cl.map_shared_rank(S, lane);
+      R->part[group][0][rank] = s0;
+      if (NDOT > 1) R->part[group][1][rank] = s1;
+    }
   }
   cl.sync();
   double t0 = 0.0, t1 = 0.0;
   for (int r = 0; r < nranks; ++r) {
-    const ClShared* R = cl.map_shared_rank(S, r);
-    t0 += R->part[group][0];
-    if (NDOT > 1) t1 += R->part[group][1];
+    t0 += S->part[group][0][r];
+    if (NDOT > 1) t1 += S->part[group][1][r];
   }
   d0 = t0; d1 = t1;
 }
@@ -71,7 +80,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
   const int rank = (int)cl.block_rank();
   const int NY = A.NY;
   const int r0 = min(rank * A.rows_per, A.NX), r1 = min(r0 + A.rows_per, A.NX);
-  const int nloc = (r1 - r0) * NY;
+  const int nrows = r1 - r0;
   const int cap = A.rows_per * NY;                        // plane slice capacity (same on every CTA)
   T* base = reinterpret_cast<T*>(smem_raw + ((sizeof(ClShared) + 15) / 16) * 16);
   T* c0 = base; T* c1 = c0 + cap; T* c2 = c1 + cap; T* c3 = c2 + cap; T* c4 = c3 + cap;
@@ -82,9 +91,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
   const bool own_rt = A.warm != 0;
   const T* rt = own_rt ? qs : bs;
 
+  // thread -> (row group, column) map fixed for the whole solve: no integer division inside the phases.
+  const int TC = min(NY, CL_THREADS), TR = CL_THREADS / TC;
+  const int tx = threadIdx.x % TC;
+  const int ty = (threadIdx.x / TC < TR) ? threadIdx.x / TC : nrows;     // surplus threads own no rows
+#define CL_FOR(li, j, e) \
+  for (int j = tx; j < NY; j += TC) for (int li = ty, e = ty * NY + j; li < nrows; li += TR, e += TR * NY)
+
   // ---- load this CTA's rows into shared memory (compact rows of NY) ----------------------------------------------
-  for (int e = threadIdx.x; e < nloc; e += CL_THREADS) {
-    const int li = e / NY, j = e - li * NY;
+  CL_FOR(li, j, e) {
     const size_t g = (size_t)(r0 + li) * A.pitch + j;
     c0[e] = A.coef[g]; c1[e] = A.coef[A.plane + g]; c2[e] = A.coef[2 * A.plane + g];
     c3[e] = A.coef[3 * A.plane + g]; c4[e] = A.coef[4 * A.plane + g];
@@ -102,41 +117,38 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
   cl.sync();
 
   // neighbours' slices (row r0-1 is the last row of rank-1, row r1 the first row of rank+1: every lower rank is full)
-  const bool has_lo = r0 > 0 && nloc > 0, has_hi = r1 < A.NX && nloc > 0;
+  const bool has_lo = r0 > 0 && nrows > 0, has_hi = r1 < A.NX && nrows > 0;
   const int lo_rank = rank > 0 ? rank - 1 : 0, hi_rank = rank < A.nranks - 1 ? rank + 1 : rank;
   const int lo_off = (A.rows_per - 1) * NY;               // offset of the neighbour's last row
+  // remote views of the operand planes (DSMEM), resolved once
+  const T* ps_lo = cl.map_shared_rank(ps, lo_rank); const T* ps_hi = cl.map_shared_rank(ps, hi_rank);
+  const T* rs_lo = cl.map_shared_rank(rs, lo_rank); const T* rs_hi = cl.map_shared_rank(rs, hi_rank);
+  const T* vs_lo = cl.map_shared_rank(vs, lo_rank); const T* vs_hi = cl.map_shared_rank(vs, hi_rank);
+  const T* xs_lo = cl.map_shared_rank(xs, lo_rank); const T* xs_hi = cl.map_shared_rank(xs, hi_rank);
+  const T* ms_lo = cl.map_shared_rank(ms, lo_rank); const T* ms_hi = cl.map_shared_rank(ms, hi_rank);
 
-  // operand value at local element e shifted by one row / column, operand given by a functor f(slice pointer set, idx)
-  // ---- stencil product y = A * hat(src) for the owned rows; src selected by MODE -------------------------------------
-  //   MODE 0: src = ps (p)          hat = minv * p
-  //   MODE 1: src = rs - alpha * vs (s, recomputed also for halo rows)
-  //   MODE 2: src = xs (warm-start residual)     hat = xs (no preconditioner: karman_taichi.py:360-367 uses x itself)
-  auto src_at = [&](int mode, const T* a0, const T* a1, const T* mm, int idx, T alpha) -> T {
-    T val = (mode == 1) ? (a0[idx] - alpha * a1[idx]) : a0[idx];
-    if (PRE && mode != 2) val = mm[idx] * val;
-    return val;
+  // ---- stencil product y = A * hat(src) at local element e = (li, j); src selected by MODE -----------------------
+  //   MODE 0: src = p                  hat = 1/M * p
+  //   MODE 1: src = s = r - alpha v    hat = 1/M * s     (halo rows recomputed from the neighbour's r, v)
+  //   MODE 2: src = x (warm-start residual, karman_taichi.py:360-367: no preconditioner)
+  auto val = [&](int mode, const T* a0, const T* a1, const T* mm, int idx, T alpha) -> T {
+    T v_ = (mode == 1) ? (a0[idx] - alpha * a1[idx]) : a0[idx];
+    if (PRE && mode != 2) v_ = mm[idx] * v_;
+    return v_;
   };
-  auto spmv_elem = [&](int mode, int e, T alpha, T& centre_raw) -> T {
-    const int li = e / NY, j = e - li * NY;
+  auto spmv_elem = [&](int mode, int li, int j, int e, T alpha, T& centre_raw) -> T {
     const T* a0 = (mode == 0) ? ps : (mode == 1) ? rs : xs;
-    const T* a1 = vs;
-    const T xc = src_at(mode, a0, a1, ms, e, alpha);
+    const T* a0_lo = (mode == 0) ? ps_lo : (mode == 1) ? rs_lo : xs_lo;
+    const T* a0_hi = (mode == 0) ? ps_hi : (mode == 1) ? rs_hi : xs_hi;
     centre_raw = (mode == 1) ? (rs[e] - alpha * vs[e]) : a0[e];
+    const T xc = (PRE && mode != 2) ? ms[e] * centre_raw : centre_raw;
     T xw = T(0), xe = T(0), xn = T(0), xso = T(0);
-    if (li > 0) xw = src_at(mode, a0, a1, ms, e - NY, alpha);
-    else if (has_lo) {
-      const T* b0 = cl.map_shared_rank(const_cast<T*>(a0), lo_rank); const T* b1 = cl.map_shared_rank(const_cast<T*>(a1), lo_rank);
-      const T* bm = cl.map_shared_rank(ms, lo_rank);
-      xw = src_at(mode, b0, b1, bm, lo_off + j, alpha);
-    }
-    if (li < (r1 - r0) - 1) xe = src_at(mode, a0, a1, ms, e + NY, alpha);
-    else if (has_hi) {
-      const T* b0 = cl.map_shared_rank(const_cast<T*>(a0), hi_rank); const T* b1 = cl.map_shared_rank(const_cast<T*>(a1), hi_rank);
-      const T* bm = cl.map_shared_rank(ms, hi_rank);
-      xe = src_at(mode, b0, b1, bm, j, alpha);
-    }
-    if (j < NY - 1) xn = src_at(mode, a0, a1, ms, e + 1, alpha);
-    if (j > 0) xso = src_at(mode, a0, a1, ms, e - 1, alpha);
+    if (li > 0) xw = val(mode, a0, vs, ms, e - NY, alpha);
+    else if (has_lo) xw = val(mode, a0_lo, vs_lo, ms_lo, lo_off + j, alpha);
+    if (li < nrows - 1) xe = val(mode, a0, vs, ms, e + NY, alpha);
+    else if (has_hi) xe = val(mode, a0_hi, vs_hi, ms_hi, j, alpha);
+    if (j < NY - 1) xn = val(mode, a0, vs, ms, e + 1, alpha);
+    if (j > 0) xso = val(mode, a0, vs, ms, e - 1, alpha);
     // cgsolver.py:59-60, left to right
     T acc = c0[e] * xc;
     acc = acc + c1[e] * xw;
@@ -148,16 +160,16 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
 
   // ---- K0: r = b - A x0 (warm) or r = b ; r~ = r ; (r,r) -----------------------------------------------------------
   double d0 = 0.0, d1 = 0.0;
-  for (int e = threadIdx.x; e < nloc; e += CL_THREADS) {
+  CL_FOR(li, j, e) {
     T rr;
-    if (A.warm) { T dummy; rr = bs[e] - spmv_elem(2, e, T(0), dummy); }
+    if (A.warm) { T dummy; rr = bs[e] - spmv_elem(2, li, j, e, T(0), dummy); }
     else rr = bs[e];
     rs[e] = rr;
     if (own_rt) qs[e] = rr;
     if (A.is_cg) ps[e] = rr;                               // cgsolver.py:90 p = r + 0 * p
     d0 += (double)rr * (double)rr;
   }
-  cluster_sum<1>(cl, S, 0, d0, d1, A.nranks);
+  cluster_sum<1>(cl, S, 0, d0, d1, A.nranks, rank);
   if (threadIdx.x == 0) scalar_algebra(A.is_cg ? FIN_CG_INIT : FIN_BICG_INIT, &S->sc, d0, d0, rank == 0 ? A.history : nullptr, A.hist_cap);
   __syncthreads();
 
@@ -167,39 +179,38 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
       // P1
       const bool first = S->sc.iter == 0;
       const T beta = T(S->sc.beta), omega_prev = T(S->sc.omega);
-      for (int e = threadIdx.x; e < nloc; e += CL_THREADS)
-        ps[e] = first ? rs[e] : rs[e] + beta * (ps[e] - omega_prev * vs[e]);
+      CL_FOR(li, j, e) ps[e] = first ? rs[e] : rs[e] + beta * (ps[e] - omega_prev * vs[e]);
       cl.sync();
       // P2
       d0 = 0.0; d1 = 0.0;
-      for (int e = threadIdx.x; e < nloc; e += CL_THREADS) {
+      CL_FOR(li, j, e) {
         T raw;
-        const T y = spmv_elem(0, e, T(0), raw);
+        const T y = spmv_elem(0, li, j, e, T(0), raw);
         d0 += (double)rt[e] * (double)y;
         vs[e] = y;      // v of the previous iteration is needed by nobody any more (P1 is behind the barrier)
       }
-      cluster_sum<1>(cl, S, 0, d0, d1, A.nranks);
+      cluster_sum<1>(cl, S, 0, d0, d1, A.nranks, rank);
       if (threadIdx.x == 0) scalar_algebra(FIN_BICG_ALPHA, &S->sc, d0, d1, nullptr, 0);
       __syncthreads();
       if (S->sc.done) break;
-      // P3 (vs of the neighbours is final since the barrier inside cluster_sum)
+      // P3 (v of the neighbours is final since the barrier inside cluster_sum)
       const T alpha = T(S->sc.alpha);
       d0 = 0.0; d1 = 0.0;
-      for (int e = threadIdx.x; e < nloc; e += CL_THREADS) {
+      CL_FOR(li, j, e) {
         T sraw;
-        const T y = spmv_elem(1, e, alpha, sraw);
+        const T y = spmv_elem(1, li, j, e, alpha, sraw);
         ss[e] = sraw; ts[e] = y;
         d0 += (double)y * (double)sraw;
         d1 += (double)y * (double)y;
       }
-      cluster_sum<2>(cl, S, 1, d0, d1, A.nranks);
+      cluster_sum<2>(cl, S, 1, d0, d1, A.nranks, rank);
       if (threadIdx.x == 0) scalar_algebra(FIN_BICG_OMEGA, &S->sc, d0, d1, nullptr, 0);
       __syncthreads();
       if (S->sc.done) break;
       // P4
       const T omega = T(S->sc.omega);
       d0 = 0.0; d1 = 0.0;
-      for (int e = threadIdx.x; e < nloc; e += CL_THREADS) {
+      CL_FOR(li, j, e) {
         const T ph = PRE ? ms[e] * ps[e] : ps[e];
         const T sh = PRE ? ms[e] * ss[e] : ss[e];
         xs[e] = xs[e] + (alpha * ph + omega * sh);
@@ -208,50 +219,50 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         d0 += (double)rn * (double)rn;
         d1 += (double)rn * (double)rt[e];
       }
-      cluster_sum<2>(cl, S, 2, d0, d1, A.nranks);
+      cluster_sum<2>(cl, S, 2, d0, d1, A.nranks, rank);
       if (threadIdx.x == 0) scalar_algebra(FIN_BICG_END, &S->sc, d0, d1, rank == 0 ? A.history : nullptr, A.hist_cap);
       __syncthreads();
     } else {
       // C1: Ap = A p ; (p, Ap)
       d0 = 0.0; d1 = 0.0;
-      for (int e = threadIdx.x; e < nloc; e += CL_THREADS) {
+      CL_FOR(li, j, e) {
         T raw;
-        const T y = spmv_elem(0, e, T(0), raw);
+        const T y = spmv_elem(0, li, j, e, T(0), raw);
         vs[e] = y;
         d0 += (double)raw * (double)y;
       }
-      cluster_sum<1>(cl, S, 0, d0, d1, A.nranks);
+      cluster_sum<1>(cl, S, 0, d0, d1, A.nranks, rank);
       if (threadIdx.x == 0) scalar_algebra(FIN_CG_ALPHA, &S->sc, d0, d1, nullptr, 0);
       __syncthreads();
       if (S->sc.done) break;
       // C2: x += alpha p ; r -= alpha Ap ; (r,r)
       const T alpha = T(S->sc.alpha);
       d0 = 0.0; d1 = 0.0;
-      for (int e = threadIdx.x; e < nloc; e += CL_THREADS) {
+      CL_FOR(li, j, e) {
         xs[e] = xs[e] + alpha * ps[e];
         const T rn = rs[e] - alpha * vs[e];
         rs[e] = rn;
         d0 += (double)rn * (double)rn;
       }
-      cluster_sum<1>(cl, S, 1, d0, d1, A.nranks);
+      cluster_sum<1>(cl, S, 1, d0, d1, A.nranks, rank);
       if (threadIdx.x == 0) scalar_algebra(FIN_CG_END, &S->sc, d0, d1, rank == 0 ? A.history : nullptr, A.hist_cap);
       __syncthreads();
       if (S->sc.done) break;
       // C3: p = r + beta p
       const T beta = T(S->sc.beta);
-      for (int e = threadIdx.x; e < nloc; e += CL_THREADS) ps[e] = rs[e] + beta * ps[e];
+      CL_FOR(li, j, e) ps[e] = rs[e] + beta * ps[e];
       cl.sync();
     }
   }
   // every CTA leaves the loop at the same iteration (identical scalars); make sure nobody still reads our slices
   cl.sync();
-  for (int e = threadIdx.x; e < nloc; e += CL_THREADS) {
-    const int li = e / NY, j = e - li * NY;
+  CL_FOR(li, j, e) {
     const size_t g = (size_t)(r0 + li) * A.pitch + j;
     A.x[g] = xs[e];
     if (A.r_out) A.r_out[g] = rs[e];
   }
   if (rank == 0 && threadIdx.x == 0) *A.sc = S->sc;
+#undef CL_FOR
 }
 
 static int cluster_env(const char* name, int dflt) {
@@ -261,13 +272,17 @@ static int cluster_env(const char* name, int dflt) {
 
 // Can this geometry be solved inside one cluster?  Returns the cluster size (0 = no) and the shared memory per CTA.
 template <typename T, bool PRE>
-static int cluster_fit(const kt_handle_s* h, bool warm, size_t* smem_out, int* rows_per_out) {
+static int cluster_fit(const kt_handle_s* h, bool warm, size_t* smem_out, int* rows_per_out, int limit_c) {
   static int enabled = cluster_env("KT_CLUSTER", 1);
   if (!enabled || !h->allow_cluster || h->row_lo != 0 || h->row_hi != h->NX) return 0;
   const int planes = 12 + (PRE ? 1 : 0) + (warm ? 1 : 0);
   const size_t ctrl = ((sizeof(ClShared) + 15) / 16) * 16;
   const size_t max_smem = 227 * 1024;
-  for (int C : {8, 16}) {
+  // 16 CTAs (non-portable size, one GPC) whenever every CTA still gets >= 2 rows: the phases are instruction-issue
+  // bound, so twice the SMs is twice the speed (measured 9.5 -> ~5 us / BiCGSTAB iteration at 130^2); else 8.
+  static int max_c = cluster_env("KT_CLUSTER_MAX", 16);
+  for (int C : {16, 8}) {
+    if (C > max_c || C > limit_c || (C == 16 && h->NX < 32)) continue;
     const int rows_per = (h->NX + C - 1) / C;
     const size_t need = ctrl + (size_t)planes * rows_per * h->NY * sizeof(T);
     if (need <= max_smem) { *smem_out = need; *rows_per_out = rows_per; return C; }
@@ -301,8 +316,9 @@ template <typename T>
 int cluster_try_solve(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, void* r_out,
                       double* history, long long hist_cap, double eps, long long max_iter, int flags, bool is_cg) {
   const bool pre = Minv != nullptr, warm = (flags & KT_FLAG_WARM_START) != 0;
+  static int sched_limit = 16;          // drops to 8 for the process if a 16-CTA cluster cannot be scheduled here
   size_t smem = 0; int rows_per = 0;
-  const int C = pre ? cluster_fit<T, true>(h, warm, &smem, &rows_per) : cluster_fit<T, false>(h, warm, &smem, &rows_per);
+  int C = pre ? cluster_fit<T, true>(h, warm, &smem, &rows_per, sched_limit) : cluster_fit<T, false>(h, warm, &smem, &rows_per, sched_limit);
   if (C == 0) return 0;
   ClArgs<T> A;
   A.coef = (const T*)coef; A.plane = (size_t)h->NX * h->pitch; A.b = (const T*)b; A.x = (T*)x; A.minv = (const T*)Minv;
@@ -310,8 +326,17 @@ int cluster_try_solve(kt_handle_s* h, const void* coef, const void* b, void* x, 
   A.sc = h->sc; A.history = history; A.hist_cap = hist_cap; A.eps = eps; A.max_iter = max_iter; A.flags = flags;
   A.warm = warm ? 1 : 0; A.is_cg = is_cg ? 1 : 0;
   int rc = pre ? cluster_launch<T, true>(h, A, C, smem) : cluster_launch<T, false>(h, A, C, smem);
+  if (rc && C == 16) {
+    // a 16-CTA cluster could not be scheduled on this device: retry with the portable size
+    cudaGetLastError();
+    sched_limit = 8;
+    C = pre ? cluster_fit<T, true>(h, warm, &smem, &rows_per, 8) : cluster_fit<T, false>(h, warm, &smem, &rows_per, 8);
+    if (C == 0) return 0;
+    A.rows_per = rows_per; A.nranks = C;
+    rc = pre ? cluster_launch<T, true>(h, A, C, smem) : cluster_launch<T, false>(h, A, C, smem);
+  }
   if (rc) {
-    // a cluster of this size could not be scheduled (e.g. MIG slice): fall back to the streaming path
+    // no cluster of a usable size can be scheduled (e.g. MIG slice): fall back to the streaming path
     cudaGetLastError();
     return 0;
   }

@@ -189,6 +189,22 @@ class KarmanSolver:
         self.time_forward()
         return n
 
+    # -- checkpoint / restart (the README run is 500 000 time steps, karman_taichi.py:628) ------
+    _STATE = ('u', 'v', 'p', 'u0', 'v0', 'pcor', 'x_u', 'x_v')
+
+    def save_checkpoint(self, path, time_step=0):
+        np.savez_compressed(path, nx=self.nx, ny=self.ny, time_step=time_step, ct=self.ct_numpy(),
+                            **{k: getattr(self, k).to_numpy() for k in self._STATE})
+
+    def load_checkpoint(self, path):
+        z = np.load(path)
+        if (int(z['nx']), int(z['ny'])) != (self.nx, self.ny):
+            raise ValueError('checkpoint grid does not match this solver')
+        for k in self._STATE:
+            getattr(self, k).from_numpy(z[k])
+        self.ct[:, :self.ny + 2] = torch.from_numpy(z['ct']).to(self.ct.device)
+        return int(z['time_step'])
+
     def run(self, time_steps, max_sub=500, eps=1e-8):
         self.init()
         return [self.time_step(max_sub, eps) for _ in range(time_steps)]

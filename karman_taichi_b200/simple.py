@@ -20,6 +20,7 @@ import numpy as np
 from . import _lib
 from .bicgsolver import BICGSolver
 from .cgsolver import CGSolver, _Handle, _p
+from .display import Display
 from .field import Field
 
 
@@ -62,6 +63,7 @@ class SIMPLESolver:
         self.u_momentum_solver = None
         self.v_momentum_solver = None
         self.p_correction_solver = None
+        self.disp = Display(self)           # simple.py:49
         self.quiet = True
         self.log = []                       # (momentum_residual, continuity_residual, {'u','v','p': iters})
 
@@ -228,6 +230,22 @@ class SIMPLESolver:
                     print('>>> Solution converged.')
                 break
         return n
+
+
+    # -- checkpoint / restart (absent in the reference) -------------------------------------
+    _STATE = ('u', 'v', 'p', 'u0', 'v0', 'pcor')
+
+    def save_checkpoint(self, path):
+        np.savez_compressed(path, nx=self.nx, ny=self.ny, lx=self.lx, ly=self.ly, variant=self.variant,
+                            outer_iterations=len(self.log), **{k: getattr(self, k).to_numpy() for k in self._STATE})
+
+    def load_checkpoint(self, path):
+        z = np.load(path)
+        if (int(z['nx']), int(z['ny'])) != (self.nx, self.ny):
+            raise ValueError('checkpoint grid does not match this solver')
+        for k in self._STATE:
+            getattr(self, k).from_numpy(z[k])
+        return int(z['outer_iterations'])
 
 
 def lid_driven_cavity(n=50, lid=1.0, variant='bicgsimp', **kw):

@@ -154,3 +154,28 @@ def test_cavity50_full_run_vs_golden_and_ghia(cuda):
     tot = {k: sum(l[2][k] for l in g.log) for k in 'uvp'}
     for k in 'uvp':
         assert abs(tot[k] - gold['krylov_totals'][k]) <= 0.02 * gold['krylov_totals'][k]
+
+
+def test_checkpoint_display_dumps(cuda, tmp_path):
+    """The 'next' rows of SURVEY.md 8f: CSV dumps (simple.py:51-75), the display frame (display.py:28-49), restart."""
+    import karman_taichi_b200 as kt
+    g = kt.lid_driven_cavity(16, device=cuda)
+    g.init(); g._make_solvers()
+    for _ in range(3):
+        g.step()
+    ck = str(tmp_path / 'ck.npz')
+    g.save_checkpoint(ck)
+    h = kt.lid_driven_cavity(16, device=cuda)
+    assert h.load_checkpoint(ck) == 3
+    h._make_solvers()
+    a, b = g.step(), h.step()
+    assert a == b                                            # restart continues bit-identically (deterministic kernels)
+    np.testing.assert_array_equal(g.u.to_numpy(), h.u.to_numpy())
+    img = g.disp.display(str(tmp_path / 'frame.png'))
+    assert img.shape == (18, 5 * 18) and 0.0 <= img.min() and img.max() <= 1.0
+    assert open(tmp_path / 'frame.png', 'rb').read(8) == b'\x89PNG\r\n\x1a\n'
+    g.dump_matrix(1, 'corfin', directory=str(tmp_path / 'log'))
+    g.dump_coef(1, 'corfin', directory=str(tmp_path / 'log'))
+    u_csv = np.loadtxt(tmp_path / 'log' / '000001-u-corfin.csv', delimiter=',')
+    np.testing.assert_allclose(u_csv, g.u.to_numpy(), rtol=1e-15, atol=0)
+    assert (tmp_path / 'log' / '000001-app-corfin.csv').exists()
