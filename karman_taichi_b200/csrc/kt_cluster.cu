@@ -34,29 +34,34 @@ template <typename T> struct ClArgs {
 constexpr int CL_THREADS = 512;
 
 struct ClShared {           // per-CTA control block at the start of dynamic shared memory
-  Scalars sc;
   double part[3][2][16];    // [dot group][value][source rank]: every CTA PUSHES its block sums into all CTAs' slots
   double red[2][CL_THREADS / 32];
 };
 
-// fixed-order cluster-wide sum of up to two values.  Block reduce -> lanes 0..C-1 of warp 0 store the block sums into
-// slot [rank] of EVERY CTA (remote DSMEM stores, fire and forget) -> cluster barrier (release / acquire) -> every thread
-// sums its own CTA's C slots in rank order from local shared memory.  Identical bits on every CTA and thread; no remote
-// load sits on the critical path after the barrier.
+// 16-lane fixed-shape tree: every lane of the warp ends up with v[0] + ... + v[15] (lanes >= 16 mirror lane - 16).
+__device__ __forceinline__ double tree16(double v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// fixed-order cluster-wide sum of up to two values.  Warp shuffle tree -> one value per warp in shared memory ->
+// warp 0 adds the (16) warp sums with a fixed tree and its lanes 0..C-1 store the block sum into slot [rank] of EVERY
+// CTA (remote DSMEM stores, fire and forget) -> cluster barrier (release / acquire) -> every warp adds the C slots of
+// its own CTA with the same fixed tree.  Identical bits on every CTA, warp and thread; no serial chain, no remote load
+// after the barrier.
 template <int NDOT>
 __device__ __forceinline__ void cluster_sum(cg::cluster_group& cl, ClShared* S, int group, double& d0, double& d1, int nranks,
                                             int rank) {
+  static_assert(CL_THREADS / 32 == 16, "tree16 assumes 16 warps per CTA");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   d0 = warp_sum(d0);
   if (NDOT > 1) d1 = warp_sum(d1);
   if (lane == 0) { S->red[0][wid] = d0; if (NDOT > 1) S->red[1][wid] = d1; }
   __syncthreads();
   if (wid == 0) {
-    double s0 = 0.0, s1 = 0.0;
-    if (lane == 0)
-      for (int w = 0; w < CL_THREADS / 32; ++w) { s0 += S->red[0][w]; if (NDOT > 1) s1 += S->red[1][w]; }
-    s0 = __shfl_sync(0xffffffffu, s0, 0);
-    if (NDOT > 1) s1 = __shfl_sync(0xffffffffu, s1, 0);
+    double s0 = tree16(S->red[0][lane & 15]);
+    double s1 = (NDOT > 1) ? tree16(S->red[1][lane & 15]) : 0.0;
     if (lane < nranks) {
       ClShared* R = cl.map_shared_rank(S, lane);
       R->part[group][0][rank] = s0;
@@ -64,12 +69,9 @@ __device__ __forceinline__ void cluster_sum(cg::cluster_group& cl, ClShared* S, 
     }
   }
   cl.sync();
-  double t0 = 0.0, t1 = 0.0;
-  for (int r = 0; r < nranks; ++r) {
-    t0 += S->part[group][0][r];
-    if (NDOT > 1) t1 += S->part[group][1][r];
-  }
-  d0 = t0; d1 = t1;
+  const int r = lane & 15;
+  d0 = tree16(r < nranks ? S->part[group][0][r] : 0.0);
+  d1 = (NDOT > 1) ? tree16(r < nranks ? S->part[group][1][r] : 0.0) : 0.0;
 }
 
 template <typename T, bool PRE>
@@ -108,12 +110,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
     ps[e] = T(0); vs[e] = T(0); ss[e] = T(0); ts[e] = T(0);
     if (PRE) ms[e] = A.minv[g];
   }
-  if (threadIdx.x == 0) {
-    Scalars& sc = S->sc;
-    sc.rho = 0.0; sc.rho_1 = 1.0; sc.alpha = 1.0; sc.beta = 1.0; sc.omega = 1.0;
-    sc.rTr0 = sc.rTr = sc.old_rTr = 0.0; sc.dot0 = sc.dot1 = 0.0;
-    sc.eps = A.eps; sc.iter = 0; sc.max_iter = A.max_iter; sc.status = 1; sc.done = 0; sc.first = 1; sc.flags = A.flags;
-  }
+  // Every thread keeps its own copy of the Krylov scalars and runs the (cheap) scalar algebra itself on the identical
+  // reduced sums: no shared-memory round trip and no block barrier between a reduction and its consumers.
+  Scalars sc;
+  sc.rho = 0.0; sc.rho_1 = 1.0; sc.alpha = 1.0; sc.beta = 1.0; sc.omega = 1.0;
+  sc.rTr0 = sc.rTr = sc.old_rTr = 0.0; sc.dot0 = sc.dot1 = 0.0;
+  sc.eps = A.eps; sc.iter = 0; sc.max_iter = A.max_iter; sc.status = 1; sc.done = 0; sc.first = 1; sc.flags = A.flags;
+  double* const hist = (rank == 0 && threadIdx.x == 0) ? A.history : nullptr;
   cl.sync();
 
   // neighbours' slices (row r0-1 is the last row of rank-1, row r1 the first row of rank+1: every lower rank is full)
@@ -170,15 +173,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
     d0 += (double)rr * (double)rr;
   }
   cluster_sum<1>(cl, S, 0, d0, d1, A.nranks, rank);
-  if (threadIdx.x == 0) scalar_algebra(A.is_cg ? FIN_CG_INIT : FIN_BICG_INIT, &S->sc, d0, d0, rank == 0 ? A.history : nullptr, A.hist_cap);
-  __syncthreads();
+  scalar_algebra(A.is_cg ? FIN_CG_INIT : FIN_BICG_INIT, &sc, d0, d0, hist, A.hist_cap);
 
   // ---- iterations ----------------------------------------------------------------------------------------------
-  while (!S->sc.done) {
+  while (!sc.done) {
     if (!A.is_cg) {
       // P1
-      const bool first = S->sc.iter == 0;
-      const T beta = T(S->sc.beta), omega_prev = T(S->sc.omega);
+      const bool first = sc.iter == 0;
+      const T beta = T(sc.beta), omega_prev = T(sc.omega);
       CL_FOR(li, j, e) ps[e] = first ? rs[e] : rs[e] + beta * (ps[e] - omega_prev * vs[e]);
       cl.sync();
       // P2
@@ -190,11 +192,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         vs[e] = y;      // v of the previous iteration is needed by nobody any more (P1 is behind the barrier)
       }
       cluster_sum<1>(cl, S, 0, d0, d1, A.nranks, rank);
-      if (threadIdx.x == 0) scalar_algebra(FIN_BICG_ALPHA, &S->sc, d0, d1, nullptr, 0);
-      __syncthreads();
-      if (S->sc.done) break;
+      scalar_algebra(FIN_BICG_ALPHA, &sc, d0, d1, nullptr, 0);
+      if (sc.done) break;
       // P3 (v of the neighbours is final since the barrier inside cluster_sum)
-      const T alpha = T(S->sc.alpha);
+      const T alpha = T(sc.alpha);
       d0 = 0.0; d1 = 0.0;
       CL_FOR(li, j, e) {
         T sraw;
@@ -204,11 +205,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         d1 += (double)y * (double)y;
       }
       cluster_sum<2>(cl, S, 1, d0, d1, A.nranks, rank);
-      if (threadIdx.x == 0) scalar_algebra(FIN_BICG_OMEGA, &S->sc, d0, d1, nullptr, 0);
-      __syncthreads();
-      if (S->sc.done) break;
+      scalar_algebra(FIN_BICG_OMEGA, &sc, d0, d1, nullptr, 0);
+      if (sc.done) break;
       // P4
-      const T omega = T(S->sc.omega);
+      const T omega = T(sc.omega);
       d0 = 0.0; d1 = 0.0;
       CL_FOR(li, j, e) {
         const T ph = PRE ? ms[e] * ps[e] : ps[e];
@@ -220,8 +220,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         d1 += (double)rn * (double)rt[e];
       }
       cluster_sum<2>(cl, S, 2, d0, d1, A.nranks, rank);
-      if (threadIdx.x == 0) scalar_algebra(FIN_BICG_END, &S->sc, d0, d1, rank == 0 ? A.history : nullptr, A.hist_cap);
-      __syncthreads();
+      scalar_algebra(FIN_BICG_END, &sc, d0, d1, hist, A.hist_cap);
     } else {
       // C1: Ap = A p ; (p, Ap)
       d0 = 0.0; d1 = 0.0;
@@ -232,11 +231,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         d0 += (double)raw * (double)y;
       }
       cluster_sum<1>(cl, S, 0, d0, d1, A.nranks, rank);
-      if (threadIdx.x == 0) scalar_algebra(FIN_CG_ALPHA, &S->sc, d0, d1, nullptr, 0);
-      __syncthreads();
-      if (S->sc.done) break;
+      scalar_algebra(FIN_CG_ALPHA, &sc, d0, d1, nullptr, 0);
+      if (sc.done) break;
       // C2: x += alpha p ; r -= alpha Ap ; (r,r)
-      const T alpha = T(S->sc.alpha);
+      const T alpha = T(sc.alpha);
       d0 = 0.0; d1 = 0.0;
       CL_FOR(li, j, e) {
         xs[e] = xs[e] + alpha * ps[e];
@@ -245,11 +243,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         d0 += (double)rn * (double)rn;
       }
       cluster_sum<1>(cl, S, 1, d0, d1, A.nranks, rank);
-      if (threadIdx.x == 0) scalar_algebra(FIN_CG_END, &S->sc, d0, d1, rank == 0 ? A.history : nullptr, A.hist_cap);
-      __syncthreads();
-      if (S->sc.done) break;
+      scalar_algebra(FIN_CG_END, &sc, d0, d1, hist, A.hist_cap);
+      if (sc.done) break;
       // C3: p = r + beta p
-      const T beta = T(S->sc.beta);
+      const T beta = T(sc.beta);
       CL_FOR(li, j, e) ps[e] = rs[e] + beta * ps[e];
       cl.sync();
     }
@@ -261,7 +258,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
     A.x[g] = xs[e];
     if (A.r_out) A.r_out[g] = rs[e];
   }
-  if (rank == 0 && threadIdx.x == 0) *A.sc = S->sc;
+  if (rank == 0 && threadIdx.x == 0) *A.sc = sc;
 #undef CL_FOR
 }
 
