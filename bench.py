@@ -45,7 +45,7 @@ METRIC = 'bicgstab_mcell_iters_per_s'
 UNIT = 'Mcell-iters/s'
 BYTES_PER_CELL_ITER = 28 * 8            # BiCGSTAB algorithmic traffic, f64
 # dram__bytes_read.sum + dram__bytes_write.sum per launch and per plane word of each kernel come from the committed
-# ncu captures (profiles/r01_launch_list_summary.md, 16386 x 16400-word planes).
+# ncu captures (profiles/r01_launch_list_default.md: the default command, 32770 x 32784-word planes).
 FUSED_TRAFFIC_BYTES_PER_WORD = 86.9
 
 
@@ -295,11 +295,11 @@ def run_ours(a):
     # ---- roofline of the dominant kernel (largest share of the step), timed live with CUDA-event pairs ---------------
     peak, peak_kind = peaks()
     fused = cnt[0] == 0                       # BICGSolver.fuse_p_update: K1 folded into K2 (11 N instead of 4 N + 8 N)
-    classes = {0: ('p_update', 'k_bicg_p: p = r + beta (p - omega v)', 4, 29.9),
+    classes = {0: ('p_update', 'k_bicg_p: p = r + beta (p - omega v)', 4, 31.6),
                1: (('p_update+v=Ap+dot', 'k_stencil<SRC_P,EPI_DOT_Q_ST>: p = r + beta (p - omega v), v = A p, (r~, v)', 11, FUSED_TRAFFIC_BYTES_PER_WORD)
-                   if fused else ('v=Ap+dot', 'k_stencil<SRC_X,EPI_DOT_Q>: v = A p, (r~, v)', 8, 63.9)),
-               2: ('s,t+2dots', 'k_stencil<SRC_S,EPI_ST>: s = r - alpha v, t = A s, (t,s), (t,t)', 9, 72.8),
-               3: ('x,r+2dots', 'k_bicg_xr: x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 7, 55.8)}
+                   if fused else ('v=Ap+dot', 'k_stencil<SRC_X,EPI_DOT_Q>: v = A p, (r~, v)', 8, 64.0)),
+               2: ('s,t+2dots', 'k_stencil<SRC_S,EPI_ST>: s = r - alpha v, t = A s, (t,s), (t,t)', 9, 73.1),
+               3: ('x,r+2dots', 'k_bicg_xr: x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 7, 55.9)}
     tots = [allmax(tot[i]) for i in range(4)]
     dom = max(range(4), key=lambda i: tots[i])
     d_name, d_desc, d_words, d_traffic = classes[dom]
@@ -312,7 +312,7 @@ def run_ours(a):
     roofline = {'bound': 'hbm', 'kernel': f'{d_desc}  [{d_words} N words]',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_kind': peak_kind,
                 'traffic': (d_traffic * (l1 - l0) * coef.pitch) if d_traffic else None,
-                'traffic_source': 'profiles/r01_launch_list_summary.md (ncu dram__bytes_read+write per launch at 16384^2), scaled by plane words',
+                'traffic_source': 'profiles/r01_launch_list_default.md (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of this command), scaled by plane words',
                 'ms_per_launch': d_ms, 'launches_timed': int(cnt[dom]), 'algorithmic_bytes_per_launch': alg_bytes,
                 'kernel_share_of_step': kernel_share,
                 'whole_iteration': {'algorithmic_bytes_per_cell_iter': BYTES_PER_CELL_ITER, 'bytes_per_cell_iter_as_run': iter_bytes,
