@@ -259,10 +259,18 @@ def run_ours(a):
         def step():
             solver.solve(eps=0.0, quiet=True)          # the public call: BICGSolver.solve (bicgsolver.py:88)
             assert solver.iterations == iters, (solver.iterations, solver.status)
-    else:
+    elif a.comm == 'nccl':
         ops = CudaSlabOps(coef, b, x, part, rank)
         drv = DistBiCGSTAB(ops, HaloExchanger(part, rank))
         handle = ops._hd
+
+        def step():
+            it, st = drv.solve(eps=0.0, max_iter=iters, fixed_iters=True)
+            assert it == iters, (it, st)
+    else:
+        from karman_taichi_b200.slab import P2PSlabSolver
+        drv = P2PSlabSolver(coef, b, x, part, rank)
+        handle = drv._hd
 
         def step():
             it, st = drv.solve(eps=0.0, max_iter=iters, fixed_iters=True)
@@ -340,7 +348,7 @@ def run_ours(a):
                 'data': 'synthetic',
                 'config': {'workload': a.workload, 'description': desc, 'grid': [n, n], 'bicgstab_iters_per_step': iters,
                            'system': 'S1 Poisson-sin, offset 0, zero-coefficient ghost ring (SURVEY.md 8d)',
-                           'parallelism': f'x-slab x{world}' if world > 1 else 'single GPU',
+                           'parallelism': (f'x-slab x{world}, halo + all-reduce: ' + ('NVLink peer memory inside the library' if a.comm == 'p2p' else 'NCCL send/recv + all_reduce')) if world > 1 else 'single GPU',
                            'cache': 'working set 103 GB >> 126 MB L2 (inputs larger than L2; no flush needed)'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
@@ -409,6 +417,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='pcor32768', choices=sorted(WORKLOADS))
     ap.add_argument('--iters', type=int, default=50, help='BiCGSTAB iterations per step')
+    ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'],
+                    help='N > 1: halo exchange + all-reduce inside the library over NVLink peer memory (p2p) or via NCCL')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     a = ap.parse_args()

@@ -48,7 +48,8 @@ enum {
   KT_STATUS_ALPHA_DIV_ZERO = 3, /* (r_tld, Ap) == 0 or (p, Ap) == 0: reference raises ZeroDivisionError */
   KT_STATUS_OMEGA_DIV_ZERO = 4, /* (t, t) == 0: reference raises ZeroDivisionError */
   KT_STATUS_NON_FINITE = 5,
-  KT_STATUS_OMEGA_ZERO = 6      /* karman_taichi.py:451-454 */
+  KT_STATUS_OMEGA_ZERO = 6,     /* karman_taichi.py:451-454 */
+  KT_STATUS_COMM_TIMEOUT = 7    /* x-slab peer-memory solve: a neighbour's flag never arrived */
 };
 
 /* kt_bicgstab_solve flags */
@@ -176,6 +177,28 @@ int kt_dist_bicg_phase(kt_handle_t h, int phase, const void* coef, const void* a
                        void* o0, void* o1, void* o2, double* dots_dev);
 int kt_dist_scalar(kt_handle_t h, int fin, const double* dots_dev, double* history_dev, long history_cap);
 int kt_dist_poll(kt_handle_t h, int* done, long* iters, int* status, double* rel_res);
+
+/* Same solve with the halo exchange and the all-reduce done by the library itself over NVLink peer memory (no NCCL
+ * in the loop): every rank passes device pointers, mapped into ITS address space (CUDA IPC), of its neighbours' p / v /
+ * r planes and of every rank's comm block (kt_p2p_comm_block_bytes() bytes, zero-initialised once, never reset).
+ * peer_*[0] = lower neighbour (rank-1) or NULL, [1] = upper neighbour or NULL; peer_halo_row[k] = the row of THAT
+ * rank's plane this rank's boundary row goes to.  local_dots: 2 doubles of device scratch.  All ranks must call this
+ * with the same eps / max_iter, in lock step. */
+typedef struct {
+  int rank, nranks;
+  void* peer_p[2];
+  void* peer_v[2];
+  void* peer_r[2];
+  int peer_halo_row[2];
+  void* comm_block[16];
+  void* local_dots;
+} kt_p2p_comm;
+int kt_p2p_comm_block_bytes(void);
+/* enable direct loads/stores from the handle's device to peer_device's memory (idempotent) */
+int kt_enable_peer_access(kt_handle_t h, int peer_device);
+int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws,
+                          const kt_p2p_comm* comm, double eps, long max_iter, int fixed_iters,
+                          long* iters, double* rel_res, int* status);
 
 /* ---- per-kernel device timing (bench.py roofline) ----------------------------------------------
  * Between kt_prof_begin and kt_prof_end every launch of the solver kernels is bracketed by a CUDA event pair on

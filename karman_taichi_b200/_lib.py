@@ -37,6 +37,13 @@ class KrylovWs(C.Structure):
                 ('p2', C.c_void_p), ('Ap2', C.c_void_p)]
 
 
+class P2PComm(C.Structure):
+    """``kt_p2p_comm``"""
+    _fields_ = [('rank', C.c_int), ('nranks', C.c_int),
+                ('peer_p', C.c_void_p * 2), ('peer_v', C.c_void_p * 2), ('peer_r', C.c_void_p * 2),
+                ('peer_halo_row', C.c_int * 2), ('comm_block', C.c_void_p * 16), ('local_dots', C.c_void_p)]
+
+
 class ChannelParams(C.Structure):
     """``kt_channel_params``"""
     _fields_ = [('nx', C.c_int), ('ny', C.c_int),
@@ -100,6 +107,9 @@ SIGNATURES = {
     'kt_dist_bicg_phase': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'kt_dist_scalar': (_I, [_P, _I, _P, _P, _L]),
     'kt_dist_poll': (_I, [_P, _PI, _PL, _PI, _PD]),
+    'kt_p2p_comm_block_bytes': (_I, []),
+    'kt_enable_peer_access': (_I, [_P, _I]),
+    'kt_p2p_bicgstab_solve': (_I, [_P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _PL, _PD, _PI]),
     'kt_prof_begin': (_I, [_P, _I]),
     'kt_prof_end': (_I, [_P, _PD, _PL, _I]),
     'kt_assemble_uv': (_I, [_P, _SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -129,6 +129,19 @@ int kt_set_rows(kt_handle_t h, int row_lo, int row_hi) {
 
 long long kt_launch_count(kt_handle_t h) { return h ? h->launches : 0; }
 
+int kt_enable_peer_access(kt_handle_t h, int peer_device) {
+  KT_CHECK_ARG(h, "kt_enable_peer_access: null handle");
+  if (peer_device == h->device) return 0;
+  KT_CUDA(cudaSetDevice(h->device));
+  int can = 0;
+  KT_CUDA(cudaDeviceCanAccessPeer(&can, h->device, peer_device));
+  if (!can) { set_error("kt_enable_peer_access: device " + std::to_string(h->device) + " cannot access device " + std::to_string(peer_device)); return -4; }
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+  return 0;
+}
+
 int kt_set_cluster(kt_handle_t h, int enable) {
   KT_CHECK_ARG(h, "kt_set_cluster: null handle");
   h->allow_cluster = enable != 0;

@@ -778,6 +778,165 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// x-slab BiCGSTAB over NVLink peer memory (no NCCL in the loop)
+// ---------------------------------------------------------------------------------------------
+// Every rank maps its neighbours' p / v / r planes and every rank's small comm block (CUDA IPC).  The halo exchange and
+// the all-reduce become two tiny kernels that live on the same stream as the big ones:
+//   k_p2p_halo  : one block per side copies this rank's boundary row straight into the neighbour's halo row over
+//                 NVLink (16-byte peer stores), fences system-wide, bumps the neighbour's flag, then waits for the
+//                 neighbour's row to land here (flag >= seq).
+//   k_p2p_reduce: lane r stores this rank's local sums into slot [rank] of rank r's comm block and bumps its flag; the
+//                 warp then waits for all nranks flags of its own block, sums the slots in rank order (every rank gets
+//                 the same bits) and runs the step's scalar algebra -- all-reduce + k_scalar_step in one launch.
+// Flags are monotonically increasing sequence numbers (never reset), so a late reader can never see a stale "ready".
+// Write-after-read safety: a neighbour can only overwrite a halo row of iteration k after it has seen this rank's
+// sums of the kernel that read that row (the sums are published by the last block, after all reads).
+struct P2PBlock {                     // layout of the comm block every rank allocates (zero-initialised)
+  double dots[3][16][2];
+  unsigned long long dot_flag[3][16];
+  unsigned long long halo_flag[3][2]; // [plane p/v/r][0: from lower neighbour, 1: from upper neighbour]
+};
+
+__device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flag, unsigned long long seq, Scalars* sc) {
+  const long long t0 = clock64();
+  while (*flag < seq) {
+    __nanosleep(32);
+    if (clock64() - t0 > 8000000000LL) {   // ~4 s: a peer died or the ranks disagree on the schedule -- fail, never hang
+      *(volatile int*)&sc->status = 7; *(volatile int*)&sc->done = 1;
+      return false;
+    }
+  }
+  __threadfence_system();
+  return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_p2p_halo(const T* plane, int pitch, int row_first, int row_last, T* peer_lo, int peer_lo_row,
+                                                  T* peer_hi, int peer_hi_row, P2PBlock* mine, P2PBlock* blk_lo, P2PBlock* blk_hi,
+                                                  int which, unsigned long long seq, Scalars* sc) {
+  constexpr int V = VT<T>::V;
+  // Once the solve is over (every rank reaches `done` at the same logical step, from identical sums) nobody needs
+  // another row: return without signalling or waiting, so ranks whose hosts enqueued a different number of surplus
+  // iterations never wait for each other.
+  if (sc->done) return;
+  const int side = blockIdx.x;                                   // 0: talk to the lower neighbour, 1: to the upper one
+  T* peer = side == 0 ? peer_lo : peer_hi;
+  if (!peer) return;
+  const T* src = plane + (size_t)(side == 0 ? row_first : row_last) * pitch;
+  T* dst = peer + (size_t)(side == 0 ? peer_lo_row : peer_hi_row) * pitch;
+  for (int j = threadIdx.x * V; j < pitch; j += blockDim.x * V) st_vec(dst + j, ld_rw(src + j));
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // my row sits in the lower neighbour's "from upper" slot (1) and in the upper neighbour's "from lower" slot (0)
+    P2PBlock* pb = side == 0 ? blk_lo : blk_hi;
+    volatile unsigned long long* f = &pb->halo_flag[which][side == 0 ? 1 : 0];
+    *f = seq;
+    p2p_wait(&mine->halo_flag[which][side == 0 ? 0 : 1], seq, sc);
+  }
+}
+
+struct P2PPeers { P2PBlock* blk[16]; };
+
+__global__ void k_p2p_reduce(P2PPeers peers, int rank, int nranks, int group, int ndot, const double* local, int fin,
+                             unsigned long long seq, Scalars* sc, double* history, long long cap) {
+  const int lane = threadIdx.x;
+  if (sc->done) return;
+  P2PBlock* mine = peers.blk[rank];
+  if (lane < nranks) {
+    P2PBlock* pb = peers.blk[lane];
+    pb->dots[group][rank][0] = local[0];
+    pb->dots[group][rank][1] = ndot > 1 ? local[1] : 0.0;
+    __threadfence_system();
+    *(volatile unsigned long long*)&pb->dot_flag[group][rank] = seq;
+    p2p_wait(&mine->dot_flag[group][lane], seq, sc);
+  }
+  __syncwarp();
+  if (lane == 0 && !sc->done) {
+    double d0 = 0.0, d1 = 0.0;
+    for (int r = 0; r < nranks; ++r) {
+      d0 += *(volatile double*)&mine->dots[group][r][0];
+      d1 += *(volatile double*)&mine->dots[group][r][1];
+    }
+    scalar_algebra(fin, sc, d0, d1, history, cap);
+  }
+}
+
+// Sequence numbers: (solve epoch << 32) | exchange index within the solve.  The epoch advances once per solve on every
+// rank, the index once per enqueued exchange; surplus exchanges enqueued after convergence never touch a flag, so the
+// ranks stay consistent even though their hosts notice `done` at different times.
+struct P2PState {
+  unsigned long long epoch = 0;
+  unsigned long long halo_k[3] = {0, 0, 0};
+  unsigned long long dot_k[3] = {0, 0, 0};
+};
+
+static P2PState g_p2p_state;      // one rank per process (one GPU per process under torchrun)
+
+template <typename T>
+static int t_p2p_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, const kt_krylov_ws* w, const kt_p2p_comm* cm,
+                          double eps, long long max_iter, bool fixed_iters, long* iters, double* rel_res, int* status) {
+  KT_CHECK_ARG(cm->nranks >= 1 && cm->nranks <= 16 && cm->rank >= 0 && cm->rank < cm->nranks, "kt_p2p_comm: bad rank / nranks (max 16)");
+  T* r = (T*)w->r; T* p = (T*)w->p; T* v = (T*)w->Ap; T* s = (T*)w->s; T* t = (T*)w->t;
+  KT_CHECK_ARG(r && p && v && s && t, "kt_krylov_ws: r, p, Ap, s, t are required");
+  P2PState& st = g_p2p_state;
+  P2PPeers peers;
+  for (int k = 0; k < 16; ++k) peers.blk[k] = k < cm->nranks ? (P2PBlock*)cm->comm_block[k] : nullptr;
+  P2PBlock* mine = peers.blk[cm->rank];
+  P2PBlock* blk_lo = cm->rank > 0 ? peers.blk[cm->rank - 1] : nullptr;
+  P2PBlock* blk_hi = cm->rank < cm->nranks - 1 ? peers.blk[cm->rank + 1] : nullptr;
+  double* dots = (double*)cm->local_dots;
+  KT_CHECK_ARG(dots && mine, "kt_p2p_comm: local_dots / comm_block missing");
+  int rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0);
+  if (rc) return rc;
+  ++st.epoch;
+  for (int k = 0; k < 3; ++k) st.halo_k[k] = st.dot_k[k] = 0;
+  const unsigned long long base = st.epoch << 32;
+
+  auto halo = [&](int which, const T* plane, void* const peer[2]) -> int {
+    if (cm->nranks == 1) return 0;
+    ++st.halo_k[which];
+    k_p2p_halo<T><<<2, 256, 0, h->stream>>>(plane, h->pitch, h->row_lo, h->row_hi - 1, (T*)peer[0], cm->peer_halo_row[0], (T*)peer[1],
+                                            cm->peer_halo_row[1], mine, blk_lo, blk_hi, which, base | st.halo_k[which], h->sc);
+    KT_LAUNCH_CHECK(h);
+    return 0;
+  };
+  auto reduce = [&](int group, int ndot, int fin) -> int {
+    ++st.dot_k[group];
+    k_p2p_reduce<<<1, 32, 0, h->stream>>>(peers, cm->rank, cm->nranks, group, ndot, dots, fin, base | st.dot_k[group], h->sc, w->history,
+                                          w->history_cap);
+    KT_LAUNCH_CHECK(h);
+    return 0;
+  };
+#define KT_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+  KT_TRY(t_dist_phase<T>(h, 0, coef, b, nullptr, nullptr, r, x, nullptr, dots));
+  KT_TRY(reduce(0, 1, FIN_BICG_INIT));
+  KT_TRY(halo(2, r, cm->peer_r));
+  auto iter = [&]() -> int {
+    KT_TRY(t_dist_phase<T>(h, 1, coef, r, v, nullptr, p, nullptr, nullptr, dots));
+    KT_TRY(halo(0, p, cm->peer_p));
+    KT_TRY(t_dist_phase<T>(h, 2, coef, p, b, nullptr, v, nullptr, nullptr, dots));
+    KT_TRY(reduce(0, 1, FIN_BICG_ALPHA));
+    KT_TRY(halo(1, v, cm->peer_v));
+    KT_TRY(t_dist_phase<T>(h, 3, coef, r, v, nullptr, s, t, nullptr, dots));
+    KT_TRY(reduce(1, 2, FIN_BICG_OMEGA));
+    KT_TRY(t_dist_phase<T>(h, 4, coef, p, s, t, x, r, (void*)b, dots));
+    KT_TRY(reduce(2, 2, FIN_BICG_END));
+    KT_TRY(halo(2, r, cm->peer_r));
+    return 0;
+  };
+#undef KT_TRY
+  rc = run_chunks(h, max_iter, iter);
+  if (rc) return rc;
+  const Scalars& S = *h->sc_host;
+  if (iters) *iters = (long)S.iter;
+  if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
+  if (status) *status = S.status;
+  return 0;
+}
+
 }  // namespace kt
 
 using namespace kt;
@@ -917,6 +1076,15 @@ int kt_dist_poll(kt_handle_t h, int* done, long* iters, int* status, double* rel
   if (status) *status = S.status;
   if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
   return 0;
+}
+
+int kt_p2p_comm_block_bytes(void) { return (int)sizeof(P2PBlock); }
+
+int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, const kt_p2p_comm* comm,
+                          double eps, long max_iter, int fixed_iters, long* iters, double* rel_res, int* status) {
+  KT_CHECK_ARG(h && coef && b && x && ws && comm, "kt_p2p_bicgstab_solve: null argument");
+  return KT_DISPATCH(h, t_p2p_bicgstab<double>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status),
+                     t_p2p_bicgstab<float>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status));
 }
 
 int kt_prof_begin(kt_handle_t h, int max_launches) {

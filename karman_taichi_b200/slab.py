@@ -192,3 +192,99 @@ class DistBiCGSTAB:
                     break
         done, self.iterations, self.status, self.rel_res = ops.poll()
         return self.iterations, self.status
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Peer-memory (NVLink) variant: no NCCL in the solver loop
+# ---------------------------------------------------------------------------------------------------------------
+def _share(t: torch.Tensor):
+    """CUDA-IPC description of a tensor's storage (what torch.multiprocessing sends), picklable."""
+    st = t.untyped_storage()
+    return st._share_cuda_(), t.storage_offset() * t.element_size()
+
+
+def _open(desc):
+    """Map a peer's storage into this process; returns (storage kept alive, device address of the tensor)."""
+    handle, off = desc
+    st = torch.UntypedStorage._new_shared_cuda(*handle)
+    return st, st.data_ptr() + off
+
+
+class P2PSlabSolver:
+    """x-slab BiCGSTAB whose halo exchange and inner-product all-reduce run inside the library over NVLink peer memory
+    (``kt_p2p_bicgstab_solve``): every rank maps its neighbours' p / v / r planes and every rank's small comm block
+    through CUDA IPC once, at construction (the only collective use of ``torch.distributed`` here: exchanging the IPC
+    handles); after that a solve is one C-ABI call per rank and no host code runs per iteration."""
+
+    def __init__(self, coef, b, x, part: SlabPartition, rank, group=None):
+        from .cgsolver import _Handle
+        from .field import Field
+        self.coef, self.b, self.x, self.part, self.rank = coef, b, x, part, rank
+        self.lib = _lib.load()
+        self._hd = _Handle(b)
+        l0, l1 = part.local_owned(rank)
+        _lib.check(self.lib.kt_set_rows(self._hd.h, l0, l1))
+        mk = lambda: Field(b.shape, b.np_dtype, b.device)
+        self.r, self.p, self.v, self.s, self.t = mk(), mk(), mk(), mk(), mk()
+        nbytes = int(self.lib.kt_p2p_comm_block_bytes())
+        self.block = torch.zeros(nbytes, dtype=torch.uint8, device=b.device)
+        self.dots = torch.zeros(2, dtype=torch.float64, device=b.device)
+        torch.cuda.synchronize(b.device)
+        n = part.nranks
+        mine = {'p': _share(self.p.data), 'v': _share(self.v.data), 'r': _share(self.r.data), 'blk': _share(self.block),
+                'halo_rows': part.local_owned(rank), 'device': b.device.index or 0}
+        descs = [None] * n
+        if n > 1:
+            dist.all_gather_object(descs, mine, group=group)
+        else:
+            descs[0] = mine
+        for d in descs:
+            _lib.check(self.lib.kt_enable_peer_access(self._hd.h, int(d['device'])))
+        self._keep = []
+        cm = _lib.P2PComm()
+        cm.rank, cm.nranks = rank, n
+        for k in range(16):
+            cm.comm_block[k] = None
+        for r_ in range(n):
+            if r_ == rank:
+                cm.comm_block[r_] = self.block.data_ptr()
+            else:
+                st, ptr = _open(descs[r_]['blk'])
+                self._keep.append(st)
+                cm.comm_block[r_] = ptr
+        for side, nb in ((0, rank - 1), (1, rank + 1)):
+            if 0 <= nb < n:
+                for name, arr in (('p', cm.peer_p), ('v', cm.peer_v), ('r', cm.peer_r)):
+                    st, ptr = _open(descs[nb][name])
+                    self._keep.append(st)
+                    arr[side] = ptr
+                nl0, nl1 = descs[nb]['halo_rows']
+                # my first owned row lands in the lower neighbour's TOP halo row (its l1); my last owned row in the upper
+                # neighbour's BOTTOM halo row (its l0 - 1)
+                cm.peer_halo_row[side] = nl1 if side == 0 else nl0 - 1
+            else:
+                cm.peer_p[side] = cm.peer_v[side] = cm.peer_r[side] = None
+                cm.peer_halo_row[side] = 0
+        cm.local_dots = self.dots.data_ptr()
+        self.comm = cm
+        if n > 1:
+            dist.barrier(group=group)          # every rank has mapped everything before anyone starts signalling
+        self.iterations, self.status, self.rel_res = 0, 0, float('nan')
+
+    def launch_count(self):
+        return self._hd.launch_count()
+
+    def solve(self, eps=1e-8, max_iter=None, fixed_iters=False):
+        self._hd.use_current_stream()
+        ws = _lib.KrylovWs(r=self.r.ptr, p=self.p.ptr, Ap=self.v.ptr, r_tld=None, s=self.s.ptr, t=self.t.ptr, history=None,
+                           history_cap=0, p2=None, Ap2=None)
+        it, rel, st = C.c_long(), C.c_double(), C.c_int()
+        if max_iter is None:
+            max_iter = self.part.NX * self.b.NY
+        _lib.check(self.lib.kt_p2p_bicgstab_solve(self._hd.h, C.c_void_p(self.coef.ptr), C.c_void_p(self.b.ptr), C.c_void_p(self.x.ptr),
+                                                  C.byref(ws), C.byref(self.comm), float(eps), int(max_iter), 1 if fixed_iters else 0,
+                                                  C.byref(it), C.byref(rel), C.byref(st)))
+        self.iterations, self.status, self.rel_res = it.value, st.value, rel.value
+        if st.value == 7:
+            raise _lib.KtError('x-slab peer-memory solve: a neighbour rank never signalled (KT_STATUS_COMM_TIMEOUT)')
+        return self.iterations, self.status

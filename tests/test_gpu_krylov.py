@@ -280,3 +280,51 @@ def test_large_roundtrip_property(cuda):
     c.solve(eps=1e-8)
     assert c.status == 0
     assert rel_l2(c.x.to_numpy(), x) < 1e-7
+
+
+@pytest.mark.parametrize('n', [8192, 16384])
+def test_full_size_properties(cuda, n):
+    """BASELINE sizes (north_star: 16384^2 on one B200), checked through size-independent properties computed ON the
+    device: the converged x satisfies ||A x - b|| <= eps ||b||, the solve is bit-reproducible run to run
+    (deterministic reductions), the ghost ring stays zero, and CG agrees with BiCGSTAB."""
+    import ctypes as C
+    import torch
+    import karman_taichi_b200 as kt
+    from karman_taichi_b200 import _lib
+    from karman_taichi_b200.cgsolver import _p
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(root, 'bench.py'))   # for s1_rows_device
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    coef, b, x = bench.s1_rows_device(kt, torch, n, 0, n + 2, cuda, offset=0.1)
+    s = kt.BICGSolver(coef, b, x)
+    eps = 1e-8
+    s.solve(eps=eps)
+    assert s.status == 0 and 20 < s.iterations < 120
+    x1 = x.data.clone()
+    it1 = s.iterations
+    # residual on the device: r = b - A x through the public building blocks
+    s.compute_Ax()
+    s.compute_residual()
+    rr, bb = s.reduce(s.r, s.r), s.reduce(b, b)
+    assert (rr / bb) ** 0.5 <= 1.05 * eps
+    assert float(x.data[0].abs().sum()) == 0.0 and float(x.data[:, 0].abs().sum()) == 0.0
+    assert float(x.data[:, n + 2:].abs().sum()) == 0.0                     # pad columns stay zero
+    # bit-reproducible
+    s.solve(eps=eps)
+    assert s.iterations == it1 and torch.equal(x.data, x1)
+    # CG on the same SPD system lands on the same solution
+    c = kt.CGSolver(coef, b, x)
+    c.solve(eps=eps)
+    assert c.status == 0
+    diff = float((x.data - x1).norm() / x1.norm())
+    assert diff < 1e-7
+    # linearity of the operator on the device: A (2 p) == 2 (A p) exactly (scaling by 2 is exact in binary)
+    s.p.data.copy_(x1)
+    s.compute_Ap()
+    y1 = s.Ap.data.clone()
+    s.p.data.mul_(2.0)
+    s.compute_Ap()
+    assert torch.equal(s.Ap.data, 2.0 * y1)

@@ -111,6 +111,14 @@ def _nccl_worker(rank, world, port, out_dir):
         iters, status = drv.solve(eps=1e-10, max_iter=rhs.size)
         np.save(os.path.join(out_dir, f'x_{rank}.npy'), part.owned_of_local(fx.to_numpy(), rank))
         np.save(os.path.join(out_dir, f'meta_{rank}.npy'), np.array([iters, status]))
+        # the same solve with the exchange / all-reduce done by the library over NVLink peer memory (no NCCL in the loop)
+        from karman_taichi_b200.slab import P2PSlabSolver
+        fx2 = kt.Field(b_l.shape, np.float64, dev)
+        p2p = P2PSlabSolver(fc, fb, fx2, part, rank)
+        for rep in range(2):                      # twice: the sequence numbers must survive a second solve
+            it2, st2 = p2p.solve(eps=1e-10, max_iter=rhs.size)
+        np.save(os.path.join(out_dir, f'xp_{rank}.npy'), part.owned_of_local(fx2.to_numpy(), rank))
+        np.save(os.path.join(out_dir, f'metap_{rank}.npy'), np.array([it2, st2]))
     finally:
         dist.destroy_process_group()
 
@@ -132,3 +140,30 @@ def test_two_gpu_nccl(cuda, tmp_path):
     assert all(int(m[1]) == 0 for m in metas) and len({int(m[0]) for m in metas}) == 1
     assert abs(int(metas[0][0]) - it_ref) <= max(3, round(0.1 * it_ref))
     assert rel_l2(x, x_ref) < 1e-8
+    xp = np.concatenate([np.load(tmp_path / f'xp_{r}.npy') for r in range(world)], axis=0)
+    mp_ = [np.load(tmp_path / f'metap_{r}.npy') for r in range(world)]
+    assert all(int(m[1]) == 0 for m in mp_) and len({int(m[0]) for m in mp_}) == 1
+    # same kernels, same rank-ordered sums as the NCCL path would give with a rank-ordered all-reduce
+    assert abs(int(mp_[0][0]) - it_ref) <= max(3, round(0.1 * it_ref))
+    assert rel_l2(xp, x_ref) < 1e-8
+
+
+def test_p2p_single_rank(cuda):
+    """nranks = 1 through kt_p2p_bicgstab_solve: the peer-memory reduce kernel (store, flag, wait, rank-ordered sum, scalar
+    algebra) on its own block; must reproduce the plain solver."""
+    import karman_taichi_b200 as kt
+    from karman_taichi_b200.slab import P2PSlabSolver, SlabPartition
+    coef, rhs = krylov.random_dd_system(130, 67, seed=1)
+    x_ref, it_ref, _ = krylov.bicgstab_solve(coef, rhs, eps=1e-10)
+    fc = kt.Field(coef.shape, np.float64, cuda).from_numpy(coef)
+    fb = kt.Field(rhs.shape, np.float64, cuda).from_numpy(rhs)
+    fx = kt.Field(rhs.shape, np.float64, cuda)
+    s = P2PSlabSolver(fc, fb, fx, SlabPartition(rhs.shape[0], 1), 0)
+    for _ in range(2):
+        it, st = s.solve(eps=1e-10, max_iter=rhs.size)
+    assert st == 0 and abs(it - it_ref) <= max(3, round(0.1 * it_ref))
+    assert rel_l2(fx.to_numpy(), x_ref) < 1e-8
+    ref = kt.BICGSolver(fc, fb, kt.Field(rhs.shape, np.float64, cuda))
+    ref.cluster = False
+    ref.solve(eps=1e-10)
+    assert ref.iterations == it          # identical kernels, identical sums: identical count
