@@ -194,6 +194,14 @@ typedef struct {
   void* local_dots;
 } kt_p2p_comm;
 int kt_p2p_comm_block_bytes(void);
+/* development aid: read / overwrite / re-read one double at a (possibly peer-mapped) device address */
+int kt_debug_poke(kt_handle_t h, void* ptr, double value, double* before_after_host);
+/* Buffers that other ranks (processes) map and write into: a dedicated zero-initialised cudaMalloc allocation plus its
+ * 64-byte cudaIpcMemHandle_t; kt_ipc_open maps a peer's handle into this rank's device (lazy peer access). */
+int kt_ipc_alloc(kt_handle_t h, size_t bytes, void** dev_ptr, unsigned char* handle64);
+int kt_ipc_open(kt_handle_t h, const unsigned char* handle64, void** mapped);
+int kt_ipc_close(kt_handle_t h, void* mapped);
+int kt_ipc_free(kt_handle_t h, void* dev_ptr);
 /* enable direct loads/stores from the handle's device to peer_device's memory (idempotent) */
 int kt_enable_peer_access(kt_handle_t h, int peer_device);
 int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws,

@@ -108,7 +108,12 @@ SIGNATURES = {
     'kt_dist_scalar': (_I, [_P, _I, _P, _P, _L]),
     'kt_dist_poll': (_I, [_P, _PI, _PL, _PI, _PD]),
     'kt_p2p_comm_block_bytes': (_I, []),
+    'kt_ipc_alloc': (_I, [_P, C.c_size_t, C.POINTER(_P), C.c_char_p]),
+    'kt_ipc_open': (_I, [_P, C.c_char_p, C.POINTER(_P)]),
+    'kt_ipc_close': (_I, [_P, _P]),
+    'kt_ipc_free': (_I, [_P, _P]),
     'kt_enable_peer_access': (_I, [_P, _I]),
+    'kt_debug_poke': (_I, [_P, _P, _D, _PD]),
     'kt_p2p_bicgstab_solve': (_I, [_P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _PL, _PD, _PI]),
     'kt_prof_begin': (_I, [_P, _I]),
     'kt_prof_end': (_I, [_P, _PD, _PL, _I]),

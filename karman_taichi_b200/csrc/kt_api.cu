@@ -1,5 +1,6 @@
 // kt_api.cu -- handle lifetime, error reporting, host<->device staging and layout conversion.
 #include <algorithm>
+#include <cstring>
 #include <string>
 #include "kt_handle.h"
 
@@ -139,6 +140,59 @@ int kt_enable_peer_access(kt_handle_t h, int peer_device) {
   cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
   if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
   if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+  return 0;
+}
+
+// ---- CUDA-IPC helpers for the peer-memory x-slab solver: buffers other ranks (processes) map and write into ----------
+int kt_ipc_alloc(kt_handle_t h, size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  KT_CHECK_ARG(h && dev_ptr && handle64 && bytes > 0, "kt_ipc_alloc: bad argument");
+  KT_CUDA(cudaSetDevice(h->device));
+  void* p = nullptr;
+  KT_CUDA(cudaMalloc(&p, bytes));                 // a dedicated allocation: its base address IS the pointer
+  KT_CUDA(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t mh;
+  KT_CUDA(cudaIpcGetMemHandle(&mh, p));
+  static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &mh, 64);
+  KT_CUDA(cudaDeviceSynchronize());
+  *dev_ptr = p;
+  return 0;
+}
+
+int kt_ipc_open(kt_handle_t h, const unsigned char* handle64, void** mapped) {
+  KT_CHECK_ARG(h && handle64 && mapped, "kt_ipc_open: bad argument");
+  KT_CUDA(cudaSetDevice(h->device));              // map into THIS rank's device, with peer access to the exporter
+  cudaIpcMemHandle_t mh;
+  memcpy(&mh, handle64, 64);
+  KT_CUDA(cudaIpcOpenMemHandle(mapped, mh, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+int kt_ipc_close(kt_handle_t h, void* mapped) {
+  KT_CHECK_ARG(h, "kt_ipc_close: null handle");
+  if (mapped) { cudaSetDevice(h->device); cudaIpcCloseMemHandle(mapped); }
+  return 0;
+}
+
+int kt_ipc_free(kt_handle_t h, void* dev_ptr) {
+  KT_CHECK_ARG(h, "kt_ipc_free: null handle");
+  if (dev_ptr) { cudaSetDevice(h->device); cudaFree(dev_ptr); }
+  return 0;
+}
+
+namespace kt {
+__global__ void k_debug_poke(double* p, double v, double* out) { out[0] = p[0]; p[0] = v; __threadfence_system(); out[1] = p[0]; }
+}
+
+// development aid: read, overwrite and re-read one double at a (possibly peer-mapped) device address
+int kt_debug_poke(kt_handle_t h, void* ptr, double value, double* before_after_host) {
+  KT_CHECK_ARG(h && ptr && before_after_host, "kt_debug_poke: null argument");
+  KT_CUDA(cudaSetDevice(h->device));
+  kt::k_debug_poke<<<1, 1, 0, h->stream>>>((double*)ptr, value, h->red_out);
+  KT_LAUNCH_CHECK(h);
+  KT_CUDA(cudaMemcpyAsync(h->red_host, h->red_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  KT_CUDA(cudaStreamSynchronize(h->stream));
+  before_after_host[0] = h->red_host[0]; before_after_host[1] = h->red_host[1];
   return 0;
 }
 

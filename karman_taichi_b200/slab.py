@@ -197,24 +197,33 @@ class DistBiCGSTAB:
 # ---------------------------------------------------------------------------------------------------------------
 # Peer-memory (NVLink) variant: no NCCL in the solver loop
 # ---------------------------------------------------------------------------------------------------------------
-def _share(t: torch.Tensor):
-    """CUDA-IPC description of a tensor's storage (what torch.multiprocessing sends), picklable."""
-    st = t.untyped_storage()
-    return st._share_cuda_(), t.storage_offset() * t.element_size()
+class _IpcBuffer:
+    """A zero-initialised device buffer owned by the library (dedicated cudaMalloc) that peer ranks can map."""
 
+    def __init__(self, hd, nbytes):
+        self.hd, self.nbytes = hd, int(nbytes)
+        ptr = C.c_void_p()
+        self.handle = C.create_string_buffer(64)
+        _lib.check(hd.lib.kt_ipc_alloc(hd.h, self.nbytes, C.byref(ptr), self.handle))
+        self.ptr = ptr.value
 
-def _open(desc):
-    """Map a peer's storage into this process; returns (storage kept alive, device address of the tensor)."""
-    handle, off = desc
-    st = torch.UntypedStorage._new_shared_cuda(*handle)
-    return st, st.data_ptr() + off
+    def handle_bytes(self):
+        return bytes(self.handle.raw)
+
+    def __del__(self):
+        try:
+            if self.ptr and self.hd.h:
+                self.hd.lib.kt_ipc_free(self.hd.h, C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
 
 
 class P2PSlabSolver:
     """x-slab BiCGSTAB whose halo exchange and inner-product all-reduce run inside the library over NVLink peer memory
     (``kt_p2p_bicgstab_solve``): every rank maps its neighbours' p / v / r planes and every rank's small comm block
-    through CUDA IPC once, at construction (the only collective use of ``torch.distributed`` here: exchanging the IPC
-    handles); after that a solve is one C-ABI call per rank and no host code runs per iteration."""
+    through CUDA IPC once, at construction (the only collective use of ``torch.distributed`` here: exchanging the 64-byte
+    IPC handles); after that a solve is one C-ABI call per rank and no host code runs per iteration."""
 
     def __init__(self, coef, b, x, part: SlabPartition, rank, group=None):
         from .cgsolver import _Handle
@@ -224,40 +233,37 @@ class P2PSlabSolver:
         self._hd = _Handle(b)
         l0, l1 = part.local_owned(rank)
         _lib.check(self.lib.kt_set_rows(self._hd.h, l0, l1))
-        mk = lambda: Field(b.shape, b.np_dtype, b.device)
-        self.r, self.p, self.v, self.s, self.t = mk(), mk(), mk(), mk(), mk()
-        nbytes = int(self.lib.kt_p2p_comm_block_bytes())
-        self.block = torch.zeros(nbytes, dtype=torch.uint8, device=b.device)
+        self.s, self.t = Field(b.shape, b.np_dtype, b.device), Field(b.shape, b.np_dtype, b.device)
+        plane_bytes = b.data.numel() * b.data.element_size()
+        # the planes neighbours write halo rows into, and the comm block every rank writes sums / flags into
+        self._r, self._p, self._v = (_IpcBuffer(self._hd, plane_bytes) for _ in range(3))
+        self._blk = _IpcBuffer(self._hd, int(self.lib.kt_p2p_comm_block_bytes()))
         self.dots = torch.zeros(2, dtype=torch.float64, device=b.device)
-        torch.cuda.synchronize(b.device)
         n = part.nranks
-        mine = {'p': _share(self.p.data), 'v': _share(self.v.data), 'r': _share(self.r.data), 'blk': _share(self.block),
-                'halo_rows': part.local_owned(rank), 'device': b.device.index or 0}
+        mine = {'p': self._p.handle_bytes(), 'v': self._v.handle_bytes(), 'r': self._r.handle_bytes(), 'blk': self._blk.handle_bytes(),
+                'halo_rows': part.local_owned(rank)}
         descs = [None] * n
         if n > 1:
             dist.all_gather_object(descs, mine, group=group)
         else:
             descs[0] = mine
-        for d in descs:
-            _lib.check(self.lib.kt_enable_peer_access(self._hd.h, int(d['device'])))
-        self._keep = []
+        self._mapped = []
+
+        def open_(hb):
+            out = C.c_void_p()
+            _lib.check(self.lib.kt_ipc_open(self._hd.h, hb, C.byref(out)))
+            self._mapped.append(out.value)
+            return out.value
+
         cm = _lib.P2PComm()
         cm.rank, cm.nranks = rank, n
         for k in range(16):
             cm.comm_block[k] = None
         for r_ in range(n):
-            if r_ == rank:
-                cm.comm_block[r_] = self.block.data_ptr()
-            else:
-                st, ptr = _open(descs[r_]['blk'])
-                self._keep.append(st)
-                cm.comm_block[r_] = ptr
+            cm.comm_block[r_] = self._blk.ptr if r_ == rank else open_(descs[r_]['blk'])
         for side, nb in ((0, rank - 1), (1, rank + 1)):
             if 0 <= nb < n:
-                for name, arr in (('p', cm.peer_p), ('v', cm.peer_v), ('r', cm.peer_r)):
-                    st, ptr = _open(descs[nb][name])
-                    self._keep.append(st)
-                    arr[side] = ptr
+                cm.peer_p[side], cm.peer_v[side], cm.peer_r[side] = (open_(descs[nb][k]) for k in ('p', 'v', 'r'))
                 nl0, nl1 = descs[nb]['halo_rows']
                 # my first owned row lands in the lower neighbour's TOP halo row (its l1); my last owned row in the upper
                 # neighbour's BOTTOM halo row (its l0 - 1)
@@ -271,12 +277,20 @@ class P2PSlabSolver:
             dist.barrier(group=group)          # every rank has mapped everything before anyone starts signalling
         self.iterations, self.status, self.rel_res = 0, 0, float('nan')
 
+    def __del__(self):
+        try:
+            for m in getattr(self, '_mapped', []):
+                self.lib.kt_ipc_close(self._hd.h, C.c_void_p(m))
+            self._mapped = []
+        except Exception:
+            pass
+
     def launch_count(self):
         return self._hd.launch_count()
 
     def solve(self, eps=1e-8, max_iter=None, fixed_iters=False):
         self._hd.use_current_stream()
-        ws = _lib.KrylovWs(r=self.r.ptr, p=self.p.ptr, Ap=self.v.ptr, r_tld=None, s=self.s.ptr, t=self.t.ptr, history=None,
+        ws = _lib.KrylovWs(r=self._r.ptr, p=self._p.ptr, Ap=self._v.ptr, r_tld=None, s=self.s.ptr, t=self.t.ptr, history=None,
                            history_cap=0, p2=None, Ap2=None)
         it, rel, st = C.c_long(), C.c_double(), C.c_int()
         if max_iter is None:

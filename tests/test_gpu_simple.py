@@ -224,3 +224,33 @@ def test_pressure_and_momentum_valid_recipes(cuda):
     zero = kt.Field(g.pcor.shape, np.float64, cuda)
     n = _jacobi(c, g.coef_p, g.b_p, zero, 200000, 1e-15)
     assert rel_l2(g.pcor.to_numpy(), p_cg) < 1e-6
+
+
+def test_f32_mode(cuda):
+    """f32 variant (north_star allows 1e-4 in float32; the reference itself is f64-only).  Assembly against the f64
+    oracle to f32 rounding; two outer iterations of the cavity with solver tolerances f32 can reach."""
+    import karman_taichi_b200 as kt
+    o = SimpleOracle(1.0, 1.0, 40, 40)
+    g = kt.SIMPLESolver(1.0, 1.0, 40, 40, dtype=np.float32, device=cuda)
+    rng = np.random.default_rng(5)
+    for s in (o, g):
+        s.bc['n'][1] = 1.0
+        s.eps_u = s.eps_v = 1e-4
+        s.eps_p = 1e-5                                   # 1e-8 is below what an f32 residual can resolve
+    for name in ('u', 'v', 'p'):
+        a = getattr(o, name)
+        a[...] = 0.1 * rng.standard_normal(a.shape)
+        getattr(g, name).from_numpy(a.astype(np.float32))
+    o.compute_coef_u(); o.compute_coef_v(); o.set_bc(); o.compute_coef_p()
+    g.compute_coef_u(); g.set_bc(); g.compute_coef_p()
+    for name in ('coef_u', 'coef_v', 'b_u', 'b_v', 'coef_p', 'b_p'):
+        ref = getattr(o, name)
+        np.testing.assert_allclose(getattr(g, name).to_numpy(), ref, rtol=2e-5, atol=2e-6 * np.abs(ref).max(), err_msg=name)
+    o.init(); g.init(); g._make_solvers()
+    for _ in range(2):
+        o.step(); g.step()
+    errs = {n: rel_l2(getattr(g, n).to_numpy().astype(np.float64), getattr(o, n)) for n in ('u', 'v', 'p')}
+    if os.path.isdir('gpurun_out'):
+        with open('gpurun_out/parity_errors.txt', 'a') as f:
+            f.write(f'cavity f32 n=40: {errs}\n')
+    assert errs['u'] < 1e-3 and errs['v'] < 1e-3 and errs['p'] < 1e-2, errs
