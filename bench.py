@@ -47,6 +47,8 @@ BYTES_PER_CELL_ITER = 28 * 8            # BiCGSTAB algorithmic t
 # dram__bytes_read.sum + dram__bytes_write.sum per launch and per plane word of each kernel come from the committed
 # ncu captures (profiles/r01_launch_list_default.md: the default command, 32770 x 32784-word planes).
 FUSED_TRAFFIC_BYTES_PER_WORD = 86.9
+NO_S_K3_TRAFFIC = None      # filled from profiles/r01_launch_list_default.md once captured
+NO_S_K4_TRAFFIC = None
 
 
 def peaks():
@@ -303,11 +305,14 @@ def run_ours(a):
     # ---- roofline of the dominant kernel (largest share of the step), timed live with CUDA-event pairs ---------------
     peak, peak_kind = peaks()
     fused = cnt[0] == 0                       # BICGSolver.fuse_p_update: K1 folded into K2 (11 N instead of 4 N + 8 N)
+    store_s = world > 1 and a.comm == 'nccl'  # the single-GPU and peer-memory paths recompute s in K4 instead of storing it
     classes = {0: ('p_update', 'k_bicg_p: p = r + beta (p - omega v)', 4, 31.6),
                1: (('p_update+v=Ap+dot', 'k_stencil<SRC_P,EPI_DOT_Q_ST>: p = r + beta (p - omega v), v = A p, (r~, v)', 11, FUSED_TRAFFIC_BYTES_PER_WORD)
                    if fused else ('v=Ap+dot', 'k_stencil<SRC_X,EPI_DOT_Q>: v = A p, (r~, v)', 8, 64.0)),
-               2: ('s,t+2dots', 'k_stencil<SRC_S,EPI_ST>: s = r - alpha v, t = A s, (t,s), (t,t)', 9, 73.1),
-               3: ('x,r+2dots', 'k_bicg_xr: x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 7, 55.9)}
+               2: (('s,t+2dots', 'k_stencil<SRC_S,EPI_ST>: s = r - alpha v, t = A s, (t,s), (t,t)', 9, 73.1) if store_s else
+                   ('t=As+2dots', 'k_stencil<SRC_S,EPI_ST>: t = A (r - alpha v) [s not stored], (t,s), (t,t)', 8, NO_S_K3_TRAFFIC)),
+               3: (('x,r+2dots', 'k_bicg_xr: x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 7, 55.9) if store_s else
+                   ('x,r+2dots', 'k_bicg_xr: s = r - alpha v, x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 8, NO_S_K4_TRAFFIC))}
     tots = [allmax(tot[i]) for i in range(4)]
     dom = max(range(4), key=lambda i: tots[i])
     d_name, d_desc, d_words, d_traffic = classes[dom]

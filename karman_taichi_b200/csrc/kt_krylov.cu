@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
             if (A.s_out) st_vec(A.s_out + o, r);
           } else {
             st_vec(A.y + o, y);
-            if (EPI == EPI_ST || EPI == EPI_DOT_Q_ST) st_vec(A.s_out + o, raw_c[w]);
+            if ((EPI == EPI_ST && A.s_out) || EPI == EPI_DOT_Q_ST) st_vec(A.s_out + o, raw_c[w]);
 #pragma unroll
             for (int k = 0; k < V; ++k) {
               if (EPI == EPI_DOT_Q || EPI == EPI_DOT_Q_ST) acc0 += (double)qv[w].a[k] * (double)y.a[k];
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, cons
 template <typename T, bool PRE>
 __global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* p, const T* s, const T* t,
                                                  const T* r_tld, const T* minv, double alpha_imm, double omega_imm,
-                                                 int from_sc, ReduceWs ws, int fin) {
+                                                 int from_sc, ReduceWs ws, int fin, const T* v_for_s = nullptr) {
   constexpr int V = VT<T>::V;
   constexpr int U = (kEwUnroll > 2) ? 2 : kEwUnroll;     // 5-6 operand planes: 2 strides already keep ~190 B in flight
   if (from_sc && ws.sc->done) return;
@@ -347,9 +347,17 @@ __global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* 
   KT_EW_OUTER(U) {
     Pack<T> xx[U], pp[U], ss[U], tt[U], rt[U], mm[U];
     KT_EW_FOR(U, u, o) {
-      xx[u] = ld_rw(x + o); pp[u] = ld_stream(p + o); ss[u] = ld_stream(s + o); tt[u] = ld_stream(t + o);
+      xx[u] = ld_rw(x + o); pp[u] = ld_stream(p + o); tt[u] = ld_stream(t + o);
       rt[u] = ld_stream(r_tld + o);
       if (PRE) mm[u] = ld_stream(minv + o);
+      if (v_for_s) {
+        // s was not stored by K3: recompute s = r - alpha v (same expression, same bits) from the old r and v
+        Pack<T> ro = ld_rw(r + o), vv = ld_stream(v_for_s + o);
+#pragma unroll
+        for (int k = 0; k < V; ++k) ss[u].a[k] = ro.a[k] - alpha * vv.a[k];
+      } else {
+        ss[u] = ld_stream(s + o);
+      }
     }
     KT_EW_FOR(U, u, o) {
       Pack<T> rn;
@@ -602,7 +610,9 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
   const bool warm = (flags & KT_FLAG_WARM_START) != 0;
   T* r = (T*)w->r; T* p = (T*)w->p; T* v = (T*)w->Ap; T* s = (T*)w->s; T* t = (T*)w->t;
   T* r_tld = (T*)w->r_tld;
-  KT_CHECK_ARG(r && p && v && s && t, "kt_krylov_ws: r, p, Ap, s, t are required for BiCGSTAB");
+  KT_CHECK_ARG(r && p && v && t, "kt_krylov_ws: r, p, Ap, t are required for BiCGSTAB");
+  // ws->s == NULL: K3 does not store s and K4 recomputes it from r and v -- same 28 N words, one write stream less
+  // (K3 becomes 7 reads : 1 write like K2) and one plane of HBM saved.
   KT_CHECK_ARG(!(warm && !r_tld), "warm start needs a separate r_tld plane");
   const T* r_tld_c = r_tld ? r_tld : (const T*)b;     // x0 = 0  =>  r_tld == b exactly (bicgsolver.py:25-26)
   int rc = cluster_try_solve<T>(h, coef, b, x, Minv, r, w->history, w->history_cap, fixed_iters ? -1.0 : eps, max_iter, flags, false);
@@ -667,8 +677,9 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
     }
     if (e) return e;
     ProfScope ps(h, KT_K_BICG_XR);
-    if (pre) k_bicg_xr<T, true><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END);
-    else k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END);
+    const T* v_for_s = s ? nullptr : v_new;
+    if (pre) k_bicg_xr<T, true><<<grid_for(h, P.ew_blocks, 8), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END, v_for_s);
+    else k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, 8), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END, v_for_s);
     KT_LAUNCH_CHECK(h);
     return 0;
   };
@@ -742,7 +753,7 @@ __global__ void k_scalar_step(Scalars* sc, int fin, const double* dots, double* 
 
 template <typename T>
 static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void* a0, const void* a1, const void* a2,
-                        void* o0, void* o1, void* o2, double* dots_dev) {
+                        void* o0, void* o1, void* o2, double* dots_dev, const void* v_for_s = nullptr) {
   Plan P = make_plan(h);
   ReduceWs ws = make_ws(h, nullptr, 0, dots_dev);
   static const int cls_of_phase[5] = {KT_K_INIT, KT_K_BICG_P, KT_K_BICG_V, KT_K_BICG_ST, KT_K_BICG_XR};
@@ -769,7 +780,7 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
     }
     case 4: {   // x (o0) += alpha p (a0) + omega s (a1); r (o1) = s - omega t (a2); local (r,r), (r, r_tld (o2))
       k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(
-          P.g, (T*)o0, (T*)o1, (const T*)a0, (const T*)a1, (const T*)a2, (const T*)o2, nullptr, 0, 0, 1, ws, FIN_NONE);
+          P.g, (T*)o0, (T*)o1, (const T*)a0, (const T*)a1, (const T*)a2, (const T*)o2, nullptr, 0, 0, 1, ws, FIN_NONE, (const T*)v_for_s);
       break;
     }
     default: set_error("kt_dist_bicg_phase: unknown phase"); return -2;
@@ -880,7 +891,7 @@ static int t_p2p_bicgstab(kt_handle_s* h, const void* coef, const void* b, void*
                           double eps, long long max_iter, bool fixed_iters, long* iters, double* rel_res, int* status) {
   KT_CHECK_ARG(cm->nranks >= 1 && cm->nranks <= 16 && cm->rank >= 0 && cm->rank < cm->nranks, "kt_p2p_comm: bad rank / nranks (max 16)");
   T* r = (T*)w->r; T* p = (T*)w->p; T* v = (T*)w->Ap; T* s = (T*)w->s; T* t = (T*)w->t;
-  KT_CHECK_ARG(r && p && v && s && t, "kt_krylov_ws: r, p, Ap, s, t are required");
+  KT_CHECK_ARG(r && p && v && t, "kt_krylov_ws: r, p, Ap, t are required (s optional: NULL = recomputed, not stored)");
   P2PState& st = g_p2p_state;
   P2PPeers peers;
   for (int k = 0; k < 16; ++k) peers.blk[k] = k < cm->nranks ? (P2PBlock*)cm->comm_block[k] : nullptr;
@@ -920,9 +931,9 @@ static int t_p2p_bicgstab(kt_handle_s* h, const void* coef, const void* b, void*
     KT_TRY(t_dist_phase<T>(h, 2, coef, p, b, nullptr, v, nullptr, nullptr, dots));
     KT_TRY(reduce(0, 1, FIN_BICG_ALPHA));
     KT_TRY(halo(1, v, cm->peer_v));
-    KT_TRY(t_dist_phase<T>(h, 3, coef, r, v, nullptr, s, t, nullptr, dots));
+    KT_TRY(t_dist_phase<T>(h, 3, coef, r, v, nullptr, s, t, nullptr, dots));          // s == NULL: not stored
     KT_TRY(reduce(1, 2, FIN_BICG_OMEGA));
-    KT_TRY(t_dist_phase<T>(h, 4, coef, p, s, t, x, r, (void*)b, dots));
+    KT_TRY(t_dist_phase<T>(h, 4, coef, p, s, t, x, r, (void*)b, dots, s ? nullptr : v));
     KT_TRY(reduce(2, 2, FIN_BICG_END));
     KT_TRY(halo(2, r, cm->peer_r));
     return 0;

@@ -233,7 +233,7 @@ class P2PSlabSolver:
         self._hd = _Handle(b)
         l0, l1 = part.local_owned(rank)
         _lib.check(self.lib.kt_set_rows(self._hd.h, l0, l1))
-        self.s, self.t = Field(b.shape, b.np_dtype, b.device), Field(b.shape, b.np_dtype, b.device)
+        self.t = Field(b.shape, b.np_dtype, b.device)       # s is recomputed by the x/r kernel, never stored
         plane_bytes = b.data.numel() * b.data.element_size()
         # the planes neighbours write halo rows into, and the comm block every rank writes sums / flags into
         self._r, self._p, self._v = (_IpcBuffer(self._hd, plane_bytes) for _ in range(3))
@@ -290,7 +290,7 @@ class P2PSlabSolver:
 
     def solve(self, eps=1e-8, max_iter=None, fixed_iters=False):
         self._hd.use_current_stream()
-        ws = _lib.KrylovWs(r=self._r.ptr, p=self._p.ptr, Ap=self._v.ptr, r_tld=None, s=self.s.ptr, t=self.t.ptr, history=None,
+        ws = _lib.KrylovWs(r=self._r.ptr, p=self._p.ptr, Ap=self._v.ptr, r_tld=None, s=None, t=self.t.ptr, history=None,
                            history_cap=0, p2=None, Ap2=None)
         it, rel, st = C.c_long(), C.c_double(), C.c_int()
         if max_iter is None:

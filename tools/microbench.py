@@ -70,6 +70,7 @@ def main():
     ap.add_argument('--kernels', action='store_true', help='also time individual kernels')
     ap.add_argument('--brief', default=None, help='print one line tagged with this label')
     ap.add_argument('--fused', action='store_true', help='BiCGSTAB with the p-update fused into v = A p (27 N words)')
+    ap.add_argument('--no-s', action='store_true', help='BiCGSTAB without storing s (K4 recomputes it from r and v)')
     a = ap.parse_args()
     dtype = np.float64 if a.dtype == 'f64' else np.float32
     w = 8 if a.dtype == 'f64' else 4
@@ -82,7 +83,7 @@ def main():
 
     s = kt.BICGSolver(coef, b, x)
     L, h = s._lib, s._h
-    ws = s._ws(s=s.s.ptr, t=s.t.ptr)
+    ws = s._ws(s=(None if a.no_s else s.s.ptr), t=s.t.ptr)
     if a.fused:
         p2, ap2 = kt.Field(b.shape, dtype, dev), kt.Field(b.shape, dtype, dev)
         ws.p2, ws.Ap2 = p2.ptr, ap2.ptr
