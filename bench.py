@@ -47,8 +47,8 @@ BYTES_PER_CELL_ITER = 28 * 8            # BiCGSTAB algorithmic t
 # dram__bytes_read.sum + dram__bytes_write.sum per launch and per plane word of each kernel come from the committed
 # ncu captures (profiles/r01_launch_list_default.md: the default command, 32770 x 32784-word planes).
 FUSED_TRAFFIC_BYTES_PER_WORD = 86.9
-NO_S_K3_TRAFFIC = None      # filled from profiles/r01_launch_list_default.md once captured
-NO_S_K4_TRAFFIC = None
+NO_S_K3_TRAFFIC = 65.1      # profiles/r01_launch_list_default.md
+NO_S_K4_TRAFFIC = 63.9
 
 
 def peaks():

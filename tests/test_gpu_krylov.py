@@ -328,3 +328,79 @@ def test_full_size_properties(cuda, n):
     s.p.data.mul_(2.0)
     s.compute_Ap()
     assert torch.equal(s.Ap.data, 2.0 * y1)
+
+
+def test_stepwise_reference_loop_matches_solve(cuda):
+    """The reference's own solve() bodies (bicgsolver.py:88-135, cgsolver.py:83-114) written against the class methods
+    (init / reduce / copy / update_* / compute_*) -- i.e. the code a user of the reference could have in a script --
+    must give what the single-call device-resident solve() gives."""
+    import math
+    import karman_taichi_b200 as kt
+    coef, rhs = krylov.random_dd_system(37, 53, seed=11)
+    eps = 1e-10
+    # --- BiCGSTAB, line by line
+    s = make(cuda, coef, rhs, kt.BICGSolver)
+    s.init()
+    initial_rTr = s.reduce(s.r, s.r)
+    n_it = 0
+    for i in range(s.steps):
+        s.rho[None] = s.reduce(s.r, s.r_tld)
+        if s.rho[None] == 0.0:
+            break
+        if i == 0:
+            s.copy(s.r, s.p)
+        else:
+            s.beta[None] = (s.rho[None] / s.rho_1[None]) * (s.alpha[None] / s.omega[None])
+            s.update_p()
+        s.update_phat()
+        s.compute_Ap()
+        s.alpha[None] = s.rho[None] / s.reduce(s.r_tld, s.Ap)
+        s.update_s()
+        s.update_shat()
+        s.compute_As()
+        s.copy(s.Ashat, s.t)
+        s.omega[None] = s.reduce(s.t, s.s) / s.reduce(s.t, s.t)
+        s.update_x()
+        s.update_r()
+        rTr = s.reduce(s.r, s.r)
+        n_it = i + 1
+        if math.sqrt(rTr / initial_rTr) < eps:
+            break
+        s.rho_1[None] = s.rho[None]
+    x_step = s.x.to_numpy().copy()
+    for cluster in (True, False):
+        s2 = make(cuda, coef, rhs, kt.BICGSolver)
+        s2.cluster = cluster
+        s2.solve(eps=eps)
+        assert abs(s2.iterations - n_it) <= max(3, round(0.1 * n_it))
+        assert rel_l2(s2.x.to_numpy(), x_step) < 1e-8
+    # --- CG on an SPD system, line by line
+    coef, rhs = krylov.poisson_sin_system(48, 0.1)
+    c = make(cuda, coef, rhs, kt.CGSolver)
+    c.init()
+    initial = c.reduce(c.r, c.r)
+    old = initial
+    c.update_p()
+    n_it = 0
+    for i in range(c.steps):
+        c.compute_Ap()
+        c.alpha[None] = old / c.reduce(c.p, c.Ap)
+        c.update_x()
+        c.update_r()
+        new = c.reduce(c.r, c.r)
+        n_it = i + 1
+        if math.sqrt(new) < math.sqrt(initial) * eps:
+            break
+        c.beta[None] = new / old
+        c.update_p()
+        old = new
+    c2 = make(cuda, coef, rhs, kt.CGSolver)
+    c2.solve(eps=eps)
+    assert abs(c2.iterations - n_it) <= 1
+    assert rel_l2(c2.x.to_numpy(), c.x.to_numpy()) < 1e-8
+    # update_coef copies when given other field objects (cgsolver.py:41-47)
+    other = make(cuda, coef * 2.0, rhs * 3.0, kt.CGSolver)
+    c2.update_coef(other.coef, other.b, other.x)
+    np.testing.assert_array_equal(c2.coef.to_numpy(), coef * 2.0)
+    np.testing.assert_array_equal(c2.b.to_numpy(), rhs * 3.0)
+    assert c2.check_solution() >= 0.0
