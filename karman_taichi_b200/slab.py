@@ -255,26 +255,37 @@ class P2PSlabSolver:
             self._mapped.append(out.value)
             return out.value
 
-        cm = _lib.P2PComm()
-        cm.rank, cm.nranks = rank, n
-        for k in range(16):
-            cm.comm_block[k] = None
-        for r_ in range(n):
-            cm.comm_block[r_] = self._blk.ptr if r_ == rank else open_(descs[r_]['blk'])
-        for side, nb in ((0, rank - 1), (1, rank + 1)):
-            if 0 <= nb < n:
-                cm.peer_p[side], cm.peer_v[side], cm.peer_r[side] = (open_(descs[nb][k]) for k in ('p', 'v', 'r'))
-                nl0, nl1 = descs[nb]['halo_rows']
-                # my first owned row lands in the lower neighbour's TOP halo row (its l1); my last owned row in the upper
-                # neighbour's BOTTOM halo row (its l0 - 1)
-                cm.peer_halo_row[side] = nl1 if side == 0 else nl0 - 1
-            else:
-                cm.peer_p[side] = cm.peer_v[side] = cm.peer_r[side] = None
-                cm.peer_halo_row[side] = 0
-        cm.local_dots = self.dots.data_ptr()
-        self.comm = cm
+        err = None
+        try:
+            cm = _lib.P2PComm()
+            cm.rank, cm.nranks = rank, n
+            for k in range(16):
+                cm.comm_block[k] = None
+            for r_ in range(n):
+                cm.comm_block[r_] = self._blk.ptr if r_ == rank else open_(descs[r_]['blk'])
+            for side, nb in ((0, rank - 1), (1, rank + 1)):
+                if 0 <= nb < n:
+                    cm.peer_p[side], cm.peer_v[side], cm.peer_r[side] = (open_(descs[nb][k]) for k in ('p', 'v', 'r'))
+                    nl0, nl1 = descs[nb]['halo_rows']
+                    # my first owned row lands in the lower neighbour's TOP halo row (its l1); my last owned row in the upper
+                    # neighbour's BOTTOM halo row (its l0 - 1)
+                    cm.peer_halo_row[side] = nl1 if side == 0 else nl0 - 1
+                else:
+                    cm.peer_p[side] = cm.peer_v[side] = cm.peer_r[side] = None
+                    cm.peer_halo_row[side] = 0
+            cm.local_dots = self.dots.data_ptr()
+            self.comm = cm
+        except Exception as e:      # e.g. no peer access between two devices: every rank must learn of it (no hang)
+            err = e
         if n > 1:
-            dist.barrier(group=group)          # every rank has mapped everything before anyone starts signalling
+            # every rank has mapped everything before anyone starts signalling; a rank that could not map tells the others
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=b.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                raise _lib.KtError(f'x-slab peer-memory setup failed on rank {rank}: {err}' if err else
+                                   'x-slab peer-memory setup failed on another rank')
+        elif err:
+            raise err
         self.iterations, self.status, self.rel_res = 0, 0, float('nan')
 
     def __del__(self):
