@@ -169,7 +169,9 @@ int kt_bicgstab_solve_host(kt_handle_t h, const void* coef_host_aos, const void*
  * same kernel the single-GPU solver uses, but only publishes the LOCAL inner products into dots_dev[0..1]; the
  * host all-reduces dots_dev over the ranks and kt_dist_scalar runs the step's scalar algebra (KT_FIN_*) on every
  * rank from the identical reduced sums.  phase: 0 init (a0=b; o0=r, o1=x, o2=r_tld or NULL), 1 p-update (a0=r, a1=v;
- * o0=p), 2 v=Ap (a0=p, a1=r_tld; o0=v), 3 s,t (a0=r, a1=v; o0=s, o1=t), 4 x,r (a0=p, a1=s, a2=t; o0=x, o1=r, o2=r_tld). */
+ * o0=p), 2 v=Ap (a0=p, a1=r_tld; o0=v), 3 s,t (a0=r, a1=v; o0=s, o1=t), 4 x,r (a0=p, a1=s, a2=t; o0=x, o1=r, o2=r_tld).
+ * CG (cgsolver.py:83-114; p needs its halo rows before phase 6): 5 init (a0=b; o0=r, o1=x, o2=p), 6 Ap (a0=p; o0=Ap) with
+ * local (p,Ap), 7 x,r (a0=p, a1=Ap; o0=x, o1=r) with local (r,r), 8 p-update (a0=r; o0=p). */
 enum { KT_FIN_NONE = 0, KT_FIN_BICG_INIT = 1, KT_FIN_BICG_ALPHA = 2, KT_FIN_BICG_OMEGA = 3, KT_FIN_BICG_END = 4,
        KT_FIN_CG_INIT = 5, KT_FIN_CG_ALPHA = 6, KT_FIN_CG_END = 7 };
 int kt_dist_begin(kt_handle_t h, double eps, long max_iter, int flags);
@@ -207,6 +209,11 @@ int kt_enable_peer_access(kt_handle_t h, int peer_device);
 int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws,
                           const kt_p2p_comm* comm, double eps, long max_iter, int fixed_iters,
                           long* iters, double* rel_res, int* status);
+/* CGSolver.solve (cgsolver.py:83-114) over x-slabs, same comm kernels: one halo exchange (p: comm->peer_p, ws->p must be
+ * a kt_ipc_alloc plane) and two all-reduces per iteration.  ws: r, p, Ap. */
+int kt_p2p_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws,
+                    const kt_p2p_comm* comm, double eps, long max_iter, int fixed_iters,
+                    long* iters, double* rel_res, int* status);
 
 /* ---- per-kernel device timing (bench.py roofline) ----------------------------------------------
  * Between kt_prof_begin and kt_prof_end every launch of the solver kernels is bracketed by a CUDA event pair on

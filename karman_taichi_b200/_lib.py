@@ -115,6 +115,7 @@ SIGNATURES = {
     'kt_enable_peer_access': (_I, [_P, _I]),
     'kt_debug_poke': (_I, [_P, _P, _D, _PD]),
     'kt_p2p_bicgstab_solve': (_I, [_P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _PL, _PD, _PI]),
+    'kt_p2p_cg_solve': (_I, [_P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _PL, _PD, _PI]),
     'kt_prof_begin': (_I, [_P, _I]),
     'kt_prof_end': (_I, [_P, _PD, _PL, _I]),
     'kt_assemble_uv': (_I, [_P, _SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -756,8 +756,9 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
                         void* o0, void* o1, void* o2, double* dots_dev, const void* v_for_s = nullptr) {
   Plan P = make_plan(h);
   ReduceWs ws = make_ws(h, nullptr, 0, dots_dev);
-  static const int cls_of_phase[5] = {KT_K_INIT, KT_K_BICG_P, KT_K_BICG_V, KT_K_BICG_ST, KT_K_BICG_XR};
-  ProfScope ps(h, (phase >= 0 && phase < 5) ? cls_of_phase[phase] : KT_K_INIT);
+  static const int cls_of_phase[9] = {KT_K_INIT, KT_K_BICG_P, KT_K_BICG_V, KT_K_BICG_ST, KT_K_BICG_XR,
+                                      KT_K_INIT, KT_K_CG_AP, KT_K_CG_XR, KT_K_CG_P};
+  ProfScope ps(h, (phase >= 0 && phase < 9) ? cls_of_phase[phase] : KT_K_INIT);
   switch (phase) {
     case 0: {   // init: r = b (a0), x = 0 (o1), r (o0), r_tld (o2, may be null); local (r,r)
       k_init<T, false><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (const T*)a0, (T*)o0, (T*)o2, (T*)o1, nullptr, ws, FIN_NONE);
@@ -781,6 +782,24 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
     case 4: {   // x (o0) += alpha p (a0) + omega s (a1); r (o1) = s - omega t (a2); local (r,r), (r, r_tld (o2))
       k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(
           P.g, (T*)o0, (T*)o1, (const T*)a0, (const T*)a1, (const T*)a2, (const T*)o2, nullptr, 0, 0, 1, ws, FIN_NONE, (const T*)v_for_s);
+      break;
+    }
+    // ---- CG (cgsolver.py:83-114) ----
+    case 5: {   // init: r (o0) = b (a0), x (o1) = 0, p (o2) = r; local (r,r)
+      k_init<T, true><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (const T*)a0, (T*)o0, nullptr, (T*)o1, (T*)o2, ws, FIN_NONE);
+      break;
+    }
+    case 6: {   // Ap (o0) = A p (a0); local (p, Ap)
+      StencilArgs<T> A = stencil_args<T>(h, P, coef);
+      A.ws = ws; A.x = (const T*)a0; A.y = (T*)o0; A.check_done = 1; A.fin = FIN_NONE;
+      return launch_stencil<T, SRC_X, false, EPI_DOT_SRC>(h, P, A);
+    }
+    case 7: {   // x (o0) += alpha p (a0); r (o1) -= alpha Ap (a1); local (r,r)
+      k_cg_xr<T><<<grid_for(h, P.ew_blocks, 6), 256, 0, h->stream>>>(P.g, (T*)o0, (T*)o1, (const T*)a0, (const T*)a1, 0.0, 1, ws, FIN_NONE);
+      break;
+    }
+    case 8: {   // p (o0) = r (a0) + beta p
+      k_cg_p<T><<<grid_for(h, P.ew_blocks, 3), 256, 0, h->stream>>>(P.g, (T*)o0, (const T*)a0, h->sc);
       break;
     }
     default: set_error("kt_dist_bicg_phase: unknown phase"); return -2;
@@ -948,6 +967,65 @@ static int t_p2p_bicgstab(kt_handle_s* h, const void* coef, const void* b, void*
   return 0;
 }
 
+// CGSolver.solve (cgsolver.py:83-114) over x-slabs with the same two comm kernels: one halo exchange (p) and two
+// all-reduces ((p,Ap) and (r,r)) per iteration.
+template <typename T>
+static int t_p2p_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const kt_krylov_ws* w, const kt_p2p_comm* cm,
+                    double eps, long long max_iter, bool fixed_iters, long* iters, double* rel_res, int* status) {
+  KT_CHECK_ARG(cm->nranks >= 1 && cm->nranks <= 16 && cm->rank >= 0 && cm->rank < cm->nranks, "kt_p2p_comm: bad rank / nranks (max 16)");
+  T* r = (T*)w->r; T* p = (T*)w->p; T* Ap = (T*)w->Ap;
+  KT_CHECK_ARG(r && p && Ap, "kt_krylov_ws: r, p, Ap are required for CG");
+  P2PState& st = g_p2p_state;
+  P2PPeers peers;
+  for (int k = 0; k < 16; ++k) peers.blk[k] = k < cm->nranks ? (P2PBlock*)cm->comm_block[k] : nullptr;
+  P2PBlock* mine = peers.blk[cm->rank];
+  P2PBlock* blk_lo = cm->rank > 0 ? peers.blk[cm->rank - 1] : nullptr;
+  P2PBlock* blk_hi = cm->rank < cm->nranks - 1 ? peers.blk[cm->rank + 1] : nullptr;
+  double* dots = (double*)cm->local_dots;
+  KT_CHECK_ARG(dots && mine, "kt_p2p_comm: local_dots / comm_block missing");
+  int rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0);
+  if (rc) return rc;
+  ++st.epoch;
+  for (int k = 0; k < 3; ++k) st.halo_k[k] = st.dot_k[k] = 0;
+  const unsigned long long base = st.epoch << 32;
+  auto halo_p = [&]() -> int {
+    if (cm->nranks == 1) return 0;
+    ++st.halo_k[0];
+    k_p2p_halo<T><<<2, 256, 0, h->stream>>>(p, h->pitch, h->row_lo, h->row_hi - 1, (T*)cm->peer_p[0], cm->peer_halo_row[0],
+                                            (T*)cm->peer_p[1], cm->peer_halo_row[1], mine, blk_lo, blk_hi, 0, base | st.halo_k[0], h->sc);
+    KT_LAUNCH_CHECK(h);
+    return 0;
+  };
+  auto reduce = [&](int group, int fin) -> int {
+    ++st.dot_k[group];
+    k_p2p_reduce<<<1, 32, 0, h->stream>>>(peers, cm->rank, cm->nranks, group, 1, dots, fin, base | st.dot_k[group], h->sc, w->history,
+                                          w->history_cap);
+    KT_LAUNCH_CHECK(h);
+    return 0;
+  };
+#define KT_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+  KT_TRY(t_dist_phase<T>(h, 5, coef, b, nullptr, nullptr, r, x, p, dots));
+  KT_TRY(reduce(0, FIN_CG_INIT));
+  KT_TRY(halo_p());
+  auto iter = [&]() -> int {
+    KT_TRY(t_dist_phase<T>(h, 6, coef, p, nullptr, nullptr, Ap, nullptr, nullptr, dots));
+    KT_TRY(reduce(0, FIN_CG_ALPHA));
+    KT_TRY(t_dist_phase<T>(h, 7, coef, p, Ap, nullptr, x, r, nullptr, dots));
+    KT_TRY(reduce(1, FIN_CG_END));
+    KT_TRY(t_dist_phase<T>(h, 8, coef, r, nullptr, nullptr, p, nullptr, nullptr, dots));
+    KT_TRY(halo_p());
+    return 0;
+  };
+#undef KT_TRY
+  rc = run_chunks(h, max_iter, iter);
+  if (rc) return rc;
+  const Scalars& S = *h->sc_host;
+  if (iters) *iters = (long)S.iter;
+  if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
+  if (status) *status = S.status;
+  return 0;
+}
+
 }  // namespace kt
 
 using namespace kt;
@@ -1096,6 +1174,13 @@ int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* 
   KT_CHECK_ARG(h && coef && b && x && ws && comm, "kt_p2p_bicgstab_solve: null argument");
   return KT_DISPATCH(h, t_p2p_bicgstab<double>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status),
                      t_p2p_bicgstab<float>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status));
+}
+
+int kt_p2p_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, const kt_p2p_comm* comm,
+                    double eps, long max_iter, int fixed_iters, long* iters, double* rel_res, int* status) {
+  KT_CHECK_ARG(h && coef && b && x && ws && comm, "kt_p2p_cg_solve: null argument");
+  return KT_DISPATCH(h, t_p2p_cg<double>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status),
+                     t_p2p_cg<float>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status));
 }
 
 int kt_prof_begin(kt_handle_t h, int max_launches) {

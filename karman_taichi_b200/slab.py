@@ -22,6 +22,7 @@ import torch.distributed as dist
 from . import _lib
 
 FIN_NONE, FIN_BICG_INIT, FIN_BICG_ALPHA, FIN_BICG_OMEGA, FIN_BICG_END = 0, 1, 2, 3, 4
+FIN_CG_INIT, FIN_CG_ALPHA, FIN_CG_END = 5, 6, 7
 
 
 class SlabPartition:
@@ -140,6 +141,19 @@ class CudaSlabOps:
     def xr_dots(self):
         self._phase(4, a0=self.p, a1=self.s, a2=self.t, o0=self.x, o1=self.r, o2=self.b)
 
+    # CG phases (cgsolver.py:83-114); Ap lives in the v plane
+    def cg_init(self):
+        self._phase(5, a0=self.b, o0=self.r, o1=self.x, o2=self.p)
+
+    def cg_ap_dot(self):
+        self._phase(6, a0=self.p, o0=self.v)
+
+    def cg_xr_dot(self):
+        self._phase(7, a0=self.p, a1=self.v, o0=self.x, o1=self.r)
+
+    def cg_update_p(self):
+        self._phase(8, a0=self.r, o0=self.p)
+
     def scalar(self, fin):
         _lib.check(self.lib.kt_dist_scalar(self.h, fin, C.c_void_p(self.dots.data_ptr()), None, 0))
 
@@ -185,6 +199,44 @@ class DistBiCGSTAB:
             self._allreduce()
             ops.scalar(FIN_BICG_END)
             ex.exchange(planes['r'])
+            it += 1
+            if not fixed_iters and it % self.poll_every == 0:
+                done, _, _, _ = ops.poll()
+                if done:
+                    break
+        done, self.iterations, self.status, self.rel_res = ops.poll()
+        return self.iterations, self.status
+
+
+class DistCG:
+    """``CGSolver.solve`` (``cgsolver.py:83-114``) over x-slabs: one halo exchange (``p``) and two all-reduces per
+    iteration; same recurrence and stopping test (``sqrt(rTr) < sqrt(rTr0) * eps``, ``:102``)."""
+
+    def __init__(self, ops, exchanger: HaloExchanger, group=None, poll_every=8):
+        self.ops, self.ex, self.group, self.poll_every = ops, exchanger, group, poll_every
+        self.iterations, self.status, self.rel_res = 0, 0, float('nan')
+
+    def _allreduce(self):
+        dist.all_reduce(self.ops.dots, op=dist.ReduceOp.SUM, group=self.group)
+
+    def solve(self, eps=1e-8, max_iter=None, fixed_iters=False):
+        ops, ex = self.ops, self.ex
+        p = ops.planes()['p']
+        ops.begin(-1.0 if fixed_iters else eps, max_iter)
+        ops.cg_init()                       # r = b, x = 0, p = r (beta = 0: cgsolver.py:90)
+        self._allreduce()
+        ops.scalar(FIN_CG_INIT)
+        ex.exchange(p)
+        it = 0
+        while it < max_iter:
+            ops.cg_ap_dot()
+            self._allreduce()
+            ops.scalar(FIN_CG_ALPHA)
+            ops.cg_xr_dot()
+            self._allreduce()
+            ops.scalar(FIN_CG_END)
+            ops.cg_update_p()
+            ex.exchange(p)
             it += 1
             if not fixed_iters and it % self.poll_every == 0:
                 done, _, _, _ = ops.poll()
@@ -309,7 +361,23 @@ class P2PSlabSolver:
         _lib.check(self.lib.kt_p2p_bicgstab_solve(self._hd.h, C.c_void_p(self.coef.ptr), C.c_void_p(self.b.ptr), C.c_void_p(self.x.ptr),
                                                   C.byref(ws), C.byref(self.comm), float(eps), int(max_iter), 1 if fixed_iters else 0,
                                                   C.byref(it), C.byref(rel), C.byref(st)))
+        return self._finish(it, rel, st)
+
+    def _finish(self, it, rel, st):
         self.iterations, self.status, self.rel_res = it.value, st.value, rel.value
         if st.value == 7:
             raise _lib.KtError('x-slab peer-memory solve: a neighbour rank never signalled (KT_STATUS_COMM_TIMEOUT)')
         return self.iterations, self.status
+
+    def solve_cg(self, eps=1e-8, max_iter=None, fixed_iters=False):
+        """``CGSolver.solve`` over the same slabs and peer mappings (``kt_p2p_cg_solve``): Ap lives in the v plane."""
+        self._hd.use_current_stream()
+        ws = _lib.KrylovWs(r=self._r.ptr, p=self._p.ptr, Ap=self._v.ptr, r_tld=None, s=None, t=None, history=None,
+                           history_cap=0, p2=None, Ap2=None)
+        it, rel, st = C.c_long(), C.c_double(), C.c_int()
+        if max_iter is None:
+            max_iter = self.part.NX * self.b.NY
+        _lib.check(self.lib.kt_p2p_cg_solve(self._hd.h, C.c_void_p(self.coef.ptr), C.c_void_p(self.b.ptr), C.c_void_p(self.x.ptr),
+                                            C.byref(ws), C.byref(self.comm), float(eps), int(max_iter), 1 if fixed_iters else 0,
+                                            C.byref(it), C.byref(rel), C.byref(st)))
+        return self._finish(it, rel, st)

@@ -78,6 +78,35 @@ class OracleSlabOps:
         self.dots[0] = float(np.sum(rn * rn))
         self.dots[1] = float(np.sum(rn * self._own(self.b)))
 
+    # ---- CG (cgsolver.py:83-114) ----
+    def cg_init(self):
+        b = torch.from_numpy(self.b)
+        self._own(self.r)[:] = self._own(b)
+        self._own(self.x)[:] = 0.0
+        self._own(self.p)[:] = self._own(b)
+        self.dots[0] = float(np.sum(self._own(self.b) * self._own(self.b)))
+        self.dots[1] = 0.0
+
+    def cg_ap_dot(self):
+        if self.sc['done']:
+            return
+        self._own(self.v)[:] = torch.from_numpy(self._spmv_owned(self.p))
+        self.dots[0] = float(np.sum(self._own(self.p).numpy() * self._own(self.v).numpy()))
+
+    def cg_xr_dot(self):
+        if self.sc['done']:
+            return
+        a = self.sc['alpha']
+        self._own(self.x)[:] = self._own(self.x) + a * self._own(self.p)
+        self._own(self.r)[:] = self._own(self.r) - a * self._own(self.v)
+        rn = self._own(self.r).numpy()
+        self.dots[0] = float(np.sum(rn * rn))
+
+    def cg_update_p(self):
+        if self.sc['done']:
+            return
+        self._own(self.p)[:] = self._own(self.r) + self.sc['beta'] * self._own(self.p)
+
     def scalar(self, fin):
         sc = self.sc
         if sc['done']:
@@ -114,6 +143,26 @@ class OracleSlabOps:
                 sc['status'], sc['done'] = 2, True
                 return
             sc['beta'] = (sc['rho'] / sc['rho_1']) * (sc['alpha'] / sc['omega'])
+
+        elif fin == 5:    # FIN_CG_INIT
+            sc['rTr0'] = sc['rTr'] = sc['old_rTr'] = d0
+            if sc['max_iter'] <= 0:
+                sc['status'], sc['done'] = 1, True
+        elif fin == 6:    # FIN_CG_ALPHA
+            if d0 == 0.0:
+                sc['status'], sc['done'] = 3, True
+            else:
+                sc['alpha'] = sc['old_rTr'] / d0
+        elif fin == 7:    # FIN_CG_END
+            sc['rTr'] = d0
+            sc['iter'] += 1
+            if math.sqrt(d0) < math.sqrt(sc['rTr0']) * sc['eps']:
+                sc['status'], sc['done'] = 0, True
+                return
+            sc['beta'] = d0 / sc['old_rTr']
+            sc['old_rTr'] = d0
+            if sc['iter'] >= sc['max_iter']:
+                sc['status'], sc['done'] = 1, True
 
     def poll(self):
         sc = self.sc

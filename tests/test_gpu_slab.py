@@ -87,6 +87,56 @@ def test_emulated_slabs_single_gpu(cuda, P, case):
     assert rel_l2(x, fx.to_numpy()) < 1e-8
 
 
+@pytest.mark.parametrize('P,n,offset', [(2, 96, 0.1), (3, 61, 0.0), (5, 130, 0.1)])
+def test_emulated_slabs_cg_single_gpu(cuda, P, n, offset):
+    """CGSolver.solve (cgsolver.py:83-114) over P virtual ranks on one device: phases 5-8 of kt_dist_bicg_phase."""
+    import karman_taichi_b200 as kt
+    from karman_taichi_b200.slab import CudaSlabOps, SlabPartition
+    coef, rhs = krylov.poisson_sin_system(n, offset)
+    eps = 1e-10
+    x_ref, it_ref, st_ref = krylov.cg_solve(coef, rhs, eps=eps)
+    part = SlabPartition(rhs.shape[0], P)
+    ranks = []
+    for r in range(P):
+        c_l = np.ascontiguousarray(part.scatter(coef, r))
+        b_l = np.ascontiguousarray(part.scatter(rhs, r))
+        ranks.append(CudaSlabOps(kt.Field(c_l.shape, np.float64, cuda).from_numpy(c_l), kt.Field(b_l.shape, np.float64, cuda).from_numpy(b_l),
+                                 kt.Field(b_l.shape, np.float64, cuda), part, r))
+
+    def exchange_p():
+        for r in range(P - 1):
+            lo, up = ranks[r].planes()['p'], ranks[r + 1].planes()['p']
+            _, l1r = part.local_owned(r)
+            l0u, _ = part.local_owned(r + 1)
+            lo[l1r].copy_(up[l0u])
+            up[l0u - 1].copy_(lo[l1r - 1])
+
+    def step(fn, fin=None):
+        for o in ranks:
+            getattr(o, fn)()
+        if fin is not None:
+            tot = sum(o.dots for o in ranks)
+            for o in ranks:
+                o.dots.copy_(tot)
+                o.scalar(fin)
+
+    for o in ranks:
+        o.begin(eps, rhs.size)
+    step('cg_init', 5); exchange_p()
+    for it in range(rhs.size):
+        step('cg_ap_dot', 6)
+        step('cg_xr_dot', 7)
+        step('cg_update_p'); exchange_p()
+        polls = [o.poll() for o in ranks]
+        assert len({(p[0], p[1], p[2]) for p in polls}) == 1
+        if polls[0][0]:
+            break
+    done, iters, status, rel = polls[0]
+    assert status == st_ref == 0 and abs(iters - it_ref) <= 1
+    x = np.concatenate([part.owned_of_local(o.x.to_numpy(), r) for r, o in enumerate(ranks)], axis=0)
+    assert rel_l2(x, x_ref) < 1e-8
+
+
 def _nccl_worker(rank, world, port, out_dir):
     import torch
     import torch.distributed as dist
@@ -119,6 +169,13 @@ def _nccl_worker(rank, world, port, out_dir):
             it2, st2 = p2p.solve(eps=1e-10, max_iter=rhs.size)
         np.save(os.path.join(out_dir, f'xp_{rank}.npy'), part.owned_of_local(fx2.to_numpy(), rank))
         np.save(os.path.join(out_dir, f'metap_{rank}.npy'), np.array([it2, st2]))
+        # CG over the same slabs: NCCL driver, then the peer-memory kernel path
+        from karman_taichi_b200.slab import DistCG
+        itc, stc = DistCG(ops, HaloExchanger(part, rank), poll_every=4).solve(eps=1e-10, max_iter=rhs.size)
+        np.save(os.path.join(out_dir, f'xc_{rank}.npy'), part.owned_of_local(fx.to_numpy(), rank))
+        itc2, stc2 = p2p.solve_cg(eps=1e-10, max_iter=rhs.size)
+        np.save(os.path.join(out_dir, f'xcp_{rank}.npy'), part.owned_of_local(fx2.to_numpy(), rank))
+        np.save(os.path.join(out_dir, f'metac_{rank}.npy'), np.array([itc, stc, itc2, stc2]))
     finally:
         dist.destroy_process_group()
 
@@ -146,6 +203,13 @@ def test_two_gpu_nccl(cuda, tmp_path):
     # same kernels, same rank-ordered sums as the NCCL path would give with a rank-ordered all-reduce
     assert abs(int(mp_[0][0]) - it_ref) <= max(3, round(0.1 * it_ref))
     assert rel_l2(xp, x_ref) < 1e-8
+    xc_ref, itc_ref, _ = krylov.cg_solve(coef, rhs, eps=1e-10)
+    mc = [np.load(tmp_path / f'metac_{r}.npy') for r in range(world)]
+    assert all(int(m[1]) == 0 and int(m[3]) == 0 for m in mc) and len({(int(m[0]), int(m[2])) for m in mc}) == 1
+    assert abs(int(mc[0][0]) - itc_ref) <= 1 and abs(int(mc[0][2]) - itc_ref) <= 1
+    for tag in ('xc', 'xcp'):
+        xc = np.concatenate([np.load(tmp_path / f'{tag}_{r}.npy') for r in range(world)], axis=0)
+        assert rel_l2(xc, xc_ref) < 1e-8
 
 
 def test_p2p_single_rank(cuda):
@@ -167,3 +231,13 @@ def test_p2p_single_rank(cuda):
     ref.cluster = False
     ref.solve(eps=1e-10)
     assert ref.iterations == it          # identical kernels, identical sums: identical count
+    # CG through kt_p2p_cg_solve
+    coef, rhs = krylov.poisson_sin_system(150, 0.1)
+    xc_ref, itc_ref, _ = krylov.cg_solve(coef, rhs, eps=1e-10)
+    fc = kt.Field(coef.shape, np.float64, cuda).from_numpy(coef)
+    fb = kt.Field(rhs.shape, np.float64, cuda).from_numpy(rhs)
+    fx = kt.Field(rhs.shape, np.float64, cuda)
+    s = P2PSlabSolver(fc, fb, fx, SlabPartition(rhs.shape[0], 1), 0)
+    it, st = s.solve_cg(eps=1e-10, max_iter=rhs.size)
+    assert st == 0 and abs(it - itc_ref) <= 1
+    assert rel_l2(fx.to_numpy(), xc_ref) < 1e-8

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
-from karman_taichi_b200.slab import DistBiCGSTAB, HaloExchanger, SlabPartition  # noqa: E402
+from karman_taichi_b200.slab import DistBiCGSTAB, DistCG, HaloExchanger, SlabPartition  # noqa: E402
 from oracle import krylov  # noqa: E402
 
 
@@ -52,7 +52,7 @@ def _worker(rank, world, port, case, out_dir):
     try:
         from slab_cpu_ops import OracleSlabOps
         kind, a, b, eps = case
-        coef, rhs = krylov.poisson_sin_system(a, b) if kind == 'poisson' else krylov.random_dd_system(a, b, seed=0)
+        coef, rhs = krylov.poisson_sin_system(a, b) if kind.startswith('poisson') else krylov.random_dd_system(a, b, seed=0)
         part = SlabPartition(rhs.shape[0], world)
         l0, l1 = part.local_owned(rank)
         coef_l = np.ascontiguousarray(part.scatter(coef, rank))
@@ -69,7 +69,7 @@ def _worker(rank, world, port, case, out_dir):
             plane[l1:] = -1.0
         ex.exchange(plane)
         assert torch.equal(plane, ref)
-        solver = DistBiCGSTAB(ops, ex, poll_every=4)
+        solver = (DistCG if kind == 'poisson-cg' else DistBiCGSTAB)(ops, ex, poll_every=4)
         iters, status = solver.solve(eps=eps, max_iter=rhs.size)
         x_own = part.owned_of_local(ops.x.numpy(), rank)
         np.save(os.path.join(out_dir, f'x_{rank}.npy'), x_own)
@@ -79,13 +79,14 @@ def _worker(rank, world, port, case, out_dir):
 
 
 @pytest.mark.parametrize('world,case', [(2, ('poisson', 48, 0.1, 1e-10)), (2, ('random', 37, 29, 1e-10)),
-                                        (3, ('random', 20, 31, 1e-9))])
+                                        (3, ('random', 20, 31, 1e-9)), (2, ('poisson-cg', 40, 0.1, 1e-10)),
+                                        (3, ('poisson-cg', 23, 0.0, 1e-9))])
 def test_slab_bicgstab_matches_global_oracle(tmp_path, world, case):
     port = free_port()
     mp.spawn(_worker, args=(world, port, case, str(tmp_path)), nprocs=world, join=True)
     kind, a, b, eps = case
-    coef, rhs = krylov.poisson_sin_system(a, b) if kind == 'poisson' else krylov.random_dd_system(a, b, seed=0)
-    x_ref, it_ref, st_ref = krylov.bicgstab_solve(coef, rhs, eps=eps)
+    coef, rhs = krylov.poisson_sin_system(a, b) if kind.startswith('poisson') else krylov.random_dd_system(a, b, seed=0)
+    x_ref, it_ref, st_ref = (krylov.cg_solve if kind == 'poisson-cg' else krylov.bicgstab_solve)(coef, rhs, eps=eps)
     x = np.concatenate([np.load(tmp_path / f'x_{r}.npy') for r in range(world)], axis=0)
     metas = [np.load(tmp_path / f'meta_{r}.npy') for r in range(world)]
     assert all(int(m[1]) == st_ref == 0 for m in metas)
