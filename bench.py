@@ -10,6 +10,9 @@ count is exact) on synthetic inputs.  Default workload at every N: ``pcor32768``
 it fits one B200: 103 GB).  N > 1 splits the same grid into x-slabs (strong scaling), one rank per GPU under torchrun,
 halo rows over NCCL send/recv and the inner products over NCCL all-reduce.
 
+``--workload cavity128 | karman320 | karman16384`` measures the other half of BASELINE.json's metric instead, SIMPLE
+outer-iterations/s on configs 2, 1 and 4 (one step = one outer iteration through SIMPLESolver / KarmanSolver).
+
 One JSON line on stdout (rank 0): value (inputs resident in HBM), e2e (host buffers in the reference layout through
 the C ABI, H2D/D2H inside the timed region), roofline (dominant kernel, timed live with CUDA events), cpu_baseline
 (the oracle's C/OpenMP port of the reference algorithm on this box's host cores), clocks, gpu_launches.
@@ -41,6 +44,16 @@ WORKLOADS = {
     'pcor4096': (4096, 'BASELINE config 3: standalone 4096x4096 pressure-correction BiCGSTAB'),
     'pcor1024': (1024, 'development size'),
 }
+SIMPLE_WORKLOADS = {
+    # name: (case, nx, ny, Krylov cap per solve (0 = none), description) -- the other half of BASELINE.json's metric
+    'cavity128': ('cavity', 128, 128, 0, 'BASELINE config 2: lid-driven cavity 128x128, Re=100, SIMPLE (bicgsimp.py), alpha_p = 0.02 '
+                                         '(the committed 0.1 diverges at 128^2: SURVEY.md 8d)'),
+    'karman320': ('karman', 320, 64, 0, 'BASELINE config 1: 320x64 channel + square-cell cylinder, SIMPLE sub-iterations (karman_taichi.py)'),
+    'karman16384': ('karman', 16384, 3276, 200, 'BASELINE config 4: channel scaled to 16384x3276, full SIMPLE sub-iterations, '
+                                                'BiCGSTAB capped at 200 iterations per solve'),
+}
+SIMPLE_METRIC = 'simple_outer_iters_per_s'
+SIMPLE_UNIT = 'outer-iters/s'
 METRIC = 'bicgstab_mcell_iters_per_s'
 UNIT = 'Mcell-iters/s'
 BYTES_PER_CELL_ITER = 28 * 8            # BiCGSTAB algorithmic traffic, f64
@@ -422,13 +435,220 @@ def run_e2e(a, kt, _lib, lib, torch, dist, world, rank, dev, n, g0, g1, coef, b,
             'call': 'kt_upload_coef + kt_upload_field + BICGSolver.solve + kt_download_field (= kt_bicgstab_solve_host) on pinned host buffers'}
 
 
+# ---------------------------------------------------------------------------------------------------------
+# SIMPLE outer-iterations / s (BASELINE configs 1, 2, 4): --workload cavity128 | karman320 | karman16384
+# ---------------------------------------------------------------------------------------------------------
+def simple_oracle_rate(case, nx, ny, cap, steps):
+    """The NumPy oracle (oracle/simple.py, oracle/karman.py) timed on the host: outer iterations / s on a bounded
+    sample.  Returns (rate scaled to the workload's grid, description)."""
+    cells = nx * ny
+    if case == 'cavity':
+        from oracle.simple import SimpleOracle
+        o = SimpleOracle(1.0, 1.0, nx, ny)
+        o.bc['n'][1] = 1.0
+        o.alpha_p = 0.02
+        o.init()
+        o.step()
+        t = time.perf_counter()
+        for _ in range(steps):
+            o.step()
+        dt = time.perf_counter() - t
+        return steps / dt, f'{steps} outer iterations of the same {nx}x{ny} cavity, NumPy restatement of bicgsimp.py (1 thread)'
+    from oracle.karman import KarmanOracle
+    sx, sy = (nx, ny) if cells <= 1 << 20 else (1024, 204)
+    cyl = (64, 32, 144) if (sx, sy) == (320, 64) else (sx // 5, sy // 2, int(round((0.1875 * sy) ** 2)))
+    o = KarmanOracle(nx=sx, ny=sy, cyl=cyl, dt=1e-5 * 320 / sx)
+    if cap:
+        o.max_iter = cap
+    o.init()
+    o.sub_iteration(1e-8)
+    t = time.perf_counter()
+    for _ in range(steps):
+        o.sub_iteration(1e-8)
+    dt = time.perf_counter() - t
+    scale = (sx * sy) / cells
+    what = f'{steps} sub-iterations of the {sx}x{sy} channel' + ('' if scale == 1 else f' (same geometry and Krylov cap; rate scaled by the cell ratio {scale:.3e})')
+    return steps / dt * scale, what + ', NumPy restatement of karman_taichi.py (1 thread)'
+
+
+def run_simple_reference(a):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return 0
+    case, nx, ny, cap, desc = SIMPLE_WORKLOADS[a.workload]
+    k = max(1, min(a.steps, 5))
+    val, sample = simple_oracle_rate(case, nx, ny, cap, k)
+    line = {'impl': 'reference', 'metric': SIMPLE_METRIC, 'value': val, 'unit': SIMPLE_UNIT, 'n_gpus': a.gpus, 'steps': k, 'warmup': 1,
+            'ms_per_step': 1e3 / val, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': a.workload, 'description': desc, 'cpu_sample': sample},
+            'cpu_baseline': {'value': val, 'unit': SIMPLE_UNIT, 'cores': 1, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': val, 'unit': SIMPLE_UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'note': 'Taichi ti.cpu itself cannot run offline; NumPy restatement of the reference (oracle/)'}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_simple(a):
+    """One step = one SIMPLE outer iteration (bicgsimp.py:313-317) / sub-iteration (karman_taichi.py:633-652) through the
+    reference-facing classes.  Not sharded (BASELINE configs 1, 2, 4 are single-GPU): N > 1 runs N replicas."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if a.gpus > 1 and world == 1:
+        port = 29500 + (os.getpid() % 2000)
+        return subprocess.call([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={a.gpus}', '--master-addr',
+                                '127.0.0.1', '--master-port', str(port), os.path.abspath(__file__)] + sys.argv[1:])
+    assert torch.cuda.is_available(), 'bench.py needs CUDA (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import karman_taichi_b200 as kt
+    from karman_taichi_b200 import _lib
+    from karman_taichi_b200.cgsolver import _Handle
+    lib = _lib.load()
+    case, nx, ny, cap, desc = SIMPLE_WORKLOADS[a.workload]
+    cells = nx * ny
+    if case == 'cavity':
+        s = kt.lid_driven_cavity(nx, device=dev)
+        s.alpha_p = 0.02
+        s.init()
+        s._make_solvers()
+        solvers = {'u': s.u_momentum_solver, 'v': s.v_momentum_solver, 'p': s.p_correction_solver}
+        step = s.step
+        its = lambda: s.log[-1][2]
+        words = {'u': 28, 'v': 28, 'p': 16}           # SURVEY.md 8(d): BiCGSTAB 28 N, CG 16 N words per iteration
+    else:
+        cyl = (64, 32, 144) if (nx, ny) == (320, 64) else (nx // 5, ny // 2, int(round((0.1875 * ny) ** 2)))
+        s = kt.KarmanSolver(nx=nx, ny=ny, cyl=cyl, dt=1e-5 * 320 / nx, device=dev)
+        s.init()
+        solvers = {'u': s.u_solver, 'v': s.v_solver, 'p': s.p_solver}
+        step = s.sub_iteration
+        its = lambda: dict(s.last_iters)
+        words = {'u': 31, 'v': 31, 'p': 31}           # Jacobi-preconditioned BiCGSTAB: 31 N words per iteration
+    if cap:
+        for sol in solvers.values():
+            sol.max_steps = cap
+    handles = [s._hd] + [sol._hd for sol in solvers.values()]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(range(world))
+    if rank == 0:
+        sampler.start()
+    hp = solvers['p']._hd
+    _lib.check(lib.kt_prof_begin(hp.h, 4 * (cap or 4096) * a.steps + 64))
+    l0 = sum(h.launch_count() for h in handles)
+    tot_its = {'u': 0, 'v': 0, 'p': 0}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+        for k, v in its().items():
+            tot_its[k] += v
+    e1.record()
+    barrier()
+    ms_total = allmax(e0.elapsed_time(e1))
+    launches = (sum(h.launch_count() for h in handles) - l0) * world
+    tot = (C.c_double * 8)()
+    cnt = (C.c_long * 8)()
+    _lib.check(lib.kt_prof_end(hp.h, tot, cnt, 8))
+    clocks = sampler.stop() if rank == 0 else None
+    value = a.steps * world / (ms_total * 1e-3)
+
+    # roofline: whole-step algorithmic bytes (SURVEY.md 8d: ~51 N words of assembly / BC / relaxation / correction per outer
+    # iteration + the Krylov iterations actually run); the dominant kernel class of the p' solve when it streams from HBM
+    peak, peak_kind = peaks()
+    N = (nx + 2) * (ny + 2)
+    step_bytes = 8.0 * N * (51 * a.steps + sum(words[k] * tot_its[k] for k in words))
+    achieved = step_bytes / (ms_total * 1e-3) / 1e9
+    streamed = sum(cnt[i] for i in range(4)) > 0
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_kind': peak_kind, 'traffic': None,
+                'kernel': 'whole SIMPLE step: algorithmic bytes of assembly + Krylov iterations actually run / step time',
+                'krylov_iterations_per_step': {k: v / a.steps for k, v in tot_its.items()}, 'krylov_cap': cap,
+                'krylov_mcell_iters_per_s': cells * sum(tot_its.values()) / (ms_total * 1e-3) / 1e6}
+    if streamed:
+        names = {0: ('p_update', 4), 1: ('v=A M^-1 p + dot', 9), 2: ('t=A M^-1 s + 2 dots', 9), 3: ('x,r + 2 dots', 9)}
+        dom = max(range(4), key=lambda i: tot[i])
+        d_ms = tot[dom] / max(cnt[dom], 1)
+        roofline['dominant_kernel'] = {'name': names[dom][0], 'words': names[dom][1], 'ms_per_launch': d_ms,
+                                       'achieved': names[dom][1] * 8.0 * N / (d_ms * 1e-3) / 1e9,
+                                       'frac': names[dom][1] * 8.0 * N / (d_ms * 1e-3) / 1e9 / peak,
+                                       'share_of_step': {names[i][0]: tot[i] / ms_total for i in range(4)}}
+    else:
+        roofline['note'] = ('all planes of a solve fit the shared memory of one thread-block cluster: the Krylov solves run as ONE '
+                            'cluster-resident kernel each (csrc/kt_cluster.cu) and are bound by barrier latency, not by HBM')
+
+    # e2e: u, v, p arrive in pinned host arrays and go back every step (kt_upload_field / kt_download_field)
+    e2e = None
+    if not a.no_e2e:
+        fields = [s.u, s.v, s.p]
+        hs = [_Handle(f) for f in fields]
+        host = [torch.from_numpy(f.to_numpy()).pin_memory() for f in fields]
+        P = lambda t: C.c_void_p(t.data_ptr())
+
+        def e2e_step():
+            for f, h, t in zip(fields, hs, host):
+                h.use_current_stream()
+                _lib.check(lib.kt_upload_field(h.h, C.c_void_p(f.ptr), P(t)))
+            step()
+            for f, h, t in zip(fields, hs, host):
+                _lib.check(lib.kt_download_field(h.h, P(t), C.c_void_p(f.ptr)))
+        k_e = max(1, min(a.steps, 5))
+        e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(k_e):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms = allmax(e0.elapsed_time(e1))
+        nbytes = sum(t.numel() * 8 for t in host) * world
+        e2e = {'value': k_e * world / (ms * 1e-3), 'unit': SIMPLE_UNIT, 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': nbytes,
+               'steps': k_e, 'ms_per_step': ms / k_e,
+               'call': 'kt_upload_field(u, v, p) + SIMPLESolver.step / KarmanSolver.sub_iteration + kt_download_field(u, v, p) on pinned host buffers'}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, sample = simple_oracle_rate(case, nx, ny, cap, 3)
+        cpu = {'value': v, 'unit': SIMPLE_UNIT, 'cores': 1, 'kind': 'port', 'sample': sample}
+    if rank == 0:
+        line = {'metric': SIMPLE_METRIC, 'value': value, 'unit': SIMPLE_UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+                'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'data': 'synthetic',
+                'config': {'workload': a.workload, 'description': desc, 'grid': [nx, ny],
+                           'parallelism': 'single GPU' if world == 1 else f'{world} independent replicas (the SIMPLE configs are not sharded)',
+                           'cache': ('working set >> 126 MB L2' if cells > 1 << 22 else
+                                     'working set resident in shared memory / L2 by design (reference-sized grid); inputs change every step')},
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='pcor32768', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='pcor32768', choices=sorted(WORKLOADS) + sorted(SIMPLE_WORKLOADS))
     ap.add_argument('--iters', type=int, default=50, help='BiCGSTAB iterations per step')
     ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'],
                     help='N > 1: halo exchange + all-reduce inside the library over NVLink peer memory (p2p) or via NCCL')
@@ -437,6 +657,8 @@ def main():
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == 'ours':
         a.warmup = 3                                   # timing rules: W >= 3
+    if a.workload in SIMPLE_WORKLOADS:
+        sys.exit(run_simple_reference(a) if a.impl == 'reference' else run_simple(a))
     sys.exit(run_reference(a) if a.impl == 'reference' else run_ours(a))
 
 

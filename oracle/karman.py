@@ -172,7 +172,7 @@ class KarmanOracle:
         self.M_p[ic, jc] = M
 
     def _solve(self, which, coef, M, b, x, eps, n):
-        xs, it, st = krylov.jacobi_bicgstab(coef, M, b, x, eps=eps, n=n)
+        xs, it, st = krylov.jacobi_bicgstab(coef, M, b, x, eps=eps, n=n, max_iter=getattr(self, 'max_iter', None))
         x[:] = xs
         self.last_iters[which], self.last_status[which] = it, st
 
