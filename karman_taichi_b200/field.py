@@ -36,6 +36,8 @@ class Field:
         shape = tuple(int(s) for s in shape)
         if len(shape) not in (2, 3) or (len(shape) == 3 and shape[2] != 5):
             raise ValueError('Field shape must be (NX, NY) or (NX, NY, 5)')
+        if shape[0] < 1 or shape[1] < 1:
+            raise ValueError(f'Field shape {shape}: NX and NY must be at least 1 (an empty field has nothing to solve)')
         self.shape = shape
         self.np_dtype = np.dtype(dtype)
         self.dtype = _TORCH[self.np_dtype]

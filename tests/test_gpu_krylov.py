@@ -404,3 +404,58 @@ def test_stepwise_reference_loop_matches_solve(cuda):
     np.testing.assert_array_equal(c2.coef.to_numpy(), coef * 2.0)
     np.testing.assert_array_equal(c2.b.to_numpy(), rhs * 3.0)
     assert c2.check_solution() >= 0.0
+
+
+@pytest.mark.parametrize('shape', [(1, 1), (1, 9), (9, 1), (2, 3), (3, 2), (2, 129), (129, 2)])
+@pytest.mark.parametrize('cluster', [True, False])
+def test_degenerate_shapes(cuda, shape, cluster):
+    """Arrays with no ghost ring at all and as small as one element: every neighbour that leaves the array contributes 0
+    (cgsolver.py:56-60 reads it and multiplies by a never-written coefficient); SpMV bit-exact, both solvers converge."""
+    import karman_taichi_b200 as kt
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    coef = -rng.random(shape + (5,))
+    coef[..., 0] = -coef[..., 1:].sum(axis=-1) + 0.5          # diagonally dominant, non-symmetric
+    b = rng.random(shape)
+    s = make(cuda, coef, b, kt.BICGSolver)
+    s.cluster = cluster
+    s.p.from_numpy(b)
+    s.compute_Ap()
+    np.testing.assert_array_equal(s.Ap.to_numpy(), krylov.spmv(coef, b))
+    try:
+        x_ref, it_ref, st_ref = krylov.bicgstab_solve(coef, b, eps=1e-10)
+    except ZeroDivisionError:
+        # e.g. the 1 x 1 system: s = r - alpha v vanishes exactly in the first iteration and the reference divides
+        # (t,s) by (t,t) = 0 in Python (bicgsolver.py:118); the drop-in must raise the same exception
+        with pytest.raises(ZeroDivisionError):
+            s.solve(eps=1e-10)
+    else:
+        s.solve(eps=1e-10)
+        assert s.status == st_ref == 0 and abs(s.iterations - it_ref) <= max(3, round(0.1 * it_ref))
+        assert rel_l2(s.x.to_numpy(), x_ref) < 1e-8
+    # symmetric positive definite variant for CG
+    sym = np.zeros(shape + (5,))
+    sym[..., 0] = 4.5
+    sym[..., 1:] = -1.0
+    c = make(cuda, sym, b, kt.CGSolver)
+    c.cluster = cluster
+    try:
+        xc_ref, itc_ref, stc_ref = krylov.cg_solve(sym, b, eps=1e-10)
+    except ZeroDivisionError:
+        with pytest.raises(ZeroDivisionError):
+            c.solve(eps=1e-10)
+    else:
+        c.solve(eps=1e-10)
+        assert c.status == stc_ref == 0 and abs(c.iterations - itc_ref) <= 1
+        assert rel_l2(c.x.to_numpy(), xc_ref) < 1e-8
+
+
+def test_empty_and_mismatched_inputs_raise(cuda):
+    import karman_taichi_b200 as kt
+    with pytest.raises((ValueError, kt.KtError)):
+        kt.Field((0, 5), np.float64, cuda)
+    fc = kt.Field((6, 7, 5), np.float64, cuda)
+    fb = kt.Field((6, 7), np.float64, cuda)
+    with pytest.raises((ValueError, TypeError)):
+        kt.BICGSolver(fc, fb, kt.Field((7, 6), np.float64, cuda))       # x of the wrong shape
+    with pytest.raises((ValueError, TypeError)):
+        kt.CGSolver(fb, fb, fb)                                         # coef without the 5-plane axis
