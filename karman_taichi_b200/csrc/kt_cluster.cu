@@ -2,20 +2,29 @@
 //
 // The reference's own grids are small (cavity 30^2..128^2, Karman 320x64): ~2e4 unknowns.  At that size an iteration
 // of the streaming path is four kernel launches of a few microseconds each and the solve is launch-latency bound
-// (26-37 us per Krylov iteration measured, profiles/r01_simple_rates.txt).  Here the whole solve is one launch: a
+// (26-37 us per Krylov iteration measured, profiles/r01_simple_rates.md).  Here the whole solve is one launch: a
 // cluster of up to 16 CTAs holds every plane (5 coefficients, b, x, r, p, v, s, t [, 1/M, r~]) in its shared memory
-// (16 x 227 KB), each CTA owning a contiguous block of rows; halo rows of the stencil operand are read straight out of
-// the neighbour CTA's shared memory (DSMEM), inner products are block-reduced, exchanged through DSMEM and summed by
-// every CTA in rank order (deterministic, identical on all CTAs), and the phases of an iteration are separated by
-// hardware cluster barriers instead of kernel boundaries.  Same recurrence, same operation order per element, same
+// (16 x 227 KB), each CTA owning a contiguous block of rows.  Same recurrence, same operation order per element, same
 // scalar algebra (kt::scalar_algebra) as the streaming kernels.
 //
-// BiCGSTAB per iteration (bicgsolver.py:94-135 / karman_taichi.py:383-456): 4 cluster barriers
-//   P1 p = r + beta (p - omega v)                                 | barrier (neighbours read p)
-//   P2 v = A p^ ; (r~, v)                                         | barrier -> alpha
-//   P3 t = A s^ with s = r - alpha v (halo rows recomputed from the neighbour's r, v) ; (t,s), (t,t) | barrier -> omega
-//   P4 x += alpha p^ + omega s^ ; r = s - omega t ; (r,r), (r,r~) | barrier -> test, rho, beta
-// CG per iteration (cgsolver.py:92-114): 3 barriers (Ap,(p,Ap) | x,r,(r,r) | p = r + beta p).
+// All traffic between CTAs is PUSHED with st.async (DSMEM store that signals an mbarrier in the destination CTA with its
+// byte count) -- there is no cluster barrier and no remote load inside the iteration (measured, profiles/
+// r01_simple_rates.md: a cluster barrier that has to release 16 remote stores costs ~1000 cycles, a remote load ~215,
+// an mbarrier wake-up ~60):
+//   * halo rows: the thread that produces an element of a boundary row of p, v or r also stores it into the
+//     neighbour's private halo row; the neighbour waits on that plane's halo mbarrier right before its first use;
+//   * inner products: block tree -> lanes 0..C-1 of warp 0 st.async the block's (d0, d1) into slot [rank] of every CTA
+//     and signal that CTA's sum mbarrier; every CTA waits for C x 16 bytes and adds the C slots with a fixed tree, so
+//     all CTAs, warps and threads hold the identical bits and run the scalar algebra redundantly.
+// Every CTA needs every other CTA's contribution to pass a sum, so a sum is also a full synchronisation point; the
+// write-after-read safety of the halo rows and slots follows from that (see the comments at the pushes).
+//
+// BiCGSTAB per iteration (bicgsolver.py:94-135 / karman_taichi.py:383-456):
+//   P1 p = r + beta (p - omega v), boundary rows pushed            | wait p halo
+//   P2 v = A p^ ; (r~, v), boundary rows of v pushed               | sum -> alpha
+//   P3 t = A s^ with s = r - alpha v (halo rows from the r, v halos) ; (t,s), (t,t) | sum -> omega
+//   P4 x += alpha p^ + omega s^ ; r = s - omega t, boundary rows pushed ; (r,r), (r,r~) | sum -> test, rho, beta
+// CG per iteration (cgsolver.py:92-114): Ap,(p,Ap) | sum | x,r,(r,r) | sum | p = r + beta p, boundary rows pushed.
 #include <cooperative_groups.h>
 #include "kt_handle.h"
 
@@ -33,10 +42,69 @@ template <typename T> struct ClArgs {
 
 constexpr int CL_THREADS = 512;
 
-struct ClShared {           // per-CTA control block at the start of dynamic shared memory
-  double part[3][2][16];    // [dot group][value][source rank]: every CTA PUSHES its block sums into all CTAs' slots
+// -DKT_CLUSTER_PROF (tools/cluster_prof.py builds that variant): thread 0 of CTA 0 accumulates clock64() ticks per
+// segment of an iteration into g_clprof; compiled out of the shipped library.
+#ifdef KT_CLUSTER_PROF
+__device__ long long g_clprof[16];
+struct ClProf { long long acc[16]; long long t; };     // per-thread registers; dumped once at the end of the kernel
+#define CLP_DECL ClProf clp; for (int k_ = 0; k_ < 16; ++k_) clp.acc[k_] = 0; clp.t = clock64();
+#define CLP(k) do { const long long t_ = clock64(); clp.acc[k] += t_ - clp.t; clp.t = t_; } while (0)
+#define CLP_ARGS , ClProf& clp
+#define CLP_PASS , clp
+#define CLP_DUMP do { if (blockIdx.x == 0 && threadIdx.x == 0) for (int k_ = 0; k_ < 16; ++k_) g_clprof[k_] += clp.acc[k_]; } while (0)
+#else
+#define CLP_DECL
+#define CLP(k) do { } while (0)
+#define CLP_ARGS
+#define CLP_PASS
+#define CLP_DUMP do { } while (0)
+#endif
+
+enum { HALO_P = 0, HALO_V = 1, HALO_R = 2 };
+
+struct ClShared {                    // per-CTA control block at the start of dynamic shared memory
+  double part[3][16][2];             // [dot group][source rank][d0, d1]: 16-byte slots filled by st.async.v2
+  unsigned long long mbar_sum[3];    // one mbarrier per dot group: completes when nranks x 16 bytes have landed
+  unsigned long long mbar_halo[3];   // p / v / r halo rows: completes when both neighbours' rows have landed
   double red[2][CL_THREADS / 32];
 };
+
+// ---- PTX helpers: shared::cluster addresses, mbarrier, st.async --------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned cta_rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// Bounded wait: a peer that never signals (a bug, not a data condition) traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    if (ok) break;
+    if (clock64() - t0 > (1ll << 32)) __trap();
+  }
+}
+__device__ __forceinline__ void st_async(unsigned remote_addr, double v, unsigned remote_mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void st_async(unsigned remote_addr, float v, unsigned remote_mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_mbar) : "memory");
+}
+__device__ __forceinline__ void st_async2(unsigned remote_addr, double a, double b, unsigned remote_mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
+               ::"r"(remote_addr), "l"(__double_as_longlong(a)), "l"(__double_as_longlong(b)), "r"(remote_mbar) : "memory");
+}
 
 // 16-lane fixed-shape tree: every lane of the warp ends up with v[0] + ... + v[15] (lanes >= 16 mirror lane - 16).
 __device__ __forceinline__ double tree16(double v) {
@@ -46,32 +114,33 @@ __device__ __forceinline__ double tree16(double v) {
 }
 
 // fixed-order cluster-wide sum of up to two values.  Warp shuffle tree -> one value per warp in shared memory ->
-// warp 0 adds the (16) warp sums with a fixed tree and its lanes 0..C-1 store the block sum into slot [rank] of EVERY
-// CTA (remote DSMEM stores, fire and forget) -> cluster barrier (release / acquire) -> every warp adds the C slots of
-// its own CTA with the same fixed tree.  Identical bits on every CTA, warp and thread; no serial chain, no remote load
-// after the barrier.
-template <int NDOT>
-__device__ __forceinline__ void cluster_sum(cg::cluster_group& cl, ClShared* S, int group, double& d0, double& d1, int nranks,
-                                            int rank) {
+// warp 0 adds the (16) warp sums with a fixed tree; its lanes 0..C-1 st.async the pair into slot [rank] of CTA `lane`
+// (signalling that CTA's mbarrier with 16 bytes) -> every thread waits on its own CTA's mbarrier (C x 16 bytes) ->
+// every warp adds the C slots with the same fixed tree.  Identical bits on every CTA, warp and thread.
+// `use` counts the completed uses of this group's mbarrier (phase parity = use & 1).
+__device__ __forceinline__ void cluster_sum(ClShared* S, int group, unsigned use, double& d0, double& d1, int nranks, int rank CLP_ARGS) {
   static_assert(CL_THREADS / 32 == 16, "tree16 assumes 16 warps per CTA");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   d0 = warp_sum(d0);
-  if (NDOT > 1) d1 = warp_sum(d1);
-  if (lane == 0) { S->red[0][wid] = d0; if (NDOT > 1) S->red[1][wid] = d1; }
+  d1 = warp_sum(d1);
+  if (lane == 0) { S->red[0][wid] = d0; S->red[1][wid] = d1; }
   __syncthreads();
+  CLP(3);
+  const unsigned mbar = smem_u32(&S->mbar_sum[group]);
   if (wid == 0) {
-    double s0 = tree16(S->red[0][lane & 15]);
-    double s1 = (NDOT > 1) ? tree16(S->red[1][lane & 15]) : 0.0;
-    if (lane < nranks) {
-      ClShared* R = cl.map_shared_rank(S, lane);
-      R->part[group][0][rank] = s0;
-      if (NDOT > 1) R->part[group][1][rank] = s1;
-    }
+    const double s0 = tree16(S->red[0][lane & 15]);
+    const double s1 = tree16(S->red[1][lane & 15]);
+    if (lane == 0) mbar_arrive_expect(mbar, 16u * (unsigned)nranks);
+    if (lane < nranks) st_async2(mapa_u32(smem_u32(&S->part[group][rank][0]), lane), s0, s1, mapa_u32(mbar, lane));
   }
-  cl.sync();
+  CLP(4);
+  mbar_wait(mbar, use & 1u);
+  CLP(5);
   const int r = lane & 15;
-  d0 = tree16(r < nranks ? S->part[group][0][r] : 0.0);
-  d1 = (NDOT > 1) ? tree16(r < nranks ? S->part[group][1][r] : 0.0) : 0.0;
+  const double2 pr = (r < nranks) ? *reinterpret_cast<const double2*>(&S->part[group][r][0]) : make_double2(0.0, 0.0);
+  d0 = tree16(pr.x);
+  d1 = tree16(pr.y);
+  CLP(6);
 }
 
 template <typename T, bool PRE>
@@ -92,6 +161,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
   T* qs = PRE ? ms + cap : ms;                            // r~ when it differs from b (warm start)
   const bool own_rt = A.warm != 0;
   const T* rt = own_rt ? qs : bs;
+  // private halo rows (row r0-1 = "lo", row r1 = "hi") of p, v, r and of the constant 1/M plane
+  T* hal = qs + (own_rt ? cap : 0);
+  T* h_lo[3] = {hal, hal + 2 * NY, hal + 4 * NY};
+  T* h_hi[3] = {hal + NY, hal + 3 * NY, hal + 5 * NY};
+  T* m_lo = hal + 6 * NY; T* m_hi = hal + 7 * NY;
 
   // thread -> (row group, column) map fixed for the whole solve: no integer division inside the phases.
   const int TC = min(NY, CL_THREADS), TR = CL_THREADS / TC;
@@ -100,6 +174,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
 #define CL_FOR(li, j, e) \
   for (int j = tx; j < NY; j += TC) for (int li = ty, e = ty * NY + j; li < nrows; li += TR, e += TR * NY)
 
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 3; ++k) { mbar_init(smem_u32(&S->mbar_sum[k]), 1); mbar_init(smem_u32(&S->mbar_halo[k]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   // ---- load this CTA's rows into shared memory (compact rows of NY) ----------------------------------------------
   CL_FOR(li, j, e) {
     const size_t g = (size_t)(r0 + li) * A.pitch + j;
@@ -117,23 +195,50 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
   sc.rTr0 = sc.rTr = sc.old_rTr = 0.0; sc.dot0 = sc.dot1 = 0.0;
   sc.eps = A.eps; sc.iter = 0; sc.max_iter = A.max_iter; sc.status = 1; sc.done = 0; sc.first = 1; sc.flags = A.flags;
   double* const hist = (rank == 0 && threadIdx.x == 0) ? A.history : nullptr;
-  cl.sync();
+  cl.sync();      // mbarriers initialised and slices loaded everywhere: the one cluster barrier before the loop
 
-  // neighbours' slices (row r0-1 is the last row of rank-1, row r1 the first row of rank+1: every lower rank is full)
+  // neighbours (row r0-1 is the last row of rank-1, row r1 the first row of rank+1: every lower rank is full)
   const bool has_lo = r0 > 0 && nrows > 0, has_hi = r1 < A.NX && nrows > 0;
   const int lo_rank = rank > 0 ? rank - 1 : 0, hi_rank = rank < A.nranks - 1 ? rank + 1 : rank;
   const int lo_off = (A.rows_per - 1) * NY;               // offset of the neighbour's last row
-  // remote views of the operand planes (DSMEM), resolved once
-  const T* ps_lo = cl.map_shared_rank(ps, lo_rank); const T* ps_hi = cl.map_shared_rank(ps, hi_rank);
-  const T* rs_lo = cl.map_shared_rank(rs, lo_rank); const T* rs_hi = cl.map_shared_rank(rs, hi_rank);
-  const T* vs_lo = cl.map_shared_rank(vs, lo_rank); const T* vs_hi = cl.map_shared_rank(vs, hi_rank);
+  const unsigned halo_bytes = (unsigned)((has_lo ? 1 : 0) + (has_hi ? 1 : 0)) * (unsigned)NY * (unsigned)sizeof(T);
+  unsigned use_sum[3] = {0, 0, 0}, use_halo[3] = {0, 0, 0};
+  bool pend[3] = {false, false, false};   // rows of this plane were pushed (by everybody, same control flow) and not yet waited for
+  // my first row lands in the lower neighbour's "hi" halo row, my last row in the upper neighbour's "lo" halo row
+  unsigned dst_lo[3], dst_hi[3], mb_lo[3], mb_hi[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    dst_lo[k] = mapa_u32(smem_u32(h_hi[k]), lo_rank); dst_hi[k] = mapa_u32(smem_u32(h_lo[k]), hi_rank);
+    mb_lo[k] = mapa_u32(smem_u32(&S->mbar_halo[k]), lo_rank); mb_hi[k] = mapa_u32(smem_u32(&S->mbar_halo[k]), hi_rank);
+  }
+  // push one element of a boundary row to the neighbour that needs it (called by the thread that produced it)
+  auto push = [&](int which, int li, int j, T val) {
+    if (li == 0 && has_lo) st_async(dst_lo[which] + (unsigned)(j * sizeof(T)), val, mb_lo[which]);
+    if (li == nrows - 1 && has_hi) st_async(dst_hi[which] + (unsigned)(j * sizeof(T)), val, mb_hi[which]);
+  };
+  // wait until both neighbours' rows of this plane have landed (thread 0 posts the byte count, everybody waits)
+  auto halo_wait = [&](int which) {
+    pend[which] = false;
+    if (halo_bytes == 0) return;
+    const unsigned mbar = smem_u32(&S->mbar_halo[which]);
+    if (threadIdx.x == 0) mbar_arrive_expect(mbar, halo_bytes);
+    mbar_wait(mbar, use_halo[which] & 1u);
+    ++use_halo[which];
+  };
+  // the constant 1/M halo rows and the warm-start x halo are read once, remotely (slices final since cl.sync)
+  if (PRE) {
+    const T* ms_lo = cl.map_shared_rank(ms, lo_rank); const T* ms_hi = cl.map_shared_rank(ms, hi_rank);
+    for (int j = threadIdx.x; j < NY; j += CL_THREADS) {
+      if (has_lo) m_lo[j] = ms_lo[lo_off + j];
+      if (has_hi) m_hi[j] = ms_hi[j];
+    }
+  }
   const T* xs_lo = cl.map_shared_rank(xs, lo_rank); const T* xs_hi = cl.map_shared_rank(xs, hi_rank);
-  const T* ms_lo = cl.map_shared_rank(ms, lo_rank); const T* ms_hi = cl.map_shared_rank(ms, hi_rank);
 
   // ---- stencil product y = A * hat(src) at local element e = (li, j); src selected by MODE -----------------------
-  //   MODE 0: src = p                  hat = 1/M * p
-  //   MODE 1: src = s = r - alpha v    hat = 1/M * s     (halo rows recomputed from the neighbour's r, v)
-  //   MODE 2: src = x (warm-start residual, karman_taichi.py:360-367: no preconditioner)
+  //   MODE 0: src = p                  hat = 1/M * p     (halo rows: pushed p rows)
+  //   MODE 1: src = s = r - alpha v    hat = 1/M * s     (halo rows recomputed from the pushed r, v rows)
+  //   MODE 2: src = x (warm-start residual, karman_taichi.py:360-367: no preconditioner; halo read remotely, once)
   auto val = [&](int mode, const T* a0, const T* a1, const T* mm, int idx, T alpha) -> T {
     T v_ = (mode == 1) ? (a0[idx] - alpha * a1[idx]) : a0[idx];
     if (PRE && mode != 2) v_ = mm[idx] * v_;
@@ -141,15 +246,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
   };
   auto spmv_elem = [&](int mode, int li, int j, int e, T alpha, T& centre_raw) -> T {
     const T* a0 = (mode == 0) ? ps : (mode == 1) ? rs : xs;
-    const T* a0_lo = (mode == 0) ? ps_lo : (mode == 1) ? rs_lo : xs_lo;
-    const T* a0_hi = (mode == 0) ? ps_hi : (mode == 1) ? rs_hi : xs_hi;
+    const T* a0_lo = (mode == 0) ? h_lo[HALO_P] : (mode == 1) ? h_lo[HALO_R] : xs_lo + lo_off;
+    const T* a0_hi = (mode == 0) ? h_hi[HALO_P] : (mode == 1) ? h_hi[HALO_R] : xs_hi;
     centre_raw = (mode == 1) ? (rs[e] - alpha * vs[e]) : a0[e];
     const T xc = (PRE && mode != 2) ? ms[e] * centre_raw : centre_raw;
     T xw = T(0), xe = T(0), xn = T(0), xso = T(0);
     if (li > 0) xw = val(mode, a0, vs, ms, e - NY, alpha);
-    else if (has_lo) xw = val(mode, a0_lo, vs_lo, ms_lo, lo_off + j, alpha);
+    else if (has_lo) xw = val(mode, a0_lo, h_lo[HALO_V], m_lo, j, alpha);
     if (li < nrows - 1) xe = val(mode, a0, vs, ms, e + NY, alpha);
-    else if (has_hi) xe = val(mode, a0_hi, vs_hi, ms_hi, j, alpha);
+    else if (has_hi) xe = val(mode, a0_hi, h_hi[HALO_V], m_hi, j, alpha);
     if (j < NY - 1) xn = val(mode, a0, vs, ms, e + 1, alpha);
     if (j > 0) xso = val(mode, a0, vs, ms, e - 1, alpha);
     // cgsolver.py:59-60, left to right
@@ -162,6 +267,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
   };
 
   // ---- K0: r = b - A x0 (warm) or r = b ; r~ = r ; (r,r) -----------------------------------------------------------
+  CLP_DECL
   double d0 = 0.0, d1 = 0.0;
   CL_FOR(li, j, e) {
     T rr;
@@ -169,32 +275,53 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
     else rr = bs[e];
     rs[e] = rr;
     if (own_rt) qs[e] = rr;
-    if (A.is_cg) ps[e] = rr;                               // cgsolver.py:90 p = r + 0 * p
+    if (A.is_cg) { ps[e] = rr; push(HALO_P, li, j, rr); }  // cgsolver.py:90 p = r + 0 * p
+    else push(HALO_R, li, j, rr);                          // r halo: read by P3 of the first iteration
     d0 += (double)rr * (double)rr;
   }
-  cluster_sum<1>(cl, S, 0, d0, d1, A.nranks, rank);
+  pend[A.is_cg ? HALO_P : HALO_R] = true;
+  // group 2 for this one: the loop's first sum (group 0) may be sent by a fast CTA before a slow one has read the slots
+  // of the sum before it, unless another sum lies in between -- group 2 is next used two sums later (P4) or never (CG)
+  cluster_sum(S, 2, use_sum[2]++, d0, d1, A.nranks, rank CLP_PASS);
   scalar_algebra(A.is_cg ? FIN_CG_INIT : FIN_BICG_INIT, &sc, d0, d0, hist, A.hist_cap);
+  if (A.is_cg) { halo_wait(HALO_P); __syncthreads(); }
 
   // ---- iterations ----------------------------------------------------------------------------------------------
+  CLP(15);
   while (!sc.done) {
     if (!A.is_cg) {
-      // P1
+      // P1.  The neighbours' p halo rows were last read in their P2 of the previous iteration, which they finished
+      // before contributing to that iteration's sums -- and this CTA is past those sums: pushing is safe.
       const bool first = sc.iter == 0;
       const T beta = T(sc.beta), omega_prev = T(sc.omega);
-      CL_FOR(li, j, e) ps[e] = first ? rs[e] : rs[e] + beta * (ps[e] - omega_prev * vs[e]);
-      cl.sync();
+      CL_FOR(li, j, e) {
+        const T pn = first ? rs[e] : rs[e] + beta * (ps[e] - omega_prev * vs[e]);
+        ps[e] = pn;
+        push(HALO_P, li, j, pn);
+      }
+      pend[HALO_P] = true;
+      CLP(0);
+      halo_wait(HALO_P);
+      __syncthreads();                                     // own p rows visible to the whole CTA
+      CLP(1);
       // P2
       d0 = 0.0; d1 = 0.0;
       CL_FOR(li, j, e) {
         T raw;
         const T y = spmv_elem(0, li, j, e, T(0), raw);
         d0 += (double)rt[e] * (double)y;
-        vs[e] = y;      // v of the previous iteration is needed by nobody any more (P1 is behind the barrier)
+        vs[e] = y;      // v of the previous iteration is needed by nobody any more
+        push(HALO_V, li, j, y);                            // neighbours read their v halo in P3 only (two sums ago)
       }
-      cluster_sum<1>(cl, S, 0, d0, d1, A.nranks, rank);
+      pend[HALO_V] = true;
+      CLP(2);
+      cluster_sum(S, 0, use_sum[0]++, d0, d1, A.nranks, rank CLP_PASS);
       scalar_algebra(FIN_BICG_ALPHA, &sc, d0, d1, nullptr, 0);
+      CLP(7);
       if (sc.done) break;
-      // P3 (v of the neighbours is final since the barrier inside cluster_sum)
+      // P3 (own v rows: visible since the __syncthreads inside cluster_sum; halo rows of v and r: wait for them)
+      halo_wait(HALO_V);
+      halo_wait(HALO_R);
       const T alpha = T(sc.alpha);
       d0 = 0.0; d1 = 0.0;
       CL_FOR(li, j, e) {
@@ -204,10 +331,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         d0 += (double)y * (double)sraw;
         d1 += (double)y * (double)y;
       }
-      cluster_sum<2>(cl, S, 1, d0, d1, A.nranks, rank);
+      CLP(8);
+      cluster_sum(S, 1, use_sum[1]++, d0, d1, A.nranks, rank CLP_PASS);
       scalar_algebra(FIN_BICG_OMEGA, &sc, d0, d1, nullptr, 0);
+      CLP(7);
       if (sc.done) break;
-      // P4
+      // P4 (the neighbours read their r halo in P3, which they finished before contributing to the sum above)
       const T omega = T(sc.omega);
       d0 = 0.0; d1 = 0.0;
       CL_FOR(li, j, e) {
@@ -216,11 +345,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         xs[e] = xs[e] + (alpha * ph + omega * sh);
         const T rn = ss[e] - omega * ts[e];
         rs[e] = rn;
+        push(HALO_R, li, j, rn);
         d0 += (double)rn * (double)rn;
         d1 += (double)rn * (double)rt[e];
       }
-      cluster_sum<2>(cl, S, 2, d0, d1, A.nranks, rank);
+      pend[HALO_R] = true;
+      CLP(9);
+      cluster_sum(S, 2, use_sum[2]++, d0, d1, A.nranks, rank CLP_PASS);
       scalar_algebra(FIN_BICG_END, &sc, d0, d1, hist, A.hist_cap);
+      CLP(7);
     } else {
       // C1: Ap = A p ; (p, Ap)
       d0 = 0.0; d1 = 0.0;
@@ -230,7 +363,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         vs[e] = y;
         d0 += (double)raw * (double)y;
       }
-      cluster_sum<1>(cl, S, 0, d0, d1, A.nranks, rank);
+      cluster_sum(S, 0, use_sum[0]++, d0, d1, A.nranks, rank CLP_PASS);
       scalar_algebra(FIN_CG_ALPHA, &sc, d0, d1, nullptr, 0);
       if (sc.done) break;
       // C2: x += alpha p ; r -= alpha Ap ; (r,r)
@@ -242,16 +375,26 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         rs[e] = rn;
         d0 += (double)rn * (double)rn;
       }
-      cluster_sum<1>(cl, S, 1, d0, d1, A.nranks, rank);
+      cluster_sum(S, 1, use_sum[1]++, d0, d1, A.nranks, rank CLP_PASS);
       scalar_algebra(FIN_CG_END, &sc, d0, d1, hist, A.hist_cap);
       if (sc.done) break;
-      // C3: p = r + beta p
+      // C3: p = r + beta p (the neighbours finished reading their p halo in C1, two sums ago)
       const T beta = T(sc.beta);
-      CL_FOR(li, j, e) ps[e] = rs[e] + beta * ps[e];
-      cl.sync();
+      CL_FOR(li, j, e) {
+        const T pn = rs[e] + beta * ps[e];
+        ps[e] = pn;
+        push(HALO_P, li, j, pn);
+      }
+      pend[HALO_P] = true;
+      halo_wait(HALO_P);
+      __syncthreads();
     }
   }
-  // every CTA leaves the loop at the same iteration (identical scalars); make sure nobody still reads our slices
+  // Every CTA leaves the loop at the same point (identical scalars).  Rows pushed by a neighbour may still be in flight
+  // towards this CTA (r of the last P4, v of an aborted iteration): absorb them before this CTA exits and frees the
+  // shared memory they target; the barrier keeps every slice alive until all CTAs are past their last remote access.
+#pragma unroll
+  for (int k = 0; k < 3; ++k) if (pend[k]) halo_wait(k);
   cl.sync();
   CL_FOR(li, j, e) {
     const size_t g = (size_t)(r0 + li) * A.pitch + j;
@@ -259,6 +402,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
     if (A.r_out) A.r_out[g] = rs[e];
   }
   if (rank == 0 && threadIdx.x == 0) *A.sc = sc;
+  CLP_DUMP;
 #undef CL_FOR
 }
 
@@ -281,7 +425,7 @@ static int cluster_fit(const kt_handle_s* h, bool warm, size_t* smem_out, int* r
   for (int C : {16, 8}) {
     if (C > max_c || C > limit_c || (C == 16 && h->NX < 32)) continue;
     const int rows_per = (h->NX + C - 1) / C;
-    const size_t need = ctrl + (size_t)planes * rows_per * h->NY * sizeof(T);
+    const size_t need = ctrl + ((size_t)planes * rows_per + 8) * h->NY * sizeof(T);      // + 8 private halo rows
     if (need <= max_smem) { *smem_out = need; *rows_per_out = rows_per; return C; }
   }
   return 0;
@@ -341,6 +485,14 @@ int cluster_try_solve(kt_handle_s* h, const void* coef, const void* b, void* x, 
   KT_CUDA(cudaStreamSynchronize(h->stream));
   return 1;
 }
+
+#ifdef KT_CLUSTER_PROF
+extern "C" int kt_debug_cluster_prof(long long* out16, int reset) {
+  if (out16) cudaMemcpyFromSymbol(out16, g_clprof, sizeof(long long) * 16);
+  if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_clprof, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 template int cluster_try_solve<double>(kt_handle_s*, const void*, const void*, void*, const void*, void*, double*, long long, double,
                                        long long, int, bool);
