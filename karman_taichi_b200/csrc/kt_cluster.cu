@@ -143,8 +143,311 @@ __device__ __forceinline__ void cluster_sum(ClShared* S, int group, unsigned use
   CLP(6);
 }
 
-template <typename T, bool PRE>
+// ---------------------------------------------------------------------------------------------------------------
+// Variant for up to CL_EPT_REG elements per thread (grids up to ~2 x 512 x 16 = 16 k unknowns: cavity 50^2 ... 120^2).
+// ---------------------------------------------------------------------------------------------------------------
+// Per-thread element state.  A thread owns the same EPT elements of the CTA's slice (flat index e = threadIdx.x + k * 512)
+// for the whole solve and keeps everything only it touches in registers: the five coefficients (REGC; otherwise they stay
+// in shared memory), r~, x, r, v, p, s, t and 1/M.  Shared memory holds just the planes a NEIGHBOUR element has to read
+// (p, v, r [, 1/M]) plus the private halo rows, so an iteration moves 12 loads + 3 stores per element through the
+// shared-memory pipe instead of 35 + 6 -- the SpMV phases of the first versions were bound by exactly that pipe.
+enum { EF_VALID = 1, EF_ROW0 = 2, EF_ROWN = 4, EF_J0 = 8, EF_JN = 16 };
+
+template <typename T, bool PRE, int EPT, bool REGC>
 __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T> A) {
+  cg::cluster_group cl = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ClShared* S = reinterpret_cast<ClShared*>(smem_raw);
+  const int rank = (int)cl.block_rank();
+  const int NY = A.NY;
+  const int r0 = min(rank * A.rows_per, A.NX), r1 = min(r0 + A.rows_per, A.NX);
+  const int nrows = r1 - r0, n_el = nrows * NY;
+  const int cap = A.rows_per * NY;                        // plane slice capacity (same on every CTA)
+  T* base = reinterpret_cast<T*>(smem_raw + ((sizeof(ClShared) + 15) / 16) * 16);
+  T* ps = base; T* vs = ps + cap; T* rs = vs + cap;
+  T* ms = rs + cap;                                       // 1/M (PRE only)
+  T* cs = PRE ? ms + cap : ms;                            // five coefficient planes (!REGC only)
+  // private halo rows (row r0-1 = "lo", row r1 = "hi") of p, v, r and of the constant 1/M plane
+  T* hal = REGC ? cs : cs + 5 * cap;
+  T* h_lo[3] = {hal, hal + 2 * NY, hal + 4 * NY};
+  T* h_hi[3] = {hal + NY, hal + 3 * NY, hal + 5 * NY};
+  T* m_lo = hal + 6 * NY; T* m_hi = hal + 7 * NY;
+
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 3; ++k) { mbar_init(smem_u32(&S->mbar_sum[k]), 1); mbar_init(smem_u32(&S->mbar_halo[k]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // ---- this thread's elements ---------------------------------------------------------------------------------------
+  T c[REGC ? EPT : 1][5];
+  T rt[EPT], x[EPT], r[EPT], v[EPT], p[EPT], t[EPT], m[EPT];
+  unsigned ef[EPT];                 // EF_* flags in the low byte, the column j above it
+#define EJ(k) ((int)(ef[k] >> 8))
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int e = threadIdx.x + k * CL_THREADS;
+    ef[k] = 0;
+    x[k] = r[k] = v[k] = p[k] = t[k] = rt[k] = T(0); m[k] = T(1);
+    if (REGC) { for (int q = 0; q < 5; ++q) c[k][q] = T(0); }
+    if (e < n_el) {
+      const int li = e / NY, j = e - li * NY;
+      const size_t g = (size_t)(r0 + li) * A.pitch + j;
+      ef[k] = EF_VALID | (li == 0 ? EF_ROW0 : 0) | (li == nrows - 1 ? EF_ROWN : 0) | (j == 0 ? EF_J0 : 0) | (j == NY - 1 ? EF_JN : 0) |
+              ((unsigned)j << 8);
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const T cv = A.coef[q * A.plane + g];
+        if (REGC) c[k][q] = cv; else cs[q * cap + e] = cv;
+      }
+      if (A.warm) { x[k] = A.x[g]; ps[e] = x[k]; }         // the p plane carries x0 for the warm-start residual
+      if (PRE) { m[k] = A.minv[g]; ms[e] = m[k]; }
+    }
+  }
+  auto coef = [&](int k, int q, int e) -> T { return REGC ? c[REGC ? k : 0][q] : cs[q * cap + e]; };
+  // Every thread keeps its own copy of the Krylov scalars and runs the (cheap) scalar algebra itself on the identical
+  // reduced sums: no shared-memory round trip and no block barrier between a reduction and its consumers.
+  // Every thread keeps its own copy of the Krylov scalars and runs the (cheap) scalar algebra itself on the identical
+  // reduced sums: no shared-memory round trip and no block barrier between a reduction and its consumers.
+  Scalars sc;
+  sc.rho = 0.0; sc.rho_1 = 1.0; sc.alpha = 1.0; sc.beta = 1.0; sc.omega = 1.0;
+  sc.rTr0 = sc.rTr = sc.old_rTr = 0.0; sc.dot0 = sc.dot1 = 0.0;
+  sc.eps = A.eps; sc.iter = 0; sc.max_iter = A.max_iter; sc.status = 1; sc.done = 0; sc.first = 1; sc.flags = A.flags;
+  double* const hist = (rank == 0 && threadIdx.x == 0) ? A.history : nullptr;
+#define CL_SCALARS(fin, a0, a1, h_) scalar_algebra(fin, &sc, a0, a1, h_, A.hist_cap)
+  cl.sync();      // mbarriers initialised and slices loaded everywhere: the one cluster barrier before the loop
+
+  // neighbours (row r0-1 is the last row of rank-1, row r1 the first row of rank+1: every lower rank is full)
+  const bool has_lo = r0 > 0 && nrows > 0, has_hi = r1 < A.NX && nrows > 0;
+  const int lo_rank = rank > 0 ? rank - 1 : 0, hi_rank = rank < A.nranks - 1 ? rank + 1 : rank;
+  const int lo_off = (A.rows_per - 1) * NY;               // offset of the neighbour's last row
+  const unsigned halo_bytes = (unsigned)((has_lo ? 1 : 0) + (has_hi ? 1 : 0)) * (unsigned)NY * (unsigned)sizeof(T);
+  unsigned use_sum[3] = {0, 0, 0}, use_halo[3] = {0, 0, 0};
+  bool pend[3] = {false, false, false};   // rows of this plane were pushed (by everybody, same control flow) and not yet waited for
+  // my first row lands in the lower neighbour's "hi" halo row, my last row in the upper neighbour's "lo" halo row
+  // (plane `which` sits 2 * NY elements / one mbarrier further than plane 0)
+  const unsigned dst_lo0 = mapa_u32(smem_u32(h_hi[0]), lo_rank), dst_hi0 = mapa_u32(smem_u32(h_lo[0]), hi_rank);
+  const unsigned mb_lo0 = mapa_u32(smem_u32(&S->mbar_halo[0]), lo_rank), mb_hi0 = mapa_u32(smem_u32(&S->mbar_halo[0]), hi_rank);
+  // push one element of a boundary row to the neighbour that needs it (called by the thread that produced it)
+  auto push = [&](int which, unsigned flags, T val) {
+    const unsigned off = (unsigned)((which * 2 * NY + (int)(flags >> 8)) * sizeof(T));
+    if ((flags & EF_ROW0) && has_lo) st_async(dst_lo0 + off, val, mb_lo0 + 8u * which);
+    if ((flags & EF_ROWN) && has_hi) st_async(dst_hi0 + off, val, mb_hi0 + 8u * which);
+  };
+  // wait until both neighbours' rows of this plane have landed (thread 0 posts the byte count, everybody waits)
+  auto halo_wait = [&](int which) {
+    pend[which] = false;
+    if (halo_bytes == 0) return;
+    const unsigned mbar = smem_u32(&S->mbar_halo[which]);
+    if (threadIdx.x == 0) mbar_arrive_expect(mbar, halo_bytes);
+    mbar_wait(mbar, use_halo[which] & 1u);
+    ++use_halo[which];
+  };
+  // the constant 1/M halo rows and the warm-start x halo are read once, remotely (slices final since cl.sync)
+  if (PRE) {
+    const T* ms_lo = cl.map_shared_rank(ms, lo_rank); const T* ms_hi = cl.map_shared_rank(ms, hi_rank);
+    for (int j = threadIdx.x; j < NY; j += CL_THREADS) {
+      if (has_lo) m_lo[j] = ms_lo[lo_off + j];
+      if (has_hi) m_hi[j] = ms_hi[j];
+    }
+  }
+  const T* x0_lo = cl.map_shared_rank(ps, lo_rank) + lo_off; const T* x0_hi = cl.map_shared_rank(ps, hi_rank);
+
+  // ---- stencil product y = A * hat(src) for this thread's element k; src selected by MODE ---------------------------
+  //   MODE 0: src = p                  hat = 1/M * p     (neighbours: p plane / pushed p rows)
+  //   MODE 1: src = s = r - alpha v    hat = 1/M * s     (neighbours recomputed from the r, v planes / pushed rows)
+  //   MODE 2: src = x0 in the p plane (warm-start residual, karman_taichi.py:360-367: no preconditioner; halo read
+  //           remotely, once)
+  auto nb_in = [&](int mode, int idx, T alpha) -> T {     // neighbour inside this CTA's slice
+    T v_ = (mode == 1) ? (rs[idx] - alpha * vs[idx]) : ps[idx];
+    if (PRE && mode != 2) v_ = ms[idx] * v_;
+    return v_;
+  };
+  auto nb_halo = [&](int mode, bool lo, int j, T alpha) -> T {
+    T v_;
+    if (mode == 0) v_ = lo ? h_lo[HALO_P][j] : h_hi[HALO_P][j];
+    else if (mode == 1) v_ = lo ? (h_lo[HALO_R][j] - alpha * h_lo[HALO_V][j]) : (h_hi[HALO_R][j] - alpha * h_hi[HALO_V][j]);
+    else v_ = lo ? x0_lo[j] : x0_hi[j];
+    if (PRE && mode != 2) v_ = (lo ? m_lo[j] : m_hi[j]) * v_;
+    return v_;
+  };
+  auto spmv_elem = [&](int mode, int k, T centre_raw, T alpha) -> T {
+    const int e = threadIdx.x + k * CL_THREADS, j = EJ(k);
+    const unsigned f = ef[k];
+    const T xc = (PRE && mode != 2) ? m[k] * centre_raw : centre_raw;
+    T xw = T(0), xe = T(0), xn = T(0), xso = T(0);
+    if (!(f & EF_ROW0)) xw = nb_in(mode, e - NY, alpha);
+    else if (has_lo) xw = nb_halo(mode, true, j, alpha);
+    if (!(f & EF_ROWN)) xe = nb_in(mode, e + NY, alpha);
+    else if (has_hi) xe = nb_halo(mode, false, j, alpha);
+    if (!(f & EF_JN)) xn = nb_in(mode, e + 1, alpha);
+    if (!(f & EF_J0)) xso = nb_in(mode, e - 1, alpha);
+    // cgsolver.py:59-60, left to right
+    T acc = coef(k, 0, e) * xc;
+    acc = acc + coef(k, 1, e) * xw;
+    acc = acc + coef(k, 2, e) * xe;
+    acc = acc + coef(k, 3, e) * xn;
+    acc = acc + coef(k, 4, e) * xso;
+    return acc;
+  };
+#define CL_EACH(k, e) _Pragma("unroll") for (int k = 0; k < EPT; ++k) if (const int e = threadIdx.x + k * CL_THREADS; ef[k] & EF_VALID)
+
+  // ---- K0: r = b - A x0 (warm) or r = b ; r~ = r ; (r,r) -----------------------------------------------------------
+  CLP_DECL
+  double d0 = 0.0, d1 = 0.0;
+  CL_EACH(k, e) {
+    const int li_ = e / NY;
+    T rr = A.b[(size_t)(r0 + li_) * A.pitch + (e - li_ * NY)];
+    if (A.warm) rr = rr - spmv_elem(2, k, x[k], T(0));
+    r[k] = rr; rt[k] = rr;                                 // r~ = r0 (= b when x0 = 0): bicgsolver.py:28, karman_taichi.py:371
+    if (A.is_cg) p[k] = rr;                                // cgsolver.py:90 p = r + 0 * p
+    d0 += (double)rr * (double)rr;
+  }
+  if (A.warm) {
+    // everybody must be done reading x0 out of the p planes (locally and remotely) before anything else lands there
+    cl.sync();
+  }
+  CL_EACH(k, e) {
+    if (A.is_cg) { ps[e] = p[k]; push(HALO_P, ef[k], p[k]); }
+    else { rs[e] = r[k]; push(HALO_R, ef[k], r[k]); }   // r halo: read by P3 of the first iteration
+  }
+  pend[A.is_cg ? HALO_P : HALO_R] = true;
+  // group 2 for this one: the loop's first sum (group 0) may be sent by a fast CTA before a slow one has read the slots
+  // of the sum before it, unless another sum lies in between -- group 2 is next used two sums later (P4) or never (CG)
+  cluster_sum(S, 2, use_sum[2]++, d0, d1, A.nranks, rank CLP_PASS);
+  CL_SCALARS(A.is_cg ? FIN_CG_INIT : FIN_BICG_INIT, d0, d0, hist);
+  if (A.is_cg) { halo_wait(HALO_P); __syncthreads(); }
+
+  // ---- iterations ----------------------------------------------------------------------------------------------
+  CLP(15);
+  while (!sc.done) {
+    if (!A.is_cg) {
+      // P1.  The neighbours' p halo rows were last read in their P2 of the previous iteration, which they finished
+      // before contributing to that iteration's sums -- and this CTA is past those sums: pushing is safe.
+      const bool first = sc.iter == 0;
+      const T beta = T(sc.beta), omega_prev = T(sc.omega);
+      CL_EACH(k, e) {
+        const T pn = first ? r[k] : r[k] + beta * (p[k] - omega_prev * v[k]);
+        p[k] = pn; ps[e] = pn;
+        push(HALO_P, ef[k], pn);
+      }
+      pend[HALO_P] = true;
+      CLP(0);
+      halo_wait(HALO_P);
+      __syncthreads();                                     // own p rows visible to the whole CTA
+      CLP(1);
+      // P2
+      d0 = 0.0; d1 = 0.0;
+      CL_EACH(k, e) {
+        const T y = spmv_elem(0, k, p[k], T(0));
+        d0 += (double)rt[k] * (double)y;
+        v[k] = y; vs[e] = y;                               // the v plane was last read in P3, two sums ago
+        push(HALO_V, ef[k], y);
+      }
+      pend[HALO_V] = true;
+      CLP(2);
+      cluster_sum(S, 0, use_sum[0]++, d0, d1, A.nranks, rank CLP_PASS);
+      CL_SCALARS(FIN_BICG_ALPHA, d0, d1, nullptr);
+      CLP(7);
+      if (sc.done) break;
+      // P3 (own v, r planes: visible since the __syncthreads inside the sums; halo rows of v and r: wait for them)
+      halo_wait(HALO_V);
+      halo_wait(HALO_R);
+      const T alpha = T(sc.alpha);
+      d0 = 0.0; d1 = 0.0;
+      CL_EACH(k, e) {
+        const T sraw = r[k] - alpha * v[k];                // bicgsolver.py:63
+        const T y = spmv_elem(1, k, sraw, alpha);
+        t[k] = y;
+        d0 += (double)y * (double)sraw;
+        d1 += (double)y * (double)y;
+      }
+      CLP(8);
+      cluster_sum(S, 1, use_sum[1]++, d0, d1, A.nranks, rank CLP_PASS);
+      CL_SCALARS(FIN_BICG_OMEGA, d0, d1, nullptr);
+      CLP(7);
+      if (sc.done) break;
+      // P4 (the neighbours read their r halo in P3, which they finished before contributing to the sum above)
+      const T omega = T(sc.omega);
+      d0 = 0.0; d1 = 0.0;
+      CL_EACH(k, e) {
+        const T sk = r[k] - alpha * v[k];                  // s again (same operation, same bits as in P3): one register less
+        const T ph = PRE ? m[k] * p[k] : p[k];
+        const T sh = PRE ? m[k] * sk : sk;
+        x[k] = x[k] + (alpha * ph + omega * sh);
+        const T rn = sk - omega * t[k];
+        r[k] = rn; rs[e] = rn;
+        push(HALO_R, ef[k], rn);
+        d0 += (double)rn * (double)rn;
+        d1 += (double)rn * (double)rt[k];
+      }
+      pend[HALO_R] = true;
+      CLP(9);
+      cluster_sum(S, 2, use_sum[2]++, d0, d1, A.nranks, rank CLP_PASS);
+      CL_SCALARS(FIN_BICG_END, d0, d1, hist);
+      CLP(7);
+    } else {
+      // C1: Ap = A p ; (p, Ap)   (Ap is needed by its owner only: registers)
+      d0 = 0.0; d1 = 0.0;
+      CL_EACH(k, e) {
+        const T y = spmv_elem(0, k, p[k], T(0));
+        v[k] = y;
+        d0 += (double)p[k] * (double)y;
+      }
+      cluster_sum(S, 0, use_sum[0]++, d0, d1, A.nranks, rank CLP_PASS);
+      CL_SCALARS(FIN_CG_ALPHA, d0, d1, nullptr);
+      if (sc.done) break;
+      // C2: x += alpha p ; r -= alpha Ap ; (r,r)
+      const T alpha = T(sc.alpha);
+      d0 = 0.0; d1 = 0.0;
+      CL_EACH(k, e) {
+        x[k] = x[k] + alpha * p[k];
+        const T rn = r[k] - alpha * v[k];
+        r[k] = rn;
+        d0 += (double)rn * (double)rn;
+      }
+      cluster_sum(S, 1, use_sum[1]++, d0, d1, A.nranks, rank CLP_PASS);
+      CL_SCALARS(FIN_CG_END, d0, d1, hist);
+      if (sc.done) break;
+      // C3: p = r + beta p (the neighbours finished reading their p halo in C1, two sums ago)
+      const T beta = T(sc.beta);
+      CL_EACH(k, e) {
+        const T pn = r[k] + beta * p[k];
+        p[k] = pn; ps[e] = pn;
+        push(HALO_P, ef[k], pn);
+      }
+      pend[HALO_P] = true;
+      halo_wait(HALO_P);
+      __syncthreads();
+    }
+  }
+  // Every CTA leaves the loop at the same point (identical scalars).  Rows pushed by a neighbour may still be in flight
+  // towards this CTA (r of the last P4, v of an aborted iteration): absorb them before this CTA exits and frees the
+  // shared memory they target; the barrier keeps every slice alive until all CTAs are past their last remote access.
+#pragma unroll
+  for (int k = 0; k < 3; ++k) if (pend[k]) halo_wait(k);
+  cl.sync();
+  CL_EACH(k, e) {
+    const int li_ = e / NY;
+    const size_t g = (size_t)(r0 + li_) * A.pitch + (e - li_ * NY);
+    A.x[g] = x[k];
+    if (A.r_out) A.r_out[g] = r[k];
+  }
+  if (rank == 0 && threadIdx.x == 0) {
+    Scalars out = sc;
+    out.dot0 = out.dot1 = 0.0;          // (not kept live through the loop: nobody reads the raw sums of a cluster solve)
+    *A.sc = out;
+  }
+  CLP_DUMP;
+#undef CL_EACH
+#undef CL_SCALARS
+#undef EJ
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Variant for 3+ elements per thread: every plane in shared memory (12 planes + halo rows), row-group/column thread map.
+// At that size the register-resident kernel above spills and is slower (profiles/r01_simple_rates.md).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, bool PRE>
+__global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve_smem(const ClArgs<T> A) {
   cg::cluster_group cl = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ClShared* S = reinterpret_cast<ClShared*>(smem_raw);
@@ -411,30 +714,36 @@ static int cluster_env(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-// Can this geometry be solved inside one cluster?  Returns the cluster size (0 = no) and the shared memory per CTA.
-template <typename T, bool PRE>
-static int cluster_fit(const kt_handle_s* h, bool warm, size_t* smem_out, int* rows_per_out, int limit_c) {
+constexpr int CL_EPT_REG = 2;       // register-resident kernel up to this many elements per thread
+
+struct ClFit { int C, rows_per, ept; bool reg; size_t smem; };
+
+// Can this geometry be solved inside one cluster?  C = 0: no.
+template <typename T>
+static ClFit cluster_fit(const kt_handle_s* h, bool pre, bool warm, int limit_c) {
+  ClFit f = {0, 0, 0, false, 0};
   static int enabled = cluster_env("KT_CLUSTER", 1);
-  if (!enabled || !h->allow_cluster || h->row_lo != 0 || h->row_hi != h->NX) return 0;
-  const int planes = 12 + (PRE ? 1 : 0) + (warm ? 1 : 0);
+  if (!enabled || !h->allow_cluster || h->row_lo != 0 || h->row_hi != h->NX) return f;
   const size_t ctrl = ((sizeof(ClShared) + 15) / 16) * 16;
   const size_t max_smem = 227 * 1024;
-  // 16 CTAs (non-portable size, one GPC) whenever every CTA still gets >= 2 rows: the phases are instruction-issue
-  // bound, so twice the SMs is twice the speed (measured 9.5 -> ~5 us / BiCGSTAB iteration at 130^2); else 8.
+  // 16 CTAs (non-portable size, one GPC) whenever every CTA still gets >= 2 rows; else the portable 8.
   static int max_c = cluster_env("KT_CLUSTER_MAX", 16);
+  static int reg_max = cluster_env("KT_CLUSTER_REG", CL_EPT_REG);     // 0: always the shared-memory kernel
   for (int C : {16, 8}) {
     if (C > max_c || C > limit_c || (C == 16 && h->NX < 32)) continue;
     const int rows_per = (h->NX + C - 1) / C;
-    const size_t need = ctrl + ((size_t)planes * rows_per + 8) * h->NY * sizeof(T);      // + 8 private halo rows
-    if (need <= max_smem) { *smem_out = need; *rows_per_out = rows_per; return C; }
+    const long long cap = (long long)rows_per * h->NY;
+    const int ept = (int)((cap + CL_THREADS - 1) / CL_THREADS);
+    const bool reg = ept <= (reg_max < CL_EPT_REG ? reg_max : CL_EPT_REG);
+    const int planes = reg ? 3 + (pre ? 1 : 0) : 12 + (pre ? 1 : 0) + (warm ? 1 : 0);
+    const size_t need = ctrl + ((size_t)planes * cap + 8 * (size_t)h->NY) * sizeof(T);      // + 8 private halo rows
+    if (need <= max_smem) { f.C = C; f.rows_per = rows_per; f.ept = ept; f.reg = reg; f.smem = need; return f; }
   }
-  return 0;
+  return f;
 }
 
-template <typename T, bool PRE>
-static int cluster_launch(kt_handle_s* h, const ClArgs<T>& A0, int C, size_t smem) {
-  auto kern = k_cluster_solve<T, PRE>;
-  static bool configured = false;
+template <typename K, typename T>
+static int cluster_launch_k(kt_handle_s* h, K kern, bool& configured, const ClArgs<T>& A0, int C, size_t smem) {
   if (!configured) {
     KT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     KT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -451,30 +760,38 @@ static int cluster_launch(kt_handle_s* h, const ClArgs<T>& A0, int C, size_t sme
   return 0;
 }
 
+template <typename T, bool PRE>
+static int cluster_launch(kt_handle_s* h, const ClArgs<T>& A, const ClFit& f) {
+  static bool conf[3] = {false, false, false};
+  if (f.reg && f.ept == 1) return cluster_launch_k(h, k_cluster_solve<T, PRE, 1, true>, conf[0], A, f.C, f.smem);
+  if (f.reg && f.ept == 2) return cluster_launch_k(h, k_cluster_solve<T, PRE, 2, true>, conf[1], A, f.C, f.smem);
+  return cluster_launch_k(h, k_cluster_solve_smem<T, PRE>, conf[2], A, f.C, f.smem);
+}
+
 // Entry used by kt_bicgstab_solve / kt_cg_solve: returns 1 if the solve was done here, 0 if the geometry does not fit
 // (caller falls through to the streaming kernels), < 0 on error.
 template <typename T>
 int cluster_try_solve(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, void* r_out,
                       double* history, long long hist_cap, double eps, long long max_iter, int flags, bool is_cg) {
   const bool pre = Minv != nullptr, warm = (flags & KT_FLAG_WARM_START) != 0;
+  if (is_cg && (pre || warm)) return 0;   // CGSolver (cgsolver.py) has neither a preconditioner nor a warm start
   static int sched_limit = 16;          // drops to 8 for the process if a 16-CTA cluster cannot be scheduled here
-  size_t smem = 0; int rows_per = 0;
-  int C = pre ? cluster_fit<T, true>(h, warm, &smem, &rows_per, sched_limit) : cluster_fit<T, false>(h, warm, &smem, &rows_per, sched_limit);
-  if (C == 0) return 0;
+  ClFit f = cluster_fit<T>(h, pre, warm, sched_limit);
+  if (f.C == 0) return 0;
   ClArgs<T> A;
   A.coef = (const T*)coef; A.plane = (size_t)h->NX * h->pitch; A.b = (const T*)b; A.x = (T*)x; A.minv = (const T*)Minv;
-  A.r_out = (T*)r_out; A.NX = h->NX; A.NY = h->NY; A.pitch = h->pitch; A.rows_per = rows_per; A.nranks = C;
+  A.r_out = (T*)r_out; A.NX = h->NX; A.NY = h->NY; A.pitch = h->pitch; A.rows_per = f.rows_per; A.nranks = f.C;
   A.sc = h->sc; A.history = history; A.hist_cap = hist_cap; A.eps = eps; A.max_iter = max_iter; A.flags = flags;
   A.warm = warm ? 1 : 0; A.is_cg = is_cg ? 1 : 0;
-  int rc = pre ? cluster_launch<T, true>(h, A, C, smem) : cluster_launch<T, false>(h, A, C, smem);
-  if (rc && C == 16) {
+  int rc = pre ? cluster_launch<T, true>(h, A, f) : cluster_launch<T, false>(h, A, f);
+  if (rc && f.C == 16) {
     // a 16-CTA cluster could not be scheduled on this device: retry with the portable size
     cudaGetLastError();
     sched_limit = 8;
-    C = pre ? cluster_fit<T, true>(h, warm, &smem, &rows_per, 8) : cluster_fit<T, false>(h, warm, &smem, &rows_per, 8);
-    if (C == 0) return 0;
-    A.rows_per = rows_per; A.nranks = C;
-    rc = pre ? cluster_launch<T, true>(h, A, C, smem) : cluster_launch<T, false>(h, A, C, smem);
+    f = cluster_fit<T>(h, pre, warm, 8);
+    if (f.C == 0) return 0;
+    A.rows_per = f.rows_per; A.nranks = f.C;
+    rc = pre ? cluster_launch<T, true>(h, A, f) : cluster_launch<T, false>(h, A, f);
   }
   if (rc) {
     // no cluster of a usable size can be scheduled (e.g. MIG slice): fall back to the streaming path
