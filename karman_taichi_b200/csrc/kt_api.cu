@@ -105,6 +105,9 @@ int kt_destroy(kt_handle_t h) {
   for (int k = 0; k < 2; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
+  if (h->gev) cudaEventDestroy(h->gev);
   delete h;
   return 0;
 }

@@ -24,6 +24,15 @@ struct kt_handle_s {
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   long long launches = 0;            // kernels launched through this handle (bench: gpu_launches)
   bool allow_cluster = true;         // small grids: whole solve inside one thread-block cluster (kt_cluster.cu)
+  // mid-size grids (too big for a cluster, kernels of a few microseconds): the 16-iteration chunks of the streaming
+  // solvers are captured once into a CUDA graph per argument set and replayed, so the solve is not bound by the host's
+  // launch rate.  Replays run on a private stream (the caller's may be the legacy default stream, which cannot be captured).
+  struct GraphEntry { std::vector<const void*> key; cudaGraphExec_t exec; long long launches; unsigned long long stamp; };
+  std::vector<GraphEntry> graphs;
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t gev = nullptr;
+  int graphs_state = 0;              // 0 untested, 1 usable, -1 unavailable (capture refused)
+  unsigned long long graph_clock = 0;
   // optional per-kernel-class device timing (bench.py roofline): events bracket every launch of a class
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs (begin, end)

@@ -573,17 +573,88 @@ static int sc_reset(kt_handle_s* h, double eps, long long max_iter, int flags) {
   return 0;
 }
 
+// ---- CUDA-graph replay of iteration chunks ---------------------------------------------------------------------
+static bool graphs_wanted(const kt_handle_s* h) {
+  static int enabled = env_int("KT_GRAPH", 1);
+  static long long max_elems = env_int("KT_GRAPH_MAX_ELEMS", 1 << 22);   // planes up to 32 MB (f64): kernels of <= ~40 us
+  return enabled && !h->prof_on && h->graphs_state >= 0 && (long long)(h->row_hi - h->row_lo) * h->pitch <= max_elems;
+}
+
+// Returns the cached executable graph of `chunk` iterations for this argument set, capturing it first if needed
+// (nullptr: graphs unavailable here -- the caller enqueues directly).
+template <typename EnqueueIter>
+static kt_handle_s::GraphEntry* graph_for(kt_handle_s* h, const std::vector<const void*>& key, int chunk, EnqueueIter&& enqueue_iter,
+                                          int* rc_out) {
+  *rc_out = 0;
+  for (auto& g : h->graphs)
+    if (g.key == key) { g.stamp = ++h->graph_clock; return &g; }
+  if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    h->graphs_state = -1;
+    return nullptr;
+  }
+  const long long l0 = h->launches;
+  int rc = 0;
+  for (int k = 0; k < chunk && rc == 0; ++k) rc = enqueue_iter();
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  const long long per_chunk = h->launches - l0;
+  h->launches = l0;                      // nothing ran yet: launches are counted per replay
+  if (rc) { if (graph) cudaGraphDestroy(graph); *rc_out = rc; return nullptr; }
+  cudaGraphExec_t exec = nullptr;
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { cudaGetLastError(); h->graphs_state = -1; return nullptr; }
+  h->graphs_state = 1;
+  if (h->graphs.size() >= 8) {           // small LRU: a SIMPLE loop alternates between three argument sets at most
+    size_t victim = 0;
+    for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].stamp < h->graphs[victim].stamp) victim = i;
+    cudaGraphExecDestroy(h->graphs[victim].exec);
+    h->graphs.erase(h->graphs.begin() + victim);
+  }
+  h->graphs.push_back({key, exec, per_chunk, ++h->graph_clock});
+  return &h->graphs.back();
+}
+
 // Poll loop shared by both solvers: enqueue `chunk` iterations at a time; the device-side `done` flag makes
 // every later kernel a no-op, so the host may notice convergence late without changing the result.
+// `graph_key` (may be null): every pointer / flag the enqueued launches depend on; when given and the grid is in the
+// launch-bound range, full chunks are replayed from a CUDA graph on the handle's private stream.
 template <typename EnqueueIter>
-static int run_chunks(kt_handle_s* h, long long max_iter, EnqueueIter&& enqueue_iter) {
-  const int chunk = 16;
+static int run_chunks(kt_handle_s* h, long long max_iter, EnqueueIter&& enqueue_iter, const std::vector<const void*>* graph_key = nullptr) {
+  const int chunk = 16;                  // even: the ping-pong parity of the fused variant is the same in every chunk
   long long enq = 0;
   int slot = 0;
   bool pending[2] = {false, false};
+  cudaStream_t caller_stream = h->stream;
+  struct Restore { kt_handle_s* h; cudaStream_t s; ~Restore() { h->stream = s; } } restore{h, caller_stream};
+  bool use_graph = graph_key && max_iter >= chunk && graphs_wanted(h);
+  if (use_graph) {
+    if (!h->gstream) {
+      if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->gev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); h->graphs_state = -1; use_graph = false; }
+    }
+    if (use_graph) {
+      KT_CUDA(cudaEventRecord(h->gev, caller_stream));        // everything enqueued so far (K0, the caller's kernels)
+      KT_CUDA(cudaStreamWaitEvent(h->gstream, h->gev, 0));
+      h->stream = h->gstream;                                  // launches and polls below go to the private stream
+    }
+  }
   while (enq < max_iter) {   // iteration max_iter always sets `done`, so nothing beyond it is ever needed
     long long n = std::min<long long>(chunk, max_iter - enq);
-    for (long long k = 0; k < n; ++k) { int rc = enqueue_iter(); if (rc) return rc; }
+    kt_handle_s::GraphEntry* ge = nullptr;
+    if (use_graph && n == chunk) {
+      int rc = 0;
+      ge = graph_for(h, *graph_key, chunk, enqueue_iter, &rc);
+      if (rc) return rc;
+      if (!ge) use_graph = false;                              // capture refused: direct launches from here on
+    }
+    if (ge) {
+      KT_CUDA(cudaGraphLaunch(ge->exec, h->stream));
+      h->launches += ge->launches;
+    } else {
+      for (long long k = 0; k < n; ++k) { int rc = enqueue_iter(); if (rc) return rc; }
+    }
     enq += n;
     KT_CUDA(cudaMemcpyAsync(h->sc_host + slot, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
     KT_CUDA(cudaEventRecord(h->ev[slot], h->stream));
@@ -683,7 +754,10 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
     KT_LAUNCH_CHECK(h);
     return 0;
   };
-  rc = run_chunks(h, max_iter, iter);
+  const std::vector<const void*> gkey = {(const void*)1, coef, b, x, Minv, r, p, v, s, t, r_tld, w->p2, w->Ap2, w->history,
+                                         (const void*)(size_t)w->history_cap, (const void*)(size_t)h->row_lo, (const void*)(size_t)h->row_hi,
+                                         (const void*)(size_t)sizeof(T)};
+  rc = run_chunks(h, max_iter, iter, &gkey);
   if (rc) return rc;
   const Scalars& S = *h->sc_host;
   if (iters) *iters = (long)S.iter;
@@ -733,7 +807,9 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
     KT_LAUNCH_CHECK(h);
     return 0;
   };
-  rc = run_chunks(h, max_iter, iter);
+  const std::vector<const void*> gkey = {(const void*)2, coef, b, x, r, p, Ap, w->history, (const void*)(size_t)w->history_cap,
+                                         (const void*)(size_t)h->row_lo, (const void*)(size_t)h->row_hi, (const void*)(size_t)sizeof(T)};
+  rc = run_chunks(h, max_iter, iter, &gkey);
   if (rc) return rc;
   const Scalars& S = *h->sc_host;
   if (iters) *iters = (long)S.iter;
