@@ -74,8 +74,10 @@ int kt_sync(kt_handle_t h);
  * ownership; rows outside are halo rows that are read but never written or summed).
  * Default [0, NX).  No reference counterpart (the reference is single-address-space). */
 int kt_set_rows(kt_handle_t h, int row_lo, int row_hi);
-/* Small grids (every plane of the solve fits the shared memory of one thread-block cluster, ~35k f64 unknowns) are
- * solved by a single cluster-resident kernel instead of 3-4 launches per iteration; 0 disables it (default on). */
+/* Resident solvers.  Small grids (~35k f64 unknowns: the solve fits one thread-block cluster) are solved by a single
+ * cluster-resident kernel, mid-size grids (up to ~3e5 unknowns) by one persistent cooperative kernel with one CTA per SM,
+ * instead of 3-4 launches per iteration.  enable: 1 automatic (default), 0 streaming kernels only, 2 cooperative kernel
+ * only, 3 cluster kernel only. */
 int kt_set_cluster(kt_handle_t h, int enable);
 /* number of kernels launched through this handle so far (bench.py: gpu_launches) */
 long long kt_launch_count(kt_handle_t h);

@@ -125,7 +125,7 @@ class BICGSolver(CGSolver):
         ws = self._ws(r_tld=r_tld, s=(self.s.ptr if self.store_s else None), t=self.t.ptr, p2=p2, Ap2=ap2)
         iters, rel, status = C.c_long(), C.c_double(), C.c_int()
         steps = self.steps if self.max_steps is None else self.max_steps
-        _lib.check(self._lib.kt_set_cluster(self._h, 1 if self.cluster else 0))
+        _lib.check(self._lib.kt_set_cluster(self._h, {True: 1, False: 0, 'coop': 2, 'cluster': 3}[self.cluster]))
         _lib.check(self._lib.kt_bicgstab_solve(self._h, _p(self.coef), _p(self.b), _p(self.x), _p(self.Minv), C.byref(ws),
                                                float(eps), steps, flags, C.byref(iters), C.byref(rel), C.byref(status)))
         hist = self._finish(iters, rel, status, quiet, None, want_history=not quiet)   # history is commented out in the reference (:93,125)

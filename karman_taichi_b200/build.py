@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libkarman_b200.so')
-SOURCES = ['kt_api.cu', 'kt_krylov.cu', 'kt_simple.cu', 'kt_channel.cu', 'kt_cluster.cu']
+SOURCES = ['kt_api.cu', 'kt_krylov.cu', 'kt_simple.cu', 'kt_channel.cu', 'kt_cluster.cu', 'kt_coop.cu']
 HEADERS = ['kt_common.cuh', 'kt_handle.h', os.path.join('..', '..', 'include', 'karman_b200.h')]
 
 NVCC_FLAGS = [

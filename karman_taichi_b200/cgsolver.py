@@ -75,7 +75,9 @@ class CGSolver:
         self._hd = _Handle(b)
         self._lib = self._hd.lib
         self._hist_dev = None
-        self.cluster = True                 # small grids: solve inside one thread-block cluster (kt_cluster.cu)
+        # resident solvers: True = automatic (one thread-block cluster for small grids, one persistent cooperative kernel
+        # for mid-size ones: kt_cluster.cu / kt_coop.cu), False = streaming kernels only, 'cluster' / 'coop' = only that one
+        self.cluster = True
         self.iterations = 0                 # bookkeeping (not in the reference)
         self.status = 0
         self.rel_res = float('nan')
@@ -188,7 +190,7 @@ class CGSolver:
         """``cgsolver.py:83-114``"""
         ws = self._ws()
         iters, rel, status = C.c_long(), C.c_double(), C.c_int()
-        _lib.check(self._lib.kt_set_cluster(self._h, 1 if self.cluster else 0))
+        _lib.check(self._lib.kt_set_cluster(self._h, {True: 1, False: 0, 'coop': 2, 'cluster': 3}[self.cluster]))
         _lib.check(self._lib.kt_cg_solve(self._h, _p(self.coef), _p(self.b), _p(self.x), C.byref(ws), float(eps),
                                          self.steps, C.byref(iters), C.byref(rel), C.byref(status)))
         hist = self._finish(iters, rel, status, quiet, None)

@@ -201,7 +201,8 @@ int kt_debug_poke(kt_handle_t h, void* ptr, double value, double* before_after_h
 
 int kt_set_cluster(kt_handle_t h, int enable) {
   KT_CHECK_ARG(h, "kt_set_cluster: null handle");
-  h->allow_cluster = enable != 0;
+  h->allow_cluster = enable == 1 || enable == 3;
+  h->allow_coop = enable == 1 || enable == 2;
   return 0;
 }
 

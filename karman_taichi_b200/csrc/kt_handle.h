@@ -24,6 +24,7 @@ struct kt_handle_s {
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   long long launches = 0;            // kernels launched through this handle (bench: gpu_launches)
   bool allow_cluster = true;         // small grids: whole solve inside one thread-block cluster (kt_cluster.cu)
+  bool allow_coop = true;            // mid-size grids: whole solve in one persistent cooperative kernel (kt_coop.cu)
   // mid-size grids (too big for a cluster, kernels of a few microseconds): the 16-iteration chunks of the streaming
   // solvers are captured once into a CUDA graph per argument set and replayed, so the solve is not bound by the host's
   // launch rate.  Replays run on a private stream (the caller's may be the legacy default stream, which cannot be captured).
@@ -64,6 +65,11 @@ namespace kt {
 template <typename T>
 int cluster_try_solve(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, void* r_out,
                       double* history, long long hist_cap, double eps, long long max_iter, int flags, bool is_cg);
+// kt_coop.cu: whole solve in one persistent cooperative kernel (one CTA per SM) for grids between the cluster limit and
+// ~3e5 unknowns.  Same return convention; r_plane / v_plane are the caller's r and Ap workspace planes.
+template <typename T>
+int coop_try_solve(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, void* r_plane, void* v_plane,
+                   double* history, long long hist_cap, double eps, long long max_iter, int flags, bool is_cg);
 void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 }  // namespace kt

@@ -688,7 +688,11 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
   const T* r_tld_c = r_tld ? r_tld : (const T*)b;     // x0 = 0  =>  r_tld == b exactly (bicgsolver.py:25-26)
   int rc = cluster_try_solve<T>(h, coef, b, x, Minv, r, w->history, w->history_cap, fixed_iters ? -1.0 : eps, max_iter, flags, false);
   if (rc < 0) return rc;
-  if (rc == 1) {       // small grid: solved inside one thread-block cluster (kt_cluster.cu)
+  if (rc == 0) {       // mid-size grid: one persistent cooperative kernel (kt_coop.cu)
+    rc = coop_try_solve<T>(h, coef, b, x, Minv, r, v, w->history, w->history_cap, fixed_iters ? -1.0 : eps, max_iter, flags, false);
+    if (rc < 0) return rc;
+  }
+  if (rc == 1) {       // solved inside one resident kernel (kt_cluster.cu / kt_coop.cu)
     const Scalars& S = *h->sc_host;
     if (iters) *iters = (long)S.iter;
     if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
@@ -774,6 +778,10 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
   KT_CHECK_ARG(r && p && Ap, "kt_krylov_ws: r, p, Ap are required for CG");
   int rc = cluster_try_solve<T>(h, coef, b, x, nullptr, r, w->history, w->history_cap, fixed_iters ? -1.0 : eps, max_iter, 0, true);
   if (rc < 0) return rc;
+  if (rc == 0) {
+    rc = coop_try_solve<T>(h, coef, b, x, nullptr, r, Ap, w->history, w->history_cap, fixed_iters ? -1.0 : eps, max_iter, 0, true);
+    if (rc < 0) return rc;
+  }
   if (rc == 1) {
     const Scalars& S = *h->sc_host;
     if (iters) *iters = (long)S.iter;

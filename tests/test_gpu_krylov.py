@@ -151,17 +151,18 @@ def system(kind, a, b):
     return krylov.random_dd_system(a, b, seed=0)
 
 
-@pytest.mark.parametrize('path', ['cluster', 'stream', 'stream-fused'])
+@pytest.mark.parametrize('path', ['cluster', 'coop', 'stream', 'stream-fused'])
 @pytest.mark.parametrize('kind,a,b,eps', CASES)
 def test_bicgstab_solve_parity(cuda, kind, a, b, eps, path):
-    """Three device paths, one recurrence: 'cluster' = whole solve inside one thread-block cluster (taken only when
-    the planes fit its shared memory, else it falls through to 'stream'); 'stream' = four HBM-streaming kernels per
+    """Four device paths, one recurrence: 'cluster' = automatic choice (whole solve inside one thread-block cluster when
+    the planes fit, else the cooperative kernel, else streaming); 'coop' = whole solve in one persistent cooperative
+    kernel, one CTA per SM (falls through to 'stream' above ~3e5 unknowns); 'stream' = four HBM-streaming kernels per
     iteration (28 N words); 'stream-fused' = p-update folded into v = A p (27 N)."""
     import karman_taichi_b200 as kt
     coef, rhs = system(kind, a, b)
     x_ref, it_ref, st_ref = krylov.bicgstab_solve(coef, rhs, eps=eps)
     s = make(cuda, coef, rhs, kt.BICGSolver)
-    s.cluster = path == 'cluster'
+    s.cluster = {'cluster': True, 'coop': 'coop'}.get(path, False)
     s.fuse_p_update = path == 'stream-fused'
     s.solve(eps=eps, quiet=True)
     assert s.status == st_ref == 0
@@ -180,7 +181,7 @@ def test_bicgstab_solve_parity(cuda, kind, a, b, eps, path):
     assert np.all(s.x.to_numpy()[0, :] == 0) and np.all(s.x.to_numpy()[:, 0] == 0)
 
 
-@pytest.mark.parametrize('cluster', [True, False])
+@pytest.mark.parametrize('cluster', [True, 'coop', False])
 @pytest.mark.parametrize('kind,a,b,eps', [c for c in CASES if c[0] == 'poisson'])
 def test_cg_solve_parity(cuda, kind, a, b, eps, cluster):
     import karman_taichi_b200 as kt
@@ -256,7 +257,7 @@ def test_jacobi_warm_start_variant(cuda):
     s.warm_start = True
     s.omega_zero_break = True
     s.max_steps = 100 * 66 * 323
-    for cluster, fused in ((True, False), (False, True), (False, False)):
+    for cluster, fused in ((True, False), ('coop', False), (False, True), (False, False)):
         s.cluster, s.fuse_p_update = cluster, fused
         s.x.from_numpy(x0)
         s.solve(eps=1e-8)
@@ -407,7 +408,7 @@ def test_stepwise_reference_loop_matches_solve(cuda):
 
 
 @pytest.mark.parametrize('shape', [(1, 1), (1, 9), (9, 1), (2, 3), (3, 2), (2, 129), (129, 2)])
-@pytest.mark.parametrize('cluster', [True, False])
+@pytest.mark.parametrize('cluster', [True, 'coop', False])
 def test_degenerate_shapes(cuda, shape, cluster):
     """Arrays with no ghost ring at all and as small as one element: every neighbour that leaves the array contributes 0
     (cgsolver.py:56-60 reads it and multiplies by a never-written coefficient); SpMV bit-exact, both solvers converge."""
