@@ -205,8 +205,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
   auto coef = [&](int k, int q, int e) -> T { return REGC ? c[REGC ? k : 0][q] : cs[q * cap + e]; };
   // Every thread keeps its own copy of the Krylov scalars and runs the (cheap) scalar algebra itself on the identical
   // reduced sums: no shared-memory round trip and no block barrier between a reduction and its consumers.
-  // Every thread keeps its own copy of the Krylov scalars and runs the (cheap) scalar algebra itself on the identical
-  // reduced sums: no shared-memory round trip and no block barrier between a reduction and its consumers.
   Scalars sc;
   sc.rho = 0.0; sc.rho_1 = 1.0; sc.alpha = 1.0; sc.beta = 1.0; sc.omega = 1.0;
   sc.rTr0 = sc.rTr = sc.old_rTr = 0.0; sc.dot0 = sc.dot1 = 0.0;
