@@ -741,11 +741,12 @@ static ClFit cluster_fit(const kt_handle_s* h, bool pre, bool warm, int limit_c)
 }
 
 template <typename K, typename T>
-static int cluster_launch_k(kt_handle_s* h, K kern, bool& configured, const ClArgs<T>& A0, int C, size_t smem) {
-  if (!configured) {
+static int cluster_launch_k(kt_handle_s* h, K kern, unsigned long long& configured, const ClArgs<T>& A0, int C, size_t smem) {
+  const unsigned long long dev_bit = 1ull << (h->device & 63);   // function attributes are per device
+  if (!(configured & dev_bit)) {
     KT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     KT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    configured = true;
+    configured |= dev_bit;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
@@ -760,7 +761,7 @@ static int cluster_launch_k(kt_handle_s* h, K kern, bool& configured, const ClAr
 
 template <typename T, bool PRE>
 static int cluster_launch(kt_handle_s* h, const ClArgs<T>& A, const ClFit& f) {
-  static bool conf[3] = {false, false, false};
+  static unsigned long long conf[3] = {0, 0, 0};
   if (f.reg && f.ept == 1) return cluster_launch_k(h, k_cluster_solve<T, PRE, 1, true>, conf[0], A, f.C, f.smem);
   if (f.reg && f.ept == 2) return cluster_launch_k(h, k_cluster_solve<T, PRE, 2, true>, conf[1], A, f.C, f.smem);
   return cluster_launch_k(h, k_cluster_solve_smem<T, PRE>, conf[2], A, f.C, f.smem);

@@ -372,10 +372,11 @@ static CoFit coop_fit(const kt_handle_s* h, bool pre) {
 }
 
 template <typename K, typename T>
-static int coop_launch_k(kt_handle_s* h, K kern, bool& configured, CoArgs<T>& A, const CoFit& f) {
-  if (!configured) {
+static int coop_launch_k(kt_handle_s* h, K kern, unsigned long long& configured, CoArgs<T>& A, const CoFit& f) {
+  const unsigned long long dev_bit = 1ull << (h->device & 63);   // function attributes are per device
+  if (!(configured & dev_bit)) {
     KT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    configured |= dev_bit;
   }
   KT_CUDA(cudaMemsetAsync(A.partials, 0xFF, sizeof(double) * 6 * (size_t)f.G, h->stream));     // every slot "empty"
   void* args[] = {(void*)&A};
@@ -386,7 +387,7 @@ static int coop_launch_k(kt_handle_s* h, K kern, bool& configured, CoArgs<T>& A,
 
 template <typename T, bool PRE>
 static int coop_launch(kt_handle_s* h, CoArgs<T>& A, const CoFit& f) {
-  static bool conf[6] = {false, false, false, false, false, false};
+  static unsigned long long conf[6] = {0, 0, 0, 0, 0, 0};
   switch (f.ept) {
     case 1: return coop_launch_k(h, k_coop_solve<T, PRE, 1, true>, conf[0], A, f);
     case 2: return coop_launch_k(h, k_coop_solve<T, PRE, 2, true>, conf[1], A, f);
