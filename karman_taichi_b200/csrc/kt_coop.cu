@@ -33,6 +33,7 @@ template <typename T> struct CoArgs {
 };
 
 constexpr int CO_THREADS = 512;
+constexpr int CO_SLOTS = 8;           // slots per polling lane: up to 256 CTAs
 enum { CF_VALID = 1, CF_ROW0 = 2, CF_ROWN = 4, CF_J0 = 8, CF_JN = 16 };
 
 __device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
@@ -128,7 +129,8 @@ __global__ void __launch_bounds__(CO_THREADS, 1) k_coop_solve(const CoArgs<T> A)
   // could poll a slow CTA's slot of sum N+1 before the slow one has re-armed it.)
   int prev_group = -1, next_group = 0;
   auto slot_of = [&](int group, int cta) -> double* { return A.partials + ((size_t)group * G + cta) * 2; };
-  auto grid_sum = [&](double& d0, double& d1) {
+  // `published`: boundary rows were written to global memory in this phase (the acquire fence is only needed then).
+  auto grid_sum = [&](double& d0, double& d1, bool published) {
     const int group = next_group;
     next_group = (next_group == 2) ? 0 : next_group + 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -139,21 +141,30 @@ __global__ void __launch_bounds__(CO_THREADS, 1) k_coop_solve(const CoArgs<T> A)
       double s0 = (lane < CO_THREADS / 32) ? red[0][lane] : 0.0, s1 = (lane < CO_THREADS / 32) ? red[1][lane] : 0.0;
       s0 = warp_allsum(s0); s1 = warp_allsum(s1);
       if (lane == 0) {
-        __threadfence();
+        __threadfence();      // release: this phase's boundary rows AND the re-arm store of the previous sum come first
         asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(slot_of(group, rank)), "d"(s0), "d"(s1) : "memory");
       }
-      double a0 = 0.0, a1 = 0.0;
+      // every lane owns up to CO_SLOTS slots (l, l + 32, ...): their loads are issued back to back so that one L2 round
+      // trip covers all of them, and only the ones still empty are read again
+      double u0[CO_SLOTS], u1[CO_SLOTS];
+      unsigned pending = 0;
+#pragma unroll
+      for (int k = 0; k < CO_SLOTS; ++k) { u0[k] = 0.0; u1[k] = 0.0; if (lane + 32 * k < G) pending |= 1u << k; }
       const long long t0 = clock64();
-      for (int i = lane; i < G; i += 32) {
-        double u0, u1;
-        while (true) {
-          asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(u0), "=d"(u1) : "l"(slot_of(group, i)) : "memory");
-          if (__double_as_longlong(u0) != -1ll && __double_as_longlong(u1) != -1ll) break;
-          if (clock64() - t0 > (1ll << 32)) __trap();      // a CTA that never arrives is a bug, not a data condition
-        }
-        a0 += u0; a1 += u1;
+      while (pending) {
+#pragma unroll
+        for (int k = 0; k < CO_SLOTS; ++k)
+          if (pending & (1u << k))
+            asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(u0[k]), "=d"(u1[k]) : "l"(slot_of(group, lane + 32 * k)) : "memory");
+#pragma unroll
+        for (int k = 0; k < CO_SLOTS; ++k)
+          if ((pending & (1u << k)) && __double_as_longlong(u0[k]) != -1ll && __double_as_longlong(u1[k]) != -1ll) pending &= ~(1u << k);
+        if (pending && clock64() - t0 > (1ll << 32)) __trap();   // a CTA that never arrives is a bug, not a data condition
       }
-      __threadfence();                                     // acquire: the publishers' boundary rows are visible from here on
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < CO_SLOTS; ++k) { a0 += u0[k]; a1 += u1[k]; }     // index order; absent slots add +0.0
+      if (published) __threadfence();                      // acquire: the publishers' boundary rows are visible from here on
       a0 = warp_allsum(a0); a1 = warp_allsum(a1);
       if (lane == 0) {
         bc[0] = a0; bc[1] = a1;
@@ -226,7 +237,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) k_coop_solve(const CoArgs<T> A)
     if (A.is_cg) { p[k] = rr; ps[e] = rr; }                // cgsolver.py:90 p = r + 0 * p
     d0 += (double)rr * (double)rr;
   }
-  grid_sum(d0, d1);
+  grid_sum(d0, d1, true);
   CO_SCALARS(A.is_cg ? FIN_CG_INIT : FIN_BICG_INIT, d0, d0, hist);
   if (A.is_cg) {                                           // p = r on the halo rows too
     load_halo(r_lo, r_hi, A.gr);
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) k_coop_solve(const CoArgs<T> A)
         v[k] = y; vs[e] = y;
         publish(A.gv, ef[k], y);                           // neighbours read it in P3, after the barrier below
       }
-      grid_sum(d0, d1);
+      grid_sum(d0, d1, true);
       CO_SCALARS(FIN_BICG_ALPHA, d0, d1, nullptr);
       if (sc.done) break;
       // P3
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) k_coop_solve(const CoArgs<T> A)
         d0 += (double)y * (double)sraw;
         d1 += (double)y * (double)y;
       }
-      grid_sum(d0, d1);
+      grid_sum(d0, d1, false);
       CO_SCALARS(FIN_BICG_OMEGA, d0, d1, nullptr);
       if (sc.done) break;
       // P4 (every CTA finished reading the r rows -- P3 -- before the barrier above)
@@ -289,7 +300,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) k_coop_solve(const CoArgs<T> A)
         d0 += (double)rn * (double)rn;
         d1 += (double)rn * (double)rt[k];
       }
-      grid_sum(d0, d1);
+      grid_sum(d0, d1, true);
       CO_SCALARS(FIN_BICG_END, d0, d1, hist);
     } else {
       // C1: Ap = A p ; (p, Ap)
@@ -299,7 +310,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) k_coop_solve(const CoArgs<T> A)
         v[k] = y;
         d0 += (double)p[k] * (double)y;
       }
-      grid_sum(d0, d1);
+      grid_sum(d0, d1, false);
       CO_SCALARS(FIN_CG_ALPHA, d0, d1, nullptr);
       if (sc.done) break;
       // C2: x += alpha p ; r -= alpha Ap ; (r,r)
@@ -312,7 +323,7 @@ __global__ void __launch_bounds__(CO_THREADS, 1) k_coop_solve(const CoArgs<T> A)
         publish(A.gr, ef[k], rn);
         d0 += (double)rn * (double)rn;
       }
-      grid_sum(d0, d1);
+      grid_sum(d0, d1, true);
       CO_SCALARS(FIN_CG_END, d0, d1, hist);
       if (sc.done) break;
       // C3: p = r + beta p, halo rows included (the neighbours' r rows are final since the barrier above)
@@ -368,6 +379,7 @@ static CoFit coop_fit(const kt_handle_s* h, bool pre) {
   const size_t need = ((size_t)planes * cap + 8 * (size_t)h->NY) * sizeof(T);
   if (need > 200 * 1024) return f;
   f.G = (h->NX + rows_per - 1) / rows_per; f.rows_per = rows_per; f.ept = ept; f.regc = regc; f.smem = need;
+  if (f.G > 32 * CO_SLOTS) f.G = 0;
   return f;
 }
 
