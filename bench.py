@@ -10,7 +10,7 @@ count is exact) on synthetic inputs.  Default workload at every N: ``pcor32768``
 it fits one B200: 103 GB).  N > 1 splits the same grid into x-slabs (strong scaling), one rank per GPU under torchrun,
 halo rows over NCCL send/recv and the inner products over NCCL all-reduce.
 
-``--workload cavity128 | karman320 | karman16384`` measures the other half of BASELINE.json's metric instead, SIMPLE
+``--workload cavity128 | karman320 | karman640 | karman16384`` measures the other half of BASELINE.json's metric instead, SIMPLE
 outer-iterations/s on configs 2, 1 and 4 (one step = one outer iteration through SIMPLESolver / KarmanSolver).
 
 One JSON line on stdout (rank 0): value (inputs resident in HBM), e2e (host buffers in the reference layout through
@@ -49,6 +49,7 @@ SIMPLE_WORKLOADS = {
     'cavity128': ('cavity', 128, 128, 0, 'BASELINE config 2: lid-driven cavity 128x128, Re=100, SIMPLE (bicgsimp.py), alpha_p = 0.02 '
                                          '(the committed 0.1 diverges at 128^2: SURVEY.md 8d)'),
     'karman320': ('karman', 320, 64, 0, 'BASELINE config 1: 320x64 channel + square-cell cylinder, SIMPLE sub-iterations (karman_taichi.py)'),
+    'karman640': ('karman', 640, 128, 0, 'the size karman_taichi.py is committed with (nx = 640, ny = 128: karman_taichi.py:11-12), SIMPLE sub-iterations'),
     'karman16384': ('karman', 16384, 3276, 200, 'BASELINE config 4: channel scaled to 16384x3276, full SIMPLE sub-iterations, '
                                                 'BiCGSTAB capped at 200 iterations per solve'),
 }
@@ -591,8 +592,9 @@ def run_simple(a):
                                        'frac': names[dom][1] * 8.0 * N / (d_ms * 1e-3) / 1e9 / peak,
                                        'share_of_step': {names[i][0]: tot[i] / ms_total for i in range(4)}}
     else:
-        roofline['note'] = ('all planes of a solve fit the shared memory of one thread-block cluster: the Krylov solves run as ONE '
-                            'cluster-resident kernel each (csrc/kt_cluster.cu) and are bound by barrier latency, not by HBM')
+        roofline['note'] = ('the Krylov solves run as ONE resident kernel each -- a thread-block cluster (csrc/kt_cluster.cu) up to ~35 k '
+                            'unknowns, a persistent cooperative kernel (csrc/kt_coop.cu) above -- and are bound by the latency of the '
+                            'three dependent inner products per iteration, not by HBM')
 
     # e2e: u, v, p arrive in pinned host arrays and go back every step (kt_upload_field / kt_download_field)
     e2e = None
