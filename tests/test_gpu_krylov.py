@@ -201,11 +201,13 @@ def test_cg_solve_parity(cuda, kind, a, b, eps, cluster):
     np.testing.assert_allclose(got, ref, rtol=1e-5)
 
 
-def test_bicgstab_f32(cuda):
+@pytest.mark.parametrize('n,path', [(128, True), (128, 'coop'), (200, 'coop'), (128, False)])
+def test_bicgstab_f32(cuda, n, path):
     import karman_taichi_b200 as kt
-    coef, rhs = krylov.poisson_sin_system(128, 0.1)
+    coef, rhs = krylov.poisson_sin_system(n, 0.1)
     x_ref, it_ref, _ = krylov.bicgstab_solve(coef, rhs, eps=1e-5)
     s = make(cuda, coef.astype(np.float32), rhs.astype(np.float32), kt.BICGSolver)
+    s.cluster = path
     s.solve(eps=1e-5, quiet=True)
     assert s.status == 0
     # f32 fields (dots still accumulate in f64) against the f64 oracle: the iteration count moves by a few
