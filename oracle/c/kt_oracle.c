@@ -19,6 +19,14 @@
 
 #define IDX(i, j) ((size_t)(i) * NY + (j))
 
+/* number of OpenMP threads of every later loop (1: strictly sequential sums in index order) */
+#ifdef _OPENMP
+#include <omp.h>
+void ko_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
+#else
+void ko_set_threads(int n) { (void)n; }
+#endif
+
 /* cgsolver.py:49-54 */
 double ko_reduce(const double* p, const double* q, long n) {
   double sum = 0.0;

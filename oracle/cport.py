@@ -34,6 +34,8 @@ def load():
         dp = np.ctypeslib.ndpointer(np.float64, flags='C_CONTIGUOUS')
         L.ko_reduce.restype = C.c_double
         L.ko_reduce.argtypes = [dp, dp, C.c_long]
+        L.ko_set_threads.restype = None
+        L.ko_set_threads.argtypes = [C.c_int]
         L.ko_spmv.restype = None
         L.ko_spmv.argtypes = [dp, dp, dp, C.c_int, C.c_int]
         for fn in (L.ko_cg, L.ko_bicgstab):
@@ -44,7 +46,9 @@ def load():
 
 
 def set_threads(n):
+    """Thread count of every later call (1: strictly sequential sums in index order)."""
     os.environ['OMP_NUM_THREADS'] = str(n)
+    load().ko_set_threads(int(n))
 
 
 def spmv(coef, x):

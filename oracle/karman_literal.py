@@ -17,6 +17,8 @@ import math
 import numpy as np
 import scipy.sparse as sp
 
+from . import krylov
+
 
 class SparseMat:
     """n x n pointer-SNode matrix stand-in."""
@@ -237,12 +239,12 @@ class KarmanLiteral:
             Ax = A7 @ x
             r = b - Ax
             r_tld = r.copy()
-            residual_init = np.float64(np.sum(r * r))
+            residual_init = np.float64(krylov._sum(r * r))
             omega = alpha = beta = rho_1 = one
             p = np.zeros(n); Ap = np.zeros(n)
             iters, status = 0, 1
             for steps in range(100 * n):
-                rho = np.float64(np.sum(r * r_tld))
+                rho = np.float64(krylov._sum(r * r_tld))
                 if rho == 0.0:
                     status = 2
                     break
@@ -253,15 +255,15 @@ class KarmanLiteral:
                     p = r + beta * (p - omega * Ap)
                 p_hat = 1 / Md * p
                 Ap = A7 @ p_hat
-                alpha_lower = np.float64(np.sum(r_tld * Ap))
+                alpha_lower = np.float64(krylov._sum(r_tld * Ap))
                 alpha = rho / alpha_lower
                 s = r - alpha * Ap
                 s_hat = 1 / Md * s
                 t = A7 @ s_hat
-                omega = np.float64(np.sum(t * s)) / np.float64(np.sum(t * t))
+                omega = np.float64(krylov._sum(t * s)) / np.float64(krylov._sum(t * t))
                 x += alpha * p_hat + omega * s_hat
                 r = s - omega * t
-                residual = np.float64(np.sum(r * r))
+                residual = np.float64(krylov._sum(r * r))
                 iters = steps + 1
                 if np.sqrt(residual / residual_init) < eps:
                     status = 0
@@ -339,8 +341,8 @@ class KarmanLiteral:
     def correct_conserv(self):
         nx, ny, dx, dy = self.nx, self.ny, self.dx, self.dy
         u, v = self.u, self.v
-        mdot_inlet = float(np.sum(u[1, 1:ny + 1]))
-        mdot_outlet = float(np.sum(u[nx + 1, 1:ny + 1]))
+        mdot_inlet = float(krylov._sum(u[1, 1:ny + 1]))
+        mdot_outlet = float(krylov._sum(u[nx + 1, 1:ny + 1]))
         with np.errstate(all='ignore'):
             coef = np.float64(mdot_inlet) / np.float64(mdot_outlet)
         u[nx + 1, 1:ny + 1] = coef * u[nx + 1, 1:ny + 1]

@@ -56,9 +56,30 @@ def spmv(coef, x):
     return y
 
 
+_SERIAL = False
+
+
+def set_summation(mode):
+    """'pairwise' (default): ``np.sum``.  'serial': strictly sequential in row-major index order, starting from 0.0 --
+    the order a serial execution of the reference's ``sum += p[I] * q[I]`` loop (``cgsolver.py:51-53``) or of the
+    monolith's scalar accumulations (``karman_taichi.py:376-378,384-385``) takes; bit-identical to the C port run with
+    one thread (``tests/test_oracle_cport.py``).  Real Taichi leaves the order of that reduction unspecified."""
+    global _SERIAL
+    if mode not in ('pairwise', 'serial'):
+        raise ValueError(mode)
+    _SERIAL = mode == 'serial'
+
+
+def _sum(a):
+    if _SERIAL:
+        flat = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        return np.float64(np.add.accumulate(flat)[-1]) if flat.size else np.float64(0.0)   # ((0 + a0) + a1) + ...
+    return np.sum(a)
+
+
 def reduce(p, q):
     """``cgsolver.py:49-54``: sum over the whole array, ghosts included."""
-    return float(np.sum(p * q))
+    return float(_sum(p * q))
 
 
 def _div(a, b):
@@ -181,7 +202,7 @@ def jacobi_bicgstab(coef, M, b, x0, eps=1e-8, max_iter=None, n=None):
     Ax = spmv(coef, x)
     r = b - Ax
     r_tld = r.copy()
-    residual_init = np.float64(np.sum(r * r))
+    residual_init = np.float64(_sum(r * r))
     omega = alpha = beta = rho_1 = one
     p = np.zeros_like(b)
     Ap = np.zeros_like(b)
@@ -189,7 +210,7 @@ def jacobi_bicgstab(coef, M, b, x0, eps=1e-8, max_iter=None, n=None):
     status = MAX_ITER
     with np.errstate(all='ignore'):
         for step in range(steps):
-            rho = np.float64(np.sum(r * r_tld))
+            rho = np.float64(_sum(r * r_tld))
             if rho == 0.0:
                 status = RHO_ZERO
                 break
@@ -200,17 +221,17 @@ def jacobi_bicgstab(coef, M, b, x0, eps=1e-8, max_iter=None, n=None):
                 p = r + beta * (p - omega * Ap)
             p_hat = np.where(M != 0.0, 1 / Minv_safe * p, 0.0)   # :399 '1/M[i,i] * p[i]'
             Ap = spmv(coef, p_hat)
-            alpha_lower = np.float64(np.sum(r_tld * Ap))
+            alpha_lower = np.float64(_sum(r_tld * Ap))
             alpha = rho / alpha_lower
             s = r - alpha * Ap
             s_hat = np.where(M != 0.0, 1 / Minv_safe * s, 0.0)   # :419
             t = spmv(coef, s_hat)
-            omega_upper = np.float64(np.sum(t * s))
-            omega_lower = np.float64(np.sum(t * t))
+            omega_upper = np.float64(_sum(t * s))
+            omega_lower = np.float64(_sum(t * t))
             omega = omega_upper / omega_lower
             x = x + (alpha * p_hat + omega * s_hat)              # :437
             r = s - omega * t                                    # :440
-            residual = np.float64(np.sum(r * r))
+            residual = np.float64(_sum(r * r))
             iters = step + 1
             if np.sqrt(residual / residual_init) < eps:          # :446 (False on NaN, like Taichi)
                 status = CONVERGED

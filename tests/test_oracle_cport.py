@@ -1,4 +1,6 @@
 """The C/OpenMP port (CPU baseline of bench.py) must be the same algorithm as the NumPy oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -54,3 +56,26 @@ def test_bicgstab_count_noise_floor():
         _, ic_c, _, _ = cport.cg_solve(coef, b, eps=eps)
         assert abs(ic_np - ic_c) <= 1
     print('bicgstab iteration spread numpy-vs-C:', spread)
+
+
+def test_serial_summation_is_bit_identical_to_one_thread_port():
+    """Two independent restatements of the same recurrence (NumPy arrays vs C loops) with the same summation order
+    -- strictly sequential, the order a serial run of the reference's `sum +=` loop takes -- must agree bit for bit,
+    iteration counts included: everything else in them (SpMV order, update order, host scalar algebra) is then equal."""
+    krylov.set_summation('serial')
+    cport.set_threads(1)
+    try:
+        for (coef, b), eps in [(krylov.poisson_sin_system(48, 0.1), 1e-10), (krylov.random_dd_system(37, 53, seed=2), 1e-9),
+                               (krylov.poisson_sin_system(33, 0.0), 1e-8)]:
+            xo, ito, sto = krylov.bicgstab_solve(coef, b, eps=eps)
+            xc, itc, stc, _ = cport.bicgstab_solve(coef, b, eps=eps)
+            assert (ito, sto) == (itc, stc)
+            np.testing.assert_array_equal(xc, xo)
+        coef, b = krylov.poisson_sin_system(40, 0.1)
+        xo, ito, sto = krylov.cg_solve(coef, b, eps=1e-10)
+        xc, itc, stc, _ = cport.cg_solve(coef, b, eps=1e-10)
+        assert (ito, sto) == (itc, stc)
+        np.testing.assert_array_equal(xc, xo)
+    finally:
+        krylov.set_summation('pairwise')
+        cport.set_threads(os.cpu_count() or 1)
