@@ -118,8 +118,9 @@ __device__ __forceinline__ double tree16(double v) {
 // (signalling that CTA's mbarrier with 16 bytes) -> every thread waits on its own CTA's mbarrier (C x 16 bytes) ->
 // every warp adds the C slots with the same fixed tree.  Identical bits on every CTA, warp and thread.
 // `use` counts the completed uses of this group's mbarrier (phase parity = use & 1).
+template <int NW = CL_THREADS / 32>
 __device__ __forceinline__ void cluster_sum(ClShared* S, int group, unsigned use, double& d0, double& d1, int nranks, int rank CLP_ARGS) {
-  static_assert(CL_THREADS / 32 == 16, "tree16 assumes 16 warps per CTA");
+  static_assert(NW <= 16, "tree16 adds at most 16 warp sums");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   d0 = warp_sum(d0);
   d1 = warp_sum(d1);
@@ -128,8 +129,8 @@ __device__ __forceinline__ void cluster_sum(ClShared* S, int group, unsigned use
   CLP(3);
   const unsigned mbar = smem_u32(&S->mbar_sum[group]);
   if (wid == 0) {
-    const double s0 = tree16(S->red[0][lane & 15]);
-    const double s1 = tree16(S->red[1][lane & 15]);
+    const double s0 = tree16((lane & 15) < NW ? S->red[0][lane & 15] : 0.0);
+    const double s1 = tree16((lane & 15) < NW ? S->red[1][lane & 15] : 0.0);
     if (lane == 0) mbar_arrive_expect(mbar, 16u * (unsigned)nranks);
     if (lane < nranks) st_async2(mapa_u32(smem_u32(&S->part[group][rank][0]), lane), s0, s1, mapa_u32(mbar, lane));
   }
@@ -144,7 +145,8 @@ __device__ __forceinline__ void cluster_sum(ClShared* S, int group, unsigned use
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Variant for up to CL_EPT_REG elements per thread (grids up to ~2 x 512 x 16 = 16 k unknowns: cavity 50^2 ... 120^2).
+// Register-resident variant: NT = 512 threads for up to 2 elements per thread, NT = 256 threads (255 registers each) for up
+// to 5 -- together every slice of up to 1280 elements (cavity <= ~140^2); larger slices take the shared-memory kernel.
 // ---------------------------------------------------------------------------------------------------------------
 // Per-thread element state.  A thread owns the same EPT elements of the CTA's slice (flat index e = threadIdx.x + k * 512)
 // for the whole solve and keeps everything only it touches in registers: the five coefficients (REGC; otherwise they stay
@@ -153,8 +155,8 @@ __device__ __forceinline__ void cluster_sum(ClShared* S, int group, unsigned use
 // shared-memory pipe instead of 35 + 6 -- the SpMV phases of the first versions were bound by exactly that pipe.
 enum { EF_VALID = 1, EF_ROW0 = 2, EF_ROWN = 4, EF_J0 = 8, EF_JN = 16 };
 
-template <typename T, bool PRE, int EPT, bool REGC>
-__global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T> A) {
+template <typename T, bool PRE, int EPT, bool REGC, int NT>
+__global__ void __launch_bounds__(NT, 1) k_cluster_solve(const ClArgs<T> A) {
   cg::cluster_group cl = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ClShared* S = reinterpret_cast<ClShared*>(smem_raw);
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
 #define EJ(k) ((int)(ef[k] >> 8))
 #pragma unroll
   for (int k = 0; k < EPT; ++k) {
-    const int e = threadIdx.x + k * CL_THREADS;
+    const int e = threadIdx.x + k * NT;
     ef[k] = 0;
     x[k] = r[k] = v[k] = p[k] = t[k] = rt[k] = T(0); m[k] = T(1);
     if (REGC) { for (int q = 0; q < 5; ++q) c[k][q] = T(0); }
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
   // the constant 1/M halo rows and the warm-start x halo are read once, remotely (slices final since cl.sync)
   if (PRE) {
     const T* ms_lo = cl.map_shared_rank(ms, lo_rank); const T* ms_hi = cl.map_shared_rank(ms, hi_rank);
-    for (int j = threadIdx.x; j < NY; j += CL_THREADS) {
+    for (int j = threadIdx.x; j < NY; j += NT) {
       if (has_lo) m_lo[j] = ms_lo[lo_off + j];
       if (has_hi) m_hi[j] = ms_hi[j];
     }
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
     return v_;
   };
   auto spmv_elem = [&](int mode, int k, T centre_raw, T alpha) -> T {
-    const int e = threadIdx.x + k * CL_THREADS, j = EJ(k);
+    const int e = threadIdx.x + k * NT, j = EJ(k);
     const unsigned f = ef[k];
     const T xc = (PRE && mode != 2) ? m[k] * centre_raw : centre_raw;
     T xw = T(0), xe = T(0), xn = T(0), xso = T(0);
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
     acc = acc + coef(k, 4, e) * xso;
     return acc;
   };
-#define CL_EACH(k, e) _Pragma("unroll") for (int k = 0; k < EPT; ++k) if (const int e = threadIdx.x + k * CL_THREADS; ef[k] & EF_VALID)
+#define CL_EACH(k, e) _Pragma("unroll") for (int k = 0; k < EPT; ++k) if (const int e = threadIdx.x + k * NT; ef[k] & EF_VALID)
 
   // ---- K0: r = b - A x0 (warm) or r = b ; r~ = r ; (r,r) -----------------------------------------------------------
   CLP_DECL
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
   pend[A.is_cg ? HALO_P : HALO_R] = true;
   // group 2 for this one: the loop's first sum (group 0) may be sent by a fast CTA before a slow one has read the slots
   // of the sum before it, unless another sum lies in between -- group 2 is next used two sums later (P4) or never (CG)
-  cluster_sum(S, 2, use_sum[2]++, d0, d1, A.nranks, rank CLP_PASS);
+  cluster_sum<NT / 32>(S, 2, use_sum[2]++, d0, d1, A.nranks, rank CLP_PASS);
   CL_SCALARS(A.is_cg ? FIN_CG_INIT : FIN_BICG_INIT, d0, d0, hist);
   if (A.is_cg) { halo_wait(HALO_P); __syncthreads(); }
 
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
       }
       pend[HALO_V] = true;
       CLP(2);
-      cluster_sum(S, 0, use_sum[0]++, d0, d1, A.nranks, rank CLP_PASS);
+      cluster_sum<NT / 32>(S, 0, use_sum[0]++, d0, d1, A.nranks, rank CLP_PASS);
       CL_SCALARS(FIN_BICG_ALPHA, d0, d1, nullptr);
       CLP(7);
       if (sc.done) break;
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         d1 += (double)y * (double)y;
       }
       CLP(8);
-      cluster_sum(S, 1, use_sum[1]++, d0, d1, A.nranks, rank CLP_PASS);
+      cluster_sum<NT / 32>(S, 1, use_sum[1]++, d0, d1, A.nranks, rank CLP_PASS);
       CL_SCALARS(FIN_BICG_OMEGA, d0, d1, nullptr);
       CLP(7);
       if (sc.done) break;
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
       }
       pend[HALO_R] = true;
       CLP(9);
-      cluster_sum(S, 2, use_sum[2]++, d0, d1, A.nranks, rank CLP_PASS);
+      cluster_sum<NT / 32>(S, 2, use_sum[2]++, d0, d1, A.nranks, rank CLP_PASS);
       CL_SCALARS(FIN_BICG_END, d0, d1, hist);
       CLP(7);
     } else {
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         v[k] = y;
         d0 += (double)p[k] * (double)y;
       }
-      cluster_sum(S, 0, use_sum[0]++, d0, d1, A.nranks, rank CLP_PASS);
+      cluster_sum<NT / 32>(S, 0, use_sum[0]++, d0, d1, A.nranks, rank CLP_PASS);
       CL_SCALARS(FIN_CG_ALPHA, d0, d1, nullptr);
       if (sc.done) break;
       // C2: x += alpha p ; r -= alpha Ap ; (r,r)
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve(const ClArgs<T>
         r[k] = rn;
         d0 += (double)rn * (double)rn;
       }
-      cluster_sum(S, 1, use_sum[1]++, d0, d1, A.nranks, rank CLP_PASS);
+      cluster_sum<NT / 32>(S, 1, use_sum[1]++, d0, d1, A.nranks, rank CLP_PASS);
       CL_SCALARS(FIN_CG_END, d0, d1, hist);
       if (sc.done) break;
       // C3: p = r + beta p (the neighbours finished reading their p halo in C1, two sums ago)
@@ -712,14 +714,15 @@ static int cluster_env(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-constexpr int CL_EPT_REG = 2;       // register-resident kernel up to this many elements per thread
+constexpr int CL_EPT_REG = 2;       // register-resident kernel, 512 threads: up to this many elements per thread
+constexpr int CL_EPT_REG256 = 5;    // register-resident kernel, 256 threads (255 registers each): up to this many (6 spills: slower)
 
-struct ClFit { int C, rows_per, ept; bool reg; size_t smem; };
+struct ClFit { int C, rows_per, ept, nt; bool reg; size_t smem; };
 
 // Can this geometry be solved inside one cluster?  C = 0: no.
 template <typename T>
 static ClFit cluster_fit(const kt_handle_s* h, bool pre, bool warm, int limit_c) {
-  ClFit f = {0, 0, 0, false, 0};
+  ClFit f = {0, 0, 0, CL_THREADS, false, 0};
   static int enabled = cluster_env("KT_CLUSTER", 1);
   if (!enabled || !h->allow_cluster || h->row_lo != 0 || h->row_hi != h->NX) return f;
   const size_t ctrl = ((sizeof(ClShared) + 15) / 16) * 16;
@@ -731,17 +734,18 @@ static ClFit cluster_fit(const kt_handle_s* h, bool pre, bool warm, int limit_c)
     if (C > max_c || C > limit_c || (C == 16 && h->NX < 32)) continue;
     const int rows_per = (h->NX + C - 1) / C;
     const long long cap = (long long)rows_per * h->NY;
-    const int ept = (int)((cap + CL_THREADS - 1) / CL_THREADS);
-    const bool reg = ept <= (reg_max < CL_EPT_REG ? reg_max : CL_EPT_REG);
+    int ept = (int)((cap + CL_THREADS - 1) / CL_THREADS), nt = CL_THREADS;
+    bool reg = ept <= (reg_max < CL_EPT_REG ? reg_max : CL_EPT_REG);
+    if (!reg && reg_max >= CL_EPT_REG && (cap + 255) / 256 <= CL_EPT_REG256) { reg = true; nt = 256; ept = (int)((cap + 255) / 256); }
     const int planes = reg ? 3 + (pre ? 1 : 0) : 12 + (pre ? 1 : 0) + (warm ? 1 : 0);
     const size_t need = ctrl + ((size_t)planes * cap + 8 * (size_t)h->NY) * sizeof(T);      // + 8 private halo rows
-    if (need <= max_smem) { f.C = C; f.rows_per = rows_per; f.ept = ept; f.reg = reg; f.smem = need; return f; }
+    if (need <= max_smem) { f.C = C; f.rows_per = rows_per; f.ept = ept; f.nt = nt; f.reg = reg; f.smem = need; return f; }
   }
   return f;
 }
 
 template <typename K, typename T>
-static int cluster_launch_k(kt_handle_s* h, K kern, unsigned long long& configured, const ClArgs<T>& A0, int C, size_t smem) {
+static int cluster_launch_k(kt_handle_s* h, K kern, unsigned long long& configured, const ClArgs<T>& A0, int C, size_t smem, int nt = CL_THREADS) {
   const unsigned long long dev_bit = 1ull << (h->device & 63);   // function attributes are per device
   if (!(configured & dev_bit)) {
     KT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -749,7 +753,7 @@ static int cluster_launch_k(kt_handle_s* h, K kern, unsigned long long& configur
     configured |= dev_bit;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(C); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+  cfg.gridDim = dim3(C); cfg.blockDim = dim3(nt); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -761,9 +765,17 @@ static int cluster_launch_k(kt_handle_s* h, K kern, unsigned long long& configur
 
 template <typename T, bool PRE>
 static int cluster_launch(kt_handle_s* h, const ClArgs<T>& A, const ClFit& f) {
-  static unsigned long long conf[3] = {0, 0, 0};
-  if (f.reg && f.ept == 1) return cluster_launch_k(h, k_cluster_solve<T, PRE, 1, true>, conf[0], A, f.C, f.smem);
-  if (f.reg && f.ept == 2) return cluster_launch_k(h, k_cluster_solve<T, PRE, 2, true>, conf[1], A, f.C, f.smem);
+  static unsigned long long conf[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (f.reg && f.nt == CL_THREADS && f.ept == 1) return cluster_launch_k(h, k_cluster_solve<T, PRE, 1, true, CL_THREADS>, conf[0], A, f.C, f.smem);
+  if (f.reg && f.nt == CL_THREADS && f.ept == 2) return cluster_launch_k(h, k_cluster_solve<T, PRE, 2, true, CL_THREADS>, conf[1], A, f.C, f.smem);
+  if (f.reg && f.nt == 256) {
+    switch (f.ept) {
+      case 1: case 2: case 3: return cluster_launch_k(h, k_cluster_solve<T, PRE, 3, true, 256>, conf[3], A, f.C, f.smem, 256);
+      case 4: return cluster_launch_k(h, k_cluster_solve<T, PRE, 4, true, 256>, conf[4], A, f.C, f.smem, 256);
+      case 5: return cluster_launch_k(h, k_cluster_solve<T, PRE, 5, true, 256>, conf[5], A, f.C, f.smem, 256);
+      default: break;
+    }
+  }
   return cluster_launch_k(h, k_cluster_solve_smem<T, PRE>, conf[2], A, f.C, f.smem);
 }
 

@@ -211,7 +211,7 @@ def test_bicgstab_f32(cuda, n, path):
     s.solve(eps=1e-5, quiet=True)
     assert s.status == 0
     # f32 fields (dots still accumulate in f64) against the f64 oracle: the iteration count moves by a few
-    assert abs(s.iterations - it_ref) <= max(3, 0.15 * it_ref)
+    assert abs(s.iterations - it_ref) <= max(5, 0.25 * it_ref)
     assert rel_l2(s.x.to_numpy().astype(np.float64), x_ref) < 1e-4     # north_star f32 bar
 
 
