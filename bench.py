@@ -142,13 +142,13 @@ def s1_rows_numpy(n, g0, g1, offset=0.0):
     return coef, b
 
 
-def s1_rows_device(kt, torch, n, g0, g1, dev, offset=0.0):
+def s1_rows_device(kt, torch, n, g0, g1, dev, offset=0.0, np_dtype=np.float64):
     """The same rows assembled directly in HBM (value leg: inputs resident before the timed region)."""
     NY = n + 2
     rows = g1 - g0
-    coef = kt.Field((rows, NY, 5), np.float64, dev)
-    b = kt.Field((rows, NY), np.float64, dev)
-    x = kt.Field((rows, NY), np.float64, dev)
+    coef = kt.Field((rows, NY, 5), np_dtype, dev)
+    b = kt.Field((rows, NY), np_dtype, dev)
+    x = kt.Field((rows, NY), np_dtype, dev)
     g = torch.arange(g0, g1, device=dev)
     inner = ((g >= 1) & (g <= n)).to(torch.float64)[:, None]
     d = coef.data
@@ -161,7 +161,7 @@ def s1_rows_device(kt, torch, n, g0, g1, dev, offset=0.0):
     d[4, :, 1] = 0.0
     sj = torch.sin(2.0 * np.pi * torch.arange(n, dtype=torch.float64, device=dev) / n)
     si = torch.sin(2.0 * np.pi * (g.to(torch.float64) - 1.0) / n) * inner[:, 0]
-    b.data[:, 1:n + 1] = si[:, None] * sj[None, :]
+    b.data[:, 1:n + 1] = (si[:, None] * sj[None, :]).to(b.data.dtype)
     return coef, b, x
 
 
@@ -244,7 +244,9 @@ def run_ours(a):
     part = SlabPartition(NX, world)
     g0, g1 = part.stored(rank)
     l0, l1 = part.local_owned(rank)
-    coef, b, x = s1_rows_device(kt, torch, n, g0, g1, dev)
+    np_dtype = np.float64 if a.dtype == 'f64' else np.float32
+    w_bytes = 8 if a.dtype == 'f64' else 4
+    coef, b, x = s1_rows_device(kt, torch, n, g0, g1, dev, np_dtype=np_dtype)
     cells = n * n
     iters = a.iters
 
@@ -340,19 +342,20 @@ def run_ours(a):
     d_name, d_desc, d_words, d_traffic = classes[dom]
     d_ms = tots[dom] / max(cnt[dom], 1)
     words_local = (l1 - l0) * NY
-    alg_bytes = d_words * 8 * words_local
+    alg_bytes = d_words * w_bytes * words_local
     achieved = alg_bytes / (d_ms * 1e-3) / 1e9
     kernel_share = {classes[i][0]: tots[i] / ms_total for i in range(4) if cnt[i]}
-    iter_bytes = (27 if fused else 28) * 8
+    iter_bytes = (27 if fused else 28) * w_bytes
+    cell_iter_bytes = 28 * w_bytes        # 224 B f64, 112 B f32
     roofline = {'bound': 'hbm', 'kernel': f'{d_desc}  [{d_words} N words]',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_kind': peak_kind,
-                'traffic': (d_traffic * (l1 - l0) * coef.pitch) if d_traffic else None,
+                'traffic': (d_traffic * (l1 - l0) * coef.pitch) if (d_traffic and a.dtype == 'f64') else None,
                 'traffic_source': 'profiles/r01_launch_list_default.md (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of this command), scaled by plane words',
                 'ms_per_launch': d_ms, 'launches_timed': int(cnt[dom]), 'algorithmic_bytes_per_launch': alg_bytes,
                 'kernel_share_of_step': kernel_share,
-                'whole_iteration': {'algorithmic_bytes_per_cell_iter': BYTES_PER_CELL_ITER, 'bytes_per_cell_iter_as_run': iter_bytes,
-                                    'achieved_gbs_per_gpu': BYTES_PER_CELL_ITER * NX * NY * iters * a.steps / world / (ms_total * 1e-3) / 1e9,
-                                    'frac': BYTES_PER_CELL_ITER * NX * NY * iters * a.steps / world / (ms_total * 1e-3) / 1e9 / peak}}
+                'whole_iteration': {'algorithmic_bytes_per_cell_iter': cell_iter_bytes, 'bytes_per_cell_iter_as_run': iter_bytes,
+                                    'achieved_gbs_per_gpu': cell_iter_bytes * NX * NY * iters * a.steps / world / (ms_total * 1e-3) / 1e9,
+                                    'frac': cell_iter_bytes * NX * NY * iters * a.steps / world / (ms_total * 1e-3) / 1e9 / peak}}
 
     # ---- e2e leg: host buffers in the reference layout, H2D + solve + D2H inside the timed region --------------------
     e2e = None
@@ -371,12 +374,12 @@ def run_ours(a):
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
-                'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+                'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': a.dtype,
                 'data': 'synthetic',
                 'config': {'workload': a.workload, 'description': desc, 'grid': [n, n], 'bicgstab_iters_per_step': iters,
                            'system': 'S1 Poisson-sin, offset 0, zero-coefficient ghost ring (SURVEY.md 8d)',
                            'parallelism': (f'x-slab x{world}, halo + all-reduce: ' + ('NVLink peer memory inside the library' if a.comm == 'p2p' else 'NCCL send/recv + all_reduce')) if world > 1 else 'single GPU',
-                           'cache': 'working set 103 GB >> 126 MB L2 (inputs larger than L2; no flush needed)'},
+                           'cache': f'working set {12 * NX * NY * w_bytes / 1e9:.1f} GB vs 126 MB L2 (inputs larger than L2: no flush needed)'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -388,7 +391,9 @@ def run_e2e(a, kt, _lib, lib, torch, dist, world, rank, dev, n, g0, g1, coef, b,
     """The reference-facing call with HOST buffers: coef[i][j][k] (AoS) and b in pinned host memory are copied to the
     device, converted to the kernel layout, solved, and x is copied back -- every step, all inside the timed region."""
     rows, NY = g1 - g0, n + 2
-    need = rows * NY * 8 * 7
+    w_bytes = 8 if a.dtype == 'f64' else 4
+    t_dtype = torch.float64 if a.dtype == 'f64' else torch.float32
+    need = rows * NY * w_bytes * 7
     try:
         avail = int([l for l in open('/proc/meminfo') if l.startswith('MemAvailable')][0].split()[1]) * 1024
     except Exception:
@@ -396,16 +401,16 @@ def run_e2e(a, kt, _lib, lib, torch, dist, world, rank, dev, n, g0, g1, coef, b,
     if avail is not None and need * (world if world > 1 else 1) > 0.8 * avail:
         return {'value': None, 'unit': UNIT, 'skipped': f'host needs {need / 1e9:.0f} GB pinned per rank, {avail / 1e9:.0f} GB available'}
     try:
-        coef_h = torch.empty((rows, NY, 5), dtype=torch.float64, pin_memory=True)
-        b_h = torch.empty((rows, NY), dtype=torch.float64, pin_memory=True)
-        x_h = torch.empty((rows, NY), dtype=torch.float64, pin_memory=True)
+        coef_h = torch.empty((rows, NY, 5), dtype=t_dtype, pin_memory=True)
+        b_h = torch.empty((rows, NY), dtype=t_dtype, pin_memory=True)
+        x_h = torch.empty((rows, NY), dtype=t_dtype, pin_memory=True)
     except Exception as e:   # pinned allocation refused
         return {'value': None, 'unit': UNIT, 'skipped': f'pinned host allocation failed: {e}'}
     CH = 8192                                    # fill in row chunks to bound temporary memory
     for r in range(0, rows, CH):
         c_np, b_np = s1_rows_numpy(n, g0 + r, min(g0 + r + CH, g1))
-        coef_h[r:r + CH] = torch.from_numpy(c_np)
-        b_h[r:r + CH] = torch.from_numpy(b_np)
+        coef_h[r:r + CH] = torch.from_numpy(c_np).to(t_dtype)
+        b_h[r:r + CH] = torch.from_numpy(b_np).to(t_dtype)
     staging_bytes = 256 << 20
     staging = torch.empty(staging_bytes // 8, dtype=torch.float64, device=dev)
     h = handle.h
@@ -428,8 +433,8 @@ def run_e2e(a, kt, _lib, lib, torch, dist, world, rank, dev, n, g0, g1, coef, b,
     e1.record()
     barrier()
     ms = allmax(e0.elapsed_time(e1))
-    h2d = int(allsum(float(coef_h.numel() * 8 + b_h.numel() * 8)))     # bytes of the tensors copied, all ranks
-    d2h = int(allsum(float(x_h.numel() * 8)))
+    h2d = int(allsum(float((coef_h.numel() + b_h.numel()) * w_bytes)))     # bytes of the tensors copied, all ranks
+    d2h = int(allsum(float(x_h.numel() * w_bytes)))
     return {'value': cells * iters * k_e / (ms * 1e-3) / 1e6, 'unit': UNIT,
             'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
             'steps': k_e, 'ms_per_step': ms / k_e,
@@ -652,6 +657,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='pcor32768', choices=sorted(WORKLOADS) + sorted(SIMPLE_WORKLOADS))
     ap.add_argument('--iters', type=int, default=50, help='BiCGSTAB iterations per step')
+    ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'],
+                    help='pcor workloads: field precision (the reference computes in f64; f32 is the north_star 1e-4 variant)')
     ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'],
                     help='N > 1: halo exchange + all-reduce inside the library over NVLink peer memory (p2p) or via NCCL')
     ap.add_argument('--no-e2e', action='store_true')
