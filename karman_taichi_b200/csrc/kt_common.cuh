@@ -178,7 +178,12 @@ __device__ __forceinline__ void scalar_algebra(int fin, Scalars* sc, double d0, 
       sc->rTr = d0;
       sc->iter += 1;
       if (history && sc->iter < history_cap) history[sc->iter] = sqrt(d0);
-      double ratio = d0 / sc->rTr0;
+      // The three divisions and the square root of this step are independent: issued together they overlap instead of
+      // queueing behind the branches below (the resident solvers run this on their critical path).  Same operations, same
+      // operands, same results as the reference's order.
+      const double ratio = d0 / sc->rTr0;
+      const double q_rho = d1 / sc->rho;                        // rho_new / rho_1 with rho_1 := the current rho
+      const double q_ao = sc->alpha / sc->omega;
       if (sqrt(ratio) < sc->eps) { sc->status = 0; sc->done = 1; break; }   // :130
       if ((sc->flags & 2) && sc->omega == 0.0) { sc->status = 6; sc->done = 1; break; }  // karman_taichi.py:451
       if (!isfinite(d0)) { sc->status = 5; sc->done = 1; break; }
@@ -187,7 +192,7 @@ __device__ __forceinline__ void scalar_algebra(int fin, Scalars* sc, double d0, 
       sc->rho = d1;                                             // :95 of the next body
       if (d1 == 0.0) { sc->status = 2; sc->done = 1; break; }   // :96-98
       if (!(sc->flags & 2) && sc->omega == 0.0) { sc->status = 4; sc->done = 1; break; }  // :102 alpha/omega raises
-      sc->beta = (sc->rho / sc->rho_1) * (sc->alpha / sc->omega);  // :102
+      sc->beta = q_rho * q_ao;                                  // :102 (rho / rho_1) * (alpha / omega)
       break;
     }
     case FIN_CG_INIT: {
@@ -204,9 +209,10 @@ __device__ __forceinline__ void scalar_algebra(int fin, Scalars* sc, double d0, 
     case FIN_CG_END: {
       sc->rTr = d0;
       sc->iter += 1;
+      const double beta_new = d0 / sc->old_rTr;                 // :107 (issued before the test: overlaps the square roots)
       if (sqrt(d0) < sqrt(sc->rTr0) * sc->eps) { sc->status = 0; sc->done = 1; break; }  // :102
       if (!isfinite(d0)) { sc->status = 5; sc->done = 1; break; }
-      sc->beta = d0 / sc->old_rTr;                              // :107
+      sc->beta = beta_new;
       sc->old_rTr = d0;                                         // :110
       if (history && sc->iter < history_cap) history[sc->iter] = sqrt(d0);  // :111
       if (sc->iter >= sc->max_iter) { sc->status = 1; sc->done = 1; }
