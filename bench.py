@@ -172,9 +172,11 @@ def cpu_port_run(n_sample, iters, reps):
     """Time `reps` fixed-iteration BiCGSTAB runs of the C/OpenMP port on an n_sample^2 S1 system.  Returns
     (best seconds per run, threads)."""
     from oracle import cport
-    threads = os.cpu_count() or 1
-    os.environ.setdefault('OMP_NUM_THREADS', str(threads))
+    # every host core, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers, which would turn the reference arm
+    # into a single-thread run at N > 1
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     cport.load()
+    cport.set_threads(threads)
     coef, b = s1_rows_numpy(n_sample, 0, n_sample + 2)
     work = np.zeros(9 * b.size)
     best = float('inf')
@@ -183,7 +185,7 @@ def cpu_port_run(n_sample, iters, reps):
         _, it, st, _ = cport.bicgstab_solve(coef, b, eps=0.0, max_iter=iters, work=work)
         best = min(best, time.perf_counter() - t)
         assert it == iters, (it, st)
-    return best, int(os.environ['OMP_NUM_THREADS'])
+    return best, threads
 
 
 def run_reference(a):
@@ -198,7 +200,7 @@ def run_reference(a):
     t0 = time.perf_counter()
     per = [cpu_port_run(n_s, its, 1)[0] for _ in range(a.steps)]
     total = time.perf_counter() - t0
-    threads = int(os.environ.get('OMP_NUM_THREADS', os.cpu_count() or 1))
+    threads = cpu_port_run(n_s, 1, 1)[1]
     val = n_s * n_s * its * a.steps / sum(per) / 1e6
     sample = f'{n_s}x{n_s} sub-grid of the S1 system, {its} BiCGSTAB iterations per step (reference kernel granularity: 14 loops + 5 reductions per iteration)'
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
