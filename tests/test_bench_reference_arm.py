@@ -1,0 +1,47 @@
+"""bench.py --impl reference is a CPU-only arm (the oracle / its C port timed on the host): it must run without a GPU and
+print one JSON line with the contract's keys.  (The GPU arm is exercised by the driver on a B200.)"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = {'impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+        'dtype', 'data', 'config', 'cpu_baseline', 'e2e'}
+
+
+def run(args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py')] + args, capture_output=True, text=True, timeout=600, env=e, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, out.stdout
+    return json.loads(lines[0])
+
+
+@pytest.mark.parametrize('workload,metric,unit', [('pcor1024', 'bicgstab_mcell_iters_per_s', 'Mcell-iters/s'),
+                                                  ('karman320', 'simple_outer_iters_per_s', 'outer-iters/s')])
+def test_reference_arm_line(workload, metric, unit):
+    d = run(['--impl', 'reference', '--workload', workload, '--steps', '1', '--warmup', '1'])
+    assert KEYS <= set(d), KEYS - set(d)
+    assert d['impl'] == 'reference' and d['metric'] == metric and d['unit'] == unit
+    assert d['value'] > 0 and d['higher_is_better'] is True and d['vs_baseline'] is None
+    assert d['config']['workload'] == workload
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+
+def test_reference_arm_ignores_torchrun_thread_cap():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the arm must still use every host core it may run on."""
+    d = run(['--impl', 'reference', '--workload', 'pcor1024', '--steps', '1', '--warmup', '1'], env={'OMP_NUM_THREADS': '1'})
+    want = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    assert d['cpu_baseline']['cores'] == want
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'pcor1024', '--gpus', '2'],
+                         capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK='1', WORLD_SIZE='2'), cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == ''
