@@ -594,6 +594,11 @@ def run_simple(a):
         names = {0: ('p_update', 4), 1: ('v=A M^-1 p + dot', 9), 2: ('t=A M^-1 s + 2 dots', 9), 3: ('x,r + 2 dots', 9)}
         dom = max(range(4), key=lambda i: tot[i])
         d_ms = tot[dom] / max(cnt[dom], 1)
+        # ncu dram__bytes_read.sum + dram__bytes_write.sum per plane word of the Jacobi-variant kernels
+        # (profiles/r01_launch_list_karman16384.md, working launches only)
+        jac_traffic = {0: 30.6, 1: 71.7, 2: 73.3, 3: 70.9}
+        roofline['traffic'] = jac_traffic[dom] * N if case == 'karman' else None
+        roofline['traffic_source'] = 'profiles/r01_launch_list_karman16384.md, dominant kernel, per launch, scaled by plane words'
         roofline['dominant_kernel'] = {'name': names[dom][0], 'words': names[dom][1], 'ms_per_launch': d_ms,
                                        'achieved': names[dom][1] * 8.0 * N / (d_ms * 1e-3) / 1e9,
                                        'frac': names[dom][1] * 8.0 * N / (d_ms * 1e-3) / 1e9 / peak,
