@@ -26,5 +26,12 @@ known-answer checks -- pins the oracle's behaviour and is re-expressed in ``test
   direct solve (``benchmark/cg_to_sparse/test_cg_sparse.py:38-41``,
   ``validation.py:26-45``)
 
+Two further anchors inside the repository: the NumPy restatement in serial-summation mode
+(``oracle.krylov.set_summation('serial')``) and the C port on one thread are bit-identical
+(``tests/test_oracle_cport.py``); and ``tests/golden/make_reference_golden.py`` is ready to execute the
+reference's own source files under a serial stand-in for ``taichi`` and commit the outputs as
+fixtures (``tests/test_reference_golden.py`` holds the oracle to them) -- NOT YET RUN: executing the
+external sources needs the repository owner's approval, so the statement above stands.
+
 Every function cites the reference file:line it follows.
 """
