@@ -56,6 +56,20 @@ def spmv(coef, x):
     return y
 
 
+def spmv_monolith(coef, x):
+    """y = A x in the monolith's term order (``karman_taichi.py:362-367,401-406,421-426``): its product walks the
+    flat offsets ``[i-ny-1, i-ny, i-1, i, i+1, i+ny, i+ny+1]`` of a row and accumulates from 0.0, i.e. in stencil terms
+    (i-1) W, (j-1) S, centre, (j+1) N, (i+1) E -- the two outer offsets never hold a non-zero.  Same five
+    products as ``spmv`` but a different rounding sequence: the reference-run fixtures
+    (``tests/golden/reference_channel.npz``) pin this order bit for bit."""
+    y = coef[:, :, 1] * _shift(x, -1, 0)
+    y = y + coef[:, :, 4] * _shift(x, 0, -1)
+    y = y + coef[:, :, 0] * x
+    y = y + coef[:, :, 3] * _shift(x, 0, +1)
+    y = y + coef[:, :, 2] * _shift(x, +1, 0)
+    return y
+
+
 _SERIAL = False
 
 
@@ -187,7 +201,8 @@ def jacobi_bicgstab(coef, M, b, x0, eps=1e-8, max_iter=None, n=None):
     exits on ``rho == 0`` (``:386-389``), convergence (``:446-449``) or ``omega == 0``
     (``:451-454``).  The 7-offset product of ``:365`` equals the 5-point stencil because
     the two extra offsets never hold a non-zero (SURVEY A.4 [probe], re-checked by
-    ``tests/test_oracle_karman.py`` against the literal matrix oracle).
+    ``tests/test_oracle_karman.py`` against the literal matrix oracle); its terms are added
+    in the monolith's flat-index order (``spmv_monolith``).
     ``n`` is the unknown count of the system (interior of the stencil arrays).
     Division by zero inside the Taichi kernel yields inf/nan rather than raising;
     NumPy float64 scalars reproduce that.
@@ -199,7 +214,7 @@ def jacobi_bicgstab(coef, M, b, x0, eps=1e-8, max_iter=None, n=None):
     steps = 100 * n if max_iter is None else max_iter
     x = x0.copy()
     Minv_safe = np.where(M != 0.0, M, one)  # ghost ring: M = 0 there, vectors stay 0
-    Ax = spmv(coef, x)
+    Ax = spmv_monolith(coef, x)
     r = b - Ax
     r_tld = r.copy()
     residual_init = np.float64(_sum(r * r))
@@ -220,12 +235,12 @@ def jacobi_bicgstab(coef, M, b, x0, eps=1e-8, max_iter=None, n=None):
                 beta = (rho / rho_1) * (alpha / omega)
                 p = r + beta * (p - omega * Ap)
             p_hat = np.where(M != 0.0, 1 / Minv_safe * p, 0.0)   # :399 '1/M[i,i] * p[i]'
-            Ap = spmv(coef, p_hat)
+            Ap = spmv_monolith(coef, p_hat)
             alpha_lower = np.float64(_sum(r_tld * Ap))
             alpha = rho / alpha_lower
             s = r - alpha * Ap
             s_hat = np.where(M != 0.0, 1 / Minv_safe * s, 0.0)   # :419
-            t = spmv(coef, s_hat)
+            t = spmv_monolith(coef, s_hat)
             omega_upper = np.float64(_sum(t * s))
             omega_lower = np.float64(_sum(t * t))
             omega = omega_upper / omega_lower
