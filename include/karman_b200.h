@@ -217,6 +217,32 @@ int kt_p2p_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, con
                     const kt_p2p_comm* comm, double eps, long max_iter, int fixed_iters,
                     long* iters, double* rel_res, int* status);
 
+/* ---- summation plans (test infrastructure; host-only functions, no device needed) ------------------------------------
+ * Every inner product of the library is deterministic: its summation order is a function of the geometry alone.  These
+ * two calls publish that function so that a CPU oracle can add in exactly the device's order and must then reproduce the
+ * iterates and iteration counts of a solve BIT FOR BIT (oracle/device_order.py, tests/test_gpu_exact.py).  The reference's
+ * own `sum +=` reductions (cgsolver.py:49-54) leave the order unspecified.
+ * kt_reduce_plan: launch geometry of the streaming kernel that computes the inner product(s) `kind`:
+ *   out12 = {family (0 element-wise, 1 stencil), grid, block, V (reals per 16-byte vector),
+ *            element-wise: v_lo, v_hi (vector-index range) | stencil: W, TI, nCC, nTiles, row_lo, row_hi, pitch}.
+ * kt_resident_plan: which solver kt_bicgstab_solve / kt_cg_solve picks for the geometry and how it splits it:
+ *   out8 = {path (0 streaming kernels, 1 cluster / registers, 2 cluster / shared memory, 3 cooperative), CTAs, rows per
+ *           CTA, threads per CTA, elements per thread}.  enable = the kt_set_cluster value. */
+typedef struct { int NX, NY, pitch, row_lo, row_hi, dtype, num_sms; } kt_geom;
+enum { KT_PLAN_DOT = 0,          /* kt_dot */
+       KT_PLAN_INIT = 1,         /* (r,r) of init            cgsolver.py:85, bicgsolver.py:90 */
+       KT_PLAN_BICG_V = 2,       /* (r_tld, v)               bicgsolver.py:107 */
+       KT_PLAN_BICG_ST = 3,      /* (t,s), (t,t)             bicgsolver.py:116-117 */
+       KT_PLAN_BICG_XR = 4,      /* (r,r), (r,r_tld) inside kt_bicgstab_solve   bicgsolver.py:123,95 */
+       KT_PLAN_BICG_XR_UNIT = 5, /* the same through kt_bicg_xr / the x-slab phases */
+       KT_PLAN_RESID = 6,        /* (r,r) of the warm-start residual            karman_taichi.py:376-378 */
+       KT_PLAN_CG_AP = 7,        /* (p, Ap)                  cgsolver.py:95 */
+       KT_PLAN_CG_XR = 8,        /* (r,r)                    cgsolver.py:101 */
+       KT_PLAN_BICG_PV = 9 };    /* (r_tld, v) of the fused p-update + product variant */
+int kt_reduce_plan(const kt_geom* g, int kind, int pre, long long* out12);
+int kt_resident_plan(const kt_geom* g, int is_cg, int pre, int warm, int enable, long long* out8);
+int kt_get_geom(kt_handle_t h, kt_geom* out);
+
 /* ---- per-kernel device timing (bench.py roofline) ----------------------------------------------
  * Between kt_prof_begin and kt_prof_end every launch of the solver kernels is bracketed by a CUDA event pair on
  * the handle's stream; kt_prof_end returns the summed duration and launch count per kernel class

@@ -44,6 +44,12 @@ class P2PComm(C.Structure):
                 ('peer_halo_row', C.c_int * 2), ('comm_block', C.c_void_p * 16), ('local_dots', C.c_void_p)]
 
 
+class Geom(C.Structure):
+    """``kt_geom``"""
+    _fields_ = [('NX', C.c_int), ('NY', C.c_int), ('pitch', C.c_int), ('row_lo', C.c_int), ('row_hi', C.c_int),
+                ('dtype', C.c_int), ('num_sms', C.c_int)]
+
+
 class ChannelParams(C.Structure):
     """``kt_channel_params``"""
     _fields_ = [('nx', C.c_int), ('ny', C.c_int),
@@ -116,6 +122,9 @@ SIGNATURES = {
     'kt_debug_poke': (_I, [_P, _P, _D, _PD]),
     'kt_p2p_bicgstab_solve': (_I, [_P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _PL, _PD, _PI]),
     'kt_p2p_cg_solve': (_I, [_P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _PL, _PD, _PI]),
+    'kt_reduce_plan': (_I, [C.POINTER(Geom), _I, _I, C.POINTER(C.c_longlong)]),
+    'kt_resident_plan': (_I, [C.POINTER(Geom), _I, _I, _I, _I, C.POINTER(C.c_longlong)]),
+    'kt_get_geom': (_I, [_P, C.POINTER(Geom)]),
     'kt_prof_begin': (_I, [_P, _I]),
     'kt_prof_end': (_I, [_P, _PD, _PL, _I]),
     'kt_assemble_uv': (_I, [_P, _SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

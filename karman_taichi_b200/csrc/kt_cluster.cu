@@ -280,12 +280,20 @@ __global__ void __launch_bounds__(NT, 1) k_cluster_solve(const ClArgs<T> A) {
     else if (has_hi) xe = nb_halo(mode, false, j, alpha);
     if (!(f & EF_JN)) xn = nb_in(mode, e + 1, alpha);
     if (!(f & EF_J0)) xso = nb_in(mode, e - 1, alpha);
-    // cgsolver.py:59-60, left to right
-    T acc = coef(k, 0, e) * xc;
-    acc = acc + coef(k, 1, e) * xw;
-    acc = acc + coef(k, 2, e) * xe;
-    acc = acc + coef(k, 3, e) * xn;
-    acc = acc + coef(k, 4, e) * xso;
+    T acc;
+    if (PRE || mode == 2) {   // the monolith's product (karman_taichi.py:362-367,401-406): flat offsets i-ny, i-1, i, i+1, i+ny from 0.0
+      acc = T(0) + coef(k, 1, e) * xw;
+      acc = acc + coef(k, 4, e) * xso;
+      acc = acc + coef(k, 0, e) * xc;
+      acc = acc + coef(k, 3, e) * xn;
+      acc = acc + coef(k, 2, e) * xe;
+    } else {                    // cgsolver.py:59-60, left to right
+      acc = coef(k, 0, e) * xc;
+      acc = acc + coef(k, 1, e) * xw;
+      acc = acc + coef(k, 2, e) * xe;
+      acc = acc + coef(k, 3, e) * xn;
+      acc = acc + coef(k, 4, e) * xso;
+    }
     return acc;
   };
 #define CL_EACH(k, e) _Pragma("unroll") for (int k = 0; k < EPT; ++k) if (const int e = threadIdx.x + k * NT; ef[k] & EF_VALID)
@@ -560,12 +568,20 @@ __global__ void __launch_bounds__(CL_THREADS, 1) k_cluster_solve_smem(const ClAr
     else if (has_hi) xe = val(mode, a0_hi, h_hi[HALO_V], m_hi, j, alpha);
     if (j < NY - 1) xn = val(mode, a0, vs, ms, e + 1, alpha);
     if (j > 0) xso = val(mode, a0, vs, ms, e - 1, alpha);
-    // cgsolver.py:59-60, left to right
-    T acc = c0[e] * xc;
-    acc = acc + c1[e] * xw;
-    acc = acc + c2[e] * xe;
-    acc = acc + c3[e] * xn;
-    acc = acc + c4[e] * xso;
+    T acc;
+    if (PRE || mode == 2) {   // the monolith's product (karman_taichi.py:362-367,401-406): flat offsets i-ny, i-1, i, i+1, i+ny from 0.0
+      acc = T(0) + c1[e] * xw;
+      acc = acc + c4[e] * xso;
+      acc = acc + c0[e] * xc;
+      acc = acc + c3[e] * xn;
+      acc = acc + c2[e] * xe;
+    } else {                    // cgsolver.py:59-60, left to right
+      acc = c0[e] * xc;
+      acc = acc + c1[e] * xw;
+      acc = acc + c2[e] * xe;
+      acc = acc + c3[e] * xn;
+      acc = acc + c4[e] * xso;
+    }
     return acc;
   };
 
@@ -779,6 +795,20 @@ static int cluster_launch(kt_handle_s* h, const ClArgs<T>& A, const ClFit& f) {
   return cluster_launch_k(h, k_cluster_solve_smem<T, PRE>, conf[2], A, f.C, f.smem);
 }
 
+static int g_cluster_sched_limit = 16;   // drops to 8 for the process if a 16-CTA cluster cannot be scheduled here
+
+// What cluster_try_solve would launch for this geometry (kt_resident_plan): 0 = does not fit.
+template <typename T>
+int cluster_plan(const kt_handle_s* h, bool pre, bool warm, bool is_cg, long long* out) {
+  if (is_cg && (pre || warm)) return 0;
+  const ClFit f = cluster_fit<T>(h, pre, warm, g_cluster_sched_limit);
+  if (f.C == 0) return 0;
+  out[0] = f.reg ? 1 : 2; out[1] = f.C; out[2] = f.rows_per; out[3] = f.reg ? f.nt : CL_THREADS; out[4] = f.ept;
+  return 1;
+}
+template int cluster_plan<double>(const kt_handle_s*, bool, bool, bool, long long*);
+template int cluster_plan<float>(const kt_handle_s*, bool, bool, bool, long long*);
+
 // Entry used by kt_bicgstab_solve / kt_cg_solve: returns 1 if the solve was done here, 0 if the geometry does not fit
 // (caller falls through to the streaming kernels), < 0 on error.
 template <typename T>
@@ -786,7 +816,7 @@ int cluster_try_solve(kt_handle_s* h, const void* coef, const void* b, void* x, 
                       double* history, long long hist_cap, double eps, long long max_iter, int flags, bool is_cg) {
   const bool pre = Minv != nullptr, warm = (flags & KT_FLAG_WARM_START) != 0;
   if (is_cg && (pre || warm)) return 0;   // CGSolver (cgsolver.py) has neither a preconditioner nor a warm start
-  static int sched_limit = 16;          // drops to 8 for the process if a 16-CTA cluster cannot be scheduled here
+  int& sched_limit = g_cluster_sched_limit;
   ClFit f = cluster_fit<T>(h, pre, warm, sched_limit);
   if (f.C == 0) return 0;
   ClArgs<T> A;

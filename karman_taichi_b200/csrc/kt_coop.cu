@@ -205,12 +205,20 @@ __global__ void __launch_bounds__(CO_THREADS, 1) k_coop_solve(const CoArgs<T> A)
     else if (has_hi) xe = nb_halo(mode, false, j, alpha);
     if (!(f & CF_JN)) xn = nb_in(mode, e + 1, alpha);
     if (!(f & CF_J0)) xso = nb_in(mode, e - 1, alpha);
-    // cgsolver.py:59-60, left to right
-    T acc = coef(k, 0, e) * xc;
-    acc = acc + coef(k, 1, e) * xw;
-    acc = acc + coef(k, 2, e) * xe;
-    acc = acc + coef(k, 3, e) * xn;
-    acc = acc + coef(k, 4, e) * xso;
+    T acc;
+    if (PRE) {   // the monolith's product (karman_taichi.py:362-367,401-406): flat offsets i-ny, i-1, i, i+1, i+ny from 0.0
+      acc = T(0) + coef(k, 1, e) * xw;
+      acc = acc + coef(k, 4, e) * xso;
+      acc = acc + coef(k, 0, e) * xc;
+      acc = acc + coef(k, 3, e) * xn;
+      acc = acc + coef(k, 2, e) * xe;
+    } else {                    // cgsolver.py:59-60, left to right
+      acc = coef(k, 0, e) * xc;
+      acc = acc + coef(k, 1, e) * xw;
+      acc = acc + coef(k, 2, e) * xe;
+      acc = acc + coef(k, 3, e) * xn;
+      acc = acc + coef(k, 4, e) * xso;
+    }
     return acc;
   };
   // warm-start residual (karman_taichi.py:360-367, no preconditioner): x0 straight from the caller's global plane
@@ -224,11 +232,11 @@ __global__ void __launch_bounds__(CO_THREADS, 1) k_coop_solve(const CoArgs<T> A)
     const int li = e / NY, i = r0 + li, j = e - li * NY;
     T rr = A.b[(size_t)i * A.pitch + j];
     if (A.warm) {
-      T acc = coef(k, 0, e) * x[k];
-      acc = acc + coef(k, 1, e) * x0_at(i - 1, j);
-      acc = acc + coef(k, 2, e) * x0_at(i + 1, j);
-      acc = acc + coef(k, 3, e) * x0_at(i, j + 1);
+      T acc = T(0) + coef(k, 1, e) * x0_at(i - 1, j);      // karman_taichi.py:362-367: the monolith's term order
       acc = acc + coef(k, 4, e) * x0_at(i, j - 1);
+      acc = acc + coef(k, 0, e) * x[k];
+      acc = acc + coef(k, 3, e) * x0_at(i, j + 1);
+      acc = acc + coef(k, 2, e) * x0_at(i + 1, j);
       rr = rr - acc;
     }
     r[k] = rr; rt[k] = rr;                                 // r~ = r0 (= b when x0 = 0): bicgsolver.py:28, karman_taichi.py:371
@@ -410,6 +418,18 @@ static int coop_launch(kt_handle_s* h, CoArgs<T>& A, const CoFit& f) {
     default: set_error("coop_launch: elements per thread out of range"); return -2;
   }
 }
+
+// What coop_try_solve would launch for this geometry (kt_resident_plan): 0 = does not fit.
+template <typename T>
+int coop_plan(const kt_handle_s* h, bool pre, bool warm, bool is_cg, long long* out) {
+  if (is_cg && (pre || warm)) return 0;
+  const CoFit f = coop_fit<T>(h, pre);
+  if (f.G == 0 || (size_t)6 * f.G > (size_t)KT_MAX_DOTS * h->max_blocks) return 0;
+  out[0] = 3; out[1] = f.G; out[2] = f.rows_per; out[3] = CO_THREADS; out[4] = f.ept;
+  return 1;
+}
+template int coop_plan<double>(const kt_handle_s*, bool, bool, bool, long long*);
+template int coop_plan<float>(const kt_handle_s*, bool, bool, bool, long long*);
 
 // Entry used by kt_bicgstab_solve / kt_cg_solve after the cluster path declined: returns 1 if the solve was done here,
 // 0 if the geometry does not fit or a cooperative grid cannot be launched (caller falls through to the streaming

@@ -70,6 +70,10 @@ int cluster_try_solve(kt_handle_s* h, const void* coef, const void* b, void* x, 
 template <typename T>
 int coop_try_solve(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, void* r_plane, void* v_plane,
                    double* history, long long hist_cap, double eps, long long max_iter, int flags, bool is_cg);
+// kt_resident_plan: what the two resident solvers would launch for a geometry (1 = fits; out[0..4] = path, CTAs, rows per
+// CTA, threads per CTA, elements per thread)
+template <typename T> int cluster_plan(const kt_handle_s* h, bool pre, bool warm, bool is_cg, long long* out);
+template <typename T> int coop_plan(const kt_handle_s* h, bool pre, bool warm, bool is_cg, long long* out);
 void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 }  // namespace kt

@@ -122,6 +122,9 @@ template <typename T, int SRC, bool PRE, int EPI>
 __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(const StencilArgs<T> A) {
   constexpr int V = VT<T>::V;
   constexpr int W = StencilCfg<SRC, PRE>::W;
+  // The Jacobi-preconditioned and the warm-start-residual products are the monolith's (karman_taichi.py:342-456); the
+  // class solvers (cgsolver.py / bicgsolver.py) have neither.  The two write the same five products in a different order.
+  constexpr bool MONO = PRE || EPI == EPI_RESID;
   if (A.check_done && A.ws.sc->done) return;
   SrcCoef<T> alpha;   // (named for its SRC_S role)
   alpha.a = T(0); alpha.b = T(0); alpha.first = false;
@@ -188,12 +191,23 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
         for (int k = 0; k < V; ++k) {
           const T north = (k < V - 1) ? xc[w].a[k + 1 < V ? k + 1 : k] : xn[w];
           const T south = (k > 0) ? xc[w].a[k > 0 ? k - 1 : 0] : xs[w];
-          // cgsolver.py:59-60 left-to-right: ap*x + aw*x[i-1] + ae*x[i+1] + an*x[j+1] + as*x[j-1]
-          T acc = c[w][0].a[k] * xc[w].a[k];
-          acc = acc + c[w][1].a[k] * xw[w].a[k];
-          acc = acc + c[w][2].a[k] * xe[w].a[k];
-          acc = acc + c[w][3].a[k] * north;
-          acc = acc + c[w][4].a[k] * south;
+          T acc;
+          if (MONO) {
+            // karman_taichi.py:362-367,401-406,421-426: Ap[i] = 0.0, then the flat offsets i-ny (x[i-1,j]), i-1 (x[i,j-1]),
+            // i, i+1 (x[i,j+1]), i+ny (x[i+1,j]) in that order (the outer two of the seven never hold a non-zero)
+            acc = T(0) + c[w][1].a[k] * xw[w].a[k];
+            acc = acc + c[w][4].a[k] * south;
+            acc = acc + c[w][0].a[k] * xc[w].a[k];
+            acc = acc + c[w][3].a[k] * north;
+            acc = acc + c[w][2].a[k] * xe[w].a[k];
+          } else {
+            // cgsolver.py:59-60 left-to-right: ap*x + aw*x[i-1] + ae*x[i+1] + an*x[j+1] + as*x[j-1]
+            acc = c[w][0].a[k] * xc[w].a[k];
+            acc = acc + c[w][1].a[k] * xw[w].a[k];
+            acc = acc + c[w][2].a[k] * xe[w].a[k];
+            acc = acc + c[w][3].a[k] * north;
+            acc = acc + c[w][4].a[k] * south;
+          }
           y.a[k] = acc;
         }
         if (act[w]) {
@@ -505,12 +519,17 @@ static StencilArgs<T> stencil_args(kt_handle_s* h, const Plan& P, const void* co
   return A;
 }
 
+// planes streamed by a stencil variant: 5 coefficients + operand(s) + outputs (+ q / Minv) -- sizes its grid
+constexpr int stencil_planes(int SRC, bool PRE, int EPI) {
+  return 5 + (SRC == SRC_S ? 2 : SRC == SRC_P ? 3 : 1) + (PRE ? 1 : 0) + 1 +
+         (EPI == EPI_DOT_Q || EPI == EPI_DOT_Q_ST || EPI == EPI_RESID ? 1 : 0) + (EPI == EPI_ST || EPI == EPI_DOT_Q_ST ? 1 : 0);
+}
+// planes the element-wise kernels with an inner product are sized by (the grid_for argument at their launch sites)
+enum { EWP_DOT = 2, EWP_INIT = 4, EWP_BICG_XR = 8, EWP_BICG_XR_UNIT = 7, EWP_CG_XR = 6 };
+
 template <typename T, int SRC, bool PRE, int EPI>
 static int launch_stencil(kt_handle_s* h, const Plan& P, const StencilArgs<T>& A) {
-  // planes streamed: 5 coefficients + operand(s) + outputs (+ q / Minv)
-  constexpr int planes = 5 + (SRC == SRC_S ? 2 : SRC == SRC_P ? 3 : 1) + (PRE ? 1 : 0) + 1 +
-                         (EPI == EPI_DOT_Q || EPI == EPI_DOT_Q_ST || EPI == EPI_RESID ? 1 : 0) +
-                         (EPI == EPI_ST || EPI == EPI_DOT_Q_ST ? 1 : 0);
+  constexpr int planes = stencil_planes(SRC, PRE, EPI);
   const StPlan S = stencil_plan(h, P.V, StencilCfg<SRC, PRE>::W, planes);
   StencilArgs<T> B = A;
   B.TI = S.TI; B.nCC = S.nCC; B.nTiles = S.nTiles;
@@ -561,7 +580,7 @@ static int t_ew(kt_handle_s* h, void* out, const void* x, const void* y, const v
 template <typename T>
 static int t_dot(kt_handle_s* h, const void* p, const void* q, double* out_host) {
   Plan P = make_plan(h);
-  k_dot<T><<<grid_for(h, P.ew_blocks, 2), 256, 0, h->stream>>>(P.g, (const T*)p, (const T*)q, make_ws(h));
+  k_dot<T><<<grid_for(h, P.ew_blocks, EWP_DOT), 256, 0, h->stream>>>(P.g, (const T*)p, (const T*)q, make_ws(h));
   KT_LAUNCH_CHECK(h);
   return read_dots(h, out_host, 1);
 }
@@ -709,7 +728,7 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
     rc = launch_stencil<T, SRC_X, false, EPI_RESID>(h, P, A);
     if (rc) return rc;
   } else {
-    k_init<T, false><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (const T*)b, r, r_tld, (T*)x, nullptr, ws, FIN_BICG_INIT);
+    k_init<T, false><<<grid_for(h, P.ew_blocks, EWP_INIT), 256, 0, h->stream>>>(P.g, (const T*)b, r, r_tld, (T*)x, nullptr, ws, FIN_BICG_INIT);
     KT_LAUNCH_CHECK(h);
   }
   // Fused K1+K2 (27 N words / iteration instead of 28 N) when the caller provides the second p / v planes: the
@@ -753,8 +772,8 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
     if (e) return e;
     ProfScope ps(h, KT_K_BICG_XR);
     const T* v_for_s = s ? nullptr : v_new;
-    if (pre) k_bicg_xr<T, true><<<grid_for(h, P.ew_blocks, 8), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END, v_for_s);
-    else k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, 8), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END, v_for_s);
+    if (pre) k_bicg_xr<T, true><<<grid_for(h, P.ew_blocks, EWP_BICG_XR), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END, v_for_s);
+    else k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, EWP_BICG_XR), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END, v_for_s);
     KT_LAUNCH_CHECK(h);
     return 0;
   };
@@ -792,7 +811,7 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
   rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0);
   if (rc) return rc;
   ReduceWs ws = make_ws(h, w->history, w->history_cap);
-  k_init<T, true><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (const T*)b, r, nullptr, (T*)x, p, ws, FIN_CG_INIT);
+  k_init<T, true><<<grid_for(h, P.ew_blocks, EWP_INIT), 256, 0, h->stream>>>(P.g, (const T*)b, r, nullptr, (T*)x, p, ws, FIN_CG_INIT);
   KT_LAUNCH_CHECK(h);
   StencilArgs<T> A1 = stencil_args<T>(h, P, coef);
   A1.ws = ws; A1.x = p; A1.y = Ap; A1.check_done = 1; A1.fin = FIN_CG_ALPHA;
@@ -805,7 +824,7 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
     if (e) return e;
     {
       ProfScope ps(h, KT_K_CG_XR);
-      k_cg_xr<T><<<grid_for(h, P.ew_blocks, 6), 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws, FIN_CG_END);
+      k_cg_xr<T><<<grid_for(h, P.ew_blocks, EWP_CG_XR), 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws, FIN_CG_END);
     }
     KT_LAUNCH_CHECK(h);
     {
@@ -845,7 +864,7 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
   ProfScope ps(h, (phase >= 0 && phase < 9) ? cls_of_phase[phase] : KT_K_INIT);
   switch (phase) {
     case 0: {   // init: r = b (a0), x = 0 (o1), r (o0), r_tld (o2, may be null); local (r,r)
-      k_init<T, false><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (const T*)a0, (T*)o0, (T*)o2, (T*)o1, nullptr, ws, FIN_NONE);
+      k_init<T, false><<<grid_for(h, P.ew_blocks, EWP_INIT), 256, 0, h->stream>>>(P.g, (const T*)a0, (T*)o0, (T*)o2, (T*)o1, nullptr, ws, FIN_NONE);
       break;
     }
     case 1: {   // p (o0) = r (a0) + beta (p - omega v (a1))
@@ -864,13 +883,13 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
       return launch_stencil<T, SRC_S, false, EPI_ST>(h, P, A);
     }
     case 4: {   // x (o0) += alpha p (a0) + omega s (a1); r (o1) = s - omega t (a2); local (r,r), (r, r_tld (o2))
-      k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(
+      k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, EWP_BICG_XR_UNIT), 256, 0, h->stream>>>(
           P.g, (T*)o0, (T*)o1, (const T*)a0, (const T*)a1, (const T*)a2, (const T*)o2, nullptr, 0, 0, 1, ws, FIN_NONE, (const T*)v_for_s);
       break;
     }
     // ---- CG (cgsolver.py:83-114) ----
     case 5: {   // init: r (o0) = b (a0), x (o1) = 0, p (o2) = r; local (r,r)
-      k_init<T, true><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (const T*)a0, (T*)o0, nullptr, (T*)o1, (T*)o2, ws, FIN_NONE);
+      k_init<T, true><<<grid_for(h, P.ew_blocks, EWP_INIT), 256, 0, h->stream>>>(P.g, (const T*)a0, (T*)o0, nullptr, (T*)o1, (T*)o2, ws, FIN_NONE);
       break;
     }
     case 6: {   // Ap (o0) = A p (a0); local (p, Ap)
@@ -879,7 +898,7 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
       return launch_stencil<T, SRC_X, false, EPI_DOT_SRC>(h, P, A);
     }
     case 7: {   // x (o0) += alpha p (a0); r (o1) -= alpha Ap (a1); local (r,r)
-      k_cg_xr<T><<<grid_for(h, P.ew_blocks, 6), 256, 0, h->stream>>>(P.g, (T*)o0, (T*)o1, (const T*)a0, (const T*)a1, 0.0, 1, ws, FIN_NONE);
+      k_cg_xr<T><<<grid_for(h, P.ew_blocks, EWP_CG_XR), 256, 0, h->stream>>>(P.g, (T*)o0, (T*)o1, (const T*)a0, (const T*)a1, 0.0, 1, ws, FIN_NONE);
       break;
     }
     case 8: {   // p (o0) = r (a0) + beta p
@@ -1184,10 +1203,10 @@ int kt_bicg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* s, co
   Plan P = make_plan(h);
   ReduceWs ws = make_ws(h);
   if (h->dtype == KT_F64)
-    k_bicg_xr<double, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)s,
+    k_bicg_xr<double, false><<<grid_for(h, P.ew_blocks, EWP_BICG_XR_UNIT), 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)s,
                                                               (const double*)t, (const double*)r_tld, nullptr, alpha, omega, 0, ws, FIN_NONE);
   else
-    k_bicg_xr<float, false><<<grid_for(h, P.ew_blocks, 7), 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)s,
+    k_bicg_xr<float, false><<<grid_for(h, P.ew_blocks, EWP_BICG_XR_UNIT), 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)s,
                                                              (const float*)t, (const float*)r_tld, nullptr, alpha, omega, 0, ws, FIN_NONE);
   KT_LAUNCH_CHECK(h);
   return read_dots(h, dots_host, 2);
@@ -1198,9 +1217,9 @@ int kt_cg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* Ap, dou
   Plan P = make_plan(h);
   ReduceWs ws = make_ws(h);
   if (h->dtype == KT_F64)
-    k_cg_xr<double><<<grid_for(h, P.ew_blocks, 6), 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)Ap, alpha, 0, ws, FIN_NONE);
+    k_cg_xr<double><<<grid_for(h, P.ew_blocks, EWP_CG_XR), 256, 0, h->stream>>>(P.g, (double*)x, (double*)r, (const double*)p, (const double*)Ap, alpha, 0, ws, FIN_NONE);
   else
-    k_cg_xr<float><<<grid_for(h, P.ew_blocks, 6), 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)Ap, alpha, 0, ws, FIN_NONE);
+    k_cg_xr<float><<<grid_for(h, P.ew_blocks, EWP_CG_XR), 256, 0, h->stream>>>(P.g, (float*)x, (float*)r, (const float*)p, (const float*)Ap, alpha, 0, ws, FIN_NONE);
   KT_LAUNCH_CHECK(h);
   return read_dots(h, dot_host, 1);
 }
@@ -1265,6 +1284,67 @@ int kt_p2p_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, con
   KT_CHECK_ARG(h && coef && b && x && ws && comm, "kt_p2p_cg_solve: null argument");
   return KT_DISPATCH(h, t_p2p_cg<double>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status),
                      t_p2p_cg<float>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status));
+}
+
+// Launch geometry of the kernel that computes an inner product, for a handle-free geometry: everything the summation
+// order depends on (see kt_common.cuh: per-thread sequential -> warp tree -> warps in order -> block partials ->
+// finalising block).  Test infrastructure: oracle/device_order.py adds in this order on the CPU.
+int kt_reduce_plan(const kt_geom* g, int kind, int pre, long long* out12) {
+  KT_CHECK_ARG(g && out12, "kt_reduce_plan: null argument");
+  KT_CHECK_ARG(g->NX > 0 && g->pitch >= g->NY && 0 <= g->row_lo && g->row_lo <= g->row_hi && g->row_hi <= g->NX && g->num_sms > 0,
+               "kt_reduce_plan: bad geometry");
+  kt_handle_s tmp;
+  tmp.NX = g->NX; tmp.NY = g->NY; tmp.pitch = g->pitch; tmp.dtype = g->dtype; tmp.row_lo = g->row_lo; tmp.row_hi = g->row_hi;
+  tmp.num_sms = g->num_sms; tmp.max_blocks = g->num_sms * 512;
+  const Plan P = make_plan(&tmp);
+  for (int k = 0; k < 12; ++k) out12[k] = 0;
+  int ew_planes = 0, SRC = -1, EPI = -1;
+  switch (kind) {
+    case KT_PLAN_DOT: ew_planes = EWP_DOT; break;
+    case KT_PLAN_INIT: ew_planes = EWP_INIT; break;
+    case KT_PLAN_BICG_XR: ew_planes = EWP_BICG_XR; break;
+    case KT_PLAN_BICG_XR_UNIT: ew_planes = EWP_BICG_XR_UNIT; break;
+    case KT_PLAN_CG_XR: ew_planes = EWP_CG_XR; break;
+    case KT_PLAN_BICG_V: SRC = SRC_X; EPI = EPI_DOT_Q; break;
+    case KT_PLAN_BICG_ST: SRC = SRC_S; EPI = EPI_ST; break;
+    case KT_PLAN_RESID: SRC = SRC_X; EPI = EPI_RESID; pre = 0; break;
+    case KT_PLAN_CG_AP: SRC = SRC_X; EPI = EPI_DOT_SRC; pre = 0; break;
+    case KT_PLAN_BICG_PV: SRC = SRC_P; EPI = EPI_DOT_Q_ST; break;
+    default: set_error("kt_reduce_plan: unknown kind"); return -2;
+  }
+  out12[2] = 256; out12[3] = P.V;
+  if (ew_planes) {
+    out12[0] = 0; out12[1] = grid_for(&tmp, P.ew_blocks, ew_planes); out12[4] = P.g.v_lo; out12[5] = P.g.v_hi;
+    return 0;
+  }
+  int W = 1;
+  if (SRC == SRC_X) W = pre ? StencilCfg<SRC_X, true>::W : StencilCfg<SRC_X, false>::W;
+  else if (SRC == SRC_S) W = pre ? StencilCfg<SRC_S, true>::W : StencilCfg<SRC_S, false>::W;
+  else W = pre ? StencilCfg<SRC_P, true>::W : StencilCfg<SRC_P, false>::W;
+  const StPlan S = stencil_plan(&tmp, P.V, W, stencil_planes(SRC, pre != 0, EPI));
+  out12[0] = 1; out12[1] = S.grid; out12[4] = W; out12[5] = S.TI; out12[6] = S.nCC; out12[7] = S.nTiles;
+  out12[8] = g->row_lo; out12[9] = g->row_hi; out12[10] = g->pitch;
+  return 0;
+}
+
+int kt_resident_plan(const kt_geom* g, int is_cg, int pre, int warm, int enable, long long* out8) {
+  KT_CHECK_ARG(g && out8, "kt_resident_plan: null argument");
+  kt_handle_s tmp;
+  tmp.NX = g->NX; tmp.NY = g->NY; tmp.pitch = g->pitch; tmp.dtype = g->dtype; tmp.row_lo = g->row_lo; tmp.row_hi = g->row_hi;
+  tmp.num_sms = g->num_sms; tmp.max_blocks = g->num_sms * 512;
+  tmp.allow_cluster = enable == 1 || enable == 3; tmp.allow_coop = enable == 1 || enable == 2;
+  for (int k = 0; k < 8; ++k) out8[k] = 0;
+  const bool f64 = g->dtype == KT_F64;
+  if (f64 ? cluster_plan<double>(&tmp, pre, warm, is_cg, out8) : cluster_plan<float>(&tmp, pre, warm, is_cg, out8)) return 0;
+  if (f64 ? coop_plan<double>(&tmp, pre, warm, is_cg, out8) : coop_plan<float>(&tmp, pre, warm, is_cg, out8)) return 0;
+  return 0;    // out8[0] == 0: the streaming kernels (kt_reduce_plan)
+}
+
+int kt_get_geom(kt_handle_t h, kt_geom* out) {
+  KT_CHECK_ARG(h && out, "kt_get_geom: null argument");
+  out->NX = h->NX; out->NY = h->NY; out->pitch = h->pitch; out->row_lo = h->row_lo; out->row_hi = h->row_hi;
+  out->dtype = h->dtype; out->num_sms = h->num_sms;
+  return 0;
 }
 
 int kt_prof_begin(kt_handle_t h, int max_launches) {

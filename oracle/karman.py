@@ -222,8 +222,8 @@ class KarmanOracle:
     def correct_conserv(self):
         nx, ny, dx, dy = self.nx, self.ny, self.dx, self.dy
         u, v = self.u, self.v
-        mdot_inlet = float(krylov._sum(u[1, 1:ny + 1]))
-        mdot_outlet = float(krylov._sum(u[nx + 1, 1:ny + 1]))
+        mdot_inlet = float(krylov._sum(u[1, 1:ny + 1], 'column'))
+        mdot_outlet = float(krylov._sum(u[nx + 1, 1:ny + 1], 'column'))
         with np.errstate(all='ignore'):
             coef = np.float64(mdot_inlet) / np.float64(mdot_outlet)
         u[nx + 1, 1:ny + 1] = coef * u[nx + 1, 1:ny + 1]

@@ -62,7 +62,7 @@ def spmv_monolith(coef, x):
     (i-1) W, (j-1) S, centre, (j+1) N, (i+1) E -- the two outer offsets never hold a non-zero.  Same five
     products as ``spmv`` but a different rounding sequence: the reference-run fixtures
     (``tests/golden/reference_channel.npz``) pin this order bit for bit."""
-    y = coef[:, :, 1] * _shift(x, -1, 0)
+    y = 0.0 + coef[:, :, 1] * _shift(x, -1, 0)            # 'Ap[i] = 0.0' then '+=' (:402-406)
     y = y + coef[:, :, 4] * _shift(x, 0, -1)
     y = y + coef[:, :, 0] * x
     y = y + coef[:, :, 3] * _shift(x, 0, +1)
@@ -71,29 +71,38 @@ def spmv_monolith(coef, x):
 
 
 _SERIAL = False
+_DEVICE = None
 
 
-def set_summation(mode):
+def set_summation(mode, device_order=None):
     """'pairwise' (default): ``np.sum``.  'serial': strictly sequential in row-major index order, starting from 0.0 --
     the order a serial execution of the reference's ``sum += p[I] * q[I]`` loop (``cgsolver.py:51-53``) or of the
     monolith's scalar accumulations (``karman_taichi.py:376-378,384-385``) takes; bit-identical to the C port run with
-    one thread (``tests/test_oracle_cport.py``).  Real Taichi leaves the order of that reduction unspecified."""
-    global _SERIAL
-    if mode not in ('pairwise', 'serial'):
+    one thread (``tests/test_oracle_cport.py``) and to the reference sources executed under the serial Taichi stand-in
+    (``tests/golden/reference_*.npz``).  Real Taichi leaves the order of that reduction unspecified.
+    'device': ``device_order(kind, products)`` (``oracle/device_order.py``) -- the order libkarman_b200 adds in; ``kind``
+    names the inner product ('init', 'alpha', 'omega', 'end', 'resid', 'cg_init', 'cg_alpha', 'cg_end', 'dot')."""
+    global _SERIAL, _DEVICE
+    if mode not in ('pairwise', 'serial', 'device'):
         raise ValueError(mode)
+    if mode == 'device' and device_order is None:
+        raise ValueError("set_summation('device', ...) needs a DeviceOrder")
     _SERIAL = mode == 'serial'
+    _DEVICE = device_order if mode == 'device' else None
 
 
-def _sum(a):
+def _sum(a, kind='dot'):
+    if _DEVICE is not None:
+        return np.float64(_DEVICE(kind, a))
     if _SERIAL:
         flat = np.ascontiguousarray(a, dtype=np.float64).ravel()
         return np.float64(np.add.accumulate(flat)[-1]) if flat.size else np.float64(0.0)   # ((0 + a0) + a1) + ...
     return np.sum(a)
 
 
-def reduce(p, q):
+def reduce(p, q, kind='dot'):
     """``cgsolver.py:49-54``: sum over the whole array, ghosts included."""
-    return float(_sum(p * q))
+    return float(_sum(p * q, kind))
 
 
 def _div(a, b):
@@ -114,7 +123,7 @@ def cg_solve(coef, b, eps=1e-8, max_iter=None, history=None):
     r = b.copy()
     x = np.zeros_like(b)
     p = np.zeros_like(b)
-    initial_rTr = reduce(r, r)
+    initial_rTr = reduce(r, r, 'cg_init')
     if history is not None:
         history.append(f'{math.sqrt(initial_rTr):e}\n')
     old_rTr = initial_rTr
@@ -125,11 +134,11 @@ def cg_solve(coef, b, eps=1e-8, max_iter=None, history=None):
     for i in range(steps):
         iters = i + 1
         Ap = spmv(coef, p)                 # :94
-        pAp = reduce(p, Ap)                # :95
+        pAp = reduce(p, Ap, 'cg_alpha')    # :95
         alpha = _div(old_rTr, pAp)         # :96
         x = x + alpha * p                  # :98 (update_x :68-71)
         r = r - alpha * Ap                 # :99 (update_r :73-76)
-        new_rTr = reduce(r, r)             # :101
+        new_rTr = reduce(r, r, 'cg_end')   # :101
         if math.sqrt(new_rTr) < math.sqrt(initial_rTr) * eps:  # :102
             status = CONVERGED
             break
@@ -158,11 +167,11 @@ def bicgstab_solve(coef, b, eps=1e-8, max_iter=None, history=None):
     p = np.zeros_like(b)
     Ap = np.zeros_like(b)
     omega = alpha = beta = rho_1 = 1.0
-    initial_rTr = reduce(r, r)                               # :90
+    initial_rTr = reduce(r, r, 'init')                       # :90
     iters = 0
     status = MAX_ITER
     for i in range(steps):
-        rho = reduce(r, r_tld)                               # :95
+        rho = reduce(r, r_tld, 'init' if i == 0 else 'end')  # :95 (the device forms it in the pass that produced r)
         if rho == 0.0:                                       # :96-98
             status = RHO_ZERO
             break
@@ -172,16 +181,16 @@ def bicgstab_solve(coef, b, eps=1e-8, max_iter=None, history=None):
             beta = _div(rho, rho_1) * _div(alpha, omega)     # :102
             p = r + beta * (p - omega * Ap)                  # :103 (update_p :43-46)
         Ap = spmv(coef, p)                                   # :106
-        alpha_lower = reduce(r_tld, Ap)                      # :107
+        alpha_lower = reduce(r_tld, Ap, 'alpha')             # :107
         alpha = _div(rho, alpha_lower)                       # :108
         s = r - alpha * Ap                                   # :110 (update_s :60-63)
         t = spmv(coef, s)                                    # :113-114
-        omega_upper = reduce(t, s)                           # :116
-        omega_lower = reduce(t, t)                           # :117
+        omega_upper = reduce(t, s, 'omega')                  # :116
+        omega_lower = reduce(t, t, 'omega')                  # :117
         omega = _div(omega_upper, omega_lower)               # :118
         x = x + (alpha * p + omega * s)                      # :120 (update_x :78-81)
         r = s - omega * t                                    # :121 (update_r :83-86)
-        rTr = reduce(r, r)                                   # :123
+        rTr = reduce(r, r, 'end')                            # :123
         iters = i + 1
         if history is not None:
             history.append(f'{math.sqrt(rTr):e}\n')
@@ -217,7 +226,7 @@ def jacobi_bicgstab(coef, M, b, x0, eps=1e-8, max_iter=None, n=None):
     Ax = spmv_monolith(coef, x)
     r = b - Ax
     r_tld = r.copy()
-    residual_init = np.float64(_sum(r * r))
+    residual_init = np.float64(_sum(r * r, 'resid'))
     omega = alpha = beta = rho_1 = one
     p = np.zeros_like(b)
     Ap = np.zeros_like(b)
@@ -225,7 +234,7 @@ def jacobi_bicgstab(coef, M, b, x0, eps=1e-8, max_iter=None, n=None):
     status = MAX_ITER
     with np.errstate(all='ignore'):
         for step in range(steps):
-            rho = np.float64(_sum(r * r_tld))
+            rho = np.float64(_sum(r * r_tld, 'resid' if step == 0 else 'end'))
             if rho == 0.0:
                 status = RHO_ZERO
                 break
@@ -236,17 +245,17 @@ def jacobi_bicgstab(coef, M, b, x0, eps=1e-8, max_iter=None, n=None):
                 p = r + beta * (p - omega * Ap)
             p_hat = np.where(M != 0.0, 1 / Minv_safe * p, 0.0)   # :399 '1/M[i,i] * p[i]'
             Ap = spmv_monolith(coef, p_hat)
-            alpha_lower = np.float64(_sum(r_tld * Ap))
+            alpha_lower = np.float64(_sum(r_tld * Ap, 'alpha'))
             alpha = rho / alpha_lower
             s = r - alpha * Ap
             s_hat = np.where(M != 0.0, 1 / Minv_safe * s, 0.0)   # :419
             t = spmv_monolith(coef, s_hat)
-            omega_upper = np.float64(_sum(t * s))
-            omega_lower = np.float64(_sum(t * t))
+            omega_upper = np.float64(_sum(t * s, 'omega'))
+            omega_lower = np.float64(_sum(t * t, 'omega'))
             omega = omega_upper / omega_lower
             x = x + (alpha * p_hat + omega * s_hat)              # :437
             r = s - omega * t                                    # :440
-            residual = np.float64(_sum(r * r))
+            residual = np.float64(_sum(r * r, 'end'))
             iters = step + 1
             if np.sqrt(residual / residual_init) < eps:          # :446 (False on NaN, like Taichi)
                 status = CONVERGED

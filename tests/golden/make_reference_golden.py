@@ -14,11 +14,17 @@ with two mechanical exceptions that do not touch any arithmetic:
   before execution (the cylinder ``(i-64)^2 + (j-32)^2 < 144`` of ``:149`` stays as written).  Its main loop lives under
   ``if __name__ == '__main__'`` (``:625-683``) and is likewise driven from here, call for call.
 
-STATUS: NOT YET RUN.  Executing the external reference sources needs the repository owner's explicit approval (the
-sandbox refused the first attempt); until then no ``reference_*.npz`` fixture exists and no test depends on one.
-Planned outputs: ``reference_krylov.npz``, ``reference_cavity.npz``, ``reference_channel.npz`` (to be committed, since
-the GPU box has no /root/reference), with the oracle held to them bit for bit in serial-summation mode and the CUDA
-path within the stated tolerances.
+STATUS: run in this container (the reference is plain numerics: no subprocess / network / file writes outside
+``convergence.txt``); the outputs ``reference_krylov.npz``, ``reference_cavity.npz``, ``reference_channel.npz`` are
+committed, since the GPU box has no /root/reference.  ``tests/test_reference_golden.py`` holds the oracle to them bit for
+bit in serial-summation mode (the order the stand-in's loops take), ``tests/test_gpu_reference_golden.py`` holds the CUDA
+path to them: element-wise kernels bit for bit, solves within the north_star tolerances.
+
+The ``*_tight`` cases repeat a case with smaller ``eps`` ARGUMENTS to the reference's own solver methods
+(``BICGSolver.solve(eps=...)``, ``CGSolver.solve(eps, ...)``, ``solve_momentum_bicgstab(eps, ...)``): the reference hard-codes
+``eps=1e-4`` inside ``bicg_solve_momentum_eqn`` (``bicgsimp.py:206,208``), so for those the five calls of that method's
+body are issued from here, call for call.  Two runs of the same recurrence whose inner products are added in a different
+order agree only to (condition number) x eps; the tight twins are what pins free-running fields to 1e-8.
 """
 from __future__ import annotations
 
@@ -140,7 +146,9 @@ CAVITY_FIELDS = ('u', 'v', 'p', 'pcor', 'mdiv', 'u_mid', 'v_mid', 'coef_u', 'b_u
 
 def cavity_cases(ref, out):
     for module, cases in (('bicgsimp', [('lid10x12', 10, 12, {'n': [0.0, 1.0]}, 4),
-                                         ('allbc8x7', 8, 7, {'w': [0.02, 0.3], 'e': [0.02, -0.2], 'n': [0.0, 1.0], 's': [0.0, 0.5]}, 3)]),
+                                         ('allbc8x7', 8, 7, {'w': [0.02, 0.3], 'e': [0.02, -0.2], 'n': [0.0, 1.0], 's': [0.0, 0.5]}, 3),
+                                         ('lid10x12_tight', 10, 12, {'n': [0.0, 1.0]}, 4),
+                                         ('lid21x17_tight', 21, 17, {'n': [0.0, 1.0], 'w': [0.0, -0.25], 's': [0.0, 0.125]}, 3)]),
                           ('simple', [('lid9x11', 9, 11, {'n': [0.0, 0.1]}, 3),
                                       ('allbc7x8', 7, 8, {'w': [0.01, 0.3], 'e': [0.01, -0.2], 'n': [0.0, 0.1], 's': [0.0, 0.05]}, 3)])):
         mod = load_reference(ref, module)
@@ -165,8 +173,20 @@ def cavity_cases(ref, out):
                     npc = count_calls(s.p_correction_solver, 'update_x')
                     for step in range(steps):
                         c0 = (nu[0], nv[0], npc[0])
-                        momentum_residual = s.bicg_solve_momentum_eqn(1)
-                        s.bicg_solve_pcorrection_eqn(1e-8)
+                        if name.endswith('_tight'):
+                            # the body of bicg_solve_momentum_eqn (bicgsimp.py:199-210), eps 1e-12 instead of the literal 1e-4
+                            s.compute_coef_u()
+                            s.compute_coef_v()
+                            s.set_bc()
+                            s.u_momentum_solver.update_coef(s.coef_u, s.b_u, s.u_mid)
+                            s.u_momentum_solver.solve(eps=1e-12, quiet=True)
+                            s.v_momentum_solver.update_coef(s.coef_v, s.b_v, s.v_mid)
+                            s.v_momentum_solver.solve(eps=1e-12, quiet=True)
+                            momentum_residual = s.update_velocity()
+                            s.bicg_solve_pcorrection_eqn(1e-13)
+                        else:
+                            momentum_residual = s.bicg_solve_momentum_eqn(1)
+                            s.bicg_solve_pcorrection_eqn(1e-8)
                         s.correct_pressure()
                         s.correct_velocity()
                         continuity_residual = s.compute_mdiv()
@@ -222,12 +242,17 @@ def vec_of(x, shape, row_of, n):
 
 
 def channel_cases(ref, out):
-    for name, nx, ny, subs in (('plain32x16', 32, 16, 3), ('cyl96x48', 96, 48, 2)):
+    only = os.environ.get('KT_GOLDEN_CHANNEL_CASES')
+    for name, nx, ny, subs in (('plain32x16', 32, 16, 3), ('cyl96x48', 96, 48, 2), ('plain32x16_tight', 32, 16, 3),
+                               ('cyl96x48_tight', 96, 48, 1)):
+        if only and name not in only.split(','):
+            continue
+        eps = 1e-12 if name.endswith('_tight') else 1e-8
         t0 = time.time()
         m = load_reference(ref, 'karman_taichi', keep_after_defs=True, constants={'nx': nx, 'ny': ny})
         key = f'channel/{name}'
         out[f'{key}/nx_ny_subs'] = np.array([nx, ny, subs])
-        out[f'{key}/params'] = np.array([m.lx, m.ly, m.rho, m.mu, m.dt, m.velo_rel, m.p_rel])
+        out[f'{key}/params'] = np.array([m.lx, m.ly, m.rho, m.mu, m.dt, m.velo_rel, m.p_rel, eps])
         m.init()
         out[f'{key}/init/ct'] = m.ct.to_numpy()
         out[f'{key}/init/p'] = m.p.to_numpy()
@@ -250,11 +275,11 @@ def channel_cases(ref, out):
                     out[f'{key}/asm0/coef_v'], out[f'{key}/asm0/M_v'], out[f'{key}/asm0/extra_v'] = cv, Mv, xv_
                     out[f'{key}/asm0/b_u'] = vec_of(m.bu, (nx + 3, ny + 2), row_u, n_u)
                     out[f'{key}/asm0/b_v'] = vec_of(m.bv, (nx + 2, ny + 3), row_v, n_v)
-                m.solve_momentum_bicgstab(1e-8, 1, 0, 1)
+                m.solve_momentum_bicgstab(eps, 1, 0, 1)
                 text_uv = sink.getvalue()
                 m.correct_conserv()
                 sink.truncate(0), sink.seek(0)
-                m.solve_pcorrection_bicgstab(1e-8, 1)
+                m.solve_pcorrection_bicgstab(eps, 1)
                 text_p = sink.getvalue()
                 cp, Mp, xp_ = stencil_of(m.Ap, m.Mp, n_p, ny, (nx + 2, ny + 2), row_p)
                 b_p = vec_of(m.bp, (nx + 2, ny + 2), row_p, n_p)
@@ -284,6 +309,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--reference', default='/root/reference')
     ap.add_argument('--only', default='krylov,cavity,channel')
+    ap.add_argument('--merge', action='store_true', help='keep the arrays already in reference_<part>.npz')
     a = ap.parse_args()
     sys.path.insert(0, a.reference)          # bicgsolver.py does 'from cgsolver import CGSolver'
     for part, fn in (('krylov', krylov_cases), ('cavity', cavity_cases), ('channel', channel_cases)):
@@ -293,6 +319,9 @@ def main():
         print(f'{part}:')
         fn(a.reference, out)
         path = os.path.join(HERE, f'reference_{part}.npz')
+        if a.merge and os.path.exists(path):
+            old = np.load(path)
+            out = {**{k: old[k] for k in old.files}, **out}
         np.savez_compressed(path, **out)
         print(f'  -> {path} ({os.path.getsize(path) / 1024:.0f} KiB, {len(out)} arrays)')
 

@@ -1,10 +1,9 @@
 """The oracle against golden vectors produced by executing the reference's OWN source files
 (tests/golden/make_reference_golden.py under the serial Taichi stand-in).
 
-The fixtures do not exist yet: running that script executes the external houkensjtu/karman_taichi sources and needs the
-repository owner's approval, which this sandbox requires explicitly.  Until `tests/golden/reference_*.npz` are committed
-every test here is skipped; once they are, the oracle in serial-summation mode (the order the stand-in's loops take) is
-held to them bit for bit -- inputs, intermediate vectors, iterates and iteration counts."""
+The fixtures are committed (the GPU box has no /root/reference).  The oracle in serial-summation mode (the order the
+stand-in's loops take) is held to them bit for bit -- inputs, intermediate vectors, iterates and iteration counts.  This is
+what pins the oracle, and through it every parity test, to the reference's own arithmetic."""
 import os
 
 import numpy as np
@@ -19,7 +18,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 def fixture(name):
     path = os.path.join(GOLD, name)
     if not os.path.exists(path):
-        pytest.skip(f'{name} not generated yet (make_reference_golden.py needs approval to execute the reference sources)')
+        pytest.fail(f'{name} is missing: run tests/golden/make_reference_golden.py in a container that has /root/reference')
     return np.load(path)
 
 
@@ -71,6 +70,9 @@ def test_cavity_outer_iterations_bit_exact(serial_sums):
         o = SimpleOracle(1.0, 1.0, nx, ny, variant=module)
         for side, val in zip('wens', g[f'{key}/bc']):
             o.bc[side][0], o.bc[side][1] = float(val[0]), float(val[1])
+        if key.endswith('_tight'):      # same reference methods, smaller eps arguments (make_reference_golden.py)
+            o.eps_u = o.eps_v = 1e-12
+            o.eps_p = 1e-13
         o.init()
         for step in range(steps):
             o.step()
@@ -91,6 +93,7 @@ def test_channel_against_literal_and_stencil_oracles(serial_sums):
     for key in cases:
         nx, ny, subs = (int(v) for v in g[f'{key}/nx_ny_subs'])
         dt = float(g[f'{key}/params'][4])
+        eps = float(g[f'{key}/params'][7]) if g[f'{key}/params'].size > 7 else 1e-8
         for cls, exact in ((KarmanLiteral, True), (KarmanOracle, True)):
             o = cls(nx=nx, ny=ny, dt=dt)                       # cylinder (64, 32, 144) as hard-coded in karman_taichi.py:149
             o.init()
@@ -104,7 +107,7 @@ def test_channel_against_literal_and_stencil_oracles(serial_sums):
                         np.testing.assert_array_equal(getattr(o, f'coef_{w}'), g[f'{key}/asm0/coef_{w}'], err_msg=f'{key} coef_{w}')
                         np.testing.assert_array_equal(getattr(o, f'M_{w}'), g[f'{key}/asm0/M_{w}'], err_msg=f'{key} M_{w}')
                         np.testing.assert_array_equal(getattr(o, f'b_{w}'), g[f'{key}/asm0/b_{w}'], err_msg=f'{key} b_{w}')
-                pc = o.sub_iteration(1e-8)
+                pc = o.sub_iteration(eps)
                 if cls is KarmanOracle:
                     for nm in ('coef_p', 'M_p', 'b_p'):
                         np.testing.assert_array_equal(getattr(o, nm), g[f'{key}/sub{sub}/{nm}'], err_msg=f'{key} sub {sub} {nm}')
