@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the contract benchmark of the hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--iters I]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--iters I] [--solver bicgstab|cg]
 
 Metric (BASELINE.json): BiCGSTAB Mcell-iters/s = cells x iterations / second / 1e6 on the pressure-correction-type
 system S1 (5-point Poisson stencil arrays with a zero-coefficient ghost ring, sin*sin right-hand side,
@@ -14,8 +14,17 @@ halo rows over NCCL send/recv and the inner products over NCCL all-reduce.
 outer-iterations/s on configs 2, 1 and 4 (one step = one outer iteration through SIMPLESolver / KarmanSolver).
 
 One JSON line on stdout (rank 0): value (inputs resident in HBM), e2e (host buffers in the reference layout through
-the C ABI, H2D/D2H inside the timed region), roofline (dominant kernel, timed live with CUDA events), cpu_baseline
-(the oracle's C/OpenMP port of the reference algorithm on this box's host cores), clocks, gpu_launches.
+the C ABI -- kt_bicgstab_solve_host at N = 1 -- H2D/D2H inside the timed region), roofline (dominant kernel, timed live with
+CUDA events; `traffic` from the committed ncu capture profiles/r02_traffic.json), cpu_baseline (the oracle's C/OpenMP port
+of the reference algorithm on this box's host cores), clocks, gpu_launches, and
+
+* check     -- correctness evidence that travels with the number, at every N: residual and ||x|| after the fixed
+               iterations of the timed step (must agree across N = 1, 2, 4, 8 to rounding: only the rank-ordered partial
+               sums differ) and one CONVERGED solve of the offset-0.1 system (status, iterations, ||A x - b|| / ||b||
+               recomputed on the device from the returned x with freshly exchanged halo rows);
+* secondary -- (N = 1, default workload only) the rest of BASELINE.json's metric in the same run: SIMPLE outer-iterations/s
+               on karman16384 (config 4), cavity128 (config 2), karman320 (config 1), and CG Mcell-iters/s (config 3 names
+               "BiCGSTAB and CG") on pcor32768 / pcor4096.
 
 ``--impl reference`` times the reference's own CPU implementation of the path.  The reference is Python + Taichi 0.9
 (``ti.init(arch=ti.cpu)``); Taichi cannot be installed offline for this Python (no wheel, no network), so the arm runs
@@ -56,13 +65,30 @@ SIMPLE_WORKLOADS = {
 SIMPLE_METRIC = 'simple_outer_iters_per_s'
 SIMPLE_UNIT = 'outer-iters/s'
 METRIC = 'bicgstab_mcell_iters_per_s'
+CG_METRIC = 'cg_mcell_iters_per_s'
 UNIT = 'Mcell-iters/s'
-BYTES_PER_CELL_ITER = 28 * 8            # BiCGSTAB algorithmic traffic, f64
-# dram__bytes_read.sum + dram__bytes_write.sum per launch and per plane word of each kernel come from the committed
-# ncu captures (profiles/r01_launch_list_default.md: the default command, 32770 x 32784-word planes).
-FUSED_TRAFFIC_BYTES_PER_WORD = 86.9
-NO_S_K3_TRAFFIC = 65.1      # profiles/r01_launch_list_default.md
-NO_S_K4_TRAFFIC = 63.9
+WORDS_PER_CELL_ITER = {'bicgstab': 28, 'cg': 16}      # algorithmic traffic per cell and iteration, in words
+TRAFFIC_JSON = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of every kernel, as ncu measured them on the default command
+    (tools/gpu_job.sh launches -> tools/ncu_summary.py --json), with the commit the capture was taken at.  Scaled by plane
+    words when the profiled workload is not the one being run.  None when the file is missing (never a stale constant)."""
+    try:
+        return json.load(open(TRAFFIC_JSON))
+    except Exception:
+        return None
+
+
+def traffic_of(doc, pattern, words_local):
+    """bytes per launch of the kernel whose ncu name starts with `pattern`, scaled to `words_local` plane words"""
+    if not doc:
+        return None, None
+    for name, k in doc.get('kernels', {}).items():
+        if name.startswith(pattern) and k.get('dram_bytes_per_word'):
+            return k['dram_bytes_per_word'] * words_local, f"{os.path.relpath(TRAFFIC_JSON, ROOT)} (ncu launch list of `{doc.get('command', '?')}` at commit {doc.get('commit', '?')}: {name}, {k['dram_bytes_per_word']:.1f} B per plane word, scaled by this run's plane words)"
+    return None, None
 
 
 def peaks():
@@ -168,8 +194,8 @@ def s1_rows_device(kt, torch, n, g0, g1, dev, offset=0.0, np_dtype=np.float64):
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm (oracle C/OpenMP port) -- cpu_baseline leg and --impl reference
 # ---------------------------------------------------------------------------------------------------------
-def cpu_port_run(n_sample, iters, reps):
-    """Time `reps` fixed-iteration BiCGSTAB runs of the C/OpenMP port on an n_sample^2 S1 system.  Returns
+def cpu_port_run(n_sample, iters, reps, solver='bicgstab'):
+    """Time `reps` fixed-iteration BiCGSTAB (or CG) runs of the C/OpenMP port on an n_sample^2 S1 system.  Returns
     (best seconds per run, threads)."""
     from oracle import cport
     # every host core, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers, which would turn the reference arm
@@ -182,7 +208,7 @@ def cpu_port_run(n_sample, iters, reps):
     best = float('inf')
     for _ in range(reps):
         t = time.perf_counter()
-        _, it, st, _ = cport.bicgstab_solve(coef, b, eps=0.0, max_iter=iters, work=work)
+        _, it, st, _ = (cport.cg_solve if solver == 'cg' else cport.bicgstab_solve)(coef, b, eps=0.0, max_iter=iters, work=work)
         best = min(best, time.perf_counter() - t)
         assert it == iters, (it, st)
     return best, threads
@@ -194,21 +220,24 @@ def run_reference(a):
         return 0
     n, desc = WORKLOADS[a.workload]
     n_s, its = min(n, 4096), 6
-    cpu_port_run(n_s, 2, 1)                       # page-in / first touch
+    sv = a.solver
+    cpu_port_run(n_s, 2, 1, sv)                   # page-in / first touch
     for _ in range(max(a.warmup, 1) - 1):
-        cpu_port_run(n_s, its, 1)
+        cpu_port_run(n_s, its, 1, sv)
     t0 = time.perf_counter()
-    per = [cpu_port_run(n_s, its, 1)[0] for _ in range(a.steps)]
+    per = [cpu_port_run(n_s, its, 1, sv)[0] for _ in range(a.steps)]
     total = time.perf_counter() - t0
-    threads = cpu_port_run(n_s, 1, 1)[1]
+    threads = cpu_port_run(n_s, 1, 1, sv)[1]
     val = n_s * n_s * its * a.steps / sum(per) / 1e6
-    sample = f'{n_s}x{n_s} sub-grid of the S1 system, {its} BiCGSTAB iterations per step (reference kernel granularity: 14 loops + 5 reductions per iteration)'
-    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup,
-            'ms_per_step': 1e3 * sum(per) / a.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic', 'config': {'workload': a.workload, 'description': desc, 'cpu_sample': sample},
+    gran = ('14 loops + 5 reductions per iteration' if sv == 'bicgstab' else '4 loops + 2 reductions per iteration')
+    sample = f'{n_s}x{n_s} sub-grid of the S1 system, {its} {sv} iterations per step (reference kernel granularity: {gran})'
+    line = {'impl': 'reference', 'metric': CG_METRIC if sv == 'cg' else METRIC, 'value': val, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
+            'warmup': a.warmup, 'ms_per_step': 1e3 * sum(per) / a.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'config': {'workload': a.workload, 'description': desc, 'solver': sv, 'cpu_sample': sample},
             'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'note': 'Taichi ti.cpu itself cannot run offline (no taichi wheel for this Python); C/OpenMP port of cgsolver.py/bicgsolver.py',
+            'note': 'Taichi ti.cpu itself cannot run offline (no taichi wheel for this Python); C/OpenMP port of cgsolver.py/bicgsolver.py, '
+                    'pinned to the reference-run golden vectors through the oracle (tests/test_reference_golden.py, tests/test_oracle_cport.py)',
             'wall_s': total}
     print(json.dumps(line), flush=True)
     return 0
@@ -217,181 +246,304 @@ def run_reference(a):
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
-def run_ours(a):
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if a.gpus > 1 and world == 1:
-        # convenience: relaunch under torchrun exactly as the driver does
-        port = 29500 + (os.getpid() % 2000)
-        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={a.gpus}', '--master-addr', '127.0.0.1',
-               '--master-port', str(port), os.path.abspath(__file__)] + sys.argv[1:]
-        return subprocess.call(cmd)
-    assert world == a.gpus, f'--gpus {a.gpus} but WORLD_SIZE={world}'
-    assert torch.cuda.is_available(), 'bench.py needs CUDA (no CPU fallback)'
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+def dist_env():
+    return int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
+
+
+def relaunch_under_torchrun(a):
+    """convenience: `python bench.py --gpus N` without torchrun relaunches itself exactly as the driver does"""
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={a.gpus}', '--master-addr', '127.0.0.1',
+           '--master-port', str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    return subprocess.call(cmd)
+
+
+class Comm:
+    """barrier + max / sum over the ranks (timing rule: every multi-GPU number is the max over ranks of device time)"""
+
+    def __init__(self, torch, dist, world, dev):
+        self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def _red(self, v, op):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, v):
+        return self._red(v, self.dist.ReduceOp.MAX if self.world > 1 else None)
+
+    def sum(self, v):
+        return self._red(v, self.dist.ReduceOp.SUM if self.world > 1 else None)
+
+
+# kernel classes of kt_prof_* -> (short name, description, algorithmic words, ncu kernel-name prefix for the traffic lookup)
+def kernel_classes(solver, fused, store_s):
+    if solver == 'cg':
+        return {4: ('Ap+dot', 'k_stencil<SRC_X,EPI_DOT_SRC>: Ap = A p, (p, Ap)', 7, 'k_stencil<double, 0, 0, 2>'),
+                5: ('x,r+dot', 'k_cg_xr: x += alpha p, r -= alpha Ap, (r,r)', 6, 'k_cg_xr<double>'),
+                6: ('p_update', 'k_cg_p: p = r + beta p', 3, 'k_cg_p<double>')}
+    return {0: ('p_update', 'k_bicg_p: p = r + beta (p - omega v)', 4, 'k_bicg_p<double>'),
+            1: (('p_update+v=Ap+dot', 'k_stencil<SRC_P,EPI_DOT_Q_ST>: p = r + beta (p - omega v), v = A p, (r~, v)', 11, 'k_stencil<double, 2, 0, 5>')
+                if fused else ('v=Ap+dot', 'k_stencil<SRC_X,EPI_DOT_Q>: v = A p, (r~, v)', 8, 'k_stencil<double, 0, 0, 1>')),
+            2: (('s,t+2dots', 'k_stencil<SRC_S,EPI_ST>: s = r - alpha v, t = A s, (t,s), (t,t)', 9, None) if store_s else
+                ('t=As+2dots', 'k_stencil<SRC_S,EPI_ST>: t = A (r - alpha v) [s not stored], (t,s), (t,t)', 8, 'k_stencil<double, 1, 0, 3>')),
+            3: (('x,r+2dots', 'k_bicg_xr: x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 7, None) if store_s else
+                ('x,r+2dots', 'k_bicg_xr: s = r - alpha v, x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 8, 'k_bicg_xr<double, 0>'))}
+
+
+def krylov_line(a, torch, dist, world, rank, dev, light=False, fields=None, workload=None, solver_kind=None, steps=None):
+    """One measurement of the Krylov metric.  light = a `secondary` entry: value + roofline only."""
     import karman_taichi_b200 as kt
     from karman_taichi_b200 import _lib
-    from karman_taichi_b200.cgsolver import _p
-    from karman_taichi_b200.slab import CudaSlabOps, DistBiCGSTAB, HaloExchanger, SlabPartition
+    from karman_taichi_b200.slab import CudaSlabOps, DistBiCGSTAB, DistCG, HaloExchanger, P2PSlabSolver, SlabPartition
     lib = _lib.load()
-
-    n, desc = WORKLOADS[a.workload]
+    workload = workload or a.workload
+    solver_kind = solver_kind or a.solver
+    steps = steps or a.steps
+    cg = solver_kind == 'cg'
+    n, desc = WORKLOADS[workload]
     NX = NY = n + 2
     part = SlabPartition(NX, world)
     g0, g1 = part.stored(rank)
     l0, l1 = part.local_owned(rank)
     np_dtype = np.float64 if a.dtype == 'f64' else np.float32
     w_bytes = 8 if a.dtype == 'f64' else 4
-    coef, b, x = s1_rows_device(kt, torch, n, g0, g1, dev, np_dtype=np_dtype)
+    coef, b, x = fields if fields is not None else s1_rows_device(kt, torch, n, g0, g1, dev, np_dtype=np_dtype)
     cells = n * n
     iters = a.iters
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def allmax(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    cm = Comm(torch, dist, world, dev)
+    comm_mode = a.comm
 
     if world == 1:
-        solver = kt.BICGSolver(coef, b, x)
-        solver.max_steps = iters
-        handle = solver._hd
+        solver = (kt.CGSolver if cg else kt.BICGSolver)(coef, b, x)
+        handle, scratch = solver._hd, (solver.Ap if cg else solver.t)
 
-        def step():
-            solver.solve(eps=0.0, quiet=True)          # the public call: BICGSolver.solve (bicgsolver.py:88)
-            assert solver.iterations == iters, (solver.iterations, solver.status)
-    elif a.comm == 'nccl':
-        ops = CudaSlabOps(coef, b, x, part, rank)
-        drv = DistBiCGSTAB(ops, HaloExchanger(part, rank))
-        handle = ops._hd
-
-        def step():
-            it, st = drv.solve(eps=0.0, max_iter=iters, fixed_iters=True)
-            assert it == iters, (it, st)
+        def solve(eps, max_iter):
+            if cg:
+                solver.steps = max_iter
+            else:
+                solver.max_steps = max_iter
+            solver.solve(eps=eps, quiet=True)          # the public call: BICGSolver.solve (bicgsolver.py:88) / CGSolver.solve
+            return solver.iterations, solver.status, solver.rel_res
     else:
-        from karman_taichi_b200.slab import P2PSlabSolver
-        try:
-            drv = P2PSlabSolver(coef, b, x, part, rank)
-            handle = drv._hd
-        except _lib.KtError as e:        # raised on every rank together (slab.py): e.g. no peer access on this box
-            if rank == 0:
-                print(f'bench: peer-memory setup failed ({e}); using the NCCL exchange', file=sys.stderr, flush=True)
-            a.comm = 'nccl'
+        drv = None
+        if comm_mode == 'p2p':
+            try:
+                drv = P2PSlabSolver(coef, b, x, part, rank, ipc_planes=a.ipc_planes)
+                handle, scratch = drv._hd, drv.t
+            except _lib.KtError as e:        # raised on every rank together (slab.py): e.g. no peer access on this box
+                if rank == 0:
+                    print(f'bench: peer-memory setup failed ({e}); using the NCCL exchange', file=sys.stderr, flush=True)
+                comm_mode = 'nccl'
+        if comm_mode == 'nccl':
             ops = CudaSlabOps(coef, b, x, part, rank)
-            drv = DistBiCGSTAB(ops, HaloExchanger(part, rank))
-            handle = ops._hd
+            drv = (DistCG if cg else DistBiCGSTAB)(ops, HaloExchanger(part, rank))
+            handle, scratch = ops._hd, ops.t
 
-        def step():
-            it, st = drv.solve(eps=0.0, max_iter=iters, fixed_iters=True)
-            assert it == iters, (it, st)
+        def solve(eps, max_iter):
+            fixed = eps == 0.0
+            if comm_mode == 'p2p':
+                it, st = (drv.solve_cg if cg else drv.solve)(eps=eps, max_iter=max_iter, fixed_iters=fixed)
+            else:
+                it, st = drv.solve(eps=eps, max_iter=max_iter, fixed_iters=fixed)
+            return it, st, drv.rel_res
+
+    def step():
+        it, st, _ = solve(0.0, iters)
+        assert it == iters, (it, st)
 
     # ---- value leg: inputs resident in HBM -------------------------------------------------------------
     for _ in range(a.warmup):
         step()
-    barrier()
+    cm.barrier()
     sampler = ClockSampler(range(world))
-    if rank == 0:
+    if rank == 0 and not light:
         sampler.start()
-    _lib.check(lib.kt_prof_begin(handle.h, 4 * iters * a.steps + 64))
+    _lib.check(lib.kt_prof_begin(handle.h, 4 * iters * steps + 64))
     launches0 = handle.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    cm.barrier()
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         step()
     e1.record()
-    barrier()
-    ms_total = allmax(e0.elapsed_time(e1))
-    launches = int(allsum(handle.launch_count() - launches0))
+    cm.barrier()
+    ms_total = cm.max(e0.elapsed_time(e1))
+    launches = int(cm.sum(handle.launch_count() - launches0))
     tot = (C.c_double * 8)()
     cnt = (C.c_long * 8)()
     _lib.check(lib.kt_prof_end(handle.h, tot, cnt, 8))
-    clocks = sampler.stop() if rank == 0 else None
-    value = cells * iters * a.steps / (ms_total * 1e-3) / 1e6
+    clocks = sampler.stop() if (rank == 0 and not light) else None
+    value = cells * iters * steps / (ms_total * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (largest share of the step), timed live with CUDA-event pairs ---------------
     peak, peak_kind = peaks()
-    fused = cnt[0] == 0                       # BICGSolver.fuse_p_update: K1 folded into K2 (11 N instead of 4 N + 8 N)
-    store_s = world > 1 and a.comm == 'nccl'  # the single-GPU and peer-memory paths recompute s in K4 instead of storing it
-    classes = {0: ('p_update', 'k_bicg_p: p = r + beta (p - omega v)', 4, 31.6),
-               1: (('p_update+v=Ap+dot', 'k_stencil<SRC_P,EPI_DOT_Q_ST>: p = r + beta (p - omega v), v = A p, (r~, v)', 11, FUSED_TRAFFIC_BYTES_PER_WORD)
-                   if fused else ('v=Ap+dot', 'k_stencil<SRC_X,EPI_DOT_Q>: v = A p, (r~, v)', 8, 64.0)),
-               2: (('s,t+2dots', 'k_stencil<SRC_S,EPI_ST>: s = r - alpha v, t = A s, (t,s), (t,t)', 9, 73.1) if store_s else
-                   ('t=As+2dots', 'k_stencil<SRC_S,EPI_ST>: t = A (r - alpha v) [s not stored], (t,s), (t,t)', 8, NO_S_K3_TRAFFIC)),
-               3: (('x,r+2dots', 'k_bicg_xr: x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 7, 55.9) if store_s else
-                   ('x,r+2dots', 'k_bicg_xr: s = r - alpha v, x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 8, NO_S_K4_TRAFFIC))}
-    tots = [allmax(tot[i]) for i in range(4)]
-    dom = max(range(4), key=lambda i: tots[i])
-    d_name, d_desc, d_words, d_traffic = classes[dom]
+    fused = (not cg) and cnt[0] == 0          # BICGSolver.fuse_p_update: K1 folded into K2 (11 N instead of 4 N + 8 N)
+    store_s = world > 1 and comm_mode == 'nccl'   # the single-GPU and peer-memory paths recompute s in K4 instead of storing it
+    classes = kernel_classes(solver_kind, fused, store_s)
+    tots = {i: cm.max(tot[i]) for i in classes}
+    dom = max(classes, key=lambda i: tots[i])
+    d_name, d_desc, d_words, d_pattern = classes[dom]
     d_ms = tots[dom] / max(cnt[dom], 1)
     words_local = (l1 - l0) * NY
     alg_bytes = d_words * w_bytes * words_local
     achieved = alg_bytes / (d_ms * 1e-3) / 1e9
-    kernel_share = {classes[i][0]: tots[i] / ms_total for i in range(4) if cnt[i]}
-    iter_bytes = (27 if fused else 28) * w_bytes
-    cell_iter_bytes = 28 * w_bytes        # 224 B f64, 112 B f32
+    kernel_share = {classes[i][0]: tots[i] / ms_total for i in classes if cnt[i]}
+    per_kernel = {classes[i][0]: {'ms_per_launch': tots[i] / max(cnt[i], 1), 'algorithmic_words': classes[i][2],
+                                  'achieved_gbs': classes[i][2] * w_bytes * words_local / (tots[i] / max(cnt[i], 1) * 1e-3) / 1e9,
+                                  'frac': classes[i][2] * w_bytes * words_local / (tots[i] / max(cnt[i], 1) * 1e-3) / 1e9 / peak}
+                  for i in classes if cnt[i]}
+    words_iter = WORDS_PER_CELL_ITER[solver_kind]
+    cell_iter_bytes = words_iter * w_bytes                  # SURVEY.md 8(d): BiCGSTAB 224 B f64 / CG 128 B f64
+    traffic, traffic_src = (traffic_of(measured_traffic(), d_pattern, (l1 - l0) * coef.pitch) if (d_pattern and a.dtype == 'f64')
+                            else (None, None))
+    whole = cell_iter_bytes * NX * NY * iters * steps / world / (ms_total * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'kernel': f'{d_desc}  [{d_words} N words]',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_kind': peak_kind,
-                'traffic': (d_traffic * (l1 - l0) * coef.pitch) if (d_traffic and a.dtype == 'f64') else None,
-                'traffic_source': 'profiles/r01_launch_list_default.md (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of this command), scaled by plane words',
+                'traffic': traffic, 'traffic_source': traffic_src,
                 'ms_per_launch': d_ms, 'launches_timed': int(cnt[dom]), 'algorithmic_bytes_per_launch': alg_bytes,
-                'kernel_share_of_step': kernel_share,
-                'whole_iteration': {'algorithmic_bytes_per_cell_iter': cell_iter_bytes, 'bytes_per_cell_iter_as_run': iter_bytes,
-                                    'achieved_gbs_per_gpu': cell_iter_bytes * NX * NY * iters * a.steps / world / (ms_total * 1e-3) / 1e9,
-                                    'frac': cell_iter_bytes * NX * NY * iters * a.steps / world / (ms_total * 1e-3) / 1e9 / peak}}
+                'kernel_share_of_step': kernel_share, 'per_kernel': per_kernel,
+                'whole_iteration': {'algorithmic_bytes_per_cell_iter': cell_iter_bytes,
+                                    'bytes_per_cell_iter_as_run': ((27 if fused else 28) if not cg else 16) * w_bytes,
+                                    'achieved_gbs_per_gpu': whole, 'frac': whole / peak}}
+
+    line = {'metric': CG_METRIC if cg else METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': a.warmup,
+            'ms_per_step': ms_total / steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': a.dtype,
+            'data': 'synthetic',
+            'config': {'workload': workload, 'description': desc, 'grid': [n, n], 'solver': solver_kind,
+                       f'{solver_kind}_iters_per_step': iters,
+                       'system': 'S1 Poisson-sin, offset 0, zero-coefficient ghost ring (SURVEY.md 8d)',
+                       'parallelism': (f'x-slab x{world}, halo + all-reduce: ' + ('NVLink peer memory inside the library' if comm_mode == 'p2p' else 'NCCL send/recv + all_reduce')) if world > 1 else 'single GPU',
+                       'cache': f'working set {(12 if not cg else 10) * NX * NY * w_bytes / 1e9:.1f} GB vs 126 MB L2 (inputs larger than L2: no flush needed)'},
+            'gpu_launches': launches, 'roofline': roofline}
+    if light:
+        return line
+    line['clocks'] = clocks
 
     # ---- e2e leg: host buffers in the reference layout, H2D + solve + D2H inside the timed region --------------------
-    e2e = None
+    line['e2e'] = None
     if not a.no_e2e:
-        e2e = run_e2e(a, kt, _lib, lib, torch, dist, world, rank, dev, n, g0, g1, coef, b, x, step, handle, cells, iters, barrier, allmax, allsum)
+        line['e2e'] = run_e2e(a, kt, _lib, lib, torch, world, rank, dev, n, g0, g1, coef, b, x, step, handle, cells, iters, cm,
+                              solver if (world == 1 and not cg) else None)
+
+    # ---- check: correctness evidence at this N -------------------------------------------------------------------------
+    if not a.no_check:
+        line['check'] = run_check(a, kt, _lib, lib, torch, world, rank, part, coef, b, x, scratch, handle, solve, iters, cm, cg, n)
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------------
-    cpu = None
+    line['cpu_baseline'] = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         n_s, its = 4096, 6
         cpu_port_run(n_s, 2, 1)
         t, threads = cpu_port_run(n_s, its, 3)
-        cpu = {'value': n_s * n_s * its / t / 1e6, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': f'{n_s}x{n_s} sub-grid of the same S1 system, {its} BiCGSTAB iterations, best of 3 (C/OpenMP port of bicgsolver.py, '
-                         'reference kernel granularity)'}
+        line['cpu_baseline'] = {'value': n_s * n_s * its / t / 1e6, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                'sample': f'{n_s}x{n_s} sub-grid of the same S1 system, {its} BiCGSTAB iterations, best of 3 (C/OpenMP port of '
+                                          'bicgsolver.py, reference kernel granularity)'}
 
+    # ---- secondary: the rest of BASELINE.json's metric, same run, N = 1 ------------------------------------------------
+    if world == 1 and not a.no_secondary and workload == 'pcor32768' and solver_kind == 'bicgstab':
+        sec = {}
+        del solver
+        torch.cuda.empty_cache()
+        try:
+            l = krylov_line(a, torch, dist, world, rank, dev, light=True, fields=(coef, b, x), solver_kind='cg', steps=3)
+            sec['cg_pcor32768'] = {k: l[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'roofline', 'gpu_launches')}
+        except Exception as e:
+            sec['cg_pcor32768'] = {'error': repr(e)}
+        del coef, b, x, scratch
+        torch.cuda.empty_cache()
+        for wl, kind in (('pcor4096', 'bicgstab'), ('pcor4096', 'cg')):
+            try:
+                l = krylov_line(a, torch, dist, world, rank, dev, light=True, workload=wl, solver_kind=kind, steps=5)
+                sec[f'{kind}_{wl}'] = {k: l[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'roofline', 'gpu_launches')}
+            except Exception as e:
+                sec[f'{kind}_{wl}'] = {'error': repr(e)}
+        for wl, k_steps in (('karman16384', 3), ('cavity128', 40), ('karman320', 40)):
+            try:
+                l = simple_line(a, torch, dist, world, rank, dev, wl, steps=k_steps, light=True)
+                sec[wl] = {k: l[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'roofline', 'gpu_launches', 'config')}
+            except Exception as e:
+                sec[wl] = {'error': repr(e)}
+        line['secondary'] = sec
+    return line
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    world, rank, local_rank = dist_env()
+    if a.gpus > 1 and world == 1:
+        return relaunch_under_torchrun(a)
+    assert world == a.gpus, f'--gpus {a.gpus} but WORLD_SIZE={world}'
+    assert torch.cuda.is_available(), 'bench.py needs CUDA (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    line = krylov_line(a, torch, dist, world, rank, dev)
     if rank == 0:
-        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
-                'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': a.dtype,
-                'data': 'synthetic',
-                'config': {'workload': a.workload, 'description': desc, 'grid': [n, n], 'bicgstab_iters_per_step': iters,
-                           'system': 'S1 Poisson-sin, offset 0, zero-coefficient ghost ring (SURVEY.md 8d)',
-                           'parallelism': (f'x-slab x{world}, halo + all-reduce: ' + ('NVLink peer memory inside the library' if a.comm == 'p2p' else 'NCCL send/recv + all_reduce')) if world > 1 else 'single GPU',
-                           'cache': f'working set {12 * NX * NY * w_bytes / 1e9:.1f} GB vs 126 MB L2 (inputs larger than L2: no flush needed)'},
-                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def run_e2e(a, kt, _lib, lib, torch, dist, world, rank, dev, n, g0, g1, coef, b, x, step, handle, cells, iters, barrier, allmax, allsum):
+def set_diagonal(torch, coef, value, chunk=2048):
+    """interior diagonal of the S1 system := value (4 + offset), in row chunks (no plane-sized temporary)"""
+    d0 = coef.data[0]
+    for r in range(0, d0.shape[0], chunk):
+        blk = d0[r:r + chunk]
+        blk[blk != 0] = value
+
+
+def run_check(a, kt, _lib, lib, torch, world, rank, part, coef, b, x, scratch, handle, solve, iters, cm, cg, n):
+    """Evidence that the timed work is the right work, at this N (a wrong halo row would not change the value).
+    1. the fixed-iteration step once more: relative residual and ||x|| (N-independent up to the order of the partial sums);
+    2. a converged solve of the offset-0.1 system (well conditioned: ~80 iterations at any size): status, iterations and the
+       TRUE residual ||A x - b|| / ||b||, recomputed on the device from the returned x with freshly exchanged halo rows."""
+    from karman_taichi_b200.slab import HaloExchanger
+    P = lambda f: C.c_void_p(f.ptr)
+    h = handle.h
+
+    def dot(fa, fb):
+        out = C.c_double()
+        handle.use_current_stream()
+        _lib.check(lib.kt_dot(h, P(fa), P(fb), C.byref(out)))      # owned rows of this rank (kt_set_rows), deterministic order
+        return cm.sum(out.value)
+
+    it, st, rel = solve(0.0, iters)
+    fixed = {'iterations': int(it), 'rel_res': float(rel), 'x_norm2': float(np.sqrt(dot(x, x)))}
+    set_diagonal(torch, coef, 4.1)
+    eps = 1e-8 if a.dtype == 'f64' else 1e-4
+    it, st, rel = solve(eps, 10000)
+    if world > 1:
+        HaloExchanger(part, rank).exchange(x.data)
+    handle.use_current_stream()
+    _lib.check(lib.kt_spmv(h, P(coef), P(x), P(scratch)))
+    _lib.check(lib.kt_xmay(h, P(scratch), P(b), 1.0, P(scratch)))   # scratch = b - A x
+    rr, bb = dot(scratch, scratch), dot(b, b)
+    set_diagonal(torch, coef, 4.0)
+    true_rel = float(np.sqrt(rr / bb))
+    return {'fixed_iterations': fixed,
+            'converged_offset_0.1': {'eps': eps, 'status': int(st), 'iterations': int(it), 'rel_res_recurrence': float(rel),
+                                     'true_rel_residual': true_rel, 'x_norm2': float(np.sqrt(dot(x, x))),
+                                     'ok': bool(st == 0 and true_rel <= 1.5 * eps)},
+            'note': 'all figures must agree across --gpus 1, 2, 4, 8 up to the order of the rank partial sums; the true residual is '
+                    'b - A x recomputed with kt_spmv on the returned x (halo rows re-exchanged over NCCL), not the recurrence residual'}
+
+
+def run_e2e(a, kt, _lib, lib, torch, world, rank, dev, n, g0, g1, coef, b, x, step, handle, cells, iters, cm, bicg_solver):
     """The reference-facing call with HOST buffers: coef[i][j][k] (AoS) and b in pinned host memory are copied to the
-    device, converted to the kernel layout, solved, and x is copied back -- every step, all inside the timed region."""
+    device, converted to the kernel layout, solved, and x is copied back -- every step, all inside the timed region.  At
+    N = 1 this is ONE C-ABI call, kt_bicgstab_solve_host; on x-slabs every rank uploads its slab (kt_upload_coef /
+    kt_upload_field), joins the distributed solve and downloads its rows of x (kt_download_field)."""
     rows, NY = g1 - g0, n + 2
     w_bytes = 8 if a.dtype == 'f64' else 4
     t_dtype = torch.float64 if a.dtype == 'f64' else torch.float32
@@ -402,6 +554,7 @@ def run_e2e(a, kt, _lib, lib, torch, dist, world, rank, dev, n, g0, g1, coef, b,
         avail = None
     if avail is not None and need * (world if world > 1 else 1) > 0.8 * avail:
         return {'value': None, 'unit': UNIT, 'skipped': f'host needs {need / 1e9:.0f} GB pinned per rank, {avail / 1e9:.0f} GB available'}
+    numa = bind_host_memory_near_gpu(torch, dev)
     try:
         coef_h = torch.empty((rows, NY, 5), dtype=t_dtype, pin_memory=True)
         b_h = torch.empty((rows, NY), dtype=t_dtype, pin_memory=True)
@@ -418,29 +571,82 @@ def run_e2e(a, kt, _lib, lib, torch, dist, world, rank, dev, n, g0, g1, coef, b,
     h = handle.h
     P = lambda t: C.c_void_p(t.data_ptr())
 
-    def e2e_step():
-        handle.use_current_stream()
-        _lib.check(lib.kt_upload_coef(h, C.c_void_p(coef.ptr), P(coef_h), P(staging), staging_bytes))
-        _lib.check(lib.kt_upload_field(h, C.c_void_p(b.ptr), P(b_h)))
-        step()
-        _lib.check(lib.kt_download_field(h, P(x_h), C.c_void_p(x.ptr)))
+    if bicg_solver is not None:
+        s = bicg_solver
+        ws = s._ws(r_tld=None, s=None, t=s.t.ptr, p2=None, Ap2=None)
+        it, rel, st = C.c_long(), C.c_double(), C.c_int()
+        call = 'kt_bicgstab_solve_host (one C-ABI call: upload coef + b, BiCGSTAB, download x) on pinned host buffers'
+
+        def e2e_step():
+            handle.use_current_stream()
+            _lib.check(lib.kt_bicgstab_solve_host(h, P(coef_h), P(b_h), P(x_h), C.c_void_p(coef.ptr), P(staging), staging_bytes,
+                                                  C.c_void_p(b.ptr), C.c_void_p(x.ptr), C.byref(ws), 0.0, iters,
+                                                  C.byref(it), C.byref(rel), C.byref(st)))
+            assert it.value == iters, (it.value, st.value)
+    else:
+        call = 'kt_upload_coef + kt_upload_field + solve + kt_download_field on pinned host buffers (per rank)'
+
+        def e2e_step():
+            handle.use_current_stream()
+            _lib.check(lib.kt_upload_coef(h, C.c_void_p(coef.ptr), P(coef_h), P(staging), staging_bytes))
+            _lib.check(lib.kt_upload_field(h, C.c_void_p(b.ptr), P(b_h)))
+            step()
+            _lib.check(lib.kt_download_field(h, P(x_h), C.c_void_p(x.ptr)))
 
     k_e = max(1, min(a.steps, 3))
     e2e_step()                                   # warm-up
-    barrier()
+    cm.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(k_e):
         e2e_step()
     e1.record()
-    barrier()
-    ms = allmax(e0.elapsed_time(e1))
-    h2d = int(allsum(float((coef_h.numel() + b_h.numel()) * w_bytes)))     # bytes of the tensors copied, all ranks
-    d2h = int(allsum(float(x_h.numel() * w_bytes)))
+    cm.barrier()
+    ms = cm.max(e0.elapsed_time(e1))
+    h2d = int(cm.sum(float((coef_h.numel() + b_h.numel()) * w_bytes)))     # bytes of the tensors copied, all ranks
+    d2h = int(cm.sum(float(x_h.numel() * w_bytes)))
     return {'value': cells * iters * k_e / (ms * 1e-3) / 1e6, 'unit': UNIT,
             'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-            'steps': k_e, 'ms_per_step': ms / k_e,
-            'call': 'kt_upload_coef + kt_upload_field + BICGSolver.solve + kt_download_field (= kt_bicgstab_solve_host) on pinned host buffers'}
+            'steps': k_e, 'ms_per_step': ms / k_e, 'host_numa': numa, 'call': call}
+
+
+def bind_host_memory_near_gpu(torch, dev):
+    """Prefer the NUMA node the GPU hangs off for this process's host allocations (the pinned e2e buffers) and, where the
+    container's cpuset allows it, run on that node's cores.  Best effort; reports what it did."""
+    info = {'gpu_numa_node': None, 'mempolicy': None, 'cpu_affinity': None}
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        if all(hasattr(pr, k) for k in ('pci_domain_id', 'pci_bus_id', 'pci_device_id')):
+            bus_id = f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+        else:
+            import pynvml
+            pynvml.nvmlInit()
+            bus_id = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(dev.index or 0)).busId
+            bus_id = (bus_id.decode() if isinstance(bus_id, bytes) else bus_id).lower()
+            if len(bus_id.split(':')[0]) == 8:
+                bus_id = bus_id[4:]
+        node = int(open(f'/sys/bus/pci/devices/{bus_id}/numa_node').read().strip())
+        info['gpu_numa_node'] = node
+        if node < 0:
+            return info
+        # set_mempolicy(MPOL_PREFERRED = 1, nodemask) -- x86_64 syscall 238
+        libc = C.CDLL(None, use_errno=True)
+        mask = C.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, C.byref(mask), 64)
+        info['mempolicy'] = 'preferred node %d' % node if rc == 0 else 'set_mempolicy failed (errno %d)' % C.get_errno()
+        cpus = set()
+        for part_ in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part_.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info['cpu_affinity'] = f'{len(allowed)} cores of node {node}'
+        else:
+            info['cpu_affinity'] = 'unchanged (the container cpuset has no core of that node)'
+    except Exception as e:
+        info['error'] = repr(e)
+    return info
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -495,29 +701,17 @@ def run_simple_reference(a):
     return 0
 
 
-def run_simple(a):
+def simple_line(a, torch, dist, world, rank, dev, workload, steps=None, light=False):
     """One step = one SIMPLE outer iteration (bicgsimp.py:313-317) / sub-iteration (karman_taichi.py:633-652) through the
-    reference-facing classes.  Not sharded (BASELINE configs 1, 2, 4 are single-GPU): N > 1 runs N replicas."""
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if a.gpus > 1 and world == 1:
-        port = 29500 + (os.getpid() % 2000)
-        return subprocess.call([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={a.gpus}', '--master-addr',
-                                '127.0.0.1', '--master-port', str(port), os.path.abspath(__file__)] + sys.argv[1:])
-    assert torch.cuda.is_available(), 'bench.py needs CUDA (no CPU fallback)'
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    reference-facing classes.  Not sharded here (BASELINE configs 1, 2, 4 are single-GPU): N > 1 runs N replicas."""
     import karman_taichi_b200 as kt
     from karman_taichi_b200 import _lib
     from karman_taichi_b200.cgsolver import _Handle
     lib = _lib.load()
-    case, nx, ny, cap, desc = SIMPLE_WORKLOADS[a.workload]
+    steps = steps or a.steps
+    case, nx, ny, cap, desc = SIMPLE_WORKLOADS[workload]
     cells = nx * ny
+    cm = Comm(torch, dist, world, dev)
     if case == 'cavity':
         s = kt.lid_driven_cavity(nx, device=dev)
         s.alpha_p = 0.02
@@ -540,65 +734,54 @@ def run_simple(a):
             sol.max_steps = cap
     handles = [s._hd] + [sol._hd for sol in solvers.values()]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def allmax(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     for _ in range(a.warmup):
         step()
-    barrier()
+    cm.barrier()
     sampler = ClockSampler(range(world))
-    if rank == 0:
+    if rank == 0 and not light:
         sampler.start()
     hp = solvers['p']._hd
-    _lib.check(lib.kt_prof_begin(hp.h, 4 * (cap or 4096) * a.steps + 64))
+    _lib.check(lib.kt_prof_begin(hp.h, 4 * (cap or 4096) * steps + 64))
     l0 = sum(h.launch_count() for h in handles)
     tot_its = {'u': 0, 'v': 0, 'p': 0}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    cm.barrier()
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         step()
         for k, v in its().items():
             tot_its[k] += v
     e1.record()
-    barrier()
-    ms_total = allmax(e0.elapsed_time(e1))
+    cm.barrier()
+    ms_total = cm.max(e0.elapsed_time(e1))
     launches = (sum(h.launch_count() for h in handles) - l0) * world
     tot = (C.c_double * 8)()
     cnt = (C.c_long * 8)()
     _lib.check(lib.kt_prof_end(hp.h, tot, cnt, 8))
-    clocks = sampler.stop() if rank == 0 else None
-    value = a.steps * world / (ms_total * 1e-3)
+    clocks = sampler.stop() if (rank == 0 and not light) else None
+    value = steps * world / (ms_total * 1e-3)
 
     # roofline: whole-step algorithmic bytes (~51 N words of assembly / BC / relaxation / correction per outer
     # iteration + the Krylov iterations actually run); the dominant kernel class of the p' solve when it streams from HBM
     peak, peak_kind = peaks()
     N = (nx + 2) * (ny + 2)
-    step_bytes = 8.0 * N * (51 * a.steps + sum(words[k] * tot_its[k] for k in words))
+    step_bytes = 8.0 * N * (51 * steps + sum(words[k] * tot_its[k] for k in words))
     achieved = step_bytes / (ms_total * 1e-3) / 1e9
     streamed = sum(cnt[i] for i in range(4)) > 0
-    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_kind': peak_kind, 'traffic': None,
+    n_krylov = max(1, sum(tot_its.values()))
+    roofline = {'bound': 'hbm' if streamed else 'latency', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'peak_kind': peak_kind, 'traffic': None,
                 'kernel': 'whole SIMPLE step: algorithmic bytes of assembly + Krylov iterations actually run / step time',
-                'krylov_iterations_per_step': {k: v / a.steps for k, v in tot_its.items()}, 'krylov_cap': cap,
+                'krylov_iterations_per_step': {k: v / steps for k, v in tot_its.items()}, 'krylov_cap': cap,
+                'us_per_krylov_iteration': ms_total * 1e3 / n_krylov,
                 'krylov_mcell_iters_per_s': cells * sum(tot_its.values()) / (ms_total * 1e-3) / 1e6}
     if streamed:
-        names = {0: ('p_update', 4), 1: ('v=A M^-1 p + dot', 9), 2: ('t=A M^-1 s + 2 dots', 9), 3: ('x,r + 2 dots', 9)}
+        names = {0: ('p_update', 4, 'k_bicg_p<double>'), 1: ('v=A M^-1 p + dot', 9, 'k_stencil<double, 0, 1, 1>'),
+                 2: ('t=A M^-1 s + 2 dots', 9, 'k_stencil<double, 1, 1, 3>'), 3: ('x,r + 2 dots', 9, 'k_bicg_xr<double, 1>')}
         dom = max(range(4), key=lambda i: tot[i])
         d_ms = tot[dom] / max(cnt[dom], 1)
-        # ncu dram__bytes_read.sum + dram__bytes_write.sum per plane word of the Jacobi-variant kernels
-        # (profiles/r01_launch_list_karman16384.md, working launches only)
-        jac_traffic = {0: 30.6, 1: 71.7, 2: 73.3, 3: 70.9}
-        roofline['traffic'] = jac_traffic[dom] * N if case == 'karman' else None
-        roofline['traffic_source'] = 'profiles/r01_launch_list_karman16384.md, dominant kernel, per launch, scaled by plane words'
+        if case == 'karman':
+            roofline['traffic'], roofline['traffic_source'] = traffic_of(measured_traffic(), names[dom][2], (nx + 2) * s.p.pitch)
         roofline['dominant_kernel'] = {'name': names[dom][0], 'words': names[dom][1], 'ms_per_launch': d_ms,
                                        'achieved': names[dom][1] * 8.0 * N / (d_ms * 1e-3) / 1e9,
                                        'frac': names[dom][1] * 8.0 * N / (d_ms * 1e-3) / 1e9 / peak,
@@ -606,10 +789,24 @@ def run_simple(a):
     else:
         roofline['note'] = ('the Krylov solves run as ONE resident kernel each -- a thread-block cluster (csrc/kt_cluster.cu) up to ~35 k '
                             'unknowns, a persistent cooperative kernel (csrc/kt_coop.cu) above -- and are bound by the latency of the '
-                            'three dependent inner products per iteration, not by HBM')
+                            'three dependent inner products per BiCGSTAB iteration (two per CG iteration), not by HBM: the figure that '
+                            'matters is us_per_krylov_iteration; achieved / frac are the algorithmic bytes over the step time, reported '
+                            'for completeness and NOT a roofline this size can approach (the working set lives in shared memory)')
+
+    line = {'metric': SIMPLE_METRIC, 'value': value, 'unit': SIMPLE_UNIT, 'n_gpus': world, 'steps': steps, 'warmup': a.warmup,
+            'ms_per_step': ms_total / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': workload, 'description': desc, 'grid': [nx, ny],
+                       'parallelism': 'single GPU' if world == 1 else f'{world} independent replicas (the SIMPLE configs are not sharded)',
+                       'cache': ('working set >> 126 MB L2' if cells > 1 << 22 else
+                                 'working set resident in shared memory / L2 by design (reference-sized grid); inputs change every step')},
+            'gpu_launches': launches, 'roofline': roofline}
+    if light:
+        return line
+    line['clocks'] = clocks
 
     # e2e: u, v, p arrive in pinned host arrays and go back every step (kt_upload_field / kt_download_field)
-    e2e = None
+    line['e2e'] = None
     if not a.no_e2e:
         fields = [s.u, s.v, s.p]
         hs = [_Handle(f) for f in fields]
@@ -623,33 +820,40 @@ def run_simple(a):
             step()
             for f, h, t in zip(fields, hs, host):
                 _lib.check(lib.kt_download_field(h.h, P(t), C.c_void_p(f.ptr)))
-        k_e = max(1, min(a.steps, 5))
+        k_e = max(1, min(steps, 5))
         e2e_step()
-        barrier()
+        cm.barrier()
         e0.record()
         for _ in range(k_e):
             e2e_step()
         e1.record()
-        barrier()
-        ms = allmax(e0.elapsed_time(e1))
+        cm.barrier()
+        ms = cm.max(e0.elapsed_time(e1))
         nbytes = sum(t.numel() * 8 for t in host) * world
-        e2e = {'value': k_e * world / (ms * 1e-3), 'unit': SIMPLE_UNIT, 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': nbytes,
-               'steps': k_e, 'ms_per_step': ms / k_e,
-               'call': 'kt_upload_field(u, v, p) + SIMPLESolver.step / KarmanSolver.sub_iteration + kt_download_field(u, v, p) on pinned host buffers'}
+        line['e2e'] = {'value': k_e * world / (ms * 1e-3), 'unit': SIMPLE_UNIT, 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': nbytes,
+                       'steps': k_e, 'ms_per_step': ms / k_e,
+                       'call': 'kt_upload_field(u, v, p) + SIMPLESolver.step / KarmanSolver.sub_iteration + kt_download_field(u, v, p) on pinned host buffers'}
 
-    cpu = None
+    line['cpu_baseline'] = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         v, sample = simple_oracle_rate(case, nx, ny, cap, 3)
-        cpu = {'value': v, 'unit': SIMPLE_UNIT, 'cores': 1, 'kind': 'port', 'sample': sample}
+        line['cpu_baseline'] = {'value': v, 'unit': SIMPLE_UNIT, 'cores': 1, 'kind': 'port', 'sample': sample}
+    return line
+
+
+def run_simple(a):
+    import torch
+    import torch.distributed as dist
+    world, rank, local_rank = dist_env()
+    if a.gpus > 1 and world == 1:
+        return relaunch_under_torchrun(a)
+    assert torch.cuda.is_available(), 'bench.py needs CUDA (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    line = simple_line(a, torch, dist, world, rank, dev, a.workload)
     if rank == 0:
-        line = {'metric': SIMPLE_METRIC, 'value': value, 'unit': SIMPLE_UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
-                'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-                'data': 'synthetic',
-                'config': {'workload': a.workload, 'description': desc, 'grid': [nx, ny],
-                           'parallelism': 'single GPU' if world == 1 else f'{world} independent replicas (the SIMPLE configs are not sharded)',
-                           'cache': ('working set >> 126 MB L2' if cells > 1 << 22 else
-                                     'working set resident in shared memory / L2 by design (reference-sized grid); inputs change every step')},
-                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -668,7 +872,12 @@ def main():
                     help='pcor workloads: field precision (the reference computes in f64; f32 is the north_star 1e-4 variant)')
     ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'],
                     help='N > 1: halo exchange + all-reduce inside the library over NVLink peer memory (p2p) or via NCCL')
+    ap.add_argument('--solver', default='bicgstab', choices=['bicgstab', 'cg'],
+                    help='pcor workloads: BICGSolver.solve (default; the headline metric) or CGSolver.solve (config 3 names both)')
+    ap.add_argument('--ipc-planes', action='store_true', help='measurement aid: round-1 placement of r / p / v in IPC-exported allocations')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-check', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == 'ours':

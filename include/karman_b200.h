@@ -183,23 +183,21 @@ int kt_dist_scalar(kt_handle_t h, int fin, const double* dots_dev, double* histo
 int kt_dist_poll(kt_handle_t h, int* done, long* iters, int* status, double* rel_res);
 
 /* Same solve with the halo exchange and the all-reduce done by the library itself over NVLink peer memory (no NCCL
- * in the loop): every rank passes device pointers, mapped into ITS address space (CUDA IPC), of its neighbours' p / v /
- * r planes and of every rank's comm block (kt_p2p_comm_block_bytes() bytes, zero-initialised once, never reset).
- * peer_*[0] = lower neighbour (rank-1) or NULL, [1] = upper neighbour or NULL; peer_halo_row[k] = the row of THAT
- * rank's plane this rank's boundary row goes to.  local_dots: 2 doubles of device scratch.  All ranks must call this
- * with the same eps / max_iter, in lock step. */
+ * in the loop).  Every rank allocates (kt_ipc_alloc, zero-initialised once, never reset) a comm block of
+ * kt_p2p_comm_block_bytes() bytes and a halo-receive buffer of 3 planes x 2 sides x pitch reals, and passes device
+ * pointers, mapped into ITS address space (kt_ipc_open), of every rank's comm block and of its two neighbours'
+ * halo-receive buffers: peer_halo_recv[0] = lower neighbour (rank-1) or NULL, [1] = upper neighbour or NULL.  The field
+ * planes themselves are ordinary allocations that no other rank maps: a boundary row travels plane -> neighbour's receive
+ * buffer (peer store over NVLink) -> neighbour's plane (local copy).  local_dots: 2 doubles of device scratch.  All
+ * ranks must call this with the same eps / max_iter / flags, in lock step. */
 typedef struct {
   int rank, nranks;
-  void* peer_p[2];
-  void* peer_v[2];
-  void* peer_r[2];
-  int peer_halo_row[2];
+  void* peer_halo_recv[2];
+  void* halo_recv;
   void* comm_block[16];
   void* local_dots;
 } kt_p2p_comm;
 int kt_p2p_comm_block_bytes(void);
-/* development aid: read / overwrite / re-read one double at a (possibly peer-mapped) device address */
-int kt_debug_poke(kt_handle_t h, void* ptr, double value, double* before_after_host);
 /* Buffers that other ranks (processes) map and write into: a dedicated zero-initialised cudaMalloc allocation plus its
  * 64-byte cudaIpcMemHandle_t; kt_ipc_open maps a peer's handle into this rank's device (lazy peer access). */
 int kt_ipc_alloc(kt_handle_t h, size_t bytes, void** dev_ptr, unsigned char* handle64);
@@ -208,11 +206,14 @@ int kt_ipc_close(kt_handle_t h, void* mapped);
 int kt_ipc_free(kt_handle_t h, void* dev_ptr);
 /* enable direct loads/stores from the handle's device to peer_device's memory (idempotent) */
 int kt_enable_peer_access(kt_handle_t h, int peer_device);
-int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws,
-                          const kt_p2p_comm* comm, double eps, long max_iter, int fixed_iters,
+/* BICGSolver.solve over x-slabs.  Minv / flags as in kt_bicgstab_solve: with Minv and KT_FLAG_WARM_START |
+ * KT_FLAG_OMEGA_ZERO_BREAK it is the monolith's Jacobi-preconditioned, warm-started kernel (karman_taichi.py:342-456;
+ * ws->r_tld required; the halo rows of x0 are exchanged first). */
+int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* ws,
+                          const kt_p2p_comm* comm, double eps, long max_iter, int flags, int fixed_iters,
                           long* iters, double* rel_res, int* status);
-/* CGSolver.solve (cgsolver.py:83-114) over x-slabs, same comm kernels: one halo exchange (p: comm->peer_p, ws->p must be
- * a kt_ipc_alloc plane) and two all-reduces per iteration.  ws: r, p, Ap. */
+/* CGSolver.solve (cgsolver.py:83-114) over x-slabs, same comm kernels: one halo exchange (p) and two all-reduces per
+ * iteration.  ws: r, p, Ap. */
 int kt_p2p_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws,
                     const kt_p2p_comm* comm, double eps, long max_iter, int fixed_iters,
                     long* iters, double* rel_res, int* status);

@@ -21,6 +21,7 @@ STATUS_ALPHA_DIV_ZERO = 3
 STATUS_OMEGA_DIV_ZERO = 4
 STATUS_NON_FINITE = 5
 STATUS_OMEGA_ZERO = 6
+STATUS_COMM_TIMEOUT = 7
 
 FLAG_WARM_START = 1
 FLAG_OMEGA_ZERO_BREAK = 2
@@ -39,9 +40,8 @@ class KrylovWs(C.Structure):
 
 class P2PComm(C.Structure):
     """``kt_p2p_comm``"""
-    _fields_ = [('rank', C.c_int), ('nranks', C.c_int),
-                ('peer_p', C.c_void_p * 2), ('peer_v', C.c_void_p * 2), ('peer_r', C.c_void_p * 2),
-                ('peer_halo_row', C.c_int * 2), ('comm_block', C.c_void_p * 16), ('local_dots', C.c_void_p)]
+    _fields_ = [('rank', C.c_int), ('nranks', C.c_int), ('peer_halo_recv', C.c_void_p * 2), ('halo_recv', C.c_void_p),
+                ('comm_block', C.c_void_p * 16), ('local_dots', C.c_void_p)]
 
 
 class Geom(C.Structure):
@@ -119,8 +119,7 @@ SIGNATURES = {
     'kt_ipc_close': (_I, [_P, _P]),
     'kt_ipc_free': (_I, [_P, _P]),
     'kt_enable_peer_access': (_I, [_P, _I]),
-    'kt_debug_poke': (_I, [_P, _P, _D, _PD]),
-    'kt_p2p_bicgstab_solve': (_I, [_P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _PL, _PD, _PI]),
+    'kt_p2p_bicgstab_solve': (_I, [_P, _P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _I, _PL, _PD, _PI]),
     'kt_p2p_cg_solve': (_I, [_P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _PL, _PD, _PI]),
     'kt_reduce_plan': (_I, [C.POINTER(Geom), _I, _I, C.POINTER(C.c_longlong)]),
     'kt_resident_plan': (_I, [C.POINTER(Geom), _I, _I, _I, _I, C.POINTER(C.c_longlong)]),

@@ -73,7 +73,7 @@ int kt_create(int device, int NX, int NY, int pitch, int dtype, void* stream, kt
   int ndev = 0;
   KT_CUDA(cudaGetDeviceCount(&ndev));
   KT_CHECK_ARG(device >= 0 && device < ndev, "kt_create: no such CUDA device");
-  KT_CUDA(cudaSetDevice(device));
+  kt::DeviceGuard guard(device);          // allocate on `device`, leave the caller's current device untouched
   kt_handle_s* h = new kt_handle_s();
   h->device = device; h->NX = NX; h->NY = NY; h->pitch = pitch; h->dtype = dtype;
   h->row_lo = 0; h->row_hi = NX;
@@ -99,7 +99,7 @@ int kt_create(int device, int NX, int NY, int pitch, int dtype, void* stream, kt
 
 int kt_destroy(kt_handle_t h) {
   if (!h) return 0;
-  cudaSetDevice(h->device);
+  kt::DeviceGuard guard(h->device);
   cudaFree(h->partials); cudaFree(h->ticket); cudaFree(h->sc); cudaFreeHost(h->sc_host);
   cudaFree(h->red_out); cudaFreeHost(h->red_host);
   for (int k = 0; k < 2; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
@@ -114,18 +114,21 @@ int kt_destroy(kt_handle_t h) {
 
 int kt_set_stream(kt_handle_t h, void* stream) {
   KT_CHECK_ARG(h, "kt_set_stream: null handle");
+  KT_DEV_GUARD(h);
   h->stream = (cudaStream_t)stream;
   return 0;
 }
 
 int kt_sync(kt_handle_t h) {
   KT_CHECK_ARG(h, "kt_sync: null handle");
+  KT_DEV_GUARD(h);
   KT_CUDA(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
 int kt_set_rows(kt_handle_t h, int row_lo, int row_hi) {
   KT_CHECK_ARG(h, "kt_set_rows: null handle");
+  KT_DEV_GUARD(h);
   KT_CHECK_ARG(0 <= row_lo && row_lo <= row_hi && row_hi <= h->NX, "kt_set_rows: need 0 <= row_lo <= row_hi <= NX");
   h->row_lo = row_lo; h->row_hi = row_hi;
   return 0;
@@ -135,8 +138,8 @@ long long kt_launch_count(kt_handle_t h) { return h ? h->launches : 0; }
 
 int kt_enable_peer_access(kt_handle_t h, int peer_device) {
   KT_CHECK_ARG(h, "kt_enable_peer_access: null handle");
+  KT_DEV_GUARD(h);
   if (peer_device == h->device) return 0;
-  KT_CUDA(cudaSetDevice(h->device));
   int can = 0;
   KT_CUDA(cudaDeviceCanAccessPeer(&can, h->device, peer_device));
   if (!can) { set_error("kt_enable_peer_access: device " + std::to_string(h->device) + " cannot access device " + std::to_string(peer_device)); return -4; }
@@ -149,7 +152,7 @@ int kt_enable_peer_access(kt_handle_t h, int peer_device) {
 // ---- CUDA-IPC helpers for the peer-memory x-slab solver: buffers other ranks (processes) map and write into ----------
 int kt_ipc_alloc(kt_handle_t h, size_t bytes, void** dev_ptr, unsigned char* handle64) {
   KT_CHECK_ARG(h && dev_ptr && handle64 && bytes > 0, "kt_ipc_alloc: bad argument");
-  KT_CUDA(cudaSetDevice(h->device));
+  KT_DEV_GUARD(h);
   void* p = nullptr;
   KT_CUDA(cudaMalloc(&p, bytes));                 // a dedicated allocation: its base address IS the pointer
   KT_CUDA(cudaMemset(p, 0, bytes));
@@ -164,7 +167,7 @@ int kt_ipc_alloc(kt_handle_t h, size_t bytes, void** dev_ptr, unsigned char* han
 
 int kt_ipc_open(kt_handle_t h, const unsigned char* handle64, void** mapped) {
   KT_CHECK_ARG(h && handle64 && mapped, "kt_ipc_open: bad argument");
-  KT_CUDA(cudaSetDevice(h->device));              // map into THIS rank's device, with peer access to the exporter
+  KT_DEV_GUARD(h);
   cudaIpcMemHandle_t mh;
   memcpy(&mh, handle64, 64);
   KT_CUDA(cudaIpcOpenMemHandle(mapped, mh, cudaIpcMemLazyEnablePeerAccess));
@@ -173,34 +176,21 @@ int kt_ipc_open(kt_handle_t h, const unsigned char* handle64, void** mapped) {
 
 int kt_ipc_close(kt_handle_t h, void* mapped) {
   KT_CHECK_ARG(h, "kt_ipc_close: null handle");
-  if (mapped) { cudaSetDevice(h->device); cudaIpcCloseMemHandle(mapped); }
+  KT_DEV_GUARD(h);
+  if (mapped) cudaIpcCloseMemHandle(mapped);
   return 0;
 }
 
 int kt_ipc_free(kt_handle_t h, void* dev_ptr) {
   KT_CHECK_ARG(h, "kt_ipc_free: null handle");
-  if (dev_ptr) { cudaSetDevice(h->device); cudaFree(dev_ptr); }
-  return 0;
-}
-
-namespace kt {
-__global__ void k_debug_poke(double* p, double v, double* out) { out[0] = p[0]; p[0] = v; __threadfence_system(); out[1] = p[0]; }
-}
-
-// development aid: read, overwrite and re-read one double at a (possibly peer-mapped) device address
-int kt_debug_poke(kt_handle_t h, void* ptr, double value, double* before_after_host) {
-  KT_CHECK_ARG(h && ptr && before_after_host, "kt_debug_poke: null argument");
-  KT_CUDA(cudaSetDevice(h->device));
-  kt::k_debug_poke<<<1, 1, 0, h->stream>>>((double*)ptr, value, h->red_out);
-  KT_LAUNCH_CHECK(h);
-  KT_CUDA(cudaMemcpyAsync(h->red_host, h->red_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  KT_CUDA(cudaStreamSynchronize(h->stream));
-  before_after_host[0] = h->red_host[0]; before_after_host[1] = h->red_host[1];
+  KT_DEV_GUARD(h);
+  if (dev_ptr) cudaFree(dev_ptr);
   return 0;
 }
 
 int kt_set_cluster(kt_handle_t h, int enable) {
   KT_CHECK_ARG(h, "kt_set_cluster: null handle");
+  KT_DEV_GUARD(h);
   h->allow_cluster = enable == 1 || enable == 3;
   h->allow_coop = enable == 1 || enable == 2;
   return 0;
@@ -208,6 +198,7 @@ int kt_set_cluster(kt_handle_t h, int enable) {
 
 int kt_upload_field(kt_handle_t h, void* dst, const void* src_host) {
   KT_CHECK_ARG(h && dst && src_host, "kt_upload_field: null argument");
+  KT_DEV_GUARD(h);
   const size_t es = esize(h);
   KT_CUDA(cudaMemcpy2DAsync(dst, h->pitch * es, src_host, h->NY * es, h->NY * es, h->NX, cudaMemcpyHostToDevice, h->stream));
   return 0;
@@ -215,6 +206,7 @@ int kt_upload_field(kt_handle_t h, void* dst, const void* src_host) {
 
 int kt_download_field(kt_handle_t h, void* dst_host, const void* src) {
   KT_CHECK_ARG(h && dst_host && src, "kt_download_field: null argument");
+  KT_DEV_GUARD(h);
   const size_t es = esize(h);
   KT_CUDA(cudaMemcpy2DAsync(dst_host, h->NY * es, src, h->pitch * es, h->NY * es, h->NX, cudaMemcpyDeviceToHost, h->stream));
   KT_CUDA(cudaStreamSynchronize(h->stream));
@@ -223,11 +215,13 @@ int kt_download_field(kt_handle_t h, void* dst_host, const void* src) {
 
 int kt_coef_aos_to_soa(kt_handle_t h, void* dst_soa, const void* src_aos) {
   KT_CHECK_ARG(h && dst_soa && src_aos, "kt_coef_aos_to_soa: null argument");
+  KT_DEV_GUARD(h);
   return h->dtype == KT_F64 ? coef_layout<double, true>(h, dst_soa, (void*)src_aos) : coef_layout<float, true>(h, dst_soa, (void*)src_aos);
 }
 
 int kt_coef_soa_to_aos(kt_handle_t h, void* dst_aos, const void* src_soa) {
   KT_CHECK_ARG(h && dst_aos && src_soa, "kt_coef_soa_to_aos: null argument");
+  KT_DEV_GUARD(h);
   return h->dtype == KT_F64 ? coef_layout<double, false>(h, (void*)src_soa, dst_aos) : coef_layout<float, false>(h, (void*)src_soa, dst_aos);
 }
 
@@ -235,6 +229,7 @@ int kt_coef_soa_to_aos(kt_handle_t h, void* dst_aos, const void* src_soa) {
 // (NY*5 reals): H2D copy of a chunk, then the layout kernel for those rows, on the handle's stream.
 int kt_upload_coef(kt_handle_t h, void* dst_soa, const void* src_host_aos, void* staging, size_t staging_bytes) {
   KT_CHECK_ARG(h && dst_soa && src_host_aos && staging, "kt_upload_coef: null argument");
+  KT_DEV_GUARD(h);
   const size_t row_bytes = (size_t)h->NY * 5 * esize(h);
   const int chunk = (int)std::min<size_t>(staging_bytes / row_bytes, (size_t)h->NX);
   KT_CHECK_ARG(chunk >= 1, "kt_upload_coef: staging buffer smaller than one row of coefficients");
@@ -250,6 +245,7 @@ int kt_upload_coef(kt_handle_t h, void* dst_soa, const void* src_host_aos, void*
 
 int kt_download_coef(kt_handle_t h, void* dst_host_aos, const void* src_soa, void* staging, size_t staging_bytes) {
   KT_CHECK_ARG(h && dst_host_aos && src_soa && staging, "kt_download_coef: null argument");
+  KT_DEV_GUARD(h);
   const size_t row_bytes = (size_t)h->NY * 5 * esize(h);
   const int chunk = (int)std::min<size_t>(staging_bytes / row_bytes, (size_t)h->NX);
   KT_CHECK_ARG(chunk >= 1, "kt_download_coef: staging buffer smaller than one row of coefficients");
@@ -270,6 +266,7 @@ int kt_bicgstab_solve_host(kt_handle_t h, const void* coef_host_aos, const void*
                            double eps, long max_iter, long* iters, double* rel_res, int* status) {
   KT_CHECK_ARG(h && coef_host_aos && b_host && x_host && dev_coef_soa && dev_staging && dev_b && dev_x && ws,
                "kt_bicgstab_solve_host: null argument");
+  KT_DEV_GUARD(h);
   int rc = kt_upload_coef(h, dev_coef_soa, coef_host_aos, dev_staging, staging_bytes);
   if (rc) return rc;
   rc = kt_upload_field(h, dev_b, b_host);

@@ -242,6 +242,7 @@ extern "C" {
 
 int kt_channel_init(kt_handle_t h, const kt_channel_params* P, void* p, void* u, void* u0, void* v, void* v0, int* ct) {
   KT_CHECK_ARG(h && p && u && u0 && v && v0 && ct, "kt_channel_init: null argument");
+  KT_DEV_GUARD(h);
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
   dim3 grid((P->ny + 3 + 255) / 256, P->nx + 3);
@@ -256,6 +257,7 @@ int kt_channel_assemble_uv(kt_handle_t h, const kt_channel_params* P, const int*
                            void* b_v, void* M_v, void* Minv_v) {
   KT_CHECK_ARG(h && ct && u && v && p && u0 && v0 && coef_u && b_u && M_u && Minv_u && coef_v && b_v && M_v && Minv_v,
                "kt_channel_assemble_uv: null argument");
+  KT_DEV_GUARD(h);
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
   dim3 grid((P->ny + 2 + 255) / 256, P->nx + 2, 2);
@@ -272,6 +274,7 @@ int kt_channel_assemble_uv(kt_handle_t h, const kt_channel_params* P, const int*
 int kt_channel_assemble_p(kt_handle_t h, const kt_channel_params* P, const int* ct, const void* u, const void* v, const void* coef_u,
                           const void* coef_v, void* coef_p, void* b_p, void* M_p, void* Minv_p) {
   KT_CHECK_ARG(h && ct && u && v && coef_u && coef_v && coef_p && b_p && M_p && Minv_p, "kt_channel_assemble_p: null argument");
+  KT_DEV_GUARD(h);
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
   dim3 grid((P->ny + 2 + 255) / 256, P->nx + 1);
@@ -287,6 +290,7 @@ int kt_channel_assemble_p(kt_handle_t h, const kt_channel_params* P, const int* 
 
 int kt_channel_relax(kt_handle_t h, const kt_channel_params* P, void* u, void* v, const void* x_u, const void* x_v) {
   KT_CHECK_ARG(h && u && v && x_u && x_v, "kt_channel_relax: null argument");
+  KT_DEV_GUARD(h);
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
   dim3 grid((P->ny + 3 + 255) / 256, P->nx + 2);
@@ -298,6 +302,7 @@ int kt_channel_relax(kt_handle_t h, const kt_channel_params* P, void* u, void* v
 
 int kt_outlet_scale(kt_handle_t h, const kt_channel_params* P, void* u, const void* v, void* udiv, double* sums_host) {
   KT_CHECK_ARG(h && u && v, "kt_outlet_scale: null argument");
+  KT_DEV_GUARD(h);
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
   if (h->dtype == KT_F64) k_ch_outlet_scale<double><<<1, 256, 0, h->stream>>>(S, (double*)u, h->red_out);
@@ -316,6 +321,7 @@ int kt_outlet_scale(kt_handle_t h, const kt_channel_params* P, void* u, const vo
 int kt_channel_correct(kt_handle_t h, const kt_channel_params* P, const int* ct, void* u, void* v, void* p, const void* pcor,
                        const void* coef_u, const void* coef_v, double* pcor_max_host) {
   KT_CHECK_ARG(h && ct && u && v && p && pcor && coef_u && coef_v && pcor_max_host, "kt_channel_correct: null argument");
+  KT_DEV_GUARD(h);
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
   const int gx = (P->ny + 3 + 255) / 256;

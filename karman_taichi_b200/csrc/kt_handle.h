@@ -34,6 +34,8 @@ struct kt_handle_s {
   cudaEvent_t gev = nullptr;
   int graphs_state = 0;              // 0 untested, 1 usable, -1 unavailable (capture refused)
   unsigned long long graph_clock = 0;
+  // x-slab peer-memory solves (kt_p2p_*): solve epoch and exchange counters behind the flag sequence numbers
+  unsigned long long p2p_epoch = 0, p2p_halo_k[3] = {0, 0, 0}, p2p_dot_k[3] = {0, 0, 0};
   // optional per-kernel-class device timing (bench.py roofline): events bracket every launch of a class
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs (begin, end)
@@ -77,6 +79,19 @@ template <typename T> int coop_plan(const kt_handle_s* h, bool pre, bool warm, b
 void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 }  // namespace kt
+
+namespace kt {
+// Every extern "C" entry point runs on the handle's device and leaves the caller's current device as it found it (a
+// single process may drive several GPUs: Field(device='cuda:1')).
+struct DeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(int want) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != want) switched = cudaSetDevice(want) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+}  // namespace kt
+#define KT_DEV_GUARD(h) kt::DeviceGuard _kt_dev_guard((h)->device)
 
 #define KT_CUDA(expr)                                                   \
   do {                                                                  \

@@ -915,17 +915,21 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
 // ---------------------------------------------------------------------------------------------
 // x-slab BiCGSTAB over NVLink peer memory (no NCCL in the loop)
 // ---------------------------------------------------------------------------------------------
-// Every rank maps its neighbours' p / v / r planes and every rank's small comm block (CUDA IPC).  The halo exchange and
-// the all-reduce become two tiny kernels that live on the same stream as the big ones:
-//   k_p2p_halo  : one block per side copies this rank's boundary row straight into the neighbour's halo row over
-//                 NVLink (16-byte peer stores), fences system-wide, bumps the neighbour's flag, then waits for the
-//                 neighbour's row to land here (flag >= seq).
+// Every rank maps its two neighbours' small halo-receive buffers and every rank's comm block (CUDA IPC); the planes
+// themselves are ordinary allocations nobody else maps.  The halo exchange and the all-reduce are two tiny kernels that
+// live on the same stream as the big ones:
+//   k_p2p_halo  : one block per side stores this rank's boundary row straight into the neighbour's receive buffer over
+//                 NVLink (16-byte peer stores), fences system-wide, bumps the neighbour's flag, waits for the neighbour's
+//                 row to land in its own receive buffer (flag >= seq) and copies it into the halo row of the local plane.
 //   k_p2p_reduce: lane r stores this rank's local sums into slot [rank] of rank r's comm block and bumps its flag; the
 //                 warp then waits for all nranks flags of its own block, sums the slots in rank order (every rank gets
 //                 the same bits) and runs the step's scalar algebra -- all-reduce + k_scalar_step in one launch.
 // Flags are monotonically increasing sequence numbers (never reset), so a late reader can never see a stale "ready".
-// Write-after-read safety: a neighbour can only overwrite a halo row of iteration k after it has seen this rank's
-// sums of the kernel that read that row (the sums are published by the last block, after all reads).
+// Write-after-read safety: a neighbour can only overwrite a receive row of iteration k after it has seen this rank's
+// sums of a later kernel (the sums are published after the halo kernel that copied the row out, in stream order).
+// Slot reuse of the sums: passing a sum proves that every rank has WRITTEN its slot, not that every rank has READ all of
+// them, so two consecutive sums never share a slot group: BiCGSTAB INIT 2, ALPHA 0, OMEGA 1, END 2; CG INIT 1, ALPHA 0,
+// END 1 (a rank can be at most one sum ahead of the slowest reader of the previous one).
 struct P2PBlock {                     // layout of the comm block every rank allocates (zero-initialised)
   double dots[3][16][2];
   unsigned long long dot_flag[3][16];
@@ -936,7 +940,7 @@ __device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flag
   const long long t0 = clock64();
   while (*flag < seq) {
     __nanosleep(32);
-    if (clock64() - t0 > 8000000000LL) {   // ~4 s: a peer died or the ranks disagree on the schedule -- fail, never hang
+    if (clock64() - t0 > 60000000000LL) {  // ~30 s: a peer died or the ranks disagree on the schedule -- fail, never hang
       *(volatile int*)&sc->status = 7; *(volatile int*)&sc->done = 1;
       return false;
     }
@@ -945,30 +949,38 @@ __device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flag
   return true;
 }
 
+// halo-receive buffer of a rank: [plane p/v/r][0: row from the lower neighbour, 1: row from the upper neighbour][pitch]
 template <typename T>
-__global__ void __launch_bounds__(256) k_p2p_halo(const T* plane, int pitch, int row_first, int row_last, T* peer_lo, int peer_lo_row,
-                                                  T* peer_hi, int peer_hi_row, P2PBlock* mine, P2PBlock* blk_lo, P2PBlock* blk_hi,
-                                                  int which, unsigned long long seq, Scalars* sc) {
+__global__ void __launch_bounds__(1024) k_p2p_halo(T* plane, int pitch, int row_first, int row_last, T* recv_lo, T* recv_hi, T* recv_mine,
+                                                   P2PBlock* mine, P2PBlock* blk_lo, P2PBlock* blk_hi, int which, unsigned long long seq,
+                                                   Scalars* sc) {
   constexpr int V = VT<T>::V;
+  __shared__ int ok;
   // Once the solve is over (every rank reaches `done` at the same logical step, from identical sums) nobody needs
   // another row: return without signalling or waiting, so ranks whose hosts enqueued a different number of surplus
   // iterations never wait for each other.
   if (sc->done) return;
   const int side = blockIdx.x;                                   // 0: talk to the lower neighbour, 1: to the upper one
-  T* peer = side == 0 ? peer_lo : peer_hi;
+  T* peer = side == 0 ? recv_lo : recv_hi;
   if (!peer) return;
+  // my first owned row is the lower neighbour's "from upper" row (1); my last owned row the upper neighbour's "from lower" (0)
   const T* src = plane + (size_t)(side == 0 ? row_first : row_last) * pitch;
-  T* dst = peer + (size_t)(side == 0 ? peer_lo_row : peer_hi_row) * pitch;
+  T* dst = peer + (size_t)(which * 2 + (side == 0 ? 1 : 0)) * pitch;
   for (int j = threadIdx.x * V; j < pitch; j += blockDim.x * V) st_vec(dst + j, ld_rw(src + j));
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    // my row sits in the lower neighbour's "from upper" slot (1) and in the upper neighbour's "from lower" slot (0)
     P2PBlock* pb = side == 0 ? blk_lo : blk_hi;
     volatile unsigned long long* f = &pb->halo_flag[which][side == 0 ? 1 : 0];
     *f = seq;
-    p2p_wait(&mine->halo_flag[which][side == 0 ? 0 : 1], seq, sc);
+    ok = p2p_wait(&mine->halo_flag[which][side == 0 ? 0 : 1], seq, sc) ? 1 : 0;
   }
+  __syncthreads();
+  if (!ok) return;
+  // the neighbour's row has landed in my receive buffer: move it into the plane's halo row (row_first - 1 / row_last + 1)
+  const T* got = recv_mine + (size_t)(which * 2 + (side == 0 ? 0 : 1)) * pitch;
+  T* halo = plane + (size_t)(side == 0 ? row_first - 1 : row_last + 1) * pitch;
+  for (int j = threadIdx.x * V; j < pitch; j += blockDim.x * V) st_vec(halo + j, ld_rw(got + j));
 }
 
 struct P2PPeers { P2PBlock* blk[16]; };
@@ -999,69 +1011,113 @@ __global__ void k_p2p_reduce(P2PPeers peers, int rank, int nranks, int group, in
 
 // Sequence numbers: (solve epoch << 32) | exchange index within the solve.  The epoch advances once per solve on every
 // rank, the index once per enqueued exchange; surplus exchanges enqueued after convergence never touch a flag, so the
-// ranks stay consistent even though their hosts notice `done` at different times.
-struct P2PState {
-  unsigned long long epoch = 0;
-  unsigned long long halo_k[3] = {0, 0, 0};
-  unsigned long long dot_k[3] = {0, 0, 0};
+// ranks stay consistent even though their hosts notice `done` at different times.  The state belongs to the handle (one
+// handle per set of comm blocks); every rank drives its handle through the same sequence of solves.
+struct P2PCtx {
+  kt_handle_s* h; const kt_p2p_comm* cm; P2PPeers peers; P2PBlock* mine; P2PBlock* blk_lo; P2PBlock* blk_hi; double* dots;
+  unsigned long long base;
 };
 
-static P2PState g_p2p_state;      // one rank per process (one GPU per process under torchrun)
+static int p2p_begin(kt_handle_s* h, const kt_p2p_comm* cm, P2PCtx* c) {
+  KT_CHECK_ARG(cm->nranks >= 1 && cm->nranks <= 16 && cm->rank >= 0 && cm->rank < cm->nranks, "kt_p2p_comm: bad rank / nranks (max 16)");
+  c->h = h; c->cm = cm;
+  for (int k = 0; k < 16; ++k) c->peers.blk[k] = k < cm->nranks ? (P2PBlock*)cm->comm_block[k] : nullptr;
+  c->mine = c->peers.blk[cm->rank];
+  c->blk_lo = cm->rank > 0 ? c->peers.blk[cm->rank - 1] : nullptr;
+  c->blk_hi = cm->rank < cm->nranks - 1 ? c->peers.blk[cm->rank + 1] : nullptr;
+  c->dots = (double*)cm->local_dots;
+  KT_CHECK_ARG(c->dots && c->mine, "kt_p2p_comm: local_dots / comm_block missing");
+  KT_CHECK_ARG(cm->nranks == 1 || cm->halo_recv, "kt_p2p_comm: halo_recv missing");
+  KT_CHECK_ARG((cm->rank == 0 || cm->peer_halo_recv[0]) && (cm->rank == cm->nranks - 1 || cm->peer_halo_recv[1]),
+               "kt_p2p_comm: a neighbour's halo-receive buffer is not mapped");
+  ++h->p2p_epoch;
+  for (int k = 0; k < 3; ++k) h->p2p_halo_k[k] = h->p2p_dot_k[k] = 0;
+  c->base = h->p2p_epoch << 32;
+  return 0;
+}
 
 template <typename T>
-static int t_p2p_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, const kt_krylov_ws* w, const kt_p2p_comm* cm,
-                          double eps, long long max_iter, bool fixed_iters, long* iters, double* rel_res, int* status) {
-  KT_CHECK_ARG(cm->nranks >= 1 && cm->nranks <= 16 && cm->rank >= 0 && cm->rank < cm->nranks, "kt_p2p_comm: bad rank / nranks (max 16)");
-  T* r = (T*)w->r; T* p = (T*)w->p; T* v = (T*)w->Ap; T* s = (T*)w->s; T* t = (T*)w->t;
-  KT_CHECK_ARG(r && p && v && t, "kt_krylov_ws: r, p, Ap, t are required (s optional: NULL = recomputed, not stored)");
-  P2PState& st = g_p2p_state;
-  P2PPeers peers;
-  for (int k = 0; k < 16; ++k) peers.blk[k] = k < cm->nranks ? (P2PBlock*)cm->comm_block[k] : nullptr;
-  P2PBlock* mine = peers.blk[cm->rank];
-  P2PBlock* blk_lo = cm->rank > 0 ? peers.blk[cm->rank - 1] : nullptr;
-  P2PBlock* blk_hi = cm->rank < cm->nranks - 1 ? peers.blk[cm->rank + 1] : nullptr;
-  double* dots = (double*)cm->local_dots;
-  KT_CHECK_ARG(dots && mine, "kt_p2p_comm: local_dots / comm_block missing");
-  int rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0);
-  if (rc) return rc;
-  ++st.epoch;
-  for (int k = 0; k < 3; ++k) st.halo_k[k] = st.dot_k[k] = 0;
-  const unsigned long long base = st.epoch << 32;
+static int p2p_halo(P2PCtx& c, int which, T* plane) {
+  kt_handle_s* h = c.h;
+  if (c.cm->nranks == 1) return 0;
+  ++h->p2p_halo_k[which];
+  k_p2p_halo<T><<<2, 1024, 0, h->stream>>>(plane, h->pitch, h->row_lo, h->row_hi - 1, (T*)c.cm->peer_halo_recv[0], (T*)c.cm->peer_halo_recv[1],
+                                           (T*)c.cm->halo_recv, c.mine, c.blk_lo, c.blk_hi, which, c.base | h->p2p_halo_k[which], h->sc);
+  KT_LAUNCH_CHECK(h);
+  return 0;
+}
 
-  auto halo = [&](int which, const T* plane, void* const peer[2]) -> int {
-    if (cm->nranks == 1) return 0;
-    ++st.halo_k[which];
-    k_p2p_halo<T><<<2, 256, 0, h->stream>>>(plane, h->pitch, h->row_lo, h->row_hi - 1, (T*)peer[0], cm->peer_halo_row[0], (T*)peer[1],
-                                            cm->peer_halo_row[1], mine, blk_lo, blk_hi, which, base | st.halo_k[which], h->sc);
-    KT_LAUNCH_CHECK(h);
-    return 0;
-  };
-  auto reduce = [&](int group, int ndot, int fin) -> int {
-    ++st.dot_k[group];
-    k_p2p_reduce<<<1, 32, 0, h->stream>>>(peers, cm->rank, cm->nranks, group, ndot, dots, fin, base | st.dot_k[group], h->sc, w->history,
-                                          w->history_cap);
-    KT_LAUNCH_CHECK(h);
-    return 0;
-  };
+static int p2p_reduce(P2PCtx& c, int group, int ndot, int fin, double* history, long long cap) {
+  kt_handle_s* h = c.h;
+  ++h->p2p_dot_k[group];
+  k_p2p_reduce<<<1, 32, 0, h->stream>>>(c.peers, c.cm->rank, c.cm->nranks, group, ndot, c.dots, fin, c.base | h->p2p_dot_k[group], h->sc,
+                                        history, cap);
+  KT_LAUNCH_CHECK(h);
+  return 0;
+}
+
 #define KT_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
-  KT_TRY(t_dist_phase<T>(h, 0, coef, b, nullptr, nullptr, r, x, nullptr, dots));
-  KT_TRY(reduce(0, 1, FIN_BICG_INIT));
-  KT_TRY(halo(2, r, cm->peer_r));
+
+// BICGSolver.solve (bicgsolver.py:88-135) over x-slabs; with Minv != NULL / KT_FLAG_WARM_START the monolith's Jacobi
+// variant (karman_taichi.py:342-456: warm start needs ws->r_tld and the halo rows of x, exchanged through plane slot 0).
+template <typename T>
+static int t_p2p_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* w,
+                          const kt_p2p_comm* cm, double eps, long long max_iter, int flags, bool fixed_iters, long* iters, double* rel_res,
+                          int* status) {
+  T* r = (T*)w->r; T* p = (T*)w->p; T* v = (T*)w->Ap; T* s = (T*)w->s; T* t = (T*)w->t; T* r_tld = (T*)w->r_tld;
+  KT_CHECK_ARG(r && p && v && t, "kt_krylov_ws: r, p, Ap, t are required (s optional: NULL = recomputed, not stored)");
+  const bool warm = (flags & KT_FLAG_WARM_START) != 0, pre = Minv != nullptr;
+  KT_CHECK_ARG(!(warm && !r_tld), "warm start needs a separate r_tld plane");
+  P2PCtx c;
+  KT_TRY(p2p_begin(h, cm, &c));
+  KT_TRY(sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, flags & KT_FLAG_OMEGA_ZERO_BREAK));
+  const T* r_tld_c = r_tld ? r_tld : (const T*)b;
+  Plan P = make_plan(h);
+  ReduceWs ws = make_ws(h, nullptr, 0, c.dots);
+  if (warm) {
+    KT_TRY(p2p_halo<T>(c, 0, (T*)x));                               // halo rows of x0 for r = b - A x0
+    StencilArgs<T> A = stencil_args<T>(h, P, coef);
+    A.ws = ws; A.x = (const T*)x; A.q = (const T*)b; A.y = r; A.s_out = r_tld; A.fin = FIN_NONE;
+    KT_TRY((launch_stencil<T, SRC_X, false, EPI_RESID>(h, P, A)));
+  } else {
+    KT_TRY(t_dist_phase<T>(h, 0, coef, b, nullptr, nullptr, r, x, r_tld, c.dots));
+  }
+  KT_TRY(p2p_reduce(c, 2, 1, FIN_BICG_INIT, w->history, w->history_cap));
+  KT_TRY(p2p_halo<T>(c, 2, r));
+  StencilArgs<T> A2 = stencil_args<T>(h, P, coef);
+  A2.ws = ws; A2.x = p; A2.minv = (const T*)Minv; A2.q = r_tld_c; A2.y = v; A2.check_done = 1; A2.fin = FIN_NONE;
+  StencilArgs<T> A3 = stencil_args<T>(h, P, coef);
+  A3.ws = ws; A3.x = r; A3.v = v; A3.minv = (const T*)Minv; A3.y = t; A3.s_out = s; A3.alpha_from_sc = 1; A3.check_done = 1; A3.fin = FIN_NONE;
   auto iter = [&]() -> int {
-    KT_TRY(t_dist_phase<T>(h, 1, coef, r, v, nullptr, p, nullptr, nullptr, dots));
-    KT_TRY(halo(0, p, cm->peer_p));
-    KT_TRY(t_dist_phase<T>(h, 2, coef, p, b, nullptr, v, nullptr, nullptr, dots));
-    KT_TRY(reduce(0, 1, FIN_BICG_ALPHA));
-    KT_TRY(halo(1, v, cm->peer_v));
-    KT_TRY(t_dist_phase<T>(h, 3, coef, r, v, nullptr, s, t, nullptr, dots));          // s == NULL: not stored
-    KT_TRY(reduce(1, 2, FIN_BICG_OMEGA));
-    KT_TRY(t_dist_phase<T>(h, 4, coef, p, s, t, x, r, (void*)b, dots, s ? nullptr : v));
-    KT_TRY(reduce(2, 2, FIN_BICG_END));
-    KT_TRY(halo(2, r, cm->peer_r));
+    {
+      ProfScope ps(h, KT_K_BICG_P);
+      k_bicg_p<T><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, p, r, v, h->sc);
+      KT_LAUNCH_CHECK(h);
+    }
+    KT_TRY(p2p_halo<T>(c, 0, p));
+    {
+      ProfScope ps(h, KT_K_BICG_V);
+      KT_TRY(pre ? (launch_stencil<T, SRC_X, true, EPI_DOT_Q>(h, P, A2)) : (launch_stencil<T, SRC_X, false, EPI_DOT_Q>(h, P, A2)));
+    }
+    KT_TRY(p2p_reduce(c, 0, 1, FIN_BICG_ALPHA, nullptr, 0));
+    KT_TRY(p2p_halo<T>(c, 1, v));
+    {
+      ProfScope ps(h, KT_K_BICG_ST);
+      KT_TRY(pre ? (launch_stencil<T, SRC_S, true, EPI_ST>(h, P, A3)) : (launch_stencil<T, SRC_S, false, EPI_ST>(h, P, A3)));
+    }
+    KT_TRY(p2p_reduce(c, 1, 2, FIN_BICG_OMEGA, nullptr, 0));
+    {
+      ProfScope ps(h, KT_K_BICG_XR);
+      const T* v_for_s = s ? nullptr : v;
+      if (pre) k_bicg_xr<T, true><<<grid_for(h, P.ew_blocks, EWP_BICG_XR_UNIT), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_NONE, v_for_s);
+      else k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, EWP_BICG_XR_UNIT), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_NONE, v_for_s);
+      KT_LAUNCH_CHECK(h);
+    }
+    KT_TRY(p2p_reduce(c, 2, 2, FIN_BICG_END, w->history, w->history_cap));
+    KT_TRY(p2p_halo<T>(c, 2, r));
     return 0;
   };
-#undef KT_TRY
-  rc = run_chunks(h, max_iter, iter);
+  int rc = run_chunks(h, max_iter, iter);
   if (rc) return rc;
   const Scalars& S = *h->sc_host;
   if (iters) *iters = (long)S.iter;
@@ -1075,52 +1131,24 @@ static int t_p2p_bicgstab(kt_handle_s* h, const void* coef, const void* b, void*
 template <typename T>
 static int t_p2p_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const kt_krylov_ws* w, const kt_p2p_comm* cm,
                     double eps, long long max_iter, bool fixed_iters, long* iters, double* rel_res, int* status) {
-  KT_CHECK_ARG(cm->nranks >= 1 && cm->nranks <= 16 && cm->rank >= 0 && cm->rank < cm->nranks, "kt_p2p_comm: bad rank / nranks (max 16)");
   T* r = (T*)w->r; T* p = (T*)w->p; T* Ap = (T*)w->Ap;
   KT_CHECK_ARG(r && p && Ap, "kt_krylov_ws: r, p, Ap are required for CG");
-  P2PState& st = g_p2p_state;
-  P2PPeers peers;
-  for (int k = 0; k < 16; ++k) peers.blk[k] = k < cm->nranks ? (P2PBlock*)cm->comm_block[k] : nullptr;
-  P2PBlock* mine = peers.blk[cm->rank];
-  P2PBlock* blk_lo = cm->rank > 0 ? peers.blk[cm->rank - 1] : nullptr;
-  P2PBlock* blk_hi = cm->rank < cm->nranks - 1 ? peers.blk[cm->rank + 1] : nullptr;
-  double* dots = (double*)cm->local_dots;
-  KT_CHECK_ARG(dots && mine, "kt_p2p_comm: local_dots / comm_block missing");
-  int rc = sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0);
-  if (rc) return rc;
-  ++st.epoch;
-  for (int k = 0; k < 3; ++k) st.halo_k[k] = st.dot_k[k] = 0;
-  const unsigned long long base = st.epoch << 32;
-  auto halo_p = [&]() -> int {
-    if (cm->nranks == 1) return 0;
-    ++st.halo_k[0];
-    k_p2p_halo<T><<<2, 256, 0, h->stream>>>(p, h->pitch, h->row_lo, h->row_hi - 1, (T*)cm->peer_p[0], cm->peer_halo_row[0],
-                                            (T*)cm->peer_p[1], cm->peer_halo_row[1], mine, blk_lo, blk_hi, 0, base | st.halo_k[0], h->sc);
-    KT_LAUNCH_CHECK(h);
-    return 0;
-  };
-  auto reduce = [&](int group, int fin) -> int {
-    ++st.dot_k[group];
-    k_p2p_reduce<<<1, 32, 0, h->stream>>>(peers, cm->rank, cm->nranks, group, 1, dots, fin, base | st.dot_k[group], h->sc, w->history,
-                                          w->history_cap);
-    KT_LAUNCH_CHECK(h);
-    return 0;
-  };
-#define KT_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
-  KT_TRY(t_dist_phase<T>(h, 5, coef, b, nullptr, nullptr, r, x, p, dots));
-  KT_TRY(reduce(0, FIN_CG_INIT));
-  KT_TRY(halo_p());
+  P2PCtx c;
+  KT_TRY(p2p_begin(h, cm, &c));
+  KT_TRY(sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0));
+  KT_TRY(t_dist_phase<T>(h, 5, coef, b, nullptr, nullptr, r, x, p, c.dots));
+  KT_TRY(p2p_reduce(c, 1, 1, FIN_CG_INIT, w->history, w->history_cap));
+  KT_TRY(p2p_halo<T>(c, 0, p));
   auto iter = [&]() -> int {
-    KT_TRY(t_dist_phase<T>(h, 6, coef, p, nullptr, nullptr, Ap, nullptr, nullptr, dots));
-    KT_TRY(reduce(0, FIN_CG_ALPHA));
-    KT_TRY(t_dist_phase<T>(h, 7, coef, p, Ap, nullptr, x, r, nullptr, dots));
-    KT_TRY(reduce(1, FIN_CG_END));
-    KT_TRY(t_dist_phase<T>(h, 8, coef, r, nullptr, nullptr, p, nullptr, nullptr, dots));
-    KT_TRY(halo_p());
+    KT_TRY(t_dist_phase<T>(h, 6, coef, p, nullptr, nullptr, Ap, nullptr, nullptr, c.dots));
+    KT_TRY(p2p_reduce(c, 0, 1, FIN_CG_ALPHA, nullptr, 0));
+    KT_TRY(t_dist_phase<T>(h, 7, coef, p, Ap, nullptr, x, r, nullptr, c.dots));
+    KT_TRY(p2p_reduce(c, 1, 1, FIN_CG_END, w->history, w->history_cap));
+    KT_TRY(t_dist_phase<T>(h, 8, coef, r, nullptr, nullptr, p, nullptr, nullptr, c.dots));
+    KT_TRY(p2p_halo<T>(c, 0, p));
     return 0;
   };
-#undef KT_TRY
-  rc = run_chunks(h, max_iter, iter);
+  int rc = run_chunks(h, max_iter, iter);
   if (rc) return rc;
   const Scalars& S = *h->sc_host;
   if (iters) *iters = (long)S.iter;
@@ -1128,6 +1156,7 @@ static int t_p2p_cg(kt_handle_s* h, const void* coef, const void* b, void* x, co
   if (status) *status = S.status;
   return 0;
 }
+#undef KT_TRY
 
 }  // namespace kt
 
@@ -1139,12 +1168,14 @@ extern "C" {
 
 int kt_spmv(kt_handle_t h, const void* coef, const void* x, void* y) {
   KT_CHECK_ARG(h && coef && x && y, "kt_spmv: null argument");
+  KT_DEV_GUARD(h);
   KT_CHECK_ARG(x != y, "kt_spmv: x and y must not alias");
   return KT_DISPATCH(h, t_spmv<double>(h, coef, x, y, nullptr, nullptr), t_spmv<float>(h, coef, x, y, nullptr, nullptr));
 }
 
 int kt_spmv_dot(kt_handle_t h, const void* coef, const void* x, void* y, const void* q, double* dot_host) {
   KT_CHECK_ARG(h && coef && x && y && q && dot_host, "kt_spmv_dot: null argument");
+  KT_DEV_GUARD(h);
   KT_CHECK_ARG(x != y, "kt_spmv_dot: x and y must not alias");
   return KT_DISPATCH(h, t_spmv<double>(h, coef, x, y, q, dot_host), t_spmv<float>(h, coef, x, y, q, dot_host));
 }
@@ -1152,47 +1183,56 @@ int kt_spmv_dot(kt_handle_t h, const void* coef, const void* x, void* y, const v
 int kt_bicg_s_t(kt_handle_t h, const void* coef, const void* r, const void* v, double alpha, void* s, void* t,
                 double* dots_host) {
   KT_CHECK_ARG(h && coef && r && v && s && t && dots_host, "kt_bicg_s_t: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, t_bicg_s_t<double>(h, coef, r, v, alpha, s, t, dots_host),
                      t_bicg_s_t<float>(h, coef, r, v, alpha, s, t, dots_host));
 }
 
 int kt_dot(kt_handle_t h, const void* p, const void* q, double* out_host) {
   KT_CHECK_ARG(h && p && q && out_host, "kt_dot: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, t_dot<double>(h, p, q, out_host), t_dot<float>(h, p, q, out_host));
 }
 
 int kt_copy(kt_handle_t h, void* dst, const void* src) {
   KT_CHECK_ARG(h && dst && src, "kt_copy: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, (t_ew<double, EW_COPY>(h, dst, src, nullptr, nullptr, 0, 0)),
                      (t_ew<float, EW_COPY>(h, dst, src, nullptr, nullptr, 0, 0)));
 }
 int kt_fill(kt_handle_t h, void* dst, double value) {
   KT_CHECK_ARG(h && dst, "kt_fill: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, (t_ew<double, EW_FILL>(h, dst, nullptr, nullptr, nullptr, value, 0)),
                      (t_ew<float, EW_FILL>(h, dst, nullptr, nullptr, nullptr, value, 0)));
 }
 int kt_axpy(kt_handle_t h, void* y, double a, const void* x) {
   KT_CHECK_ARG(h && y && x, "kt_axpy: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, (t_ew<double, EW_AXPY>(h, y, x, nullptr, nullptr, a, 0)),
                      (t_ew<float, EW_AXPY>(h, y, x, nullptr, nullptr, a, 0)));
 }
 int kt_xpay(kt_handle_t h, void* out, const void* x, double a, const void* y) {
   KT_CHECK_ARG(h && out && x && y, "kt_xpay: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, (t_ew<double, EW_XPAY>(h, out, x, y, nullptr, a, 0)),
                      (t_ew<float, EW_XPAY>(h, out, x, y, nullptr, a, 0)));
 }
 int kt_xmay(kt_handle_t h, void* out, const void* x, double a, const void* y) {
   KT_CHECK_ARG(h && out && x && y, "kt_xmay: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, (t_ew<double, EW_XMAY>(h, out, x, y, nullptr, a, 0)),
                      (t_ew<float, EW_XMAY>(h, out, x, y, nullptr, a, 0)));
 }
 int kt_bicg_update_p(kt_handle_t h, void* p, const void* r, const void* v, double beta, double omega) {
   KT_CHECK_ARG(h && p && r && v, "kt_bicg_update_p: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, (t_ew<double, EW_BICG_P>(h, p, r, v, nullptr, beta, omega)),
                      (t_ew<float, EW_BICG_P>(h, p, r, v, nullptr, beta, omega)));
 }
 int kt_bicg_update_x(kt_handle_t h, void* x, const void* p, const void* s, double alpha, double omega) {
   KT_CHECK_ARG(h && x && p && s, "kt_bicg_update_x: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, (t_ew<double, EW_BICG_X>(h, x, p, s, nullptr, alpha, omega)),
                      (t_ew<float, EW_BICG_X>(h, x, p, s, nullptr, alpha, omega)));
 }
@@ -1200,6 +1240,7 @@ int kt_bicg_update_x(kt_handle_t h, void* x, const void* p, const void* s, doubl
 int kt_bicg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* s, const void* t, const void* r_tld,
                double alpha, double omega, double* dots_host) {
   KT_CHECK_ARG(h && x && r && p && s && t && r_tld && dots_host, "kt_bicg_xr: null argument");
+  KT_DEV_GUARD(h);
   Plan P = make_plan(h);
   ReduceWs ws = make_ws(h);
   if (h->dtype == KT_F64)
@@ -1214,6 +1255,7 @@ int kt_bicg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* s, co
 
 int kt_cg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* Ap, double alpha, double* dot_host) {
   KT_CHECK_ARG(h && x && r && p && Ap && dot_host, "kt_cg_xr: null argument");
+  KT_DEV_GUARD(h);
   Plan P = make_plan(h);
   ReduceWs ws = make_ws(h);
   if (h->dtype == KT_F64)
@@ -1227,6 +1269,7 @@ int kt_cg_xr(kt_handle_t h, void* x, void* r, const void* p, const void* Ap, dou
 int kt_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, double eps, long max_iter,
                 long* iters, double* rel_res, int* status) {
   KT_CHECK_ARG(h && coef && b && x && ws, "kt_cg_solve: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, t_cg<double>(h, coef, b, x, ws, eps, max_iter, iters, rel_res, status, false),
                      t_cg<float>(h, coef, b, x, ws, eps, max_iter, iters, rel_res, status, false));
 }
@@ -1234,6 +1277,7 @@ int kt_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, const k
 int kt_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* ws,
                       double eps, long max_iter, int flags, long* iters, double* rel_res, int* status) {
   KT_CHECK_ARG(h && coef && b && x && ws, "kt_bicgstab_solve: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, t_bicgstab<double>(h, coef, b, x, Minv, ws, eps, max_iter, flags, iters, rel_res, status, false),
                      t_bicgstab<float>(h, coef, b, x, Minv, ws, eps, max_iter, flags, iters, rel_res, status, false));
 }
@@ -1241,18 +1285,21 @@ int kt_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, c
 
 int kt_dist_begin(kt_handle_t h, double eps, long max_iter, int flags) {
   KT_CHECK_ARG(h, "kt_dist_begin: null handle");
+  KT_DEV_GUARD(h);
   return sc_reset(h, eps, max_iter, flags);
 }
 
 int kt_dist_bicg_phase(kt_handle_t h, int phase, const void* coef, const void* a0, const void* a1, const void* a2, void* o0,
                        void* o1, void* o2, double* dots_dev) {
   KT_CHECK_ARG(h, "kt_dist_bicg_phase: null handle");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, t_dist_phase<double>(h, phase, coef, a0, a1, a2, o0, o1, o2, dots_dev),
                      t_dist_phase<float>(h, phase, coef, a0, a1, a2, o0, o1, o2, dots_dev));
 }
 
 int kt_dist_scalar(kt_handle_t h, int fin, const double* dots_dev, double* history_dev, long history_cap) {
   KT_CHECK_ARG(h && dots_dev, "kt_dist_scalar: null argument");
+  KT_DEV_GUARD(h);
   k_scalar_step<<<1, 1, 0, h->stream>>>(h->sc, fin, dots_dev, history_dev, history_cap);
   KT_LAUNCH_CHECK(h);
   return 0;
@@ -1260,6 +1307,7 @@ int kt_dist_scalar(kt_handle_t h, int fin, const double* dots_dev, double* histo
 
 int kt_dist_poll(kt_handle_t h, int* done, long* iters, int* status, double* rel_res) {
   KT_CHECK_ARG(h, "kt_dist_poll: null handle");
+  KT_DEV_GUARD(h);
   KT_CUDA(cudaMemcpyAsync(h->sc_host, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
   KT_CUDA(cudaStreamSynchronize(h->stream));
   const Scalars& S = *h->sc_host;
@@ -1272,16 +1320,19 @@ int kt_dist_poll(kt_handle_t h, int* done, long* iters, int* status, double* rel
 
 int kt_p2p_comm_block_bytes(void) { return (int)sizeof(P2PBlock); }
 
-int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, const kt_p2p_comm* comm,
-                          double eps, long max_iter, int fixed_iters, long* iters, double* rel_res, int* status) {
+int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* ws,
+                          const kt_p2p_comm* comm, double eps, long max_iter, int flags, int fixed_iters, long* iters, double* rel_res,
+                          int* status) {
   KT_CHECK_ARG(h && coef && b && x && ws && comm, "kt_p2p_bicgstab_solve: null argument");
-  return KT_DISPATCH(h, t_p2p_bicgstab<double>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status),
-                     t_p2p_bicgstab<float>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status));
+  KT_DEV_GUARD(h);
+  return KT_DISPATCH(h, t_p2p_bicgstab<double>(h, coef, b, x, Minv, ws, comm, eps, max_iter, flags, fixed_iters != 0, iters, rel_res, status),
+                     t_p2p_bicgstab<float>(h, coef, b, x, Minv, ws, comm, eps, max_iter, flags, fixed_iters != 0, iters, rel_res, status));
 }
 
 int kt_p2p_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, const kt_p2p_comm* comm,
                     double eps, long max_iter, int fixed_iters, long* iters, double* rel_res, int* status) {
   KT_CHECK_ARG(h && coef && b && x && ws && comm, "kt_p2p_cg_solve: null argument");
+  KT_DEV_GUARD(h);
   return KT_DISPATCH(h, t_p2p_cg<double>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status),
                      t_p2p_cg<float>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status));
 }
@@ -1342,6 +1393,7 @@ int kt_resident_plan(const kt_geom* g, int is_cg, int pre, int warm, int enable,
 
 int kt_get_geom(kt_handle_t h, kt_geom* out) {
   KT_CHECK_ARG(h && out, "kt_get_geom: null argument");
+  KT_DEV_GUARD(h);
   out->NX = h->NX; out->NY = h->NY; out->pitch = h->pitch; out->row_lo = h->row_lo; out->row_hi = h->row_hi;
   out->dtype = h->dtype; out->num_sms = h->num_sms;
   return 0;
@@ -1349,6 +1401,7 @@ int kt_get_geom(kt_handle_t h, kt_geom* out) {
 
 int kt_prof_begin(kt_handle_t h, int max_launches) {
   KT_CHECK_ARG(h && max_launches > 0, "kt_prof_begin: bad argument");
+  KT_DEV_GUARD(h);
   while ((int)h->prof_ev.size() < 2 * max_launches) {
     cudaEvent_t e;
     KT_CUDA(cudaEventCreate(&e));
@@ -1362,6 +1415,7 @@ int kt_prof_begin(kt_handle_t h, int max_launches) {
 
 int kt_prof_end(kt_handle_t h, double* total_ms, long* count, int n_classes) {
   KT_CHECK_ARG(h && total_ms && count && n_classes > 0, "kt_prof_end: bad argument");
+  KT_DEV_GUARD(h);
   h->prof_on = false;
   KT_CUDA(cudaStreamSynchronize(h->stream));
   for (int c = 0; c < n_classes; ++c) { total_ms[c] = 0.0; count[c] = 0; }
@@ -1377,6 +1431,7 @@ int kt_prof_end(kt_handle_t h, double* total_ms, long* count, int n_classes) {
 
 int kt_bicgstab_bench(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, long n_iter, float* ms) {
   KT_CHECK_ARG(h && coef && b && x && ws && ms, "kt_bicgstab_bench: null argument");
+  KT_DEV_GUARD(h);
   KT_CUDA(cudaEventRecord(h->t0, h->stream));
   long it = 0; int st = 0; double rr = 0;
   int rc = KT_DISPATCH(h, t_bicgstab<double>(h, coef, b, x, nullptr, ws, 0.0, n_iter, 0, &it, &rr, &st, true),
@@ -1391,6 +1446,7 @@ int kt_bicgstab_bench(kt_handle_t h, const void* coef, const void* b, void* x, c
 
 int kt_cg_bench(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, long n_iter, float* ms) {
   KT_CHECK_ARG(h && coef && b && x && ws && ms, "kt_cg_bench: null argument");
+  KT_DEV_GUARD(h);
   KT_CUDA(cudaEventRecord(h->t0, h->stream));
   long it = 0; int st = 0; double rr = 0;
   int rc = KT_DISPATCH(h, t_cg<double>(h, coef, b, x, ws, 0.0, n_iter, &it, &rr, &st, true),

@@ -254,6 +254,7 @@ extern "C" {
 int kt_assemble_uv(kt_handle_t h, const kt_simple_params* P, const void* u, const void* v, const void* p, const void* u0,
                    const void* v0, void* coef_u, void* b_u, void* coef_v, void* b_v) {
   KT_CHECK_ARG(h && u && v && p && u0 && v0 && coef_u && b_u && coef_v && b_v, "kt_assemble_uv: null argument");
+  KT_DEV_GUARD(h);
   KT_SIMPLE_ARGS_OK(P);
   SP S = make_sp(P);
   dim3 grid((P->ny + 2 + 255) / 256, P->nx + 1, 2);
@@ -269,6 +270,7 @@ int kt_assemble_uv(kt_handle_t h, const kt_simple_params* P, const void* u, cons
 
 int kt_set_bc_cavity(kt_handle_t h, const kt_simple_params* P, void* u, void* v, void* coef_u, void* b_u, void* coef_v, void* b_v) {
   KT_CHECK_ARG(h && u && v && coef_u && b_u && coef_v && b_v, "kt_set_bc_cavity: null argument");
+  KT_DEV_GUARD(h);
   KT_SIMPLE_ARGS_OK(P);
   SP S = make_sp(P);
   const int n = (P->nx > P->ny ? P->nx : P->ny);
@@ -289,6 +291,7 @@ int kt_set_bc_cavity(kt_handle_t h, const kt_simple_params* P, void* u, void* v,
 int kt_assemble_p(kt_handle_t h, const kt_simple_params* P, const void* u, const void* v, const void* coef_u, const void* coef_v,
                   void* coef_p, void* b_p, void* mdiv) {
   KT_CHECK_ARG(h && u && v && coef_u && coef_v && coef_p && b_p && mdiv, "kt_assemble_p: null argument");
+  KT_DEV_GUARD(h);
   KT_SIMPLE_ARGS_OK(P);
   SP S = make_sp(P);
   dim3 grid((P->ny + 2 + 255) / 256, P->nx + 1);
@@ -304,6 +307,7 @@ int kt_assemble_p(kt_handle_t h, const kt_simple_params* P, const void* u, const
 
 int kt_relax_uv(kt_handle_t h, const kt_simple_params* P, void* u, void* v, const void* u_mid, const void* v_mid, double* residual_host) {
   KT_CHECK_ARG(h && u && v && u_mid && v_mid && residual_host, "kt_relax_uv: null argument");
+  KT_DEV_GUARD(h);
   KT_SIMPLE_ARGS_OK(P);
   SP S = make_sp(P);
   const int gx = (P->ny + 2 + 255) / 256;
@@ -325,6 +329,7 @@ int kt_relax_uv(kt_handle_t h, const kt_simple_params* P, void* u, void* v, cons
 int kt_correct_puv(kt_handle_t h, const kt_simple_params* P, void* p, void* u, void* v, const void* pcor, const void* coef_u,
                    const void* coef_v) {
   KT_CHECK_ARG(h && pcor, "kt_correct_puv: null argument");
+  KT_DEV_GUARD(h);
   const int do_p = p != nullptr, do_uv = (u != nullptr) || (v != nullptr);
   KT_CHECK_ARG(do_p || do_uv, "kt_correct_puv: nothing to correct");
   KT_CHECK_ARG(!do_uv || (u && v && coef_u && coef_v), "kt_correct_puv: velocity correction needs u, v, coef_u, coef_v");
@@ -343,6 +348,7 @@ int kt_correct_puv(kt_handle_t h, const kt_simple_params* P, void* p, void* u, v
 
 int kt_mdiv_max(kt_handle_t h, const kt_simple_params* P, const void* u, const void* v, void* mdiv, double* max_host) {
   KT_CHECK_ARG(h && u && v && mdiv && max_host, "kt_mdiv_max: null argument");
+  KT_DEV_GUARD(h);
   KT_SIMPLE_ARGS_OK(P);
   SP S = make_sp(P);
   const int gx = (P->ny + 2 + 255) / 256;

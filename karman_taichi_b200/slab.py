@@ -101,7 +101,7 @@ class CudaSlabOps:
     def __init__(self, coef, b, x, part: SlabPartition, rank):
         from .cgsolver import _Handle
         from .field import Field
-        self.coef, self.b, self.x = coef, b, x
+        self.coef, self.b, self.x, self.part = coef, b, x, part
         self.lib = _lib.load()
         self._hd = _Handle(b)
         l0, l1 = part.local_owned(rank)
@@ -122,6 +122,9 @@ class CudaSlabOps:
 
     def planes(self):
         return {'p': self.p.data, 'v': self.v.data, 'r': self.r.data}
+
+    def default_max_iter(self):
+        return self.part.NX * self.b.NY
 
     def begin(self, eps, max_iter):
         _lib.check(self.lib.kt_dist_begin(self.h, float(eps), int(max_iter), 0))
@@ -179,6 +182,8 @@ class DistBiCGSTAB:
     def solve(self, eps=1e-8, max_iter=None, fixed_iters=False):
         ops, ex = self.ops, self.ex
         planes = ops.planes()
+        if max_iter is None:
+            max_iter = ops.default_max_iter()          # the reference's `steps` = NX * NY of the whole grid (cgsolver.py:14)
         ops.begin(-1.0 if fixed_iters else eps, max_iter)
         ops.init()
         self._allreduce()
@@ -222,6 +227,8 @@ class DistCG:
     def solve(self, eps=1e-8, max_iter=None, fixed_iters=False):
         ops, ex = self.ops, self.ex
         p = ops.planes()['p']
+        if max_iter is None:
+            max_iter = ops.default_max_iter()
         ops.begin(-1.0 if fixed_iters else eps, max_iter)
         ops.cg_init()                       # r = b, x = 0, p = r (beta = 0: cgsolver.py:90)
         self._allreduce()
@@ -272,12 +279,17 @@ class _IpcBuffer:
 
 
 class P2PSlabSolver:
-    """x-slab BiCGSTAB whose halo exchange and inner-product all-reduce run inside the library over NVLink peer memory
-    (``kt_p2p_bicgstab_solve``): every rank maps its neighbours' p / v / r planes and every rank's small comm block
-    through CUDA IPC once, at construction (the only collective use of ``torch.distributed`` here: exchanging the 64-byte
-    IPC handles); after that a solve is one C-ABI call per rank and no host code runs per iteration."""
+    """x-slab BiCGSTAB / CG whose halo exchange and inner-product all-reduce run inside the library over NVLink peer memory
+    (``kt_p2p_bicgstab_solve`` / ``kt_p2p_cg_solve``).  Every rank maps its two neighbours' small halo-receive buffers
+    (3 planes x 2 sides x one pitched row) and every rank's comm block through CUDA IPC once, at construction (the only
+    collective use of ``torch.distributed`` here: exchanging the 64-byte IPC handles); the field planes are ordinary
+    allocations nobody else maps.  After that a solve is one C-ABI call per rank and no host code runs per iteration.
 
-    def __init__(self, coef, b, x, part: SlabPartition, rank, group=None):
+    ``Minv`` / ``warm_start`` / ``omega_zero_break``: the monolith's Jacobi-preconditioned, warm-started variant
+    (``karman_taichi.py:342-456``), as on ``BICGSolver``.  ``ipc_planes=True`` (measurement aid) puts r / p / v themselves
+    into IPC-exported allocations, which is how round 1 ran (profiles/r02_p2p.md)."""
+
+    def __init__(self, coef, b, x, part: SlabPartition, rank, group=None, ipc_planes=False):
         from .cgsolver import _Handle
         from .field import Field
         self.coef, self.b, self.x, self.part, self.rank = coef, b, x, part, rank
@@ -286,14 +298,22 @@ class P2PSlabSolver:
         l0, l1 = part.local_owned(rank)
         _lib.check(self.lib.kt_set_rows(self._hd.h, l0, l1))
         self.t = Field(b.shape, b.np_dtype, b.device)       # s is recomputed by the x/r kernel, never stored
-        plane_bytes = b.data.numel() * b.data.element_size()
-        # the planes neighbours write halo rows into, and the comm block every rank writes sums / flags into
-        self._r, self._p, self._v = (_IpcBuffer(self._hd, plane_bytes) for _ in range(3))
+        esize = b.data.element_size()
+        if ipc_planes:
+            plane_bytes = b.data.numel() * esize
+            self._planes = [_IpcBuffer(self._hd, plane_bytes) for _ in range(3)]
+            self._r, self._p, self._v = (pl.ptr for pl in self._planes)
+        else:
+            self._planes = [Field(b.shape, b.np_dtype, b.device) for _ in range(3)]
+            self._r, self._p, self._v = (pl.ptr for pl in self._planes)
+        self._r_tld = None
+        self.Minv, self.warm_start, self.omega_zero_break = None, False, False
+        # what neighbours write into: boundary rows (3 planes x 2 sides x pitch) and every rank's sums / flags
+        self._halo = _IpcBuffer(self._hd, 6 * b.pitch * esize)
         self._blk = _IpcBuffer(self._hd, int(self.lib.kt_p2p_comm_block_bytes()))
         self.dots = torch.zeros(2, dtype=torch.float64, device=b.device)
         n = part.nranks
-        mine = {'p': self._p.handle_bytes(), 'v': self._v.handle_bytes(), 'r': self._r.handle_bytes(), 'blk': self._blk.handle_bytes(),
-                'halo_rows': part.local_owned(rank)}
+        mine = {'halo': self._halo.handle_bytes(), 'blk': self._blk.handle_bytes()}
         descs = [None] * n
         if n > 1:
             dist.all_gather_object(descs, mine, group=group)
@@ -316,15 +336,8 @@ class P2PSlabSolver:
             for r_ in range(n):
                 cm.comm_block[r_] = self._blk.ptr if r_ == rank else open_(descs[r_]['blk'])
             for side, nb in ((0, rank - 1), (1, rank + 1)):
-                if 0 <= nb < n:
-                    cm.peer_p[side], cm.peer_v[side], cm.peer_r[side] = (open_(descs[nb][k]) for k in ('p', 'v', 'r'))
-                    nl0, nl1 = descs[nb]['halo_rows']
-                    # my first owned row lands in the lower neighbour's TOP halo row (its l1); my last owned row in the upper
-                    # neighbour's BOTTOM halo row (its l0 - 1)
-                    cm.peer_halo_row[side] = nl1 if side == 0 else nl0 - 1
-                else:
-                    cm.peer_p[side] = cm.peer_v[side] = cm.peer_r[side] = None
-                    cm.peer_halo_row[side] = 0
+                cm.peer_halo_recv[side] = open_(descs[nb]['halo']) if 0 <= nb < n else None
+            cm.halo_recv = self._halo.ptr
             cm.local_dots = self.dots.data_ptr()
             self.comm = cm
         except Exception as e:      # e.g. no peer access between two devices: every rank must learn of it (no hang)
@@ -351,29 +364,39 @@ class P2PSlabSolver:
     def launch_count(self):
         return self._hd.launch_count()
 
+    def _ws(self, t=True):
+        r_tld = None
+        if self.warm_start:
+            if self._r_tld is None:
+                from .field import Field
+                self._r_tld = Field(self.b.shape, self.b.np_dtype, self.b.device)
+            r_tld = self._r_tld.ptr
+        return _lib.KrylovWs(r=self._r, p=self._p, Ap=self._v, r_tld=r_tld, s=None, t=(self.t.ptr if t else None), history=None,
+                             history_cap=0, p2=None, Ap2=None)
+
     def solve(self, eps=1e-8, max_iter=None, fixed_iters=False):
         self._hd.use_current_stream()
-        ws = _lib.KrylovWs(r=self._r.ptr, p=self._p.ptr, Ap=self._v.ptr, r_tld=None, s=None, t=self.t.ptr, history=None,
-                           history_cap=0, p2=None, Ap2=None)
+        ws = self._ws()
         it, rel, st = C.c_long(), C.c_double(), C.c_int()
         if max_iter is None:
             max_iter = self.part.NX * self.b.NY
-        _lib.check(self.lib.kt_p2p_bicgstab_solve(self._hd.h, C.c_void_p(self.coef.ptr), C.c_void_p(self.b.ptr), C.c_void_p(self.x.ptr),
-                                                  C.byref(ws), C.byref(self.comm), float(eps), int(max_iter), 1 if fixed_iters else 0,
+        flags = (_lib.FLAG_WARM_START if self.warm_start else 0) | (_lib.FLAG_OMEGA_ZERO_BREAK if self.omega_zero_break else 0)
+        minv = C.c_void_p(self.Minv.ptr) if self.Minv is not None else None
+        _lib.check(self.lib.kt_p2p_bicgstab_solve(self._hd.h, C.c_void_p(self.coef.ptr), C.c_void_p(self.b.ptr), C.c_void_p(self.x.ptr), minv,
+                                                  C.byref(ws), C.byref(self.comm), float(eps), int(max_iter), flags, 1 if fixed_iters else 0,
                                                   C.byref(it), C.byref(rel), C.byref(st)))
         return self._finish(it, rel, st)
 
     def _finish(self, it, rel, st):
         self.iterations, self.status, self.rel_res = it.value, st.value, rel.value
-        if st.value == 7:
+        if st.value == _lib.STATUS_COMM_TIMEOUT:
             raise _lib.KtError('x-slab peer-memory solve: a neighbour rank never signalled (KT_STATUS_COMM_TIMEOUT)')
         return self.iterations, self.status
 
     def solve_cg(self, eps=1e-8, max_iter=None, fixed_iters=False):
         """``CGSolver.solve`` over the same slabs and peer mappings (``kt_p2p_cg_solve``): Ap lives in the v plane."""
         self._hd.use_current_stream()
-        ws = _lib.KrylovWs(r=self._r.ptr, p=self._p.ptr, Ap=self._v.ptr, r_tld=None, s=None, t=None, history=None,
-                           history_cap=0, p2=None, Ap2=None)
+        ws = self._ws(t=False)
         it, rel, st = C.c_long(), C.c_double(), C.c_int()
         if max_iter is None:
             max_iter = self.part.NX * self.b.NY

@@ -27,11 +27,13 @@ lane of a ``shfl_xor`` butterfly compute).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import numpy as np
 
-PLAN = {'dot': 0, 'init': 1, 'alpha': 2, 'omega': 3, 'end': 4, 'end_unit': 5, 'resid': 6, 'cg_init': 1, 'cg_alpha': 7, 'cg_end': 8}
+PLAN = {'dot': 0, 'init': 1, 'alpha': 2, 'omega': 3, 'end': 4, 'end_unit': 5, 'resid': 6, 'cg_init': 1, 'cg_alpha': 7, 'cg_end': 8,
+        'alpha_fused': 9}
 
 
 def tree(a):
@@ -77,19 +79,30 @@ def _lib():
     return L, L.load()
 
 
+@contextlib.contextmanager
+def installed(order):
+    """``with installed(DeviceOrder(...)):`` -- the oracle adds in the device's order inside the block."""
+    from . import krylov
+    krylov.set_summation('device', order)
+    try:
+        yield order
+    finally:
+        krylov.set_summation('pairwise')
+
+
 class DeviceOrder:
     """``summer(kind, products)`` for one geometry.  ``shape`` = logical (NX, NY) of the planes.
 
     ``enable``: the solver's ``cluster`` setting (1 automatic, 0 streaming kernels only, 2 cooperative only, 3 cluster
     only).  ``rows`` = (row_lo, row_hi) restricts the streaming plans to a slab's owned rows (``kt_set_rows``)."""
 
-    def __init__(self, shape, is_cg=False, pre=False, warm=False, enable=1, num_sms=148, rows=None, xr_unit=False):
+    def __init__(self, shape, is_cg=False, pre=False, warm=False, enable=1, num_sms=148, rows=None, xr_unit=False, fused=False):
         L, lib = _lib()
         self.NX, self.NY = int(shape[0]), int(shape[1])
         self.pitch = L.pitch_for(self.NY)
         r0, r1 = rows if rows is not None else (0, self.NX)
         self.geom = L.Geom(self.NX, self.NY, self.pitch, r0, r1, L.KT_F64, num_sms)
-        self.pre, self.xr_unit = bool(pre), bool(xr_unit)
+        self.pre, self.xr_unit, self.fused = bool(pre), bool(xr_unit), bool(fused)   # fused: BICGSolver.fuse_p_update
         out = (C.c_longlong * 8)()
         L.check(lib.kt_resident_plan(C.byref(self.geom), int(is_cg), int(pre), int(warm), int(enable), out))
         self.path, self.C, self.rows_per, self.NT, self.EPT = (int(v) for v in out[:5])
@@ -112,6 +125,8 @@ class DeviceOrder:
     def _plan(self, kind):
         if kind == 'end' and self.xr_unit:
             kind = 'end_unit'
+        if kind == 'alpha' and self.fused:
+            kind = 'alpha_fused'
         key = PLAN[kind]
         if key not in self._cache:
             out = (C.c_longlong * 12)()

@@ -10,12 +10,21 @@ import numpy as np
 import pytest
 
 from oracle import krylov
+from oracle.device_order import DeviceOrder, installed
 
 pytestmark = pytest.mark.gpu
 
 
 def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def sms(cuda):
+    import torch
+    return torch.cuda.get_device_properties(cuda).multi_processor_count
+
+
+ENABLE = {True: 1, False: 0, 'coop': 2, 'cluster': 3}      # BICGSolver.cluster -> kt_set_cluster / DeviceOrder(enable=)
 
 
 def make(cuda, coef, b, cls):
@@ -166,10 +175,15 @@ def test_bicgstab_solve_parity(cuda, kind, a, b, eps, path):
     s.fuse_p_update = path == 'stream-fused'
     s.solve(eps=eps, quiet=True)
     assert s.status == st_ref == 0
-    # BiCGSTAB's residual is erratic near convergence: the stopping iteration moves by a few steps with the
-    # summation order of the inner products alone (NumPy pairwise vs the C port's sequential sums differ by the
-    # same amount -- tests/test_oracle_cport.py::test_bicgstab_count_noise_floor), and the reference's own
-    # parallel reduction order is not even deterministic.  CG (below) is held to +-1.
+    # The oracle adding in the DEVICE's order (oracle/device_order.py) must reproduce the solve bit for bit: same count, same x.
+    with installed(DeviceOrder(rhs.shape, enable=ENABLE[s.cluster], fused=s.fuse_p_update, num_sms=sms(cuda))):
+        x_dev, it_dev, st_dev = krylov.bicgstab_solve(coef, rhs, eps=eps)
+    assert (s.iterations, s.status) == (it_dev, st_dev)
+    np.testing.assert_array_equal(s.x.to_numpy(), x_dev)
+    # Against NumPy's pairwise order (x_ref, it_ref) the same recurrence stops a few iterations apart: BiCGSTAB's residual
+    # is erratic near convergence and the stopping iteration moves with the last bits of the inner products (NumPy pairwise
+    # vs the C port's sequential sums differ by the same amount: tests/test_oracle_cport.py::test_bicgstab_count_noise_floor;
+    # the reference's own parallel reduction order is not even deterministic).  Exact twin: the three lines above.
     assert abs(s.iterations - it_ref) <= max(3, round(0.1 * it_ref))
     # two iterates that both satisfy ||r|| <= eps ||b|| differ by O(cond * eps): the 1e-8 field bar applies
     # when the solve itself is converged that far
@@ -264,7 +278,11 @@ def test_jacobi_warm_start_variant(cuda):
         s.x.from_numpy(x0)
         s.solve(eps=1e-8)
         assert s.status == st_ref == 0
-        assert abs(s.iterations - it_ref) <= max(3, round(0.1 * it_ref))
+        with installed(DeviceOrder(rhs.shape, pre=True, warm=True, enable=ENABLE[cluster], fused=fused, num_sms=sms(cuda))):
+            x_dev, it_dev, st_dev = krylov.jacobi_bicgstab(coef, M, rhs, x0, eps=1e-8)
+        assert (s.iterations, s.status) == (it_dev, st_dev)                    # order pinned: equal
+        np.testing.assert_array_equal(s.x.to_numpy(), x_dev)
+        assert abs(s.iterations - it_ref) <= max(3, round(0.1 * it_ref))       # NumPy's pairwise order: see test_bicgstab_solve_parity
         assert rel_l2(s.x.to_numpy(), x_ref) < 1e-8
 
 
@@ -375,6 +393,8 @@ def test_stepwise_reference_loop_matches_solve(cuda):
         s2 = make(cuda, coef, rhs, kt.BICGSolver)
         s2.cluster = cluster
         s2.solve(eps=eps)
+        # the kernel-by-kernel loop above adds every inner product in kt_dot's order, solve() in the fused kernels' orders:
+        # different last bits, a few iterations apart (exact-order twin: tests/test_gpu_exact.py)
         assert abs(s2.iterations - n_it) <= max(3, round(0.1 * n_it))
         assert rel_l2(s2.x.to_numpy(), x_step) < 1e-8
     # --- CG on an SPD system, line by line
@@ -433,7 +453,11 @@ def test_degenerate_shapes(cuda, shape, cluster):
             s.solve(eps=1e-10)
     else:
         s.solve(eps=1e-10)
-        assert s.status == st_ref == 0 and abs(s.iterations - it_ref) <= max(3, round(0.1 * it_ref))
+        with installed(DeviceOrder(shape, enable=ENABLE[cluster], num_sms=sms(cuda))):
+            x_dev, it_dev, st_dev = krylov.bicgstab_solve(coef, b, eps=1e-10)
+        assert (s.iterations, s.status) == (it_dev, st_dev)                    # order pinned: equal
+        np.testing.assert_array_equal(s.x.to_numpy(), x_dev)
+        assert s.status == st_ref == 0 and abs(s.iterations - it_ref) <= max(3, round(0.1 * it_ref))   # pairwise order
         assert rel_l2(s.x.to_numpy(), x_ref) < 1e-8
     # symmetric positive definite variant for CG
     sym = np.zeros(shape + (5,))
@@ -462,3 +486,34 @@ def test_empty_and_mismatched_inputs_raise(cuda):
         kt.BICGSolver(fc, fb, kt.Field((7, 6), np.float64, cuda))       # x of the wrong shape
     with pytest.raises((ValueError, TypeError)):
         kt.CGSolver(fb, fb, fb)                                         # coef without the 5-plane axis
+
+
+@pytest.mark.parametrize('shape,seed', [((37, 53), 3), ((258, 1030), 4)])
+def test_bicgstab_solve_host_parity(cuda, shape, seed):
+    """kt_bicgstab_solve_host: the reference-facing call with HOST buffers in the reference layout (coef[i][j][k] AoS, dense
+    b and x) -- what bench.py's e2e leg times.  Upload + layout conversion + solve + download must equal the oracle's solve
+    in the device's summation order bit for bit, and must leave the caller's host inputs untouched."""
+    import torch
+    import karman_taichi_b200 as kt
+    from karman_taichi_b200 import _lib
+    coef, b = krylov.random_dd_system(shape[0] - 2, shape[1] - 2, seed=seed)
+    s = make(cuda, np.zeros_like(coef), np.zeros_like(b), kt.BICGSolver)         # device buffers the call fills itself
+    ws = s._ws(r_tld=None, s=None, t=s.t.ptr, p2=None, Ap2=None)
+    coef_h = torch.from_numpy(coef.copy()).pin_memory()
+    b_h = torch.from_numpy(b.copy()).pin_memory()
+    x_h = torch.full(b.shape, np.nan, dtype=torch.float64).pin_memory()
+    staging = torch.empty(3 * shape[1] * 5 + 7, dtype=torch.float64, device=cuda)   # three rows per chunk: exercises the chunk loop
+    it, rel, st = C.c_long(), C.c_double(), C.c_int()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(s._lib.kt_bicgstab_solve_host(s._h, P(coef_h), P(b_h), P(x_h), C.c_void_p(s.coef.ptr), P(staging), staging.numel() * 8,
+                                             C.c_void_p(s.b.ptr), C.c_void_p(s.x.ptr), C.byref(ws), 1e-9, shape[0] * shape[1],
+                                             C.byref(it), C.byref(rel), C.byref(st)))
+    with installed(DeviceOrder(shape, num_sms=sms(cuda))):
+        x_dev, it_dev, st_dev = krylov.bicgstab_solve(coef, b, eps=1e-9)
+    assert (it.value, st.value) == (it_dev, st_dev)
+    np.testing.assert_array_equal(x_h.numpy(), x_dev)
+    np.testing.assert_array_equal(coef_h.numpy(), coef)
+    np.testing.assert_array_equal(b_h.numpy(), b)
+    np.testing.assert_array_equal(s.coef.to_numpy(), coef)                           # AoS -> SoA conversion on the device
+    res = krylov.spmv(coef, x_h.numpy()) - b
+    assert np.linalg.norm(res) <= 1.01e-9 * np.linalg.norm(b)

@@ -122,7 +122,9 @@ def test_cavity_first_steps_vs_oracle(cuda, n, eps_uv, eps_p, tol):
         assert cg == pytest.approx(co, rel=1e-3)
         for key in 'uvp':
             ref_it = o.last_iters[key]
-            tol_it = 1 if key == 'p' else max(3, round(0.15 * ref_it))    # CG +-1; BiCGSTAB: see test_gpu_krylov.py
+            # CG +-1; BiCGSTAB against NumPy's pairwise order: a band (test_gpu_krylov.py).  With the order pinned the counts
+            # are EQUAL: tests/test_gpu_exact.py::test_simple_outer_iterations_bit_exact
+            tol_it = 1 if key == 'p' else max(3, round(0.15 * ref_it))
             assert abs(g.log[-1][2][key] - ref_it) <= tol_it, (k, key)
     errs = {name: rel_l2(getattr(g, name).to_numpy(), getattr(o, name)) for name in ('u', 'v', 'p')}
     if os.path.isdir('gpurun_out'):

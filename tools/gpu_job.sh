@@ -28,15 +28,19 @@ run_mode() {
       echo "multi ${tag} rc=$?"; tail -c 3000 "gpurun_out/bench_${tag}.json"; tail -n 8 "gpurun_out/bench_${tag}.err"
       ;;
     launches)       # <tag> [bench.py args]: ncu launch list of the bench command (per-launch times are cold and serialised)
+      # env: KT_NCU_SKIP / KT_NCU_COUNT (window), KT_WORDS (plane words -> traffic per word), KT_COMMIT (recorded in the json)
       local tag="$1"; shift
-      timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c "${KT_NCU_COUNT:-600}" --csv \
-        --log-file "gpurun_out/launches_${tag}.csv" python bench.py --no-e2e --no-cpu-baseline "$@" > "gpurun_out/launches_${tag}.log" 2>&1
-      echo "launches ${tag} rc=$?"; python tools/ncu_summary.py "gpurun_out/launches_${tag}.csv" | tee "gpurun_out/launches_${tag}.md"
+      timeout 1800 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+        -s "${KT_NCU_SKIP:-0}" -c "${KT_NCU_COUNT:-600}" --csv --log-file "gpurun_out/launches_${tag}.csv" \
+        python bench.py --no-e2e --no-cpu-baseline --no-check --no-secondary "$@" > "gpurun_out/launches_${tag}.log" 2>&1
+      echo "launches ${tag} rc=$?"
+      python tools/ncu_summary.py "gpurun_out/launches_${tag}.csv" --words "${KT_WORDS:-0}" --json "gpurun_out/traffic_${tag}.json" \
+        --commit "${KT_COMMIT:-unknown}" --command "python bench.py $*" | tee "gpurun_out/launches_${tag}.md"
       ;;
     ncufull)        # <tag> <kernel regex> [bench.py args]: one full capture of a kernel
       local tag="$1" kern="$2"; shift 2
       timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:${kern}" -s "${KT_NCU_SKIP:-8}" -c "${KT_NCU_COUNT:-2}" \
-        -o "gpurun_out/ncu_${tag}" -f python bench.py --no-e2e --no-cpu-baseline "$@" > "gpurun_out/ncu_${tag}.log" 2>&1
+        -o "gpurun_out/ncu_${tag}" -f python bench.py --no-e2e --no-cpu-baseline --no-check --no-secondary "$@" > "gpurun_out/ncu_${tag}.log" 2>&1
       echo "ncufull ${tag} rc=$?"; ls -la gpurun_out/ncu_${tag}.ncu-rep
       ;;
     py)             # <script> [args]
