@@ -389,6 +389,11 @@ def krylov_line(a, torch, dist, world, rank, dev, light=False, fields=None, work
     store_s = world > 1 and comm_mode == 'nccl'   # the single-GPU and peer-memory paths recompute s in K4 instead of storing it
     classes = kernel_classes(solver_kind, fused, store_s)
     tots = {i: cm.max(tot[i]) for i in classes}
+    per_rank = None
+    if world > 1:                     # which rank is the slow one?  (ms per launch of every class, rank by rank)
+        mine = {classes[i][0]: tot[i] / max(cnt[i], 1) for i in classes if cnt[i]}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     dom = max(classes, key=lambda i: tots[i])
     d_name, d_desc, d_words, d_pattern = classes[dom]
     d_ms = tots[dom] / max(cnt[dom], 1)
@@ -409,7 +414,7 @@ def krylov_line(a, torch, dist, world, rank, dev, light=False, fields=None, work
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_kind': peak_kind,
                 'traffic': traffic, 'traffic_source': traffic_src,
                 'ms_per_launch': d_ms, 'launches_timed': int(cnt[dom]), 'algorithmic_bytes_per_launch': alg_bytes,
-                'kernel_share_of_step': kernel_share, 'per_kernel': per_kernel,
+                'kernel_share_of_step': kernel_share, 'per_kernel': per_kernel, 'per_rank_ms_per_launch': per_rank,
                 'whole_iteration': {'algorithmic_bytes_per_cell_iter': cell_iter_bytes,
                                     'bytes_per_cell_iter_as_run': ((27 if fused else 28) if not cg else 16) * w_bytes,
                                     'achieved_gbs_per_gpu': whole, 'frac': whole / peak}}

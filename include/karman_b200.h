@@ -12,8 +12,9 @@
  * Conventions
  *  - All array arguments are DEVICE pointers unless the name ends in _host.
  *  - A "field" is a (NX, pitch) row-major plane of reals (double for KT_F64, float
- *    for KT_F32); logical shape (NX, NY), NY <= pitch, pitch % 16 == 0 (f64) or
- *    % 32 == 0 (f32) so every row starts 128-byte aligned.  Pad columns
+ *    for KT_F32); logical shape (NX, NY), NY <= pitch, pitch a multiple of 128 bytes (required: 16-byte vector accesses
+ *    never straddle a row) -- kt_pitch_for() returns the recommended multiple of 512 bytes (a warp's 32 x 16 B request then
+ *    never straddles a 512-byte boundary: 13 % on the element-wise kernels, profiles/r02_p2p.md).  Pad columns
  *    [NY, pitch) must be zero in every field and stay zero.
  *  - A "coef" array is 5 consecutive planes (ap, aw, ae, an, as), plane stride
  *    NX*pitch: the SoA form of the reference's coef[i,j,0..4] (cgsolver.py:59-60;

@@ -166,5 +166,5 @@ def check(rc):
 
 
 def pitch_for(ny, dtype_code=KT_F64):
-    q = 16 if dtype_code == KT_F64 else 32
-    return (ny + q - 1) // q * q
+    """``kt_pitch_for``: the row pitch (elements) the kernels run fastest with -- rows padded to 512 bytes."""
+    return int(load().kt_pitch_for(int(ny), int(dtype_code)))

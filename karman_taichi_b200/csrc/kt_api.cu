@@ -1,5 +1,6 @@
 // kt_api.cu -- handle lifetime, error reporting, host<->device staging and layout conversion.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include "kt_handle.h"
@@ -60,8 +61,13 @@ int kt_version(void) { return 100; }
 
 const char* kt_last_error(void) { return g_err.c_str(); }
 
+// Rows are padded to a multiple of 512 bytes: a warp moves 32 x 16 B = 512 B per array and request, and on B200 a warp-wide
+// request that straddles a 512 B boundary costs DRAM efficiency (measured, profiles/r02_p2p.md: the x/r kernel at a 128 B
+// phase runs 13 % slower, at 256 B 4 % slower).  With this pitch every row -- hence the first owned row of every x-slab --
+// starts on such a boundary.  (KT_PITCH_BYTES: measurement aid; kt_create accepts any multiple of 128 bytes.)
 int kt_pitch_for(int NY, int dtype) {
-  const int q = (dtype == KT_F64) ? 16 : 32;  // 128-byte rows
+  static int bytes = [] { const char* v = getenv("KT_PITCH_BYTES"); int b = (v && *v) ? atoi(v) : 512; return (b >= 128 && b % 128 == 0) ? b : 512; }();
+  const int q = bytes / ((dtype == KT_F64) ? 8 : 4);
   return (NY + q - 1) / q * q;
 }
 

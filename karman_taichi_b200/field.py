@@ -4,7 +4,7 @@ The reference places dense Taichi fields of shape ``(NX, NY)`` (vectors) and ``(
 (stencil coefficients, ``simple.py:42-47``) and reads them back with ``to_numpy()``.  Here a field is a
 PyTorch CUDA tensor (PyTorch only owns the memory) in the layout the kernels want:
 
-* vector  ``(NX, NY)``    -> one pitched plane ``(NX, pitch)``, ``pitch`` = NY rounded up to 128 bytes,
+* vector  ``(NX, NY)``    -> one pitched plane ``(NX, pitch)``, ``pitch`` = NY rounded up to 512 bytes (``kt_pitch_for``),
   pad columns always zero;
 * coef    ``(NX, NY, 5)`` -> five such planes ``(5, NX, pitch)`` (SoA: ap, aw, ae, an, as).
 

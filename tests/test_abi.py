@@ -36,8 +36,8 @@ def test_ctypes_binding_covers_header(lib_path):
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
     assert lib.kt_version() >= 100
-    assert lib.kt_pitch_for(130, _lib.KT_F64) == 144 == _lib.pitch_for(130, _lib.KT_F64)
-    assert lib.kt_pitch_for(130, _lib.KT_F32) == 160
+    assert lib.kt_pitch_for(130, _lib.KT_F64) == 192 == _lib.pitch_for(130, _lib.KT_F64)      # rows padded to 512 bytes
+    assert lib.kt_pitch_for(130, _lib.KT_F32) == 256
 
 
 def test_library_is_sm100a_and_has_no_torch_types(lib_path):

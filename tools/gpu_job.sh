@@ -43,6 +43,14 @@ run_mode() {
         -o "gpurun_out/ncu_${tag}" -f python bench.py --no-e2e --no-cpu-baseline --no-check --no-secondary "$@" > "gpurun_out/ncu_${tag}.log" 2>&1
       echo "ncufull ${tag} rc=$?"; ls -la gpurun_out/ncu_${tag}.ncu-rep
       ;;
+    ncumulti)       # <N> <tag> <kernel regex> [bench.py args]: full capture of one launch of a kernel on every rank of a torchrun job
+      local n="$1" tag="$2" kern="$3"; shift 3
+      PORT=$((PORT + 1))
+      timeout 1500 ncu --target-processes all --set full --clock-control none --import-source on -k "regex:${kern}" -s "${KT_NCU_SKIP:-8}" -c 1 \
+        -o "gpurun_out/ncu_${tag}_%p" -f $TR --nproc-per-node "$n" --master-port "$PORT" bench.py --gpus "$n" --no-e2e --no-cpu-baseline --no-check --no-secondary "$@" \
+        > "gpurun_out/ncu_${tag}.log" 2>&1
+      echo "ncumulti ${tag} rc=$?"; ls -la gpurun_out/ncu_${tag}_*.ncu-rep; tail -n 5 "gpurun_out/ncu_${tag}.log"
+      ;;
     py)             # <script> [args]
       timeout "${KT_PY_TIMEOUT:-1200}" python "$@" 2>&1 | tail -n "${KT_TAIL:-60}"
       ;;
