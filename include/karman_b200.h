@@ -313,6 +313,28 @@ int kt_outlet_scale(kt_handle_t h, const kt_channel_params* P, void* u, const vo
 int kt_channel_correct(kt_handle_t h, const kt_channel_params* P, const int* ct, void* u, void* v, void* p,
                        const void* pcor, const void* coef_u, const void* coef_v, double* pcor_max_host);
 
+/* ---- either side of the hot path -------------------------------------------------------------- */
+/* The reference's display frame.  scale = 1, monolith = 0: Display.post_process_field + display (display.py:17-49):
+ * panels (u, v, p, pcor, mdiv), each scaled by its own min / max (f_max starting at -1e9), img = (nx+2) x 5 (ny+2).
+ * scale = 3, monolith = 1: post_process_field + the ti.GUI frame of karman_taichi.py:544-583,662-665: udiv recomputed in
+ * the interior (and stored to div, as the reference does), every panel upsampled x3, f_max starting at 0.0, panel order
+ * (pcor, udiv, p, u, v), img = 3 (nx+2) x 15 (ny+2).  img: dense row-major device array of reals, img[I][J] with I along x.
+ * minmax_host10 (may be NULL): {max u, v, p, pcor, div, min u, v, p, pcor, div}. */
+typedef struct {
+  int nx, ny, pitch_u, pitch_v, pitch_p;
+  int scale, monolith;
+  double dx, dy;
+} kt_frame_params;
+int kt_display_frame(kt_handle_t h, const kt_frame_params* P, const void* u, const void* v, const void* p, const void* pcor,
+                     void* div, void* img, double* minmax_host10);
+/* One point-Jacobi sweep of the 5-point system (coef, rhs) over rows [i_lo, i_hi) x columns [j_lo, j_hi) of x -- the
+ * alternative solver of the reference's validation scripts: jacobian_solve_p (pressure_valid.py:220-232, relax = 1) and
+ * jacobian_solve_u (momentum_valid.py:157-170, relax = alpha_u).  x_mid: scratch plane (the reference's pcor_mid / u_mid);
+ * *residual_host = max |x - x_mid| before the update.  Every read of the sweep sees the OLD iterate (the reference updates
+ * in place in whatever order its threads run). */
+int kt_jacobi_sweep(kt_handle_t h, const void* coef, const void* rhs, void* x, void* x_mid, int i_lo, int i_hi, int j_lo,
+                    int j_hi, double relax, double* residual_host);
+
 #ifdef __cplusplus
 }
 #endif

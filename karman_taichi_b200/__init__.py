@@ -13,6 +13,7 @@ from .bicgsolver import BICGSolver
 from .simple import SIMPLESolver, lid_driven_cavity
 from .karman import KarmanSolver
 from .display import Display
+from .jacobi import JacobiSolver
 
-__all__ = ['Field', 'ScalarField', 'CGSolver', 'BICGSolver', 'SIMPLESolver', 'lid_driven_cavity', 'KarmanSolver', 'Display', 'KtError']
+__all__ = ['Field', 'ScalarField', 'CGSolver', 'BICGSolver', 'SIMPLESolver', 'lid_driven_cavity', 'KarmanSolver', 'Display', 'JacobiSolver', 'KtError']
 __version__ = '0.1.0'

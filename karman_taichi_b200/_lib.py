@@ -50,6 +50,12 @@ class Geom(C.Structure):
                 ('dtype', C.c_int), ('num_sms', C.c_int)]
 
 
+class FrameParams(C.Structure):
+    """``kt_frame_params``"""
+    _fields_ = [('nx', C.c_int), ('ny', C.c_int), ('pitch_u', C.c_int), ('pitch_v', C.c_int), ('pitch_p', C.c_int),
+                ('scale', C.c_int), ('monolith', C.c_int), ('dx', C.c_double), ('dy', C.c_double)]
+
+
 class ChannelParams(C.Structure):
     """``kt_channel_params``"""
     _fields_ = [('nx', C.c_int), ('ny', C.c_int),
@@ -138,6 +144,8 @@ SIGNATURES = {
     'kt_channel_relax': (_I, [_P, _CP, _P, _P, _P, _P]),
     'kt_outlet_scale': (_I, [_P, _CP, _P, _P, _P, _PD]),
     'kt_channel_correct': (_I, [_P, _CP, _P, _P, _P, _P, _P, _P, _P, _PD]),
+    'kt_display_frame': (_I, [_P, C.POINTER(FrameParams), _P, _P, _P, _P, _P, _P, _PD]),
+    'kt_jacobi_sweep': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _D, _PD]),
 }
 
 _lib = None

@@ -21,8 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, '_obj')
 LIB = os.path.join(HERE, 'libkarman_b200.so')
-SOURCES = ['kt_api.cu', 'kt_krylov.cu', 'kt_simple.cu', 'kt_channel.cu', 'kt_cluster.cu', 'kt_coop.cu', 'kt_post.cu',
-           'kt_slab.cu']
+SOURCES = ['kt_api.cu', 'kt_krylov.cu', 'kt_simple.cu', 'kt_channel.cu', 'kt_cluster.cu', 'kt_coop.cu', 'kt_post.cu']
 HEADERS = ['kt_common.cuh', 'kt_handle.h', os.path.join('..', '..', 'include', 'karman_b200.h')]
 
 COMPILE_FLAGS = [

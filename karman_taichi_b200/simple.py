@@ -14,8 +14,10 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
+import torch
 
 from . import _lib
 from .bicgsolver import BICGSolver
@@ -65,6 +67,12 @@ class SIMPLESolver:
         self.p_correction_solver = None
         self.disp = Display(self)           # simple.py:49
         self.quiet = True
+        # The u- and v-momentum systems are independent once assembled (bicgsimp.py:202-208 solves them one after the other
+        # only because Python is sequential): solve them at the same time, each on its own stream -- two thread-block
+        # clusters of 16 SMs side by side.  Same kernels, same deterministic sums: the results are bit-identical either way.
+        self.concurrent_uv = True
+        self._pool = None
+        self._streams = None
         self.log = []                       # (momentum_residual, continuity_residual, {'u','v','p': iters})
 
     # -- plumbing ---------------------------------------------------------------------------
@@ -179,11 +187,32 @@ class SIMPLESolver:
             self.compute_coef_u()          # assembles u and v
             self.set_bc()
             self.u_momentum_solver.update_coef(self.coef_u, self.b_u, self.u_mid)
-            self.u_momentum_solver.solve(eps=self.eps_u, quiet=True)
             self.v_momentum_solver.update_coef(self.coef_v, self.b_v, self.v_mid)
-            self.v_momentum_solver.solve(eps=self.eps_v, quiet=True)
+            if self.concurrent_uv:
+                self._solve_uv_concurrently()
+            else:
+                self.u_momentum_solver.solve(eps=self.eps_u, quiet=True)
+                self.v_momentum_solver.solve(eps=self.eps_v, quiet=True)
             residual = self.update_velocity()
         return residual
+
+    def _solve_uv_concurrently(self):
+        dev = self.p.device
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix='kt-v-momentum')
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))          # the assembly / BC kernels enqueued so far
+
+        def run(solver, stream, eps):
+            with torch.cuda.device(dev), torch.cuda.stream(stream):   # current device and stream are per thread
+                stream.wait_event(ready)
+                solver.solve(eps=eps, quiet=True)                      # returns when the solve has finished on `stream`
+        fut = self._pool.submit(run, self.v_momentum_solver, self._streams[1], self.eps_v)
+        try:
+            run(self.u_momentum_solver, self._streams[0], self.eps_u)
+        finally:
+            fut.result()                                               # re-raises e.g. the reference's ZeroDivisionError
 
     solve_momentum_eqn = bicg_solve_momentum_eqn      # simple.py:243-250
 

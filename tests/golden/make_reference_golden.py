@@ -205,6 +205,10 @@ def cavity_cases(ref, out):
                         res.append([0.0, float(np.abs(s.mdiv.to_numpy()).max()), 0, 0, 0])
                         for f in CAVITY_FIELDS:
                             out[f'{key}/step{step}/{f}'] = getattr(s, f).to_numpy()
+                # the display frame of the final state (display.py:28-40: Display.post_process_field of the reference's own class)
+                s.disp.post_process_field()
+                for f in ('udisp', 'vdisp', 'pdisp', 'pcordisp', 'mdivdisp'):
+                    out[f'{key}/display/{f}'] = getattr(s.disp, f).to_numpy()
             out[f'{key}/residuals'] = np.array(res)
             print(f'  cavity {key}: {steps} outer iterations, last residuals {res[-1][:2]}, Krylov its {res[-1][2:]}')
 
@@ -299,6 +303,10 @@ def channel_cases(ref, out):
             for f in ('u', 'v', 'p', 'pcor', 'udiv'):
                 out[f'{key}/sub{sub}/{f}'] = getattr(m, f).to_numpy()
             print(f'  {key} sub-iteration {sub}: pcor {pc:.6e}, Krylov its u/v/p {it_u}/{it_v}/{it_p} ({time.time() - t0:.0f} s)')
+        # the monolith's frame of the final state (karman_taichi.py:544-570: post_process_field; the five *_disp canvases)
+        m.post_process_field()
+        for f in ('u_disp', 'v_disp', 'p_disp', 'pcor_disp', 'udiv_disp', 'udiv'):
+            out[f'{key}/display/{f}'] = getattr(m, f).to_numpy()
         m.time_forward()
         out[f'{key}/after_time_forward/u0'] = m.u0.to_numpy()
         out[f'{key}/after_time_forward/v0'] = m.v0.to_numpy()

@@ -191,3 +191,50 @@ def test_channel_sub_iterations_bit_exact(cuda, device_sums, kw, nsub):
         assert g.last_iters == o.last_iters and g.last_status == o.last_status, k
     for name in ('u', 'v', 'p', 'pcor', 'udiv'):
         np.testing.assert_array_equal(getattr(g, name).to_numpy(), getattr(o, name), err_msg=name)
+
+
+def test_channel_config4_geometry_bit_exact(cuda, device_sums):
+    """BASELINE config 4's geometry at 1/8 scale: 2048 x 410 channel, cylinder scaled proportionally (centre (nx/5, ny/2),
+    radius 0.1875 ny: SURVEY.md 8d), dt = 1e-5 * 320 / nx -- large enough that all three systems take the STREAMING kernels
+    (Jacobi plane, warm start, the monolith's term order).  One full sub-iteration (karman_taichi.py:634-653) with the Krylov
+    solves capped at 60 iterations on both sides (the p' system needs thousands at this size; bench.py caps config 4 the same
+    way): assembly, every iterate and every field equal bit for bit."""
+    import karman_taichi_b200 as kt
+    from oracle.karman import KarmanOracle
+    nx, ny = 2048, 410
+    kw = dict(nx=nx, ny=ny, cyl=(nx // 5, ny // 2, int(round((0.1875 * ny) ** 2))), dt=1e-5 * 320 / nx)
+    o, g = KarmanOracle(**kw), kt.KarmanSolver(device=cuda, **kw)
+    o.max_iter = 60
+    for s in (g.u_solver, g.v_solver, g.p_solver):
+        s.max_steps = 60
+    device_sums('device', AutoOrder(jacobi=True, num_sms=sms(cuda)))
+    o.init(); g.init()
+    np.testing.assert_array_equal(g.ct_numpy(), o.ct)
+    po, pg = o.sub_iteration(1e-8), g.sub_iteration(1e-8)
+    for w in 'uvp':
+        np.testing.assert_array_equal(getattr(g, f'coef_{w}').to_numpy(), getattr(o, f'coef_{w}'), err_msg=f'coef_{w}')
+        np.testing.assert_array_equal(getattr(g, f'b_{w}').to_numpy(), getattr(o, f'b_{w}'), err_msg=f'b_{w}')
+        np.testing.assert_array_equal(getattr(g, f'M_{w}').to_numpy(), getattr(o, f'M_{w}'), err_msg=f'M_{w}')
+    assert g.last_iters == o.last_iters and g.last_status == o.last_status
+    assert o.last_iters['p'] == 60                                   # the cap, not convergence: the streaming kernels ran 60 bodies
+    assert pg == po
+    for name in ('u', 'v', 'p', 'pcor', 'udiv'):
+        np.testing.assert_array_equal(getattr(g, name).to_numpy(), getattr(o, name), err_msg=name)
+
+
+def test_concurrent_uv_momentum_solves_change_nothing(cuda):
+    """SIMPLESolver.concurrent_uv: the u and v momentum solves on two streams at once vs one after the other
+    (bicgsimp.py:205-208) -- same kernels, same deterministic sums, so every bit and every count is the same."""
+    import karman_taichi_b200 as kt
+    runs = []
+    for conc in (True, False):
+        g = kt.lid_driven_cavity(40, device=cuda)
+        g.concurrent_uv = conc
+        g.init(); g._make_solvers()
+        for _ in range(8):
+            g.step()
+        runs.append(g)
+    a, b = runs
+    assert [l[:2] for l in a.log] == [l[:2] for l in b.log] and [l[2] for l in a.log] == [l[2] for l in b.log]
+    for name in ('u', 'v', 'p', 'u_mid', 'v_mid'):
+        np.testing.assert_array_equal(getattr(a, name).to_numpy(), getattr(b, name).to_numpy(), err_msg=name)

@@ -1,0 +1,182 @@
+"""GPU parity of the rows either side of the hot path: the display frames (kt_display_frame) and the Jacobi
+sweeps of the validation scripts (kt_jacobi_sweep), against the oracle (oracle/post.py, itself pinned bit for bit to the
+reference's own display output) and against the reference-run fixtures; the `validate` command line; BASELINE config 2 at its
+stated size (cavity 128 x 128) against the stored oracle run and Ghia et al. 1982."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import post
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.mark.parametrize('nx,ny', [(3, 5), (24, 17), (130, 67)])
+def test_class_display_frame_bit_exact(cuda, nx, ny, tmp_path):
+    import karman_taichi_b200 as kt
+    rng = np.random.default_rng(nx + ny)
+    g = kt.SIMPLESolver(1.3, 0.9, nx, ny, device=cuda)
+    state = {}
+    for name in ('u', 'v', 'p', 'pcor', 'mdiv'):
+        a = rng.standard_normal(getattr(g, name).shape)
+        getattr(g, name).from_numpy(a)
+        state[name] = a
+    img = g.disp.display(str(tmp_path / 'frame.png'))
+    ref, panels = post.class_frame(state['u'], state['v'], state['p'], state['pcor'], state['mdiv'])
+    np.testing.assert_array_equal(img, ref)
+    np.testing.assert_array_equal(g.disp.udisp, panels['u'])
+    np.testing.assert_array_equal(g.disp.mdivdisp, panels['div'])
+    assert img.shape == (nx + 2, 5 * (ny + 2)) and 0.0 <= img.min() and img.max() <= 1.0
+    assert g.disp.minmax['p'] == (state['p'].min(), state['p'].max())
+    assert open(tmp_path / 'frame.png', 'rb').read(8) == b'\x89PNG\r\n\x1a\n'
+    # a constant field: max - min + 1e-9 in the denominator (display.py:26), no division by zero
+    g.pcor.from_numpy(np.full(g.pcor.shape, 2.5))
+    g.disp.post_process_field()
+    assert np.all(g.disp.pcordisp == 0.0)
+
+
+@pytest.mark.parametrize('kw', [dict(nx=48, ny=16, cyl=(12, 8, 10)), dict(nx=96, ny=48, cyl=(64, 32, 144))])
+def test_monolith_display_frame_bit_exact(cuda, kw, tmp_path):
+    import karman_taichi_b200 as kt
+    g = kt.KarmanSolver(device=cuda, **kw)
+    g.init()
+    g.sub_iteration(1e-8)
+    before = {n: getattr(g, n).to_numpy() for n in ('u', 'v', 'p', 'pcor', 'udiv')}
+    d = kt.Display(g)
+    img = d.display(str(tmp_path / 'timestep000000.png'))
+    ref, panels, udiv = post.monolith_frame(before['u'], before['v'], before['p'], before['pcor'], before['udiv'], g.dx, g.dy)
+    np.testing.assert_array_equal(img, ref)
+    np.testing.assert_array_equal(g.udiv.to_numpy(), udiv)             # post_process_field recomputes udiv in place (:555-556)
+    nx, ny = kw['nx'], kw['ny']
+    assert img.shape == (3 * (nx + 2), 15 * (ny + 2))
+    # panel order of the GUI frame (karman_taichi.py:665): pcor, udiv, p, u, v
+    w = 3 * (ny + 2)
+    np.testing.assert_array_equal(img[:, 0:w], panels['pcor'])
+    np.testing.assert_array_equal(img[:, 3 * w:4 * w], panels['u'])
+    # f_max starts at 0.0 (karman_taichi.py:575): an all-negative field is scaled against 0, not against its own maximum
+    g.pcor.from_numpy(-1.0 - np.abs(before['pcor']))
+    d.post_process_field()
+    assert d.minmax['pcor'][1] == 0.0 and d.pcordisp.max() < 1.0
+
+
+def test_display_frames_vs_reference_fixtures(cuda):
+    """The frames the REFERENCE produced (display.py / karman_taichi.py executed by tests/golden/make_reference_golden.py) from
+    the reference's own final states: loaded into the CUDA classes, the device frame must be identical."""
+    import karman_taichi_b200 as kt
+    g = np.load(os.path.join(GOLD, 'reference_cavity.npz'))
+    for key in sorted({'/'.join(k.split('/')[:2]) for k in g.files}):
+        nx, ny, steps = (int(v) for v in g[f'{key}/nx_ny_steps'])
+        s = kt.SIMPLESolver(1.0, 1.0, nx, ny, variant=key.split('/')[0], device=cuda)
+        for n in ('u', 'v', 'p', 'pcor', 'mdiv'):
+            getattr(s, n).from_numpy(g[f'{key}/step{steps - 1}/{n}'])
+        s.disp.post_process_field()
+        for mine, ref in (('udisp', 'udisp'), ('vdisp', 'vdisp'), ('pdisp', 'pdisp'), ('pcordisp', 'pcordisp'), ('mdivdisp', 'mdivdisp')):
+            np.testing.assert_array_equal(getattr(s.disp, mine), g[f'{key}/display/{ref}'], err_msg=f'{key} {ref}')
+    c = np.load(os.path.join(GOLD, 'reference_channel.npz'))
+    seen = 0
+    for key in sorted({'/'.join(k.split('/')[:2]) for k in c.files}):
+        if f'{key}/display/u_disp' not in c.files:
+            continue
+        seen += 1
+        nx, ny, subs = (int(v) for v in c[f'{key}/nx_ny_subs'])
+        s = kt.KarmanSolver(nx=nx, ny=ny, dt=float(c[f'{key}/params'][4]), device=cuda)
+        s.init()
+        for n in ('u', 'v', 'p', 'pcor', 'udiv'):
+            getattr(s, n).from_numpy(c[f'{key}/sub{subs - 1}/{n}'])
+        d = kt.Display(s)
+        d.post_process_field()
+        for mine, ref in (('udisp', 'u_disp'), ('vdisp', 'v_disp'), ('pdisp', 'p_disp'), ('pcordisp', 'pcor_disp'), ('mdivdisp', 'udiv_disp')):
+            np.testing.assert_array_equal(getattr(d, mine), c[f'{key}/display/{ref}'], err_msg=f'{key} {ref}')
+        np.testing.assert_array_equal(s.udiv.to_numpy(), c[f'{key}/display/udiv'])
+    assert seen >= 1
+
+
+@pytest.mark.parametrize('shape,relax', [((7, 9), 1.0), ((53, 37), 0.8), ((130, 260), 1.0)])
+def test_jacobi_sweep_bit_exact(cuda, shape, relax):
+    import karman_taichi_b200 as kt
+    from oracle import krylov
+    coef, b = krylov.random_dd_system(shape[0] - 2, shape[1] - 2, seed=shape[0])
+    rng = np.random.default_rng(1)
+    x = np.zeros(shape)
+    x[1:-1, 1:-1] = rng.standard_normal((shape[0] - 2, shape[1] - 2))
+    mk = lambda a: kt.Field(a.shape, np.float64, cuda).from_numpy(a)
+    fx = mk(x)
+    rows, cols = (2, shape[0] - 1), (1, shape[1] - 2)                     # a sub-range, like the u-momentum sweep (momentum_valid.py:160)
+    j = kt.JacobiSolver(mk(coef), mk(b), fx, rows=rows, cols=cols, relax=relax)
+    for _ in range(3):
+        res = j.sweep()
+        x, res_ref = post.jacobi_sweep(coef, b, x, rows, cols, relax)
+        assert res == res_ref
+        np.testing.assert_array_equal(fx.to_numpy(), x)
+    with pytest.raises(kt.KtError):
+        kt.JacobiSolver(j.coef, j.b, fx, rows=(0, 3)).sweep()             # the stencil needs a one-cell ring
+
+
+def test_pressure_and_momentum_valid_recipes_with_the_jacobi_kernel(cuda, capsys):
+    """pressure_valid.py:254-281 and momentum_valid.py:210-225 through the library's own Jacobi solver and through the command
+    line, which prints both wall-clocks like the reference scripts do."""
+    import karman_taichi_b200 as kt
+    from karman_taichi_b200.__main__ import main
+    g = kt.lid_driven_cavity(24, device=cuda)
+    g.init(); g._make_solvers()
+    g.step()
+    g.compute_coef_u(); g.set_bc()
+    g.u_momentum_solver.solve(eps=1e-12)
+    u_bicg = g.u_mid.to_numpy().copy()
+    u0 = kt.Field(g.u.shape, np.float64, cuda).from_numpy(g.u.to_numpy() * 0.0 + g.u.to_numpy() * np.isin(np.arange(g.u.shape[0]), (1, 25))[:, None])
+    jac = kt.JacobiSolver(g.coef_u, g.b_u, u0, rows=(2, 25), cols=(1, 25))
+    n = jac.solve(eps=1e-13, max_sweeps=100000)
+    assert n < 100000 and rel_l2(u0.to_numpy()[2:25, 1:25], u_bicg[2:25, 1:25]) < 1e-8
+    g.compute_coef_p()
+    g.p_correction_solver.solve(eps=1e-12)
+    p_cg = g.pcor.to_numpy().copy()
+    z = kt.Field(g.pcor.shape, np.float64, cuda)
+    jac = kt.JacobiSolver(g.coef_p, g.b_p, z, rows=(1, 25), cols=(1, 25))
+    jac.solve(eps=1e-14, max_sweeps=400000)
+    assert rel_l2(z.to_numpy(), p_cg) < 1e-6
+    for which in ('pressure', 'momentum'):
+        assert main(['validate', which, '--n', '20', '--sweeps', '200']) == 0
+        out = capsys.readouterr().out
+        assert 'Jacobian' in out and 'BICG' in out and out.count('took') == 2
+
+
+def test_cavity128_full_run_vs_golden_and_ghia(cuda):
+    """BASELINE config 2 at its stated size: 128 x 128, Re = 100, alpha_p = 0.02 (the committed 0.1 diverges above ~80^2:
+    SURVEY.md 6), run to the reference's own stopping test (bicgsimp.py:326) -- ~2720 outer iterations, ~3.4 million Krylov
+    iterations -- against the stored oracle run (tests/golden/cavity128_oracle.json: the oracle with the C port's serial sums)
+    and against Ghia et al. 1982 (data/ghia1982.dat: bicgsimp.py:291-304)."""
+    import karman_taichi_b200 as kt
+    gold = json.load(open(os.path.join(GOLD, 'cavity128_oracle.json')))
+    ghia = json.load(open(os.path.join(GOLD, 'ghia1982_re100.json')))
+    g = kt.lid_driven_cavity(128, device=cuda)
+    g.alpha_p = 0.02
+    n = g.solve()
+    # the first outer iterations: residuals and Krylov counts
+    for k, ref in enumerate(gold['first_steps']):
+        assert g.log[k][0] == pytest.approx(ref['momentum'], rel=1e-3) and g.log[k][1] == pytest.approx(ref['continuity'], rel=1e-3)
+        assert abs(g.log[k][2]['p'] - ref['iters']['p']) <= 1
+    # the stopping test (momentum < 1e-2 and continuity < 1e-6) fires within a few outer iterations of the oracle's
+    assert abs(n - gold['outer_iterations']) <= 3, (n, gold['outer_iterations'])
+    tot = {k: sum(l[2][k] for l in g.log) for k in 'uvp'}
+    for k in 'uvp':
+        assert abs(tot[k] - gold['krylov_totals'][k]) <= 0.02 * gold['krylov_totals'][k], (k, tot[k], gold['krylov_totals'][k])
+    u = g.u.to_numpy()[65, 1:129]                      # bicgsimp.py:293
+    v = g.v.to_numpy()[1:129, 65]                      # bicgsimp.py:302
+    du, dv = np.abs(u - np.array(gold['u_centre'])).max(), np.abs(v - np.array(gold['v_centre'])).max()
+    yc = (np.arange(128) + 0.5) / 128
+    gu = np.abs(np.interp(ghia['y'], yc, u) - np.array(ghia['u']))[1:-1].max()
+    gv = np.abs(np.interp(ghia['x'], yc, v) - np.array(ghia['v']))[1:-1].max()
+    if os.path.isdir('gpurun_out'):
+        with open('gpurun_out/parity_errors.txt', 'a') as f:
+            f.write(f'cavity128: outer {n} (oracle {gold["outer_iterations"]}), Krylov totals {tot} (oracle {gold["krylov_totals"]}), '
+                    f'centreline max diff vs oracle u {du:.2e} v {dv:.2e}, vs Ghia u {gu:.4f} v {gv:.4f}\n')
+    # every late outer iteration still moves the profiles by ~1e-5; a few iterations apart -> ~1e-4, far below the distance to Ghia
+    assert du < 2e-4 and dv < 2e-4
+    assert gu < 0.0045 and gv < 0.0100                 # 0.0042 / 0.0098 at 128^2

@@ -122,3 +122,33 @@ def test_channel_against_literal_and_stencil_oracles(serial_sums):
         # nothing outside the five stencil offsets (the 7-offset product of karman_taichi.py:365 is a 5-point stencil)
         for which in ('asm0/extra_u', 'asm0/extra_v', 'sub0/extra_p'):
             assert g[f'{key}/{which}'].shape[0] == 0
+
+
+def test_display_frames_bit_exact():
+    """oracle/post.py against the display fields the reference's own Display.post_process_field (display.py:28-40) and the
+    monolith's post_process_field (karman_taichi.py:544-570) produced from the final states of the fixture runs."""
+    from oracle import post
+    g = fixture('reference_cavity.npz')
+    cases = sorted({'/'.join(k.split('/')[:2]) for k in g.files})
+    for key in cases:
+        steps = int(g[f'{key}/nx_ny_steps'][2])
+        last = f'{key}/step{steps - 1}'
+        img, panels = post.class_frame(g[f'{last}/u'], g[f'{last}/v'], g[f'{last}/p'], g[f'{last}/pcor'], g[f'{last}/mdiv'])
+        for name, f in (('u', 'udisp'), ('v', 'vdisp'), ('p', 'pdisp'), ('pcor', 'pcordisp'), ('div', 'mdivdisp')):
+            np.testing.assert_array_equal(panels[name], g[f'{key}/display/{f}'], err_msg=f'{key} {f}')
+    c = fixture('reference_channel.npz')
+    seen = 0
+    for key in sorted({'/'.join(k.split('/')[:2]) for k in c.files}):
+        if f'{key}/display/u_disp' not in c.files:
+            continue
+        seen += 1
+        nx, ny, subs = (int(v) for v in c[f'{key}/nx_ny_subs'])
+        lx, ly = float(c[f'{key}/params'][0]), float(c[f'{key}/params'][1])
+        last = f'{key}/sub{subs - 1}'
+        img, panels, udiv = post.monolith_frame(c[f'{last}/u'], c[f'{last}/v'], c[f'{last}/p'], c[f'{last}/pcor'], c[f'{last}/udiv'],
+                                                lx / nx, ly / ny)
+        np.testing.assert_array_equal(udiv, c[f'{key}/display/udiv'])
+        for name, f in (('u', 'u_disp'), ('v', 'v_disp'), ('p', 'p_disp'), ('pcor', 'pcor_disp'), ('div', 'udiv_disp')):
+            np.testing.assert_array_equal(panels[name], c[f'{key}/display/{f}'], err_msg=f'{key} {f}')
+        assert img.shape == (3 * (nx + 2), 15 * (ny + 2))
+    assert seen >= 1
