@@ -185,7 +185,7 @@ int kt_dist_poll(kt_handle_t h, int* done, long* iters, int* status, double* rel
 
 /* Same solve with the halo exchange and the all-reduce done by the library itself over NVLink peer memory (no NCCL
  * in the loop).  Every rank allocates (kt_ipc_alloc, zero-initialised once, never reset) a comm block of
- * kt_p2p_comm_block_bytes() bytes and a halo-receive buffer of 3 planes x 2 sides x pitch reals, and passes device
+ * kt_p2p_comm_block_bytes() bytes and a halo-receive buffer of kt_p2p_halo_slots() x 2 sides x pitch reals, and passes device
  * pointers, mapped into ITS address space (kt_ipc_open), of every rank's comm block and of its two neighbours'
  * halo-receive buffers: peer_halo_recv[0] = lower neighbour (rank-1) or NULL, [1] = upper neighbour or NULL.  The field
  * planes themselves are ordinary allocations that no other rank maps: a boundary row travels plane -> neighbour's receive
@@ -213,6 +213,14 @@ int kt_enable_peer_access(kt_handle_t h, int peer_device);
 int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* ws,
                           const kt_p2p_comm* comm, double eps, long max_iter, int flags, int fixed_iters,
                           long* iters, double* rel_res, int* status);
+/* The SIMPLE kernels around the solves on x-slabs: exchange the boundary rows of one plane with the two neighbours (the
+ * handle's owned rows, kt_set_rows; asynchronous on the handle's stream), and all-reduce two doubles over the ranks in rank
+ * order (op 0: sum -- deterministic, the same bits on every rank; op 1: max), returned to the host.  Both use flag slots /
+ * sum groups of their own, so they may be freely interleaved with solves.  kt_p2p_halo_slots(): rows x 2 sides the
+ * halo-receive buffer must hold (kt_p2p_halo_slots() x 2 x pitch reals). */
+int kt_p2p_halo_slots(void);
+int kt_p2p_exchange(kt_handle_t h, const kt_p2p_comm* comm, void* plane);
+int kt_p2p_allreduce(kt_handle_t h, const kt_p2p_comm* comm, const double* vals_dev2, int op, double* out_host2);
 /* CGSolver.solve (cgsolver.py:83-114) over x-slabs, same comm kernels: one halo exchange (p) and two all-reduces per
  * iteration.  ws: r, p, Ap. */
 int kt_p2p_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws,
@@ -293,6 +301,11 @@ typedef struct {
   double dx, dy, dt, rho, mu, velo_rel, p_rel;
   int cyl_cx, cyl_cy, cyl_r2;       /* (i-cx)^2 + (j-cy)^2 < r2 -> solid   (karman_taichi.py:148-149) */
   int pitch_u, pitch_v, pitch_p;
+  /* x-slab window (no reference counterpart; all zero = one GPU, the whole grid): the planes passed to a call hold the GLOBAL
+   * rows [row0, row0 + rows_*) -- this rank's owned rows plus one halo row on each interior side -- and the call works on the
+   * global rows [row_lo, row_hi).  rows_u / rows_p: stored rows of the u-type (nx+3 globally) and of the v- and cell-centred
+   * planes (nx+2 globally).  nx, ny stay the GLOBAL cell counts: every boundary test of the reference is on the global index. */
+  int row0, row_lo, row_hi, rows_u, rows_p;
 } kt_channel_params;
 
 /* init (karman_taichi.py:130-154) */
@@ -309,7 +322,13 @@ int kt_channel_relax(kt_handle_t h, const kt_channel_params* P, void* u, void* v
 /* correct_conserv (karman_taichi.py:585-614): scale u[nx+1,:] by sum u[1,:] / sum u[nx+1,:]; udiv (may be NULL);
  * sums_host (may be NULL) receives {inlet sum, outlet sum before scaling, ratio} */
 int kt_outlet_scale(kt_handle_t h, const kt_channel_params* P, void* u, const void* v, void* udiv, double* sums_host);
-/* puv_correction (karman_taichi.py:506-542): returns max |pcor| */
+/* correct_conserv on x-slabs: this rank's {inlet, outlet} column sums into sums_dev[0..1] (0 where it does not own the
+ * column; add the ranks' pairs in rank order with kt_p2p_allreduce), then the scaling of the outlet column with
+ * inlet_sum / outlet_sum on the rank that owns it, then udiv on the window (needs the halo row of u above it). */
+int kt_outlet_sums(kt_handle_t h, const kt_channel_params* P, const void* u, double* sums_dev);
+int kt_outlet_apply(kt_handle_t h, const kt_channel_params* P, void* u, double inlet_sum, double outlet_sum);
+int kt_channel_udiv(kt_handle_t h, const kt_channel_params* P, const void* u, const void* v, void* udiv);
+/* puv_correction (karman_taichi.py:506-542): returns max |pcor| (over the window) */
 int kt_channel_correct(kt_handle_t h, const kt_channel_params* P, const int* ct, void* u, void* v, void* p,
                        const void* pcor, const void* coef_u, const void* coef_v, double* pcor_max_host);
 

@@ -14,6 +14,7 @@ from .simple import SIMPLESolver, lid_driven_cavity
 from .karman import KarmanSolver
 from .display import Display
 from .jacobi import JacobiSolver
+from .slab_karman import SlabKarmanSolver
 
-__all__ = ['Field', 'ScalarField', 'CGSolver', 'BICGSolver', 'SIMPLESolver', 'lid_driven_cavity', 'KarmanSolver', 'Display', 'JacobiSolver', 'KtError']
+__all__ = ['Field', 'ScalarField', 'CGSolver', 'BICGSolver', 'SIMPLESolver', 'lid_driven_cavity', 'KarmanSolver', 'Display', 'JacobiSolver', 'SlabKarmanSolver', 'KtError']
 __version__ = '0.1.0'

@@ -62,7 +62,8 @@ class ChannelParams(C.Structure):
                 ('dx', C.c_double), ('dy', C.c_double), ('dt', C.c_double), ('rho', C.c_double), ('mu', C.c_double),
                 ('velo_rel', C.c_double), ('p_rel', C.c_double),
                 ('cyl_cx', C.c_int), ('cyl_cy', C.c_int), ('cyl_r2', C.c_int),
-                ('pitch_u', C.c_int), ('pitch_v', C.c_int), ('pitch_p', C.c_int)]
+                ('pitch_u', C.c_int), ('pitch_v', C.c_int), ('pitch_p', C.c_int),
+                ('row0', C.c_int), ('row_lo', C.c_int), ('row_hi', C.c_int), ('rows_u', C.c_int), ('rows_p', C.c_int)]
 
 
 class SimpleParams(C.Structure):
@@ -126,6 +127,9 @@ SIGNATURES = {
     'kt_ipc_free': (_I, [_P, _P]),
     'kt_enable_peer_access': (_I, [_P, _I]),
     'kt_p2p_bicgstab_solve': (_I, [_P, _P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _I, _PL, _PD, _PI]),
+    'kt_p2p_halo_slots': (_I, []),
+    'kt_p2p_exchange': (_I, [_P, C.POINTER(P2PComm), _P]),
+    'kt_p2p_allreduce': (_I, [_P, C.POINTER(P2PComm), _P, _I, _PD]),
     'kt_p2p_cg_solve': (_I, [_P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _PL, _PD, _PI]),
     'kt_reduce_plan': (_I, [C.POINTER(Geom), _I, _I, C.POINTER(C.c_longlong)]),
     'kt_resident_plan': (_I, [C.POINTER(Geom), _I, _I, _I, _I, C.POINTER(C.c_longlong)]),
@@ -143,6 +147,9 @@ SIGNATURES = {
     'kt_channel_assemble_p': (_I, [_P, _CP] + [_P] * 9),
     'kt_channel_relax': (_I, [_P, _CP, _P, _P, _P, _P]),
     'kt_outlet_scale': (_I, [_P, _CP, _P, _P, _P, _PD]),
+    'kt_outlet_sums': (_I, [_P, _CP, _P, _P]),
+    'kt_outlet_apply': (_I, [_P, _CP, _P, _D, _D]),
+    'kt_channel_udiv': (_I, [_P, _CP, _P, _P, _P]),
     'kt_channel_correct': (_I, [_P, _CP, _P, _P, _P, _P, _P, _P, _P, _PD]),
     'kt_display_frame': (_I, [_P, C.POINTER(FrameParams), _P, _P, _P, _P, _P, _P, _PD]),
     'kt_jacobi_sweep': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _D, _PD]),

@@ -7,6 +7,7 @@
 // A.4): the second u-loop next to the obstacle that neither clears the stale j-1 entry nor refreshes Mu (:221-239),
 // outlet pressure rows whose diagonal becomes 1 while the off-diagonals stay (:327-339), cell (nx,1) left un-pinned.
 // Every formula keeps the reference's operation order (library built -fmad=false) => bit-identical to the oracle.
+#include <algorithm>
 #include "kt_handle.h"
 
 namespace kt {
@@ -17,6 +18,9 @@ struct CP {   // device copy of kt_channel_params
   int cx, cy, r2;
   int pu, pv, pp;
   size_t plu, plv, plp;
+  // x-slab window: the planes hold the GLOBAL rows [i0, i0 + local rows); a launch works on the global rows [ia, ib).
+  // One GPU: i0 = 0, [ia, ib) = [0, nx + 3).  Every index test below is on the global row; memory is addressed by i - i0.
+  int i0, ia, ib;
 };
 
 static CP make_cp(const kt_channel_params* P) {
@@ -24,27 +28,36 @@ static CP make_cp(const kt_channel_params* P) {
   c.nx = P->nx; c.ny = P->ny; c.dx = P->dx; c.dy = P->dy; c.dt = P->dt; c.rho = P->rho; c.mu = P->mu;
   c.velo_rel = P->velo_rel; c.p_rel = P->p_rel; c.cx = P->cyl_cx; c.cy = P->cyl_cy; c.r2 = P->cyl_r2;
   c.pu = P->pitch_u; c.pv = P->pitch_v; c.pp = P->pitch_p;
-  c.plu = (size_t)(P->nx + 3) * P->pitch_u; c.plv = (size_t)(P->nx + 2) * P->pitch_v; c.plp = (size_t)(P->nx + 2) * P->pitch_p;
+  const bool slab = P->row_hi > 0;
+  const int rows_u = slab ? P->rows_u : P->nx + 3, rows_p = slab ? P->rows_p : P->nx + 2;
+  c.plu = (size_t)rows_u * P->pitch_u; c.plv = (size_t)rows_p * P->pitch_v; c.plp = (size_t)rows_p * P->pitch_p;
+  c.i0 = slab ? P->row0 : 0; c.ia = slab ? P->row_lo : 0; c.ib = slab ? P->row_hi : P->nx + 3;
   return c;
 }
 
-#define CU(i, j) u[(size_t)(i) * S.pu + (j)]
-#define CV(i, j) v[(size_t)(i) * S.pv + (j)]
-#define CPp(i, j) p[(size_t)(i) * S.pp + (j)]
-#define CT(i, j) ct[(size_t)(i) * S.pp + (j)]
+// rows of a launch: blockIdx.y strides over [ia, ib) (gridDim.y <= 65535 whatever the grid height)
+#define KT_CH_ROWS(i) for (int i = S.ia + (int)blockIdx.y; i < S.ib; i += (int)gridDim.y)
+#define RU(i) ((size_t)((i) - S.i0) * S.pu)
+#define RV(i) ((size_t)((i) - S.i0) * S.pv)
+#define RP(i) ((size_t)((i) - S.i0) * S.pp)
+#define CU(i, j) u[RU(i) + (j)]
+#define CV(i, j) v[RV(i) + (j)]
+#define CPp(i, j) p[RP(i) + (j)]
+#define CT(i, j) ct[RP(i) + (j)]
 
 // init (karman_taichi.py:130-154): p = 100 - 4000 i / nx, u = v = u0 = v0 = 0, ct ring / fluid / cylinder
 template <typename T>
 __global__ void __launch_bounds__(256) k_ch_init(CP S, T* p, T* u, T* u0, T* v, T* v0, int* ct) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y;
-  if (i <= S.nx + 2 && j <= S.ny + 1) { CU(i, j) = T(0); u0[(size_t)i * S.pu + j] = T(0); }
-  if (i <= S.nx + 1 && j <= S.ny + 2) { CV(i, j) = T(0); v0[(size_t)i * S.pv + j] = T(0); }
-  if (i <= S.nx + 1 && j <= S.ny + 1) {
-    CPp(i, j) = T(100) - T(4000.0) * T(i) / T(S.nx);
-    int c = (i >= 1 && i <= S.nx && j >= 1 && j <= S.ny) ? -1 : 1;
-    if (i < S.nx && j < S.ny && ((i - S.cx) * (i - S.cx) + (j - S.cy) * (j - S.cy)) < S.r2) c = 1;
-    CT(i, j) = c;
+  KT_CH_ROWS(i) {
+    if (i <= S.nx + 2 && j <= S.ny + 1) { CU(i, j) = T(0); u0[RU(i) + j] = T(0); }
+    if (i <= S.nx + 1 && j <= S.ny + 2) { CV(i, j) = T(0); v0[RV(i) + j] = T(0); }
+    if (i <= S.nx + 1 && j <= S.ny + 1) {
+      CPp(i, j) = T(100) - T(4000.0) * T(i) / T(S.nx);
+      int c = (i >= 1 && i <= S.nx && j >= 1 && j <= S.ny) ? -1 : 1;
+      if (i < S.nx && j < S.ny && ((i - S.cx) * (i - S.cx) + (j - S.cy) * (j - S.cy)) < S.r2) c = 1;
+      CT(i, j) = c;
+    }
   }
 }
 
@@ -55,18 +68,18 @@ __global__ void __launch_bounds__(256) k_ch_assemble_uv(CP S, const int* __restr
                                                         const T* __restrict__ u0, const T* __restrict__ v0, T* cu, T* bu,
                                                         T* mu_, T* mui, T* cv, T* bv, T* mv_, T* mvi) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y;
   const T dx = T(S.dx), dy = T(S.dy), dt = T(S.dt), rho = T(S.rho), mu = T(S.mu);
   const T half = T(0.5), two = T(2), one = T(1), zero = T(0);
   const T tt = rho * dx * dy / dt;
+  KT_CH_ROWS(i) {
   if (blockIdx.z == 0) {
-    if (i < 1 || i > S.nx + 1 || j < 1 || j > S.ny) return;
+    if (i < 1 || i > S.nx + 1 || j < 1 || j > S.ny) continue;
     const int ctl = CT(i - 1, j), ctr = CT(i, j), ctru = CT(i, j - 1), ctrd = CT(i, j + 1), ctlu = CT(i - 1, j - 1);
     const T aN = -mu * dx / dy - rho * half * (CV(i - 1, j + 1) + CV(i, j + 1)) * dx;
     const T aS = -mu * dx / dy - (-rho * half * (CV(i - 1, j) + CV(i, j)) * dx);
     const T aW = -mu * dy / dx - rho * half * (CU(i, j) + CU(i - 1, j)) * dy;
     const T aE = -mu * dy / dx - (-rho * half * (CU(i, j) + CU(i + 1, j)) * dy);
-    const size_t o = (size_t)i * S.pu + j;
+    const size_t o = RU(i) + j;
     const T bb = (CPp(i - 1, j) - CPp(i, j)) * dy + rho * dx * dy / dt * u0[o];
     const T C_c = -aN - aW - aE + tt + two * mu * dx / dy;
     T C, W = zero, E = zero, N = zero, Sx = zero, B = zero;
@@ -84,13 +97,13 @@ __global__ void __launch_bounds__(256) k_ch_assemble_uv(CP S, const int* __restr
     cu[o] = C; cu[S.plu + o] = W; cu[2 * S.plu + o] = E; cu[3 * S.plu + o] = N; cu[4 * S.plu + o] = Sx;
     bu[o] = B; mu_[o] = M; mui[o] = one / M;
   } else {
-    if (i < 1 || i > S.nx || j < 1 || j > S.ny + 1) return;
+    if (i < 1 || i > S.nx || j < 1 || j > S.ny + 1) continue;
     const int ctc = CT(i, j), ctu = CT(i, j - 1), ctw = CT(i - 1, j), cte = CT(i + 1, j);
     const T aS = -mu * dx / dy - (-rho * half * (CV(i, j - 1) + CV(i, j)) * dx);
     const T aN = -mu * dx / dy - (rho * half * (CV(i, j + 1) + CV(i, j)) * dx);
     const T aE = -mu * dy / dx - (-rho * half * (CU(i + 1, j - 1) + CU(i + 1, j)) * dy);
     const T aW = -mu * dy / dx - (rho * half * (CU(i, j) + CU(i, j - 1)) * dy);
-    const size_t o = (size_t)i * S.pv + j;
+    const size_t o = RV(i) + j;
     const T bb = (CPp(i, j) - CPp(i, j - 1)) * dx + rho * dx * dy / dt * v0[o];
     T C, W = zero, E = zero, N = zero, Sx = zero, B;
     const int s = ctc + ctu;
@@ -101,6 +114,7 @@ __global__ void __launch_bounds__(256) k_ch_assemble_uv(CP S, const int* __restr
     cv[o] = C; cv[S.plv + o] = W; cv[2 * S.plv + o] = E; cv[3 * S.plv + o] = N; cv[4 * S.plv + o] = Sx;
     bv[o] = B; mv_[o] = C; mvi[o] = one / C;
   }
+  }
 }
 
 // fill_Ap (:296-339)
@@ -109,14 +123,14 @@ __global__ void __launch_bounds__(256) k_ch_assemble_p(CP S, const int* __restri
                                                        const T* __restrict__ v, const T* __restrict__ cu,
                                                        const T* __restrict__ cv, T* cp, T* bp, T* mp, T* mpi) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y;
-  if (i < 1 || i > S.nx || j < 1 || j > S.ny) return;
   const T dx = T(S.dx), dy = T(S.dy), rho = T(S.rho), zero = T(0), one = T(1);
+  KT_CH_ROWS(i) {
+  if (i < 1 || i > S.nx || j < 1 || j > S.ny) continue;
   T B = rho * (CU(i, j) - CU(i + 1, j)) * dy + rho * (CV(i, j + 1) - CV(i, j)) * dx;
-  T Sx = -rho * dx * dx / cv[(size_t)i * S.pv + j];
-  T N = -rho * dx * dx / cv[(size_t)i * S.pv + j + 1];
-  T W = -rho * dy * dy / cu[(size_t)i * S.pu + j];
-  T E = -rho * dy * dy / cu[(size_t)(i + 1) * S.pu + j];
+  T Sx = -rho * dx * dx / cv[RV(i) + j];
+  T N = -rho * dx * dx / cv[RV(i) + j + 1];
+  T W = -rho * dy * dy / cu[RU(i) + j];
+  T E = -rho * dy * dy / cu[RU(i + 1) + j];
   const int ctc = CT(i, j);
   if (ctc + CT(i, j - 1) == 0) Sx = zero;
   if (ctc + CT(i, j + 1) == 0) N = zero;
@@ -130,35 +144,42 @@ __global__ void __launch_bounds__(256) k_ch_assemble_p(CP S, const int* __restri
   T M = C;
   if (i == 1) { C = one; M = one; B = zero; Sx = N = W = E = zero; }          // inlet rows: identity (:327-333)
   if (i == S.nx && j >= 2) { C = one; M = one; B = zero; }                    // outlet rows n-1 .. n-ny+1: diagonal only
-  const size_t o = (size_t)i * S.pp + j;
+  const size_t o = RP(i) + j;
   cp[o] = C; cp[S.plp + o] = W; cp[2 * S.plp + o] = E; cp[3 * S.plp + o] = N; cp[4 * S.plp + o] = Sx;
   bp[o] = B; mp[o] = M; mpi[o] = one / M;
+  }
 }
 
 // xu_back / xv_back (:458-470): u += velo_rel (xu - u) on every unknown
 template <typename T>
 __global__ void __launch_bounds__(256) k_ch_relax(CP S, T* u, T* v, const T* __restrict__ xu, const T* __restrict__ xv) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y;
   const T rel = T(S.velo_rel);
-  if (i >= 1 && i <= S.nx + 1 && j >= 1 && j <= S.ny) {
-    const size_t o = (size_t)i * S.pu + j;
-    u[o] = u[o] + rel * (xu[o] - u[o]);
-  }
-  if (i >= 1 && i <= S.nx && j >= 1 && j <= S.ny + 1) {
-    const size_t o = (size_t)i * S.pv + j;
-    v[o] = v[o] + rel * (xv[o] - v[o]);
+  KT_CH_ROWS(i) {
+    if (i >= 1 && i <= S.nx + 1 && j >= 1 && j <= S.ny) {
+      const size_t o = RU(i) + j;
+      u[o] = u[o] + rel * (xu[o] - u[o]);
+    }
+    if (i >= 1 && i <= S.nx && j >= 1 && j <= S.ny + 1) {
+      const size_t o = RV(i) + j;
+      v[o] = v[o] + rel * (xv[o] - v[o]);
+    }
   }
 }
 
-// correct_conserv, first part (:586-600): scale the outlet column by sum(u[1,:]) / sum(u[nx+1,:]).  One block;
-// fixed-order (deterministic) sums.
+// correct_conserv, first part (:586-600): scale the outlet column by sum(u[1,:]) / sum(u[nx+1,:]).  One block; fixed-order
+// (deterministic) sums.  On x-slabs the inlet column belongs to the first rank and the outlet column to the last: every rank
+// publishes (its inlet sum or 0, its outlet sum or 0), the ranks' pairs are added in rank order (x + 0 == x: the same bits
+// as on one GPU) and the last rank scales with the quotient.
 template <typename T>
-__global__ void __launch_bounds__(256) k_ch_outlet_scale(CP S, T* u, double* out) {
+__global__ void __launch_bounds__(256) k_ch_outlet_sums(CP S, const T* u, double* out) {
   __shared__ double sm[2][8];
-  __shared__ double coef_s;
+  const bool has_in = S.ia <= 1 && 1 < S.ib, has_out = S.ia <= S.nx + 1 && S.nx + 1 < S.ib;
   double a = 0.0, b = 0.0;
-  for (int j = 1 + threadIdx.x; j <= S.ny; j += blockDim.x) { a += (double)CU(1, j); b += (double)CU(S.nx + 1, j); }
+  for (int j = 1 + threadIdx.x; j <= S.ny; j += blockDim.x) {
+    if (has_in) a += (double)CU(1, j);
+    if (has_out) b += (double)CU(S.nx + 1, j);
+  }
   a = warp_sum(a); b = warp_sum(b);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) { sm[0][wid] = a; sm[1][wid] = b; }
@@ -166,11 +187,15 @@ __global__ void __launch_bounds__(256) k_ch_outlet_scale(CP S, T* u, double* out
   if (threadIdx.x == 0) {
     double sa = 0.0, sb = 0.0;
     for (int w = 0; w < 8; ++w) { sa += sm[0][w]; sb += sm[1][w]; }
-    coef_s = sa / sb;
-    out[0] = sa; out[1] = sb; out[2] = coef_s;
+    out[0] = sa; out[1] = sb; out[2] = sa / sb;
   }
-  __syncthreads();
-  const T coef = T(coef_s);
+}
+
+// sums: device {inlet sum, outlet sum, ratio} (one GPU) -- or the ratio passed by value after the ranks' sums were added
+template <typename T>
+__global__ void __launch_bounds__(256) k_ch_outlet_apply(CP S, T* u, const double* sums, double ratio_imm) {
+  if (!(S.ia <= S.nx + 1 && S.nx + 1 < S.ib)) return;
+  const T coef = T(sums ? sums[2] : ratio_imm);
   for (int j = 1 + threadIdx.x; j <= S.ny; j += blockDim.x) CU(S.nx + 1, j) = coef * CU(S.nx + 1, j);
 }
 
@@ -178,9 +203,10 @@ __global__ void __launch_bounds__(256) k_ch_outlet_scale(CP S, T* u, double* out
 template <typename T>
 __global__ void __launch_bounds__(256) k_ch_udiv(CP S, const T* __restrict__ u, const T* __restrict__ v, T* udiv) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y;
-  if (i < 1 || i > S.nx || j < 1 || j > S.ny) return;
-  udiv[(size_t)i * S.pp + j] = (CU(i, j) - CU(i + 1, j)) * T(S.dy) + (CV(i, j + 1) - CV(i, j)) * T(S.dx);
+  KT_CH_ROWS(i) {
+    if (i < 1 || i > S.nx || j < 1 || j > S.ny) continue;
+    udiv[RP(i) + j] = (CU(i, j) - CU(i + 1, j)) * T(S.dy) + (CV(i, j + 1) - CV(i, j)) * T(S.dx);
+  }
 }
 
 // puv_correction (:506-542): u, v corrections on non-interface faces, p += p_rel pcor on non-solid cells, max |pcor|
@@ -191,25 +217,26 @@ __global__ void __launch_bounds__(256) k_ch_correct(CP S, const int* __restrict_
                                                     unsigned int* ticket, double* out) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   double mx = 0.0;
-  for (int i = blockIdx.y; i <= S.nx + 1; i += gridDim.y) {
+  KT_CH_ROWS(i) {
+    if (i > S.nx + 1) continue;
     if (i >= 1 && j >= 1 && j <= S.ny) {                          // u faces, i in [1, nx+1]
       const int s = CT(i - 1, j) + CT(i, j);
       if (!(s == 0 || s == 2)) {
-        const size_t o = (size_t)i * S.pu + j;
-        const T ucor = (pc[(size_t)(i - 1) * S.pp + j] - pc[(size_t)i * S.pp + j]) * T(S.dy) / cu[o];
+        const size_t o = RU(i) + j;
+        const T ucor = (pc[RP(i - 1) + j] - pc[RP(i) + j]) * T(S.dy) / cu[o];
         u[o] = u[o] + ucor;
       }
     }
     if (i >= 1 && i <= S.nx && j >= 1 && j <= S.ny + 1) {         // v faces, j in [1, ny+1]
       const int s = CT(i, j) + CT(i, j - 1);
       if (!(s == 0 || s == 2)) {
-        const size_t o = (size_t)i * S.pv + j;
-        const T vcor = (pc[(size_t)i * S.pp + j] - pc[(size_t)i * S.pp + j - 1]) * T(S.dx) / cv[o];
+        const size_t o = RV(i) + j;
+        const T vcor = (pc[RP(i) + j] - pc[RP(i) + j - 1]) * T(S.dx) / cv[o];
         v[o] = v[o] + vcor;
       }
     }
     if (j <= S.ny + 1) {                                          // all cells of the (nx+2, ny+2) plane
-      const size_t o = (size_t)i * S.pp + j;
+      const size_t o = RP(i) + j;
       const T pcv = pc[o];
       if (CT(i, j) != 1) p[o] = p[o] + T(S.p_rel) * pcv;
       mx = fmax(mx, (double)fabs(pcv));
@@ -217,6 +244,8 @@ __global__ void __launch_bounds__(256) k_ch_correct(CP S, const int* __restrict_
   }
   block_max_finalize(mx, 0.0, partials, max_blocks, ticket, out);
 }
+
+static unsigned ch_rows(const CP& S) { return (unsigned)std::max(1, std::min(S.ib - S.ia, 65535)); }
 
 static int ch_read(kt_handle_s* h, double* out, int n) {
   KT_CUDA(cudaMemcpyAsync(h->red_host, h->red_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -245,7 +274,7 @@ int kt_channel_init(kt_handle_t h, const kt_channel_params* P, void* p, void* u,
   KT_DEV_GUARD(h);
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
-  dim3 grid((P->ny + 3 + 255) / 256, P->nx + 3);
+  dim3 grid((P->ny + 3 + 255) / 256, ch_rows(S));
   if (h->dtype == KT_F64) k_ch_init<double><<<grid, 256, 0, h->stream>>>(S, (double*)p, (double*)u, (double*)u0, (double*)v, (double*)v0, ct);
   else k_ch_init<float><<<grid, 256, 0, h->stream>>>(S, (float*)p, (float*)u, (float*)u0, (float*)v, (float*)v0, ct);
   KT_LAUNCH_CHECK(h);
@@ -260,7 +289,7 @@ int kt_channel_assemble_uv(kt_handle_t h, const kt_channel_params* P, const int*
   KT_DEV_GUARD(h);
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
-  dim3 grid((P->ny + 2 + 255) / 256, P->nx + 2, 2);
+  dim3 grid((P->ny + 2 + 255) / 256, ch_rows(S), 2);
   if (h->dtype == KT_F64)
     k_ch_assemble_uv<double><<<grid, 256, 0, h->stream>>>(S, ct, (const double*)u, (const double*)v, (const double*)p, (const double*)u0,
         (const double*)v0, (double*)coef_u, (double*)b_u, (double*)M_u, (double*)Minv_u, (double*)coef_v, (double*)b_v, (double*)M_v, (double*)Minv_v);
@@ -277,7 +306,7 @@ int kt_channel_assemble_p(kt_handle_t h, const kt_channel_params* P, const int* 
   KT_DEV_GUARD(h);
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
-  dim3 grid((P->ny + 2 + 255) / 256, P->nx + 1);
+  dim3 grid((P->ny + 2 + 255) / 256, ch_rows(S));
   if (h->dtype == KT_F64)
     k_ch_assemble_p<double><<<grid, 256, 0, h->stream>>>(S, ct, (const double*)u, (const double*)v, (const double*)coef_u, (const double*)coef_v,
         (double*)coef_p, (double*)b_p, (double*)M_p, (double*)Minv_p);
@@ -293,9 +322,17 @@ int kt_channel_relax(kt_handle_t h, const kt_channel_params* P, void* u, void* v
   KT_DEV_GUARD(h);
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
-  dim3 grid((P->ny + 3 + 255) / 256, P->nx + 2);
+  dim3 grid((P->ny + 3 + 255) / 256, ch_rows(S));
   if (h->dtype == KT_F64) k_ch_relax<double><<<grid, 256, 0, h->stream>>>(S, (double*)u, (double*)v, (const double*)x_u, (const double*)x_v);
   else k_ch_relax<float><<<grid, 256, 0, h->stream>>>(S, (float*)u, (float*)v, (const float*)x_u, (const float*)x_v);
+  KT_LAUNCH_CHECK(h);
+  return 0;
+}
+
+static int outlet_udiv(kt_handle_s* h, const kt_channel_params* P, const CP& S, const void* u, const void* v, void* udiv) {
+  dim3 grid((P->ny + 2 + 255) / 256, ch_rows(S));
+  if (h->dtype == KT_F64) k_ch_udiv<double><<<grid, 256, 0, h->stream>>>(S, (const double*)u, (const double*)v, (double*)udiv);
+  else k_ch_udiv<float><<<grid, 256, 0, h->stream>>>(S, (const float*)u, (const float*)v, (float*)udiv);
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -305,17 +342,54 @@ int kt_outlet_scale(kt_handle_t h, const kt_channel_params* P, void* u, const vo
   KT_DEV_GUARD(h);
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
-  if (h->dtype == KT_F64) k_ch_outlet_scale<double><<<1, 256, 0, h->stream>>>(S, (double*)u, h->red_out);
-  else k_ch_outlet_scale<float><<<1, 256, 0, h->stream>>>(S, (float*)u, h->red_out);
-  KT_LAUNCH_CHECK(h);
-  if (udiv) {
-    dim3 grid((P->ny + 2 + 255) / 256, P->nx + 1);
-    if (h->dtype == KT_F64) k_ch_udiv<double><<<grid, 256, 0, h->stream>>>(S, (const double*)u, (const double*)v, (double*)udiv);
-    else k_ch_udiv<float><<<grid, 256, 0, h->stream>>>(S, (const float*)u, (const float*)v, (float*)udiv);
+  if (h->dtype == KT_F64) {
+    k_ch_outlet_sums<double><<<1, 256, 0, h->stream>>>(S, (const double*)u, h->red_out);
     KT_LAUNCH_CHECK(h);
+    k_ch_outlet_apply<double><<<1, 256, 0, h->stream>>>(S, (double*)u, h->red_out, 0.0);
+  } else {
+    k_ch_outlet_sums<float><<<1, 256, 0, h->stream>>>(S, (const float*)u, h->red_out);
+    KT_LAUNCH_CHECK(h);
+    k_ch_outlet_apply<float><<<1, 256, 0, h->stream>>>(S, (float*)u, h->red_out, 0.0);
   }
+  KT_LAUNCH_CHECK(h);
+  if (udiv) { int rc = outlet_udiv(h, P, S, u, v, udiv); if (rc) return rc; }
   if (sums_host) return ch_read(h, sums_host, 3);
   return 0;
+}
+
+// x-slab form of correct_conserv: (1) this rank's column sums -> sums_dev[0..1] (0 where the column is not owned); the
+// caller adds the ranks' pairs in rank order (kt_p2p_allreduce); (2) the last rank scales its outlet column with
+// inlet / outlet and every rank recomputes udiv on its rows (needs the halo row of u above).
+int kt_outlet_sums(kt_handle_t h, const kt_channel_params* P, const void* u, double* sums_dev) {
+  KT_CHECK_ARG(h && u && sums_dev, "kt_outlet_sums: null argument");
+  KT_DEV_GUARD(h);
+  KT_CH_ARGS_OK(P);
+  CP S = make_cp(P);
+  if (h->dtype == KT_F64) k_ch_outlet_sums<double><<<1, 256, 0, h->stream>>>(S, (const double*)u, h->red_out);
+  else k_ch_outlet_sums<float><<<1, 256, 0, h->stream>>>(S, (const float*)u, h->red_out);
+  KT_LAUNCH_CHECK(h);
+  KT_CUDA(cudaMemcpyAsync(sums_dev, h->red_out, 2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
+int kt_outlet_apply(kt_handle_t h, const kt_channel_params* P, void* u, double inlet_sum, double outlet_sum) {
+  KT_CHECK_ARG(h && u, "kt_outlet_apply: null argument");
+  KT_DEV_GUARD(h);
+  KT_CH_ARGS_OK(P);
+  CP S = make_cp(P);
+  const double ratio = inlet_sum / outlet_sum;        // karman_taichi.py:598 (the same IEEE division the device performs)
+  if (h->dtype == KT_F64) k_ch_outlet_apply<double><<<1, 256, 0, h->stream>>>(S, (double*)u, nullptr, ratio);
+  else k_ch_outlet_apply<float><<<1, 256, 0, h->stream>>>(S, (float*)u, nullptr, ratio);
+  KT_LAUNCH_CHECK(h);
+  return 0;
+}
+
+int kt_channel_udiv(kt_handle_t h, const kt_channel_params* P, const void* u, const void* v, void* udiv) {
+  KT_CHECK_ARG(h && u && v && udiv, "kt_channel_udiv: null argument");
+  KT_DEV_GUARD(h);
+  KT_CH_ARGS_OK(P);
+  CP S = make_cp(P);
+  return outlet_udiv(h, P, S, u, v, udiv);
 }
 
 int kt_channel_correct(kt_handle_t h, const kt_channel_params* P, const int* ct, void* u, void* v, void* p, const void* pcor,
@@ -325,7 +399,7 @@ int kt_channel_correct(kt_handle_t h, const kt_channel_params* P, const int* ct,
   KT_CH_ARGS_OK(P);
   CP S = make_cp(P);
   const int gx = (P->ny + 3 + 255) / 256;
-  int gy = h->max_blocks / gx; if (gy > P->nx + 2) gy = P->nx + 2; if (gy < 1) gy = 1;
+  int gy = h->max_blocks / gx; if (gy > S.ib - S.ia) gy = S.ib - S.ia; if (gy > 65535) gy = 65535; if (gy < 1) gy = 1;
   dim3 grid(gx, gy);
   if (h->dtype == KT_F64)
     k_ch_correct<double><<<grid, 256, 0, h->stream>>>(S, ct, (double*)u, (double*)v, (double*)p, (const double*)pcor, (const double*)coef_u,

@@ -36,6 +36,7 @@ struct kt_handle_s {
   unsigned long long graph_clock = 0;
   // x-slab peer-memory solves (kt_p2p_*): solve epoch and exchange counters behind the flag sequence numbers
   unsigned long long p2p_epoch = 0, p2p_halo_k[3] = {0, 0, 0}, p2p_dot_k[3] = {0, 0, 0};
+  unsigned long long p2p_xchg_seq = 0, p2p_red_seq = 0;      // standalone exchanges / all-reduces (kt_p2p_exchange, kt_p2p_allreduce)
   // optional per-kernel-class device timing (bench.py roofline): events bracket every launch of a class
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs (begin, end)

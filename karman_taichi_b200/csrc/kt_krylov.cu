@@ -930,10 +930,14 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
 // Slot reuse of the sums: passing a sum proves that every rank has WRITTEN its slot, not that every rank has READ all of
 // them, so two consecutive sums never share a slot group: BiCGSTAB INIT 2, ALPHA 0, OMEGA 1, END 2; CG INIT 1, ALPHA 0,
 // END 1 (a rank can be at most one sum ahead of the slowest reader of the previous one).
+// Solves use sum groups 0-2 and halo slots 0-2 (p / v / r); the standalone calls (kt_p2p_exchange, kt_p2p_allreduce: the
+// SIMPLE kernels around the solves) rotate over their own sum groups 3-5 and halo slots 3-4, so that two consecutive
+// exchanges never meet in a slot a slow neighbour may still be reading.
+constexpr int P2P_GROUPS = 6, P2P_SLOTS = 5;
 struct P2PBlock {                     // layout of the comm block every rank allocates (zero-initialised)
-  double dots[3][16][2];
-  unsigned long long dot_flag[3][16];
-  unsigned long long halo_flag[3][2]; // [plane p/v/r][0: from lower neighbour, 1: from upper neighbour]
+  double dots[P2P_GROUPS][16][2];
+  unsigned long long dot_flag[P2P_GROUPS][16];
+  unsigned long long halo_flag[P2P_SLOTS][2]; // [slot][0: from lower neighbour, 1: from upper neighbour]
 };
 
 __device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flag, unsigned long long seq, Scalars* sc) {
@@ -953,13 +957,13 @@ __device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flag
 template <typename T>
 __global__ void __launch_bounds__(1024) k_p2p_halo(T* plane, int pitch, int row_first, int row_last, T* recv_lo, T* recv_hi, T* recv_mine,
                                                    P2PBlock* mine, P2PBlock* blk_lo, P2PBlock* blk_hi, int which, unsigned long long seq,
-                                                   Scalars* sc) {
+                                                   Scalars* sc, int in_solve) {
   constexpr int V = VT<T>::V;
   __shared__ int ok;
   // Once the solve is over (every rank reaches `done` at the same logical step, from identical sums) nobody needs
   // another row: return without signalling or waiting, so ranks whose hosts enqueued a different number of surplus
-  // iterations never wait for each other.
-  if (sc->done) return;
+  // iterations never wait for each other.  (A standalone exchange is unconditional.)
+  if (in_solve && sc->done) return;
   const int side = blockIdx.x;                                   // 0: talk to the lower neighbour, 1: to the upper one
   T* peer = side == 0 ? recv_lo : recv_hi;
   if (!peer) return;
@@ -986,9 +990,9 @@ __global__ void __launch_bounds__(1024) k_p2p_halo(T* plane, int pitch, int row_
 struct P2PPeers { P2PBlock* blk[16]; };
 
 __global__ void k_p2p_reduce(P2PPeers peers, int rank, int nranks, int group, int ndot, const double* local, int fin,
-                             unsigned long long seq, Scalars* sc, double* history, long long cap) {
+                             unsigned long long seq, Scalars* sc, double* history, long long cap, int in_solve, int op_max) {
   const int lane = threadIdx.x;
-  if (sc->done) return;
+  if (in_solve && sc->done) return;
   P2PBlock* mine = peers.blk[rank];
   if (lane < nranks) {
     P2PBlock* pb = peers.blk[lane];
@@ -999,11 +1003,11 @@ __global__ void k_p2p_reduce(P2PPeers peers, int rank, int nranks, int group, in
     p2p_wait(&mine->dot_flag[group][lane], seq, sc);
   }
   __syncwarp();
-  if (lane == 0 && !sc->done) {
+  if (lane == 0 && (!in_solve || !sc->done)) {
     double d0 = 0.0, d1 = 0.0;
-    for (int r = 0; r < nranks; ++r) {
-      d0 += *(volatile double*)&mine->dots[group][r][0];
-      d1 += *(volatile double*)&mine->dots[group][r][1];
+    for (int r = 0; r < nranks; ++r) {          // rank order: the same bits on every rank
+      const double a0 = *(volatile double*)&mine->dots[group][r][0], a1 = *(volatile double*)&mine->dots[group][r][1];
+      if (op_max) { d0 = fmax(d0, a0); d1 = fmax(d1, a1); } else { d0 += a0; d1 += a1; }
     }
     scalar_algebra(fin, sc, d0, d1, history, cap);
   }
@@ -1018,7 +1022,7 @@ struct P2PCtx {
   unsigned long long base;
 };
 
-static int p2p_begin(kt_handle_s* h, const kt_p2p_comm* cm, P2PCtx* c) {
+static int p2p_begin(kt_handle_s* h, const kt_p2p_comm* cm, P2PCtx* c, bool new_solve = true) {
   KT_CHECK_ARG(cm->nranks >= 1 && cm->nranks <= 16 && cm->rank >= 0 && cm->rank < cm->nranks, "kt_p2p_comm: bad rank / nranks (max 16)");
   c->h = h; c->cm = cm;
   for (int k = 0; k < 16; ++k) c->peers.blk[k] = k < cm->nranks ? (P2PBlock*)cm->comm_block[k] : nullptr;
@@ -1030,9 +1034,26 @@ static int p2p_begin(kt_handle_s* h, const kt_p2p_comm* cm, P2PCtx* c) {
   KT_CHECK_ARG(cm->nranks == 1 || cm->halo_recv, "kt_p2p_comm: halo_recv missing");
   KT_CHECK_ARG((cm->rank == 0 || cm->peer_halo_recv[0]) && (cm->rank == cm->nranks - 1 || cm->peer_halo_recv[1]),
                "kt_p2p_comm: a neighbour's halo-receive buffer is not mapped");
+  if (!new_solve) return 0;
   ++h->p2p_epoch;
   for (int k = 0; k < 3; ++k) h->p2p_halo_k[k] = h->p2p_dot_k[k] = 0;
   c->base = h->p2p_epoch << 32;
+  return 0;
+}
+
+// Standalone halo exchange of one plane (the SIMPLE kernels between the solves read u, v, p, p' and ap_u one row beyond
+// the slab): same kernel, own rotating slots.
+template <typename T>
+static int t_p2p_exchange(kt_handle_s* h, const kt_p2p_comm* cm, void* plane) {
+  P2PCtx c;
+  int rc = p2p_begin(h, cm, &c, false);
+  if (rc) return rc;
+  if (cm->nranks == 1) return 0;
+  const unsigned long long seq = ++h->p2p_xchg_seq;
+  const int slot = 3 + (int)(seq & 1ull);
+  k_p2p_halo<T><<<2, 1024, 0, h->stream>>>((T*)plane, h->pitch, h->row_lo, h->row_hi - 1, (T*)cm->peer_halo_recv[0], (T*)cm->peer_halo_recv[1],
+                                           (T*)cm->halo_recv, c.mine, c.blk_lo, c.blk_hi, slot, seq, h->sc, 0);
+  KT_LAUNCH_CHECK(h);
   return 0;
 }
 
@@ -1042,7 +1063,7 @@ static int p2p_halo(P2PCtx& c, int which, T* plane) {
   if (c.cm->nranks == 1) return 0;
   ++h->p2p_halo_k[which];
   k_p2p_halo<T><<<2, 1024, 0, h->stream>>>(plane, h->pitch, h->row_lo, h->row_hi - 1, (T*)c.cm->peer_halo_recv[0], (T*)c.cm->peer_halo_recv[1],
-                                           (T*)c.cm->halo_recv, c.mine, c.blk_lo, c.blk_hi, which, c.base | h->p2p_halo_k[which], h->sc);
+                                           (T*)c.cm->halo_recv, c.mine, c.blk_lo, c.blk_hi, which, c.base | h->p2p_halo_k[which], h->sc, 1);
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -1051,7 +1072,7 @@ static int p2p_reduce(P2PCtx& c, int group, int ndot, int fin, double* history, 
   kt_handle_s* h = c.h;
   ++h->p2p_dot_k[group];
   k_p2p_reduce<<<1, 32, 0, h->stream>>>(c.peers, c.cm->rank, c.cm->nranks, group, ndot, c.dots, fin, c.base | h->p2p_dot_k[group], h->sc,
-                                        history, cap);
+                                        history, cap, 1, 0);
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -1327,6 +1348,30 @@ int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* 
   KT_DEV_GUARD(h);
   return KT_DISPATCH(h, t_p2p_bicgstab<double>(h, coef, b, x, Minv, ws, comm, eps, max_iter, flags, fixed_iters != 0, iters, rel_res, status),
                      t_p2p_bicgstab<float>(h, coef, b, x, Minv, ws, comm, eps, max_iter, flags, fixed_iters != 0, iters, rel_res, status));
+}
+
+int kt_p2p_halo_slots(void) { return P2P_SLOTS; }
+
+int kt_p2p_exchange(kt_handle_t h, const kt_p2p_comm* comm, void* plane) {
+  KT_CHECK_ARG(h && comm && plane, "kt_p2p_exchange: null argument");
+  KT_DEV_GUARD(h);
+  return KT_DISPATCH(h, t_p2p_exchange<double>(h, comm, plane), t_p2p_exchange<float>(h, comm, plane));
+}
+
+int kt_p2p_allreduce(kt_handle_t h, const kt_p2p_comm* comm, const double* vals_dev2, int op, double* out_host2) {
+  KT_CHECK_ARG(h && comm && vals_dev2 && out_host2 && (op == 0 || op == 1), "kt_p2p_allreduce: bad argument");
+  KT_DEV_GUARD(h);
+  P2PCtx c;
+  int rc = p2p_begin(h, comm, &c, false);
+  if (rc) return rc;
+  const unsigned long long seq = ++h->p2p_red_seq;
+  const int group = 3 + (int)(seq % 3ull);
+  k_p2p_reduce<<<1, 32, 0, h->stream>>>(c.peers, comm->rank, comm->nranks, group, 2, vals_dev2, FIN_NONE, seq, h->sc, nullptr, 0, 0, op);
+  KT_LAUNCH_CHECK(h);
+  rc = read_dots(h, out_host2, 2);
+  if (rc) return rc;
+  if (h->sc_host->status == KT_STATUS_COMM_TIMEOUT && h->sc_host->done) { set_error("kt_p2p_allreduce: a peer rank never signalled"); return -5; }
+  return 0;
 }
 
 int kt_p2p_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws, const kt_p2p_comm* comm,

@@ -37,6 +37,17 @@ class SlabPartition:
         for r in range(self.nranks):
             self.bounds.append(self.bounds[-1] + base + (1 if r < rem else 0))
 
+    @classmethod
+    def from_bounds(cls, bounds):
+        """Explicit block boundaries ``[0, b1, ..., NX]`` (the u-type planes of the staggered grid have one row more than the
+        cell-centred ones and must still be cut at the same rows)."""
+        bounds = [int(b) for b in bounds]
+        if bounds[0] != 0 or any(b1 <= b0 for b0, b1 in zip(bounds, bounds[1:])):
+            raise ValueError('bounds must start at 0 and increase strictly')
+        self = cls.__new__(cls)
+        self.NX, self.nranks, self.bounds = bounds[-1], len(bounds) - 1, bounds
+        return self
+
     def owned(self, rank):
         """Global row range owned by ``rank``."""
         return self.bounds[rank], self.bounds[rank + 1]
@@ -289,7 +300,7 @@ class P2PSlabSolver:
     (``karman_taichi.py:342-456``), as on ``BICGSolver``.  ``ipc_planes=True`` (measurement aid) puts r / p / v themselves
     into IPC-exported allocations, which is how round 1 ran (profiles/r02_p2p.md)."""
 
-    def __init__(self, coef, b, x, part: SlabPartition, rank, group=None, ipc_planes=False):
+    def __init__(self, coef, b, x, part: SlabPartition, rank, group=None, ipc_planes=False, peers='ipc'):
         from .cgsolver import _Handle
         from .field import Field
         self.coef, self.b, self.x, self.part, self.rank = coef, b, x, part, rank
@@ -309,17 +320,25 @@ class P2PSlabSolver:
         self._r_tld = None
         self.Minv, self.warm_start, self.omega_zero_break = None, False, False
         # what neighbours write into: boundary rows (3 planes x 2 sides x pitch) and every rank's sums / flags
-        self._halo = _IpcBuffer(self._hd, 6 * b.pitch * esize)
+        self._halo = _IpcBuffer(self._hd, int(self.lib.kt_p2p_halo_slots()) * 2 * b.pitch * esize)
         self._blk = _IpcBuffer(self._hd, int(self.lib.kt_p2p_comm_block_bytes()))
         self.dots = torch.zeros(2, dtype=torch.float64, device=b.device)
+        self.red_in = torch.zeros(2, dtype=torch.float64, device=b.device)
+        self.iterations, self.status, self.rel_res = 0, 0, float('nan')
+        self._mapped = []
         n = part.nranks
+        if peers == 'local':
+            # all ranks live in THIS process (one thread and one stream each, any number of them on one GPU): the buffers are
+            # reachable by their own addresses -- connect_local() wires them once every rank's solver exists.  This is how the
+            # real comm kernels are tested on a single-GPU box.
+            self.comm = None
+            return
         mine = {'halo': self._halo.handle_bytes(), 'blk': self._blk.handle_bytes()}
         descs = [None] * n
         if n > 1:
             dist.all_gather_object(descs, mine, group=group)
         else:
             descs[0] = mine
-        self._mapped = []
 
         def open_(hb):
             out = C.c_void_p()
@@ -351,7 +370,36 @@ class P2PSlabSolver:
                                    'x-slab peer-memory setup failed on another rank')
         elif err:
             raise err
-        self.iterations, self.status, self.rel_res = 0, 0, float('nan')
+
+    @staticmethod
+    def connect_local(solvers):
+        """Wire the comm structs of P solvers built with ``peers='local'`` (index = rank)."""
+        n = len(solvers)
+        for r, s in enumerate(solvers):
+            cm = _lib.P2PComm()
+            cm.rank, cm.nranks = r, n
+            for k in range(16):
+                cm.comm_block[k] = solvers[k]._blk.ptr if k < n else None
+            cm.peer_halo_recv[0] = solvers[r - 1]._halo.ptr if r > 0 else None
+            cm.peer_halo_recv[1] = solvers[r + 1]._halo.ptr if r < n - 1 else None
+            cm.halo_recv = s._halo.ptr
+            cm.local_dots = s.dots.data_ptr()
+            s.comm = cm
+
+    def exchange(self, plane_ptr):
+        """Boundary rows of one plane of this system's geometry to / from the two neighbours (``kt_p2p_exchange``)."""
+        self._hd.use_current_stream()
+        _lib.check(self.lib.kt_p2p_exchange(self._hd.h, C.byref(self.comm), C.c_void_p(plane_ptr)))
+
+    def allreduce(self, a, b=0.0, op='sum', device_pair=None):
+        """Two doubles reduced over the ranks in rank order (``kt_p2p_allreduce``); returns the pair."""
+        self._hd.use_current_stream()
+        if device_pair is None:
+            self.red_in.copy_(torch.tensor([a, b], dtype=torch.float64), non_blocking=False)
+            device_pair = self.red_in
+        out = (C.c_double * 2)()
+        _lib.check(self.lib.kt_p2p_allreduce(self._hd.h, C.byref(self.comm), C.c_void_p(device_pair.data_ptr()), 1 if op == 'max' else 0, out))
+        return out[0], out[1]
 
     def __del__(self):
         try:

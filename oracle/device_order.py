@@ -229,9 +229,9 @@ class DeviceOrder:
 
 class SlabOrder:
     """x-slab solve: every rank adds its owned rows in the streaming order, then the ranks are added in rank order
-    (``k_p2p_reduce``; the NCCL path's all-reduce order is NCCL's own and is not restated)."""
+    (``k_p2p_reduce``; the NCCL path's all-reduce order is NCCL's own and is not restated).  ``pre``: the Jacobi variant."""
 
-    def __init__(self, shape, bounds, is_cg=False, num_sms=148):
+    def __init__(self, shape, bounds, is_cg=False, pre=False, num_sms=148):
         self.bounds = list(bounds)
         self.shape = shape
         self.ranks = []
@@ -240,7 +240,7 @@ class SlabOrder:
             g1 = self.bounds[r + 1] + (1 if r < len(self.bounds) - 2 else 0)
             l0 = self.bounds[r] - g0
             l1 = l0 + self.bounds[r + 1] - self.bounds[r]
-            self.ranks.append((g0, g1, DeviceOrder((g1 - g0, shape[1]), is_cg=is_cg, enable=0, num_sms=num_sms, rows=(l0, l1),
+            self.ranks.append((g0, g1, DeviceOrder((g1 - g0, shape[1]), is_cg=is_cg, pre=pre, enable=0, num_sms=num_sms, rows=(l0, l1),
                                                    xr_unit=True)))
 
     def __call__(self, kind, prod):
@@ -248,6 +248,24 @@ class SlabOrder:
         for g0, g1, order in self.ranks:
             d = d + order(kind, prod[g0:g1])
         return float(d)
+
+
+class SlabAutoOrder:
+    """SIMPLE on x-slabs (``SlabKarmanSolver``): dispatches on the shape of the products to the ``SlabOrder`` of that system;
+    ``bounds_by_rows`` maps the number of global rows of a plane to its slab boundaries.  The inlet / outlet column sums of
+    ``correct_conserv`` live on one rank each and are added to zeros in rank order: the single-GPU order."""
+
+    def __init__(self, bounds_by_rows, jacobi=True, num_sms=148):
+        self.bounds_by_rows, self.jacobi, self.num_sms = dict(bounds_by_rows), jacobi, num_sms
+        self._orders = {}
+
+    def __call__(self, kind, prod):
+        if kind == 'column':
+            return column_sum(prod)
+        key = (prod.shape, kind.startswith('cg_'))
+        if key not in self._orders:
+            self._orders[key] = SlabOrder(prod.shape, self.bounds_by_rows[prod.shape[0]], is_cg=key[1], pre=self.jacobi, num_sms=self.num_sms)
+        return self._orders[key](kind, prod)
 
 
 def column_sum(a):
