@@ -71,6 +71,16 @@ WORDS_PER_CELL_ITER = {'bicgstab': 28, 'cg': 16}      # algorith
 TRAFFIC_JSON = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
 
 
+_JSON_OUT = sys.stdout
+
+
+def emit(line):
+    """the ONE JSON line goes to the process's real stdout; everything else the run prints (the reference's own messages such
+    as '>>> BICG failed at first place...' that the class mirror reproduces) is diverted to stderr in main()"""
+    _JSON_OUT.write(json.dumps(line) + '\n')
+    _JSON_OUT.flush()
+
+
 def measured_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of every kernel, as ncu measured them on the default command
     (tools/gpu_job.sh launches -> tools/ncu_summary.py --json), with the commit the capture was taken at.  Scaled by plane
@@ -239,7 +249,7 @@ def run_reference(a):
             'note': 'Taichi ti.cpu itself cannot run offline (no taichi wheel for this Python); C/OpenMP port of cgsolver.py/bicgsolver.py, '
                     'pinned to the reference-run golden vectors through the oracle (tests/test_reference_golden.py, tests/test_oracle_cport.py)',
             'wall_s': total}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -494,7 +504,7 @@ def run_ours(a):
         dist.init_process_group('nccl', device_id=dev)
     line = krylov_line(a, torch, dist, world, rank, dev)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -707,7 +717,7 @@ def run_simple_reference(a):
             'cpu_baseline': {'value': val, 'unit': SIMPLE_UNIT, 'cores': 1, 'kind': 'port', 'sample': sample},
             'e2e': {'value': val, 'unit': SIMPLE_UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'note': 'Taichi ti.cpu itself cannot run offline; NumPy restatement of the reference (oracle/)'}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -864,7 +874,7 @@ def run_simple(a):
         dist.init_process_group('nccl', device_id=dev)
     line = simple_line(a, torch, dist, world, rank, dev, a.workload)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -890,6 +900,7 @@ def main():
     ap.add_argument('--no-secondary', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     a = ap.parse_args()
+    sys.stdout = sys.stderr                            # stdout carries the JSON line only (emit)
     if a.warmup < 3 and a.impl == 'ours':
         a.warmup = 3                                   # timing rules: W >= 3
     if a.workload in SIMPLE_WORKLOADS:
