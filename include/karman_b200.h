@@ -80,6 +80,11 @@ int kt_set_rows(kt_handle_t h, int row_lo, int row_hi);
  * instead of 3-4 launches per iteration.  enable: 1 automatic (default), 0 streaming kernels only, 2 cooperative kernel
  * only, 3 cluster kernel only. */
 int kt_set_cluster(kt_handle_t h, int enable);
+/* Load every kernel of the library on the handle's device now (CUDA loads device functions lazily, at their first launch, and
+ * that load may wait for the device to go idle).  Returns the number of kernels (> 0) or < 0.  No reference counterpart (Taichi
+ * JIT-compiles at first call); required before kernels of different streams wait for each other on ONE device -- the in-process
+ * multi-rank mode of the x-slab solvers (slab.py, peers='local') -- and harmless otherwise. */
+int kt_preload_kernels(kt_handle_t h);
 /* number of kernels launched through this handle so far (bench.py: gpu_launches) */
 long long kt_launch_count(kt_handle_t h);
 

@@ -92,6 +92,7 @@ SIGNATURES = {
     'kt_set_rows': (_I, [_P, _I, _I]),
     'kt_launch_count': (C.c_longlong, [_P]),
     'kt_set_cluster': (_I, [_P, _I]),
+    'kt_preload_kernels': (_I, [_P]),
     'kt_upload_field': (_I, [_P, _P, _P]),
     'kt_download_field': (_I, [_P, _P, _P]),
     'kt_upload_coef': (_I, [_P, _P, _P, _P, C.c_size_t]),

@@ -194,6 +194,20 @@ int kt_ipc_free(kt_handle_t h, void* dev_ptr) {
   return 0;
 }
 
+int kt_preload_kernels(kt_handle_t h) {
+  KT_CHECK_ARG(h, "kt_preload_kernels: null handle");
+  KT_DEV_GUARD(h);
+  int (*const tus[])() = {kt::preload_kt_api, kt::preload_kt_krylov, kt::preload_kt_simple, kt::preload_kt_channel, kt::preload_kt_cluster,
+                          kt::preload_kt_coop, kt::preload_kt_post};
+  int total = 0;
+  for (auto f : tus) {
+    const int n = f();
+    if (n < 0) { set_error("kt_preload_kernels: a kernel of this library could not be loaded on this device"); return -4; }
+    total += n;
+  }
+  return total;
+}
+
 int kt_set_cluster(kt_handle_t h, int enable) {
   KT_CHECK_ARG(h, "kt_set_cluster: null handle");
   KT_DEV_GUARD(h);
@@ -283,3 +297,15 @@ int kt_bicgstab_solve_host(kt_handle_t h, const void* coef_host_aos, const void*
 }
 
 }  // extern "C"
+
+// every kernel of this translation unit, for kt_preload_kernels (kt_handle.h)
+namespace kt {
+int preload_kt_api() {
+  static const void* const fns[] = {
+#define KT_PRELOAD_TU_kt_api
+#include "kt_preload_list.inc"
+#undef KT_PRELOAD_TU_kt_api
+      nullptr};
+  return preload_list(fns);
+}
+}  // namespace kt

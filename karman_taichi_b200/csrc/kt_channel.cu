@@ -412,3 +412,15 @@ int kt_channel_correct(kt_handle_t h, const kt_channel_params* P, const int* ct,
 }
 
 }  // extern "C"
+
+// every kernel of this translation unit, for kt_preload_kernels (kt_handle.h)
+namespace kt {
+int preload_kt_channel() {
+  static const void* const fns[] = {
+#define KT_PRELOAD_TU_kt_channel
+#include "kt_preload_list.inc"
+#undef KT_PRELOAD_TU_kt_channel
+      nullptr};
+  return preload_list(fns);
+}
+}  // namespace kt

@@ -858,3 +858,15 @@ template int cluster_try_solve<float>(kt_handle_s*, const void*, const void*, vo
                                       long long, int, bool);
 
 }  // namespace kt
+
+// every kernel of this translation unit, for kt_preload_kernels (kt_handle.h)
+namespace kt {
+int preload_kt_cluster() {
+  static const void* const fns[] = {
+#define KT_PRELOAD_TU_kt_cluster
+#include "kt_preload_list.inc"
+#undef KT_PRELOAD_TU_kt_cluster
+      nullptr};
+  return preload_list(fns);
+}
+}  // namespace kt

@@ -122,6 +122,9 @@ struct Scalars {
   int done;                               // every kernel of the solve returns at once when set
   int first;                              // 1 until the first p-update has run (p = r: bicgsolver.py:99-100)
   int flags;
+  // x-slab peer-memory waits that gave up (KT_STATUS_COMM_TIMEOUT): which flag (kind << 8 | slot / group, << 16 | peer lane),
+  // the sequence number it waited for and the value it last saw -- goes into kt_last_error
+  unsigned long long wait_what, wait_seq, wait_seen;
 };
 
 // Kinds of scalar algebra run by the finalising block.

@@ -472,3 +472,15 @@ template int coop_try_solve<float>(kt_handle_s*, const void*, const void*, void*
                                    long long, int, bool);
 
 }  // namespace kt
+
+// every kernel of this translation unit, for kt_preload_kernels (kt_handle.h)
+namespace kt {
+int preload_kt_coop() {
+  static const void* const fns[] = {
+#define KT_PRELOAD_TU_kt_coop
+#include "kt_preload_list.inc"
+#undef KT_PRELOAD_TU_kt_coop
+      nullptr};
+  return preload_list(fns);
+}
+}  // namespace kt

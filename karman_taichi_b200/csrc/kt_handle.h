@@ -35,7 +35,7 @@ struct kt_handle_s {
   int graphs_state = 0;              // 0 untested, 1 usable, -1 unavailable (capture refused)
   unsigned long long graph_clock = 0;
   // x-slab peer-memory solves (kt_p2p_*): solve epoch and exchange counters behind the flag sequence numbers
-  unsigned long long p2p_epoch = 0, p2p_halo_k[3] = {0, 0, 0}, p2p_dot_k[3] = {0, 0, 0};
+  unsigned long long p2p_epoch = 0, p2p_halo_k[3] = {0, 0, 0}, p2p_dot_k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long p2p_xchg_seq = 0, p2p_red_seq = 0;      // standalone exchanges / all-reduces (kt_p2p_exchange, kt_p2p_allreduce)
   // optional per-kernel-class device timing (bench.py roofline): events bracket every launch of a class
   bool prof_on = false;
@@ -111,3 +111,22 @@ struct DeviceGuard {
     cudaError_t _e = cudaGetLastError();             \
     if (_e != cudaSuccess) return kt::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
   } while (0)
+
+// ---- kernel preloading (kt_preload_kernels) ---------------------------------------------------------------------------------
+// CUDA loads device functions lazily, at their first launch, and that load may have to wait until the device is idle.  Kernels of
+// this library WAIT FOR EACH OTHER across streams (the x-slab peer-memory exchange): when all ranks share one device (in-process
+// multi-rank mode) a rank spinning for a neighbour whose next kernel is still being loaded would dead-lock.  Every translation
+// unit lists its kernels (kt_preload_list.inc, generated from the compiled objects) and loads them up front.
+#define KT_K(...) (const void*)&__VA_ARGS__,
+namespace kt {
+inline int preload_list(const void* const* fns) {
+  int n = 0;
+  for (; fns[n]; ++n) {
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, fns[n]) != cudaSuccess) { cudaGetLastError(); return -1 - n; }
+  }
+  return n;
+}
+int preload_kt_api(); int preload_kt_krylov(); int preload_kt_simple(); int preload_kt_channel(); int preload_kt_cluster();
+int preload_kt_coop(); int preload_kt_post();
+}  // namespace kt

@@ -928,23 +928,30 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
 // Write-after-read safety: a neighbour can only overwrite a receive row of iteration k after it has seen this rank's
 // sums of a later kernel (the sums are published after the halo kernel that copied the row out, in stream order).
 // Slot reuse of the sums: passing a sum proves that every rank has WRITTEN its slot, not that every rank has READ all of
-// them, so two consecutive sums never share a slot group: BiCGSTAB INIT 2, ALPHA 0, OMEGA 1, END 2; CG INIT 1, ALPHA 0,
-// END 1 (a rank can be at most one sum ahead of the slowest reader of the previous one).
-// Solves use sum groups 0-2 and halo slots 0-2 (p / v / r); the standalone calls (kt_p2p_exchange, kt_p2p_allreduce: the
+// them, so two consecutive sums never share a slot group: BiCGSTAB INIT I, ALPHA 0, OMEGA 1, END 2; CG INIT I, ALPHA 0,
+// END 1 (a rank can be at most one sum ahead of the slowest reader of the previous one).  I = 6 + (solve epoch & 1): the
+// INIT sum of a solve follows the last sum of the PREVIOUS solve on the same handle, whichever that was (END, or INIT itself
+// when the right-hand side was already converged), so it alternates between two groups of its own.
+// Solves use sum groups 0-2, 6-7 and halo slots 0-2 (p / v / r); the standalone calls (kt_p2p_exchange, kt_p2p_allreduce: the
 // SIMPLE kernels around the solves) rotate over their own sum groups 3-5 and halo slots 3-4, so that two consecutive
 // exchanges never meet in a slot a slow neighbour may still be reading.
-constexpr int P2P_GROUPS = 6, P2P_SLOTS = 5;
+constexpr int P2P_GROUPS = 8, P2P_SLOTS = 5;
 struct P2PBlock {                     // layout of the comm block every rank allocates (zero-initialised)
   double dots[P2P_GROUPS][16][2];
   unsigned long long dot_flag[P2P_GROUPS][16];
   unsigned long long halo_flag[P2P_SLOTS][2]; // [slot][0: from lower neighbour, 1: from upper neighbour]
 };
 
-__device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flag, unsigned long long seq, Scalars* sc) {
-  const long long t0 = clock64();
-  while (*flag < seq) {
+__device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flag, unsigned long long seq, Scalars* sc, long long timeout_ns,
+                                         unsigned what) {
+  unsigned long long t0 = 0, seen;
+  while ((seen = *flag) < seq) {
     __nanosleep(32);
-    if (clock64() - t0 > 60000000000LL) {  // ~30 s: a peer died or the ranks disagree on the schedule -- fail, never hang
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    if ((long long)(now - t0) > timeout_ns) {  // a peer died or the ranks disagree on the schedule -- fail, never hang
+      sc->wait_what = what; sc->wait_seq = seq; sc->wait_seen = seen;
       *(volatile int*)&sc->status = 7; *(volatile int*)&sc->done = 1;
       return false;
     }
@@ -953,11 +960,17 @@ __device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flag
   return true;
 }
 
+// how long a wait may last (default 30 s; KT_P2P_TIMEOUT_MS: tests use a short one)
+static long long p2p_timeout_ns() {
+  static long long ns = (long long)env_int("KT_P2P_TIMEOUT_MS", 30000) * 1000000LL;
+  return ns;
+}
+
 // halo-receive buffer of a rank: [plane p/v/r][0: row from the lower neighbour, 1: row from the upper neighbour][pitch]
 template <typename T>
 __global__ void __launch_bounds__(1024) k_p2p_halo(T* plane, int pitch, int row_first, int row_last, T* recv_lo, T* recv_hi, T* recv_mine,
                                                    P2PBlock* mine, P2PBlock* blk_lo, P2PBlock* blk_hi, int which, unsigned long long seq,
-                                                   Scalars* sc, int in_solve) {
+                                                   Scalars* sc, int in_solve, long long timeout_ns) {
   constexpr int V = VT<T>::V;
   __shared__ int ok;
   // Once the solve is over (every rank reaches `done` at the same logical step, from identical sums) nobody needs
@@ -977,7 +990,7 @@ __global__ void __launch_bounds__(1024) k_p2p_halo(T* plane, int pitch, int row_
     P2PBlock* pb = side == 0 ? blk_lo : blk_hi;
     volatile unsigned long long* f = &pb->halo_flag[which][side == 0 ? 1 : 0];
     *f = seq;
-    ok = p2p_wait(&mine->halo_flag[which][side == 0 ? 0 : 1], seq, sc) ? 1 : 0;
+    ok = p2p_wait(&mine->halo_flag[which][side == 0 ? 0 : 1], seq, sc, timeout_ns, 1u << 8 | (unsigned)which | (unsigned)side << 16) ? 1 : 0;
   }
   __syncthreads();
   if (!ok) return;
@@ -990,7 +1003,8 @@ __global__ void __launch_bounds__(1024) k_p2p_halo(T* plane, int pitch, int row_
 struct P2PPeers { P2PBlock* blk[16]; };
 
 __global__ void k_p2p_reduce(P2PPeers peers, int rank, int nranks, int group, int ndot, const double* local, int fin,
-                             unsigned long long seq, Scalars* sc, double* history, long long cap, int in_solve, int op_max) {
+                             unsigned long long seq, Scalars* sc, double* history, long long cap, int in_solve, int op_max,
+                             long long timeout_ns) {
   const int lane = threadIdx.x;
   if (in_solve && sc->done) return;
   P2PBlock* mine = peers.blk[rank];
@@ -1000,7 +1014,7 @@ __global__ void k_p2p_reduce(P2PPeers peers, int rank, int nranks, int group, in
     pb->dots[group][rank][1] = ndot > 1 ? local[1] : 0.0;
     __threadfence_system();
     *(volatile unsigned long long*)&pb->dot_flag[group][rank] = seq;
-    p2p_wait(&mine->dot_flag[group][lane], seq, sc);
+    p2p_wait(&mine->dot_flag[group][lane], seq, sc, timeout_ns, 2u << 8 | (unsigned)group | (unsigned)lane << 16);
   }
   __syncwarp();
   if (lane == 0 && (!in_solve || !sc->done)) {
@@ -1036,7 +1050,8 @@ static int p2p_begin(kt_handle_s* h, const kt_p2p_comm* cm, P2PCtx* c, bool new_
                "kt_p2p_comm: a neighbour's halo-receive buffer is not mapped");
   if (!new_solve) return 0;
   ++h->p2p_epoch;
-  for (int k = 0; k < 3; ++k) h->p2p_halo_k[k] = h->p2p_dot_k[k] = 0;
+  for (int k = 0; k < 3; ++k) h->p2p_halo_k[k] = 0;
+  for (int k = 0; k < 8; ++k) h->p2p_dot_k[k] = 0;
   c->base = h->p2p_epoch << 32;
   return 0;
 }
@@ -1052,7 +1067,7 @@ static int t_p2p_exchange(kt_handle_s* h, const kt_p2p_comm* cm, void* plane) {
   const unsigned long long seq = ++h->p2p_xchg_seq;
   const int slot = 3 + (int)(seq & 1ull);
   k_p2p_halo<T><<<2, 1024, 0, h->stream>>>((T*)plane, h->pitch, h->row_lo, h->row_hi - 1, (T*)cm->peer_halo_recv[0], (T*)cm->peer_halo_recv[1],
-                                           (T*)cm->halo_recv, c.mine, c.blk_lo, c.blk_hi, slot, seq, h->sc, 0);
+                                           (T*)cm->halo_recv, c.mine, c.blk_lo, c.blk_hi, slot, seq, h->sc, 0, p2p_timeout_ns());
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -1063,7 +1078,7 @@ static int p2p_halo(P2PCtx& c, int which, T* plane) {
   if (c.cm->nranks == 1) return 0;
   ++h->p2p_halo_k[which];
   k_p2p_halo<T><<<2, 1024, 0, h->stream>>>(plane, h->pitch, h->row_lo, h->row_hi - 1, (T*)c.cm->peer_halo_recv[0], (T*)c.cm->peer_halo_recv[1],
-                                           (T*)c.cm->halo_recv, c.mine, c.blk_lo, c.blk_hi, which, c.base | h->p2p_halo_k[which], h->sc, 1);
+                                           (T*)c.cm->halo_recv, c.mine, c.blk_lo, c.blk_hi, which, c.base | h->p2p_halo_k[which], h->sc, 1, p2p_timeout_ns());
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -1072,7 +1087,7 @@ static int p2p_reduce(P2PCtx& c, int group, int ndot, int fin, double* history, 
   kt_handle_s* h = c.h;
   ++h->p2p_dot_k[group];
   k_p2p_reduce<<<1, 32, 0, h->stream>>>(c.peers, c.cm->rank, c.cm->nranks, group, ndot, c.dots, fin, c.base | h->p2p_dot_k[group], h->sc,
-                                        history, cap, 1, 0);
+                                        history, cap, 1, 0, p2p_timeout_ns());
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -1103,7 +1118,7 @@ static int t_p2p_bicgstab(kt_handle_s* h, const void* coef, const void* b, void*
   } else {
     KT_TRY(t_dist_phase<T>(h, 0, coef, b, nullptr, nullptr, r, x, r_tld, c.dots));
   }
-  KT_TRY(p2p_reduce(c, 2, 1, FIN_BICG_INIT, w->history, w->history_cap));
+  KT_TRY(p2p_reduce(c, 6 + (int)(h->p2p_epoch & 1ull), 1, FIN_BICG_INIT, w->history, w->history_cap));
   KT_TRY(p2p_halo<T>(c, 2, r));
   StencilArgs<T> A2 = stencil_args<T>(h, P, coef);
   A2.ws = ws; A2.x = p; A2.minv = (const T*)Minv; A2.q = r_tld_c; A2.y = v; A2.check_done = 1; A2.fin = FIN_NONE;
@@ -1158,7 +1173,7 @@ static int t_p2p_cg(kt_handle_s* h, const void* coef, const void* b, void* x, co
   KT_TRY(p2p_begin(h, cm, &c));
   KT_TRY(sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0));
   KT_TRY(t_dist_phase<T>(h, 5, coef, b, nullptr, nullptr, r, x, p, c.dots));
-  KT_TRY(p2p_reduce(c, 1, 1, FIN_CG_INIT, w->history, w->history_cap));
+  KT_TRY(p2p_reduce(c, 6 + (int)(h->p2p_epoch & 1ull), 1, FIN_CG_INIT, w->history, w->history_cap));
   KT_TRY(p2p_halo<T>(c, 0, p));
   auto iter = [&]() -> int {
     KT_TRY(t_dist_phase<T>(h, 6, coef, p, nullptr, nullptr, Ap, nullptr, nullptr, c.dots));
@@ -1341,13 +1356,27 @@ int kt_dist_poll(kt_handle_t h, int* done, long* iters, int* status, double* rel
 
 int kt_p2p_comm_block_bytes(void) { return (int)sizeof(P2PBlock); }
 
+// a wait gave up: say which flag, what it waited for and what it saw (kt_last_error)
+static void p2p_timeout_error(const char* where, const kt_handle_s* h, const kt_p2p_comm* cm) {
+  const Scalars& S = *h->sc_host;
+  char buf[384];
+  const unsigned w = (unsigned)S.wait_what;
+  snprintf(buf, sizeof buf, "%s: rank %d of %d gave up waiting for %s %u, %s %u: expected sequence number %llu (epoch %llu, index %llu), last saw %llu "
+           "(epoch %llu, index %llu)", where, cm->rank, cm->nranks, (w >> 8 & 0xff) == 1 ? "halo slot" : "sum group", w & 0xff,
+           (w >> 8 & 0xff) == 1 ? "side" : "peer rank", w >> 16, S.wait_seq, S.wait_seq >> 32, S.wait_seq & 0xffffffffull, S.wait_seen,
+           S.wait_seen >> 32, S.wait_seen & 0xffffffffull);
+  set_error(buf);
+}
+
 int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* ws,
                           const kt_p2p_comm* comm, double eps, long max_iter, int flags, int fixed_iters, long* iters, double* rel_res,
                           int* status) {
   KT_CHECK_ARG(h && coef && b && x && ws && comm, "kt_p2p_bicgstab_solve: null argument");
   KT_DEV_GUARD(h);
-  return KT_DISPATCH(h, t_p2p_bicgstab<double>(h, coef, b, x, Minv, ws, comm, eps, max_iter, flags, fixed_iters != 0, iters, rel_res, status),
-                     t_p2p_bicgstab<float>(h, coef, b, x, Minv, ws, comm, eps, max_iter, flags, fixed_iters != 0, iters, rel_res, status));
+  const int rc = KT_DISPATCH(h, t_p2p_bicgstab<double>(h, coef, b, x, Minv, ws, comm, eps, max_iter, flags, fixed_iters != 0, iters, rel_res, status),
+                             t_p2p_bicgstab<float>(h, coef, b, x, Minv, ws, comm, eps, max_iter, flags, fixed_iters != 0, iters, rel_res, status));
+  if (rc == 0 && h->sc_host->status == KT_STATUS_COMM_TIMEOUT) p2p_timeout_error("kt_p2p_bicgstab_solve", h, comm);   // still rc 0: reported in *status
+  return rc;
 }
 
 int kt_p2p_halo_slots(void) { return P2P_SLOTS; }
@@ -1366,11 +1395,11 @@ int kt_p2p_allreduce(kt_handle_t h, const kt_p2p_comm* comm, const double* vals_
   if (rc) return rc;
   const unsigned long long seq = ++h->p2p_red_seq;
   const int group = 3 + (int)(seq % 3ull);
-  k_p2p_reduce<<<1, 32, 0, h->stream>>>(c.peers, comm->rank, comm->nranks, group, 2, vals_dev2, FIN_NONE, seq, h->sc, nullptr, 0, 0, op);
+  k_p2p_reduce<<<1, 32, 0, h->stream>>>(c.peers, comm->rank, comm->nranks, group, 2, vals_dev2, FIN_NONE, seq, h->sc, nullptr, 0, 0, op, p2p_timeout_ns());
   KT_LAUNCH_CHECK(h);
   rc = read_dots(h, out_host2, 2);
   if (rc) return rc;
-  if (h->sc_host->status == KT_STATUS_COMM_TIMEOUT && h->sc_host->done) { set_error("kt_p2p_allreduce: a peer rank never signalled"); return -5; }
+  if (h->sc_host->status == KT_STATUS_COMM_TIMEOUT && h->sc_host->done) { p2p_timeout_error("kt_p2p_allreduce (or an exchange before it)", h, comm); return -5; }
   return 0;
 }
 
@@ -1378,8 +1407,10 @@ int kt_p2p_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, con
                     double eps, long max_iter, int fixed_iters, long* iters, double* rel_res, int* status) {
   KT_CHECK_ARG(h && coef && b && x && ws && comm, "kt_p2p_cg_solve: null argument");
   KT_DEV_GUARD(h);
-  return KT_DISPATCH(h, t_p2p_cg<double>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status),
-                     t_p2p_cg<float>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status));
+  const int rc = KT_DISPATCH(h, t_p2p_cg<double>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status),
+                             t_p2p_cg<float>(h, coef, b, x, ws, comm, eps, max_iter, fixed_iters != 0, iters, rel_res, status));
+  if (rc == 0 && h->sc_host->status == KT_STATUS_COMM_TIMEOUT) p2p_timeout_error("kt_p2p_cg_solve", h, comm);
+  return rc;
 }
 
 // Launch geometry of the kernel that computes an inner product, for a handle-free geometry: everything the summation
@@ -1505,3 +1536,15 @@ int kt_cg_bench(kt_handle_t h, const void* coef, const void* b, void* x, const k
 }
 
 }  // extern "C"
+
+// every kernel of this translation unit, for kt_preload_kernels (kt_handle.h)
+namespace kt {
+int preload_kt_krylov() {
+  static const void* const fns[] = {
+#define KT_PRELOAD_TU_kt_krylov
+#include "kt_preload_list.inc"
+#undef KT_PRELOAD_TU_kt_krylov
+      nullptr};
+  return preload_list(fns);
+}
+}  // namespace kt

@@ -202,3 +202,15 @@ int kt_jacobi_sweep(kt_handle_t h, const void* coef, const void* rhs, void* x, v
 }
 
 }  // extern "C"
+
+// every kernel of this translation unit, for kt_preload_kernels (kt_handle.h)
+namespace kt {
+int preload_kt_post() {
+  static const void* const fns[] = {
+#define KT_PRELOAD_TU_kt_post
+#include "kt_preload_list.inc"
+#undef KT_PRELOAD_TU_kt_post
+      nullptr};
+  return preload_list(fns);
+}
+}  // namespace kt

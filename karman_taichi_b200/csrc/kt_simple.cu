@@ -362,3 +362,15 @@ int kt_mdiv_max(kt_handle_t h, const kt_simple_params* P, const void* u, const v
 }
 
 }  // extern "C"
+
+// every kernel of this translation unit, for kt_preload_kernels (kt_handle.h)
+namespace kt {
+int preload_kt_simple() {
+  static const void* const fns[] = {
+#define KT_PRELOAD_TU_kt_simple
+#include "kt_preload_list.inc"
+#undef KT_PRELOAD_TU_kt_simple
+      nullptr};
+  return preload_list(fns);
+}
+}  // namespace kt

@@ -308,6 +308,9 @@ class P2PSlabSolver:
         self._hd = _Handle(b)
         l0, l1 = part.local_owned(rank)
         _lib.check(self.lib.kt_set_rows(self._hd.h, l0, l1))
+        # the comm kernels wait for kernels of other streams: nothing may be left to the lazy module loader (kt_preload_kernels)
+        if int(self.lib.kt_preload_kernels(self._hd.h)) <= 0:
+            _lib.check(-4)
         self.t = Field(b.shape, b.np_dtype, b.device)       # s is recomputed by the x/r kernel, never stored
         esize = b.data.element_size()
         if ipc_planes:
@@ -438,7 +441,8 @@ class P2PSlabSolver:
     def _finish(self, it, rel, st):
         self.iterations, self.status, self.rel_res = it.value, st.value, rel.value
         if st.value == _lib.STATUS_COMM_TIMEOUT:
-            raise _lib.KtError('x-slab peer-memory solve: a neighbour rank never signalled (KT_STATUS_COMM_TIMEOUT)')
+            raise _lib.KtError('x-slab peer-memory solve: a neighbour rank never signalled (KT_STATUS_COMM_TIMEOUT): '
+                               + (self.lib.kt_last_error() or b'').decode(errors='replace'))
         return self.iterations, self.status
 
     def solve_cg(self, eps=1e-8, max_iter=None, fixed_iters=False):

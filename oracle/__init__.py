@@ -8,30 +8,35 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``--impl reference`` legs may import or execute anything under ``oracle/``.
 ``karman_taichi_b200`` never imports it.
 
-How the oracle is pinned: Taichi 0.9.0 cannot be installed in this
-image (no wheel for Python 3.12, no network), so the reference itself cannot be run
-here, and it is pure Python + Taichi (no C/C++ sources to compile into ``oracle/_ref``).
-The reference keeps no golden vectors, no expected iteration counts and no field
-snapshots.  PARITY WITH REFERENCE *OUTPUT* IS THEREFORE UNPINNED ("parity unpinned" at the
-bit level: no number produced by the reference program itself is available to compare
-with).  What the reference does hold -- one golden data file and a handful of
-known-answer checks -- pins the oracle's behaviour and is re-expressed in ``tests/``:
+How the oracle is pinned.  The reference is pure Python + Taichi 0.9.0 (no C/C++ sources to
+compile into ``oracle/_ref``), and Taichi cannot be installed in this image (no wheel for Python 3.12, no network).  Its
+arithmetic, however, lives entirely in its own ``.py`` files, so those files are EXECUTED UNMODIFIED under a serial
+stand-in for the ``taichi`` module (``tests/golden/taichi_serial_shim.py``: fields = NumPy arrays, kernels = their Python
+bodies run loop by loop in strict IEEE doubles) by ``tests/golden/make_reference_golden.py``, and what they produce is
+committed as fixtures:
 
-* ``data/ghia1982.dat`` (Ghia et al. 1982 centreline profiles, compared at
-  ``bicgsimp.py:291-304``)              -> ``tests/golden/ghia1982_re100.json``
-* ``np.allclose`` against ``np.linalg.solve`` on a random 5-diagonal system
-  (``debug/ti_bicg_test.py:45-98``)     -> ``tests/test_oracle_krylov.py``
+* ``tests/golden/reference_krylov.npz``   ``cgsolver.py`` / ``bicgsolver.py``: every intermediate vector, iterate, count
+* ``tests/golden/reference_cavity.npz``   ``bicgsimp.py`` / ``simple.py``: coefficients, BCs, fields after outer steps
+* ``tests/golden/reference_channel.npz``  ``karman_taichi.py``: matrices, Jacobi-BiCGSTAB iterates, fields after sub-iterations
+
+``tests/test_reference_golden.py`` holds this oracle to them BIT FOR BIT in serial-summation mode (the order the stand-in's
+``sum +=`` loops take); ``tests/test_gpu_reference_golden.py`` holds the CUDA path to the same fixtures.  Parity is therefore
+pinned to the reference's own source, with one caveat stated plainly: the loops ran serially, not on Taichi's thread
+pool -- the reference's own parallel ``sum +=`` is order-nondeterministic, so no run of it is "the" bit pattern either.
+
+What the reference's own checks hold is re-expressed as well:
+
+* ``data/ghia1982.dat`` (Ghia et al. 1982 centreline profiles, compared at ``bicgsimp.py:291-304``)
+                                          -> ``tests/golden/ghia1982_re100.json``
+* ``np.allclose`` against ``np.linalg.solve`` on a random 5-diagonal system (``debug/ti_bicg_test.py:45-98``)
 * ``np.allclose(Ax, b)`` after CG (``benchmark/2dcg.py:129-132``)
-* residual / convergence-history comparison against SciPy BiCGSTAB and a sparse
-  direct solve (``benchmark/cg_to_sparse/test_cg_sparse.py:38-41``,
-  ``validation.py:26-45``)
+* residual / convergence history against SciPy BiCGSTAB and a sparse direct solve
+  (``benchmark/cg_to_sparse/test_cg_sparse.py:38-41``, ``validation.py:26-45``)
 
-Two further anchors inside the repository: the NumPy restatement in serial-summation mode
-(``oracle.krylov.set_summation('serial')``) and the C port on one thread are bit-identical
-(``tests/test_oracle_cport.py``); and ``tests/golden/make_reference_golden.py`` is ready to execute the
-reference's own source files under a serial stand-in for ``taichi`` and commit the outputs as
-fixtures (``tests/test_reference_golden.py`` holds the oracle to them) -- NOT YET RUN: executing the
-external sources needs the repository owner's approval, so the statement above stands.
+Summation orders (``oracle.krylov.set_summation``): 'pairwise' (NumPy), 'serial' (the stand-in's / a one-thread run's order;
+bit-identical with the C port on one thread, ``tests/test_oracle_cport.py``) and the DEVICE order
+(``oracle/device_order.py``: the exact order of the CUDA reductions from ``kt_reduce_plan`` / ``kt_resident_plan``), under
+which the CUDA iterates and iteration counts are reproduced bit for bit (``tests/test_gpu_exact.py``).
 
 Every function cites the reference file:line it follows.
 """

@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# a peer-memory wait that can never be satisfied (a bug) should cost a test seconds, not the library's 30 s default
+os.environ.setdefault('KT_P2P_TIMEOUT_MS', '10000')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -60,6 +60,18 @@ def test_argument_errors_do_not_need_a_gpu(lib_path):
         _lib.check(lib.kt_dot(None, None, None, None))
 
 
+def test_preload_list_names_every_kernel(lib_path):
+    """kt_preload_kernels walks csrc/kt_preload_list.inc; a kernel missing from it could dead-lock the in-process multi-rank
+    mode in CUDA's lazy loader.  The list must be exactly the kernels of the built library (tools/gen_preload.py)."""
+    elf = subprocess.run(['cuobjdump', '-elf', lib_path], capture_output=True, text=True).stdout
+    mangled = sorted({l[len('.text.'):].strip() for l in elf.splitlines() if l.startswith('.text.')})
+    dem = subprocess.run(['c++filt'], input='\n'.join(mangled), capture_output=True, text=True).stdout.splitlines()
+    built = sorted({re.sub(r'^void ', '', d.strip()).split('(')[0] for d in dem})
+    inc = open(os.path.join(ROOT, 'karman_taichi_b200', 'csrc', 'kt_preload_list.inc')).read()
+    listed = sorted(re.findall(r'^KT_K\((.*)\)$', inc, flags=re.M))
+    assert len(built) > 100 and listed == built
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, 'karman_taichi_b200')
     for dirpath, _, files in os.walk(pkg):

@@ -90,6 +90,18 @@ def karman_case(P, kw, nsub):
 
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+    print('CUDA_DEVICE_MAX_CONNECTIONS =', os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS'), 'KT_P2P_TIMEOUT_MS =', os.environ.get('KT_P2P_TIMEOUT_MS'), flush=True)
+    if which == 'stress':
+        for rep in range(4):
+            for P, case in [(2, ('poisson', 96, 0.1)), (4, ('poisson', 64, 0.1)), (5, ('random', 37, 300))]:
+                try:
+                    krylov_case(P, case)
+                except Exception as e:
+                    print('  EXC', repr(e), flush=True)
+        try:
+            karman_case(2, dict(nx=48, ny=16, cyl=(12, 8, 10)), 1)
+        except Exception as e:
+            print('  EXC', repr(e), flush=True)
     if which in ('all', 'krylov'):
         for P, case in [(2, ('poisson', 96, 0.1)), (3, ('random', 130, 67)), (5, ('random', 37, 300))]:
             try:
