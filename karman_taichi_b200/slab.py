@@ -297,7 +297,8 @@ class P2PSlabSolver:
     allocations nobody else maps.  After that a solve is one C-ABI call per rank and no host code runs per iteration.
 
     ``Minv`` / ``warm_start`` / ``omega_zero_break``: the monolith's Jacobi-preconditioned, warm-started variant
-    (``karman_taichi.py:342-456``), as on ``BICGSolver``.  ``ipc_planes=True`` (measurement aid) puts r / p / v themselves
+    (``karman_taichi.py:342-456``), as on ``BICGSolver``; the ``Minv`` plane must be valid on the halo rows as well (the operand of
+    the product is ``Minv * p``: exchange it after assembling it, ``SlabKarmanSolver.fill_Au``).  ``ipc_planes=True`` (measurement aid) puts r / p / v themselves
     into IPC-exported allocations, which is how round 1 ran (profiles/r02_p2p.md)."""
 
     def __init__(self, coef, b, x, part: SlabPartition, rank, group=None, ipc_planes=False, peers='ipc'):

@@ -118,6 +118,9 @@ class SlabKarmanSolver:
         _lib.check(self._lib.kt_channel_assemble_uv(
             self._h, C.byref(P), self._ct(), _p(self.u), _p(self.v), _p(self.p), _p(self.u0), _p(self.v0),
             _p(self.coef_u), _p(self.b_u), _p(self.M_u), _p(self.Minv_u), _p(self.coef_v), _p(self.b_v), _p(self.M_v), _p(self.Minv_v)))
+        # the solver's operand is M^-1 p: the product A (M^-1 p) reads M^-1 on the halo rows too (karman_taichi.py:399-406)
+        self.u_solver.exchange(self.Minv_u.ptr)
+        self.v_solver.exchange(self.Minv_v.ptr)
 
     fill_Av = fill_Au
 
@@ -127,6 +130,7 @@ class SlabKarmanSolver:
         P = self._params()
         _lib.check(self._lib.kt_channel_assemble_p(self._h, C.byref(P), self._ct(), _p(self.u), _p(self.v), _p(self.coef_u),
                                                    _p(self.coef_v), _p(self.coef_p), _p(self.b_p), _p(self.M_p), _p(self.Minv_p)))
+        self.p_solver.exchange(self.Minv_p.ptr)
 
     def bicgstab(self, which, eps):
         """``karman_taichi.py:341-456`` for system 'u', 'v' or 'p', over all ranks"""
