@@ -289,6 +289,44 @@ class _IpcBuffer:
             pass
 
 
+def run_local_ranks(n, fn, device=None, timeout=600.0):
+    """``fn(rank)`` for ``rank = 0 .. n-1`` on ``n`` host threads with one CUDA stream each: how an in-process multi-rank run
+    (solvers built with ``peers='local'``, all ranks on ONE device) is driven.  Returns the list of results.
+
+    The comm kernels of different ranks wait for each other, so while the threads run nothing may force the device idle:
+
+    * every kernel is loaded beforehand (``kt_preload_kernels``, called by ``P2PSlabSolver``): CUDA's lazy loader waits for
+      running kernels;
+    * no device memory may be freed: ``cudaFree`` -- a handle or an IPC buffer of an earlier solver reaching its ``__del__``
+      through the cyclic garbage collector in the middle of a solve -- waits for ALL kernels on the device, including the one
+      that spins for the thread that called it.  Garbage is therefore collected first and the collector is off until every
+      rank has returned.
+
+    One process per GPU (``peers='ipc'``) needs none of this: every process owns its device."""
+    import gc
+    from concurrent.futures import ThreadPoolExecutor
+    device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+    streams = [torch.cuda.Stream(device) for _ in range(n)]
+    torch.cuda.synchronize(device)
+
+    def wrapped(r):
+        with torch.cuda.device(device), torch.cuda.stream(streams[r]):
+            out = fn(r)
+            streams[r].synchronize()
+            return out
+
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with ThreadPoolExecutor(max_workers=n) as ex:
+            futs = [ex.submit(wrapped, r) for r in range(n)]
+            return [f.result(timeout=timeout) for f in futs]
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
 class P2PSlabSolver:
     """x-slab BiCGSTAB / CG whose halo exchange and inner-product all-reduce run inside the library over NVLink peer memory
     (``kt_p2p_bicgstab_solve`` / ``kt_p2p_cg_solve``).  Every rank maps its two neighbours' small halo-receive buffers

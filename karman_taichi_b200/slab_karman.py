@@ -70,6 +70,7 @@ class SlabKarmanSolver:
         s = P2PSlabSolver(coef, b, x, part, self.rank, group=group, peers=peers)
         s.Minv, s.warm_start, s.omega_zero_break = minv, True, True
         s.default_max = 100 * n                                # karman_taichi.py:382
+        s._ws()                                                # the r~ plane of the warm start exists before the first solve
         return s
 
     @staticmethod

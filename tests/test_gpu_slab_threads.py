@@ -5,8 +5,6 @@ exercises them on a one-GPU box (the driver's GPU test box has one; tests/test_g
 
 Every comparison is against the oracle adding in the slabs' order (oracle/device_order.py: SlabOrder / SlabAutoOrder): bit for bit.
 """
-from concurrent.futures import ThreadPoolExecutor
-
 import numpy as np
 import pytest
 
@@ -22,18 +20,9 @@ def sms(cuda):
 
 
 def run_ranks(cuda, n, fn):
-    """fn(rank) on n threads, each with its own stream (current device and stream are per thread)."""
-    import torch
-    streams = [torch.cuda.Stream(cuda) for _ in range(n)]
-
-    def wrapped(r):
-        with torch.cuda.device(cuda), torch.cuda.stream(streams[r]):
-            out = fn(r)
-            streams[r].synchronize()
-            return out
-    with ThreadPoolExecutor(max_workers=n) as ex:
-        futs = [ex.submit(wrapped, r) for r in range(n)]
-        return [f.result(timeout=300) for f in futs]
+    """fn(rank) on n threads, each with its own stream (slab.run_local_ranks: nothing may free device memory meanwhile)."""
+    from karman_taichi_b200.slab import run_local_ranks
+    return run_local_ranks(n, fn, device=cuda, timeout=300)
 
 
 def slab_solvers(cuda, coef, rhs, P):
