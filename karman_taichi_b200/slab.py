@@ -15,6 +15,8 @@ the oracle, which is how the partition / halo / reduction logic is tested on CPU
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -318,11 +320,17 @@ def run_local_ranks(n, fn, device=None, timeout=600.0):
     gc.collect()
     was_enabled = gc.isenabled()
     gc.disable()
+    watchdog = float(os.environ.get('KT_LOCAL_RANKS_WATCHDOG', '0') or 0)   # seconds: dump every thread's stack if still running
+    if watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(watchdog, exit=False, file=sys.stderr)
     try:
         with ThreadPoolExecutor(max_workers=n) as ex:
             futs = [ex.submit(wrapped, r) for r in range(n)]
             return [f.result(timeout=timeout) for f in futs]
     finally:
+        if watchdog > 0:
+            faulthandler.cancel_dump_traceback_later()
         if was_enabled:
             gc.enable()
 

@@ -4,7 +4,15 @@ multi-GPU runs use -- boundary rows stored into the neighbour's receive buffer, 
 exercises them on a one-GPU box (the driver's GPU test box has one; tests/test_gpu_slab.py::test_two_gpu_nccl needs two).
 
 Every comparison is against the oracle adding in the slabs' order (oracle/device_order.py: SlabOrder / SlabAutoOrder): bit for bit.
+
+Liveness caveat of this test set-up only: ranks that WAIT for each other while sharing one device rely on their streams making
+progress side by side, which CUDA does not promise (one process per GPU -- the real deployment -- does not depend on it).  The
+library removes the causes it can (kernels preloaded, no cudaFree meanwhile: slab.run_local_ranks); a run that still ends in
+KT_STATUS_COMM_TIMEOUT (seen once per cold box, on its first process) is repeated from scratch -- new solvers, new flags -- up
+to two more times.  Only the time-out is retried: a wrong number fails at once.
 """
+import functools
+
 import numpy as np
 import pytest
 
@@ -12,6 +20,24 @@ from oracle import krylov
 from oracle.device_order import SlabAutoOrder, SlabOrder, installed
 
 pytestmark = pytest.mark.gpu
+
+
+def retry_comm_timeout(test):
+    @functools.wraps(test)
+    def wrapper(*args, **kwargs):
+        import gc
+        import torch
+        from karman_taichi_b200 import KtError
+        for attempt in range(3):
+            try:
+                return test(*args, **kwargs)
+            except KtError as e:
+                if attempt == 2 or not ('COMM_TIMEOUT' in str(e) or 'gave up waiting' in str(e)):
+                    raise
+                print(f'{test.__name__}: attempt {attempt + 1} timed out waiting for a co-scheduled rank ({e}); repeating')
+                torch.cuda.synchronize()
+                gc.collect()
+    return wrapper
 
 
 def sms(cuda):
@@ -40,6 +66,7 @@ def slab_solvers(cuda, coef, rhs, P):
 
 
 @pytest.mark.parametrize('P,case', [(2, ('poisson', 96, 0.1)), (3, ('random', 130, 67)), (5, ('random', 37, 300))])
+@retry_comm_timeout
 def test_p2p_bicgstab_and_cg_threads_bit_exact(cuda, P, case):
     kind, a, b_ = case
     coef, rhs = krylov.poisson_sin_system(a, b_) if kind == 'poisson' else krylov.random_dd_system(a, b_, seed=0)
@@ -61,6 +88,7 @@ def test_p2p_bicgstab_and_cg_threads_bit_exact(cuda, P, case):
         np.testing.assert_array_equal(xc, xc_dev)
 
 
+@retry_comm_timeout
 def test_p2p_exchange_and_allreduce_threads(cuda):
     """kt_p2p_exchange / kt_p2p_allreduce on their own: many back-to-back calls (slot / group rotation), sums in rank order."""
     import torch
@@ -94,6 +122,7 @@ def test_p2p_exchange_and_allreduce_threads(cuda):
 
 @pytest.mark.parametrize('P,kw,nsub', [(2, dict(nx=48, ny=16, cyl=(12, 8, 10)), 3), (3, dict(nx=96, ny=48, cyl=(64, 32, 144)), 2),
                                        (4, dict(nx=320, ny=64, cyl=(64, 32, 144)), 1)])
+@retry_comm_timeout
 def test_slab_karman_threads_bit_exact(cuda, P, kw, nsub):
     """SlabKarmanSolver on P ranks (threads) against the oracle in the slabs' summation order: every field, every Krylov
     count, bit for bit; against the one-GPU KarmanSolver: assembly identical, fields to 1e-8."""
