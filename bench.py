@@ -732,6 +732,7 @@ def simple_line(a, torch, dist, world, rank, dev, workload, steps=None, light=Fa
     case, nx, ny, cap, desc = SIMPLE_WORKLOADS[workload]
     cells = nx * ny
     cm = Comm(torch, dist, world, dev)
+    slab = case == 'karman' and world > 1               # config 4 on 2-8 GPUs: one problem cut into x-slabs (strong scaling)
     if case == 'cavity':
         s = kt.lid_driven_cavity(nx, device=dev)
         s.alpha_p = 0.02
@@ -743,15 +744,23 @@ def simple_line(a, torch, dist, world, rank, dev, workload, steps=None, light=Fa
         words = {'u': 28, 'v': 28, 'p': 16}           # BiCGSTAB 28 N, CG 16 N words per iteration
     else:
         cyl = (64, 32, 144) if (nx, ny) == (320, 64) else (nx // 5, ny // 2, int(round((0.1875 * ny) ** 2)))
-        s = kt.KarmanSolver(nx=nx, ny=ny, cyl=cyl, dt=1e-5 * 320 / nx, device=dev)
+        if slab:
+            # x-slabs of the channel, one per GPU: assembly / relaxation / correction kernels on a row window, boundary rows of
+            # u, v, p, p', ap_u and the Jacobi planes over NVLink peer memory, the three solves by the peer-memory BiCGSTAB
+            s = kt.SlabKarmanSolver(rank, world, nx=nx, ny=ny, cyl=cyl, dt=1e-5 * 320 / nx, device=dev, peers='ipc')
+        else:
+            s = kt.KarmanSolver(nx=nx, ny=ny, cyl=cyl, dt=1e-5 * 320 / nx, device=dev)
         s.init()
         solvers = {'u': s.u_solver, 'v': s.v_solver, 'p': s.p_solver}
         step = s.sub_iteration
         its = lambda: dict(s.last_iters)
         words = {'u': 31, 'v': 31, 'p': 31}           # Jacobi-preconditioned BiCGSTAB: 31 N words per iteration
     if cap:
-        for sol in solvers.values():
-            sol.max_steps = cap
+        if slab:
+            s.max_steps = cap
+        else:
+            for sol in solvers.values():
+                sol.max_steps = cap
     handles = [s._hd] + [sol._hd for sol in solvers.values()]
 
     for _ in range(a.warmup):
@@ -767,24 +776,25 @@ def simple_line(a, torch, dist, world, rank, dev, workload, steps=None, light=Fa
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cm.barrier()
     e0.record()
+    returned = []
     for _ in range(steps):
-        step()
+        returned.append(step())
         for k, v in its().items():
             tot_its[k] += v
     e1.record()
     cm.barrier()
     ms_total = cm.max(e0.elapsed_time(e1))
-    launches = (sum(h.launch_count() for h in handles) - l0) * world
+    launches = int(cm.sum(sum(h.launch_count() for h in handles) - l0))
     tot = (C.c_double * 8)()
     cnt = (C.c_long * 8)()
     _lib.check(lib.kt_prof_end(hp.h, tot, cnt, 8))
     clocks = sampler.stop() if (rank == 0 and not light) else None
-    value = steps * world / (ms_total * 1e-3)
+    value = steps * (1 if slab else world) / (ms_total * 1e-3)
 
     # roofline: whole-step algorithmic bytes (~51 N words of assembly / BC / relaxation / correction per outer
     # iteration + the Krylov iterations actually run); the dominant kernel class of the p' solve when it streams from HBM
     peak, peak_kind = peaks()
-    N = (nx + 2) * (ny + 2)
+    N = (nx + 2) * (ny + 2) // (world if slab else 1)     # plane words per GPU
     step_bytes = 8.0 * N * (51 * steps + sum(words[k] * tot_its[k] for k in words))
     achieved = step_bytes / (ms_total * 1e-3) / 1e9
     streamed = sum(cnt[i] for i in range(4)) > 0
@@ -801,7 +811,7 @@ def simple_line(a, torch, dist, world, rank, dev, workload, steps=None, light=Fa
         dom = max(range(4), key=lambda i: tot[i])
         d_ms = tot[dom] / max(cnt[dom], 1)
         if case == 'karman':
-            roofline['traffic'], roofline['traffic_source'] = traffic_of(measured_traffic(), names[dom][2], (nx + 2) * s.p.pitch)
+            roofline['traffic'], roofline['traffic_source'] = traffic_of(measured_traffic(), names[dom][2], (nx + 2) * s.p.pitch // (world if slab else 1))
         roofline['dominant_kernel'] = {'name': names[dom][0], 'words': names[dom][1], 'ms_per_launch': d_ms,
                                        'achieved': names[dom][1] * 8.0 * N / (d_ms * 1e-3) / 1e9,
                                        'frac': names[dom][1] * 8.0 * N / (d_ms * 1e-3) / 1e9 / peak,
@@ -814,13 +824,22 @@ def simple_line(a, torch, dist, world, rank, dev, workload, steps=None, light=Fa
                             'for completeness and NOT a roofline this size can approach (the working set lives in shared memory)')
 
     line = {'metric': SIMPLE_METRIC, 'value': value, 'unit': SIMPLE_UNIT, 'n_gpus': world, 'steps': steps, 'warmup': a.warmup,
-            'ms_per_step': ms_total / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'ms_per_step': ms_total / steps, 'higher_is_better': True, 'scaling': 'strong' if slab else 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
             'config': {'workload': workload, 'description': desc, 'grid': [nx, ny],
-                       'parallelism': 'single GPU' if world == 1 else f'{world} independent replicas (the SIMPLE configs are not sharded)',
+                       'parallelism': ('single GPU' if world == 1 else
+                                       f'x-slab x{world} (SlabKarmanSolver): halo rows + all-reduces over NVLink peer memory inside the library' if slab else
+                                       f'{world} independent replicas (the reference-sized SIMPLE configs are not sharded)'),
                        'cache': ('working set >> 126 MB L2' if cells > 1 << 22 else
                                  'working set resident in shared memory / L2 by design (reference-sized grid); inputs change every step')},
             'gpu_launches': launches, 'roofline': roofline}
+    if case == 'karman':
+        # correctness evidence that travels with the number: what the timed sub-iterations returned (max |p'|, identical on every
+        # rank) and the Krylov counts -- the same sequence at every N up to the order of the partial sums
+        line['check'] = {'max_pcor_per_step': [float(v) for v in returned], 'krylov_iterations_last_step': its(),
+                         'krylov_status_last_step': dict(s.last_status),
+                         'note': 'same initial state, same number of warm-up + timed sub-iterations at every N: the values agree across '
+                                 '--gpus 1, 2, 4, 8 to the rounding of the rank-ordered partial sums'}
     if light:
         return line
     line['clocks'] = clocks
@@ -849,8 +868,8 @@ def simple_line(a, torch, dist, world, rank, dev, workload, steps=None, light=Fa
         e1.record()
         cm.barrier()
         ms = cm.max(e0.elapsed_time(e1))
-        nbytes = sum(t.numel() * 8 for t in host) * world
-        line['e2e'] = {'value': k_e * world / (ms * 1e-3), 'unit': SIMPLE_UNIT, 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': nbytes,
+        nbytes = int(cm.sum(sum(t.numel() * 8 for t in host)))
+        line['e2e'] = {'value': k_e * (1 if slab else world) / (ms * 1e-3), 'unit': SIMPLE_UNIT, 'h2d_bytes_per_step': nbytes, 'd2h_bytes_per_step': nbytes,
                        'steps': k_e, 'ms_per_step': ms / k_e,
                        'call': 'kt_upload_field(u, v, p) + SIMPLESolver.step / KarmanSolver.sub_iteration + kt_download_field(u, v, p) on pinned host buffers'}
 

@@ -225,6 +225,66 @@ def test_two_gpu_nccl(cuda, tmp_path):
         assert rel_l2(xc, xc_ref) < 1e-8
 
 
+KARMAN_MP = dict(nx=96, ny=48, cyl=(64, 32, 144))
+
+
+def _slab_karman_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        import karman_taichi_b200 as kt
+        s = kt.SlabKarmanSolver(rank, world, device=dev, peers='ipc', **KARMAN_MP)
+        s.init()
+        out = []
+        for k in range(2):
+            out.append((s.sub_iteration(1e-8), dict(s.last_iters), dict(s.last_status)))
+        np.savez(os.path.join(out_dir, f'karman_{rank}.npz'), pcor_max=np.array([o[0] for o in out]),
+                 iters=np.array([[o[1][w] for w in 'uvp'] for o in out]), status=np.array([[o[2][w] for w in 'uvp'] for o in out]),
+                 **{name: s.owned(getattr(s, name)) for name in ('u', 'v', 'p', 'pcor', 'udiv')})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_multi_gpu_slab_karman(cuda, tmp_path):
+    """SlabKarmanSolver, one process per GPU, peer mappings through CUDA IPC (the deployment mode; the in-process variant is
+    tests/test_gpu_slab_threads.py): two sub-iterations of the channel, every field and every Krylov count bit for bit equal
+    to the oracle adding in the slabs' order."""
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip('needs >= 2 GPUs')
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_slab_karman_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from karman_taichi_b200.slab import SlabPartition
+    from oracle.device_order import SlabAutoOrder, installed
+    from oracle.karman import KarmanOracle
+    nx = KARMAN_MP['nx']
+    part_p = SlabPartition(nx + 2, world)
+    part_u = SlabPartition.from_bounds(part_p.bounds[:-1] + [nx + 3])
+    o = KarmanOracle(**KARMAN_MP)
+    o.init()
+    res = [np.load(tmp_path / f'karman_{r}.npz') for r in range(world)]
+    with installed(SlabAutoOrder({nx + 3: part_u.bounds, nx + 2: part_p.bounds},
+                                 num_sms=torch.cuda.get_device_properties(cuda).multi_processor_count)):
+        for k in range(2):
+            po = o.sub_iteration(1e-8)
+            for r in res:
+                assert r['pcor_max'][k] == po
+                assert [int(v) for v in r['iters'][k]] == [o.last_iters[w] for w in 'uvp']
+                assert [int(v) for v in r['status'][k]] == [o.last_status[w] for w in 'uvp']
+    for name in ('u', 'v', 'p', 'pcor', 'udiv'):
+        np.testing.assert_array_equal(np.concatenate([r[name] for r in res], axis=0), getattr(o, name), err_msg=name)
+
+
 def test_p2p_single_rank(cuda):
     """nranks = 1 through kt_p2p_bicgstab_solve: the peer-memory reduce kernel (store, flag, wait, rank-ordered sum, scalar
     algebra) on its own block; must reproduce the plain solver."""
