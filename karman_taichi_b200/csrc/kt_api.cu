@@ -108,6 +108,7 @@ int kt_destroy(kt_handle_t h) {
   kt::DeviceGuard guard(h->device);
   cudaFree(h->partials); cudaFree(h->ticket); cudaFree(h->sc); cudaFreeHost(h->sc_host);
   cudaFree(h->red_out); cudaFreeHost(h->red_host);
+  if (h->p2p_peers_dev) cudaFree(h->p2p_peers_dev);
   for (int k = 0; k < 2; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);

@@ -139,6 +139,48 @@ enum Fin {
   FIN_CG_END
 };
 
+// ---- x-slab peer-memory communication (kt_krylov.cu: "x-slab BiCGSTAB over NVLink peer memory") ------------------------
+// The comm block every rank allocates (zero-initialised) and every other rank maps: the partial sums of the inner products,
+// one slot per rank and slot group, and the "row has landed" flags of the halo-receive buffer.  Flags carry monotonically
+// increasing sequence numbers, never reset.
+constexpr int P2P_GROUPS = 8, P2P_SLOTS = 5;
+struct P2PBlock {
+  double dots[P2P_GROUPS][16][2];
+  unsigned long long dot_flag[P2P_GROUPS][16];
+  unsigned long long halo_flag[P2P_SLOTS][2]; // [slot][0: from lower neighbour, 1: from upper neighbour]
+};
+
+__device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flag, unsigned long long seq, Scalars* sc, long long timeout_ns,
+                                         unsigned what) {
+  unsigned long long t0 = 0, seen;
+  while ((seen = *flag) < seq) {
+    __nanosleep(32);
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    if ((long long)(now - t0) > timeout_ns) {  // a peer died or the ranks disagree on the schedule -- fail, never hang
+      sc->wait_what = what; sc->wait_seq = seq; sc->wait_seen = seen;
+      *(volatile int*)&sc->status = 7; *(volatile int*)&sc->done = 1;
+      return false;
+    }
+  }
+  __threadfence_system();
+  return true;
+}
+
+// 16-byte load of a row another GPU wrote into this rank's receive buffer during this kernel: never through L1 / the
+// read-only path (the line may have been fetched before the neighbour's store landed)
+__device__ __forceinline__ Pack<double> ld_sys(const double* p) {
+  Pack<double> r;
+  asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.a[0]), "=d"(r.a[1]) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ Pack<float> ld_sys(const float* p) {
+  Pack<float> r;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]) : "l"(p) : "memory");
+  return r;
+}
+
 struct ReduceWs {
   double* partials;        // [KT_MAX_DOTS][max_blocks]
   unsigned int* ticket;    // one counter, reset by the finalising block
@@ -148,7 +190,25 @@ struct ReduceWs {
   long long history_cap;
   double* dots_out;        // device, may be null: raw finalised sums also land here (x-slab mode: the
                            // buffer that is all-reduced across ranks before kt_dist_scalar runs the algebra)
+  // x-slab peer-memory mode, communication fused into the compute kernels (all null / 0 otherwise):
+  //  * the kernel stored its boundary rows straight into the neighbours' receive buffers; once EVERY block has done so the
+  //    finalising block raises the neighbours' flags hflag_lo / hflag_hi to hseq;
+  //  * the finalising block is also the all-reduce: it stores this rank's sums into slot [rank] of every rank's comm block,
+  //    waits for all ranks' slots in its own block, adds them in rank order and runs the scalar algebra on the global sums.
+  unsigned long long* hflag_lo;
+  unsigned long long* hflag_hi;
+  unsigned long long hseq;
+  P2PBlock* const* peers;  // device array [nranks]: every rank's comm block as mapped by this rank
+  int rank, nranks, group;
+  unsigned long long rseq;
+  long long timeout_ns;
 };
+
+// neighbours' "row has landed" flags; called by ONE thread after every block's row stores are ordered before it
+__device__ __forceinline__ void p2p_raise_halo_flags(const ReduceWs& ws) {
+  if (ws.hflag_lo) *(volatile unsigned long long*)ws.hflag_lo = ws.hseq;
+  if (ws.hflag_hi) *(volatile unsigned long long*)ws.hflag_hi = ws.hseq;
+}
 
 __device__ __forceinline__ void scalar_algebra(int fin, Scalars* sc, double d0, double d1, double* history,
                                                long long history_cap) {
@@ -225,6 +285,33 @@ __device__ __forceinline__ void scalar_algebra(int fin, Scalars* sc, double d0, 
   }
 }
 
+// All-reduce of (up to) two sums over the ranks + the scalar algebra, by ONE WARP (all 32 lanes call it): lane r stores this
+// rank's sums into slot [rank] of rank r's comm block and raises its flag; the warp waits for all nranks flags of its own block,
+// lane 0 adds the slots in rank order (the same bits on every rank) and runs the algebra.  Slot groups: see kt_krylov.cu.
+__device__ __forceinline__ void p2p_allreduce_warp(P2PBlock* const* peers, int rank, int nranks, int group, int ndot, double l0, double l1,
+                                                   int fin, unsigned long long seq, Scalars* sc, double* history, long long cap,
+                                                   int in_solve, int op_max, long long timeout_ns) {
+  const int lane = threadIdx.x & 31;
+  P2PBlock* mine = peers[rank];
+  if (lane < nranks) {
+    P2PBlock* pb = peers[lane];
+    *(volatile double*)&pb->dots[group][rank][0] = l0;
+    *(volatile double*)&pb->dots[group][rank][1] = ndot > 1 ? l1 : 0.0;
+    __threadfence_system();
+    *(volatile unsigned long long*)&pb->dot_flag[group][rank] = seq;
+    p2p_wait(&mine->dot_flag[group][lane], seq, sc, timeout_ns, 2u << 8 | (unsigned)group | (unsigned)lane << 16);
+  }
+  __syncwarp();
+  if (lane == 0 && (!in_solve || !*(volatile int*)&sc->done)) {
+    double d0 = 0.0, d1 = 0.0;
+    for (int r = 0; r < nranks; ++r) {          // rank order: the same bits on every rank
+      const double a0 = *(volatile double*)&mine->dots[group][r][0], a1 = *(volatile double*)&mine->dots[group][r][1];
+      if (op_max) { d0 = fmax(d0, a0); d1 = fmax(d1, a1); } else { d0 += a0; d1 += a1; }
+    }
+    scalar_algebra(fin, sc, d0, d1, history, cap);
+  }
+}
+
 // Block-level deterministic reduction of up to two running sums + last-block finalisation.
 // Must be called by every thread of every block of the grid (blockDim.x multiple of 32, <= 1024).
 template <int NDOT>
@@ -241,13 +328,19 @@ __device__ __forceinline__ void block_reduce_finalize(double a0, double a1, cons
     for (int w = 0; w < nw; ++w) { s0 += sm[0][w]; if (NDOT > 1) s1 += sm[1][w]; }
     ws.partials[blockIdx.x] = s0;
     if (NDOT > 1) ws.partials[ws.max_blocks + blockIdx.x] = s1;
-    __threadfence();
+    // (rows this block stored into a neighbour GPU's receive buffer are ordered before the ticket at system scope)
+    if (ws.hflag_lo || ws.hflag_hi) __threadfence_system(); else __threadfence();
     unsigned int t = atomicAdd(ws.ticket, 1u);
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
   if (!is_last) return;
-  __threadfence();
+  if (ws.hflag_lo || ws.hflag_hi) {
+    // every block's boundary rows have landed: tell the neighbours first, the sums below are not on their critical path
+    if (threadIdx.x == 0) { __threadfence_system(); p2p_raise_halo_flags(ws); }
+  } else {
+    __threadfence();
+  }
   // fixed-order final sum: thread k owns partials k, k+B, k+2B ...; then the same tree as above.
   // (eight independent L2 loads in flight per thread, then added in index order: the sum order is fixed, the
   // latency of the partial reads is paid once per eight instead of once per partial)
@@ -274,8 +367,40 @@ __device__ __forceinline__ void block_reduce_finalize(double a0, double a1, cons
     for (int w = 0; w < nw; ++w) { s0 += sm[0][w]; if (NDOT > 1) s1 += sm[1][w]; }
     *ws.ticket = 0u;
     if (ws.dots_out) { ws.dots_out[0] = s0; if (NDOT > 1) ws.dots_out[1] = s1; }
-    scalar_algebra(fin, ws.sc, s0, s1, ws.history, ws.history_cap);
+    if (ws.nranks > 1) { sm[0][0] = s0; sm[1][0] = s1; }
+    else scalar_algebra(fin, ws.sc, s0, s1, ws.history, ws.history_cap);
   }
+  if (ws.nranks > 1) {     // fused all-reduce over the ranks: warp 0 of the finalising block
+    __syncthreads();
+    if (wid == 0) p2p_allreduce_warp(ws.peers, ws.rank, ws.nranks, ws.group, NDOT, sm[0][0], NDOT > 1 ? sm[1][0] : 0.0, fin, ws.rseq, ws.sc,
+                                     ws.history, ws.history_cap, 1, 0, ws.timeout_ns);
+  }
+}
+
+// Kernels that push boundary rows but compute no inner product (p-updates): the last block to finish raises the flags.
+// Must be called by every thread of every block.
+__device__ __forceinline__ void push_finalize(const ReduceWs& ws) {
+  if (!ws.hflag_lo && !ws.hflag_hi) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(ws.ticket, 1u) == gridDim.x - 1) {
+      *ws.ticket = 0u;
+      __threadfence_system();
+      p2p_raise_halo_flags(ws);
+    }
+  }
+}
+
+// The neighbours' receive rows for the plane an element-wise kernel writes (flat vector index -> row test by offset).
+template <typename T> struct HaloPush {
+  T* lo; T* hi;                     // null: no neighbour on that side / not pushing
+  long long first_off, last_off;    // element offsets of this rank's first / last owned row in the plane
+  int pitch;
+};
+template <typename T> __device__ __forceinline__ void ew_push(const HaloPush<T>& hp, size_t o, const Pack<T>& v) {
+  if (hp.lo) { const long long d = (long long)o - hp.first_off; if (d >= 0 && d < hp.pitch) st_vec(hp.lo + d, v); }
+  if (hp.hi) { const long long d = (long long)o - hp.last_off; if (d >= 0 && d < hp.pitch) st_vec(hp.hi + d, v); }
 }
 
 // block max -> partials[block] -> last block takes the max (order-independent, exact)

@@ -36,6 +36,8 @@ struct kt_handle_s {
   unsigned long long graph_clock = 0;
   // x-slab peer-memory solves (kt_p2p_*): solve epoch and exchange counters behind the flag sequence numbers
   unsigned long long p2p_epoch = 0, p2p_halo_k[3] = {0, 0, 0}, p2p_dot_k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void* p2p_peers_dev = nullptr;     // device array [16] of the ranks' comm blocks (fused all-reduce in the finalising blocks)
+  void* p2p_peers_host[16] = {};     // what was last uploaded into it
   unsigned long long p2p_xchg_seq = 0, p2p_red_seq = 0;      // standalone exchanges / all-reduces (kt_p2p_exchange, kt_p2p_allreduce)
   // optional per-kernel-class device timing (bench.py roofline): events bracket every launch of a class
   bool prof_on = false;

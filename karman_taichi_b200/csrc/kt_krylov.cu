@@ -49,12 +49,21 @@ template <typename T> struct StencilArgs {
   int check_done;
   int fin;
   ReduceWs ws;
+  // P2P variants (x-slab peer-memory mode, exchange fused into the kernels; unused otherwise).
+  //  in : the operand's halo rows row_lo - 1 / row_hi are read from this rank's receive buffer (hx_* for x, hv_* for v) once the
+  //       neighbour's flag fx_* / fv_* shows seq_x / seq_v -- the neighbour's producer kernel stored them there;
+  //  out: the first / last owned row of y (EPI_RESID: of r) is also stored into the neighbours' receive rows push_lo / push_hi;
+  //       ws.hflag_* / ws.hseq announce them.
+  const T* hx_lo; const T* hx_hi; const T* hv_lo; const T* hv_hi;
+  const unsigned long long* fx_lo; const unsigned long long* fx_hi; const unsigned long long* fv_lo; const unsigned long long* fv_hi;
+  unsigned long long seq_x, seq_v;
+  T* push_lo; T* push_hi;
 };
 
 // scalars of the on-the-fly operand: SRC_S: a = alpha; SRC_P: a = beta, b = omega, first = (iteration 0: p = r)
 template <typename T> struct SrcCoef { T a, b; bool first; };
 
-template <typename T, int SRC, bool PRE>
+template <typename T, int SRC, bool PRE, bool P2P = false>
 struct SrcRow {
   // vector of the stencil operand at (i, j0..j0+V-1); also returns the un-preconditioned value (x, s or p)
   static __device__ __forceinline__ void load(const StencilArgs<T>& A, int i, int j0, bool act, const SrcCoef<T>& K,
@@ -62,7 +71,16 @@ struct SrcRow {
     constexpr int V = VT<T>::V;
     if (!act || i < 0 || i >= A.NX) { hat = pack_zero<T>(); raw = hat; return; }
     const size_t o = (size_t)i * A.pitch + j0;
-    if (SRC == SRC_X) {
+    if (P2P && SRC != SRC_P && ((i == A.row_lo - 1 && A.hx_lo) || (i == A.row_hi && A.hx_hi))) {
+      // halo row: from the receive buffer the neighbour's producer kernel filled (the caller has waited for its flag)
+      const bool lo = i == A.row_lo - 1;
+      raw = ld_sys((lo ? A.hx_lo : A.hx_hi) + j0);
+      if (SRC == SRC_S) {
+        const Pack<T> v = ld_sys((lo ? A.hv_lo : A.hv_hi) + j0);
+#pragma unroll
+        for (int k = 0; k < V; ++k) raw.a[k] = raw.a[k] - K.a * v.a[k];                 // bicgsolver.py:63
+      }
+    } else if (SRC == SRC_X) {
       raw = ld_cached(A.x + o);
     } else if (SRC == SRC_S) {
       Pack<T> r = ld_cached(A.x + o), v = ld_cached(A.v + o);
@@ -118,7 +136,16 @@ template <> struct StencilCfg<SRC_X, false> { static constexpr int W = 2; static
 template <bool PRE> struct StencilCfg<SRC_P, PRE> { static constexpr int W = 1; static constexpr int MINB = 3; };
 #endif
 
-template <typename T, int SRC, bool PRE, int EPI>
+// Waits of a P2P stencil kernel for the neighbour's rows (all lanes poll the same word; every lane runs its own acquire fence)
+template <typename T, int SRC>
+__device__ __forceinline__ void stencil_halo_wait(const StencilArgs<T>& A, bool lo) {
+  const unsigned long long* fx = lo ? A.fx_lo : A.fx_hi;
+  const unsigned long long* fv = lo ? A.fv_lo : A.fv_hi;
+  if (fx) p2p_wait(fx, A.seq_x, A.ws.sc, A.ws.timeout_ns, 1u << 8 | (lo ? 0u : 1u << 16) | 0x10u);
+  if (SRC == SRC_S && fv) p2p_wait(fv, A.seq_v, A.ws.sc, A.ws.timeout_ns, 1u << 8 | (lo ? 0u : 1u << 16) | 0x11u);
+}
+
+template <typename T, int SRC, bool PRE, int EPI, bool P2P = false>
 __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(const StencilArgs<T> A) {
   constexpr int V = VT<T>::V;
   constexpr int W = StencilCfg<SRC, PRE>::W;
@@ -144,12 +171,13 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
     bool act[W];
     Pack<T> xw[W], xc[W], xe[W];   // (preconditioned) operand rows i-1, i, i+1
     Pack<T> raw_c[W], raw_e[W];    // un-preconditioned operand (s or x) rows i, i+1
+    if (P2P && i0 == A.row_lo && A.hx_lo) stencil_halo_wait<T, SRC>(A, true);     // row i0 - 1 comes from the lower neighbour
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       j0[w] = ((cc * W + w) * 32 + lane) * V;
       act[w] = j0[w] < A.pitch;
-      SrcRow<T, SRC, PRE>::load(A, i0 - 1, j0[w], act[w], alpha, xw[w], raw_c[w]);
-      SrcRow<T, SRC, PRE>::load(A, i0, j0[w], act[w], alpha, xc[w], raw_c[w]);
+      SrcRow<T, SRC, PRE, P2P>::load(A, i0 - 1, j0[w], act[w], alpha, xw[w], raw_c[w]);
+      SrcRow<T, SRC, PRE, P2P>::load(A, i0, j0[w], act[w], alpha, xc[w], raw_c[w]);
     }
 #pragma unroll kStencilUnroll
     for (int i = i0; i < i1; ++i) {
@@ -168,8 +196,9 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
           qv[w] = pack_zero<T>();
         }
       }
+      if (P2P && i + 1 == A.row_hi && A.hx_hi) stencil_halo_wait<T, SRC>(A, false);  // row i + 1 comes from the upper neighbour
 #pragma unroll
-      for (int w = 0; w < W; ++w) SrcRow<T, SRC, PRE>::load(A, i + 1, j0[w], act[w], alpha, xe[w], raw_e[w]);
+      for (int w = 0; w < W; ++w) SrcRow<T, SRC, PRE, P2P>::load(A, i + 1, j0[w], act[w], alpha, xe[w], raw_e[w]);
       // ---- j-1 / j+V neighbours of the centre row: warp shuffles; only the two outer edge lanes reload
       T xs[W], xn[W];
 #pragma unroll
@@ -181,8 +210,8 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
         if (lane == 0) xs[w] = from_prev;
         if (lane == 31) xn[w - 1] = from_next;
       }
-      if (lane == 0) xs[0] = SrcRow<T, SRC, PRE>::scalar(A, i, j0[0] - 1, alpha);
-      if (lane == 31) xn[W - 1] = SrcRow<T, SRC, PRE>::scalar(A, i, j0[W - 1] + V, alpha);
+      if (lane == 0) xs[0] = SrcRow<T, SRC, PRE, P2P>::scalar(A, i, j0[0] - 1, alpha);
+      if (lane == 31) xn[W - 1] = SrcRow<T, SRC, PRE, P2P>::scalar(A, i, j0[W - 1] + V, alpha);
 #pragma unroll
       for (int w = 0; w < W; ++w) {
         const size_t o = (size_t)i * A.pitch + j0[w];
@@ -217,8 +246,16 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
             for (int k = 0; k < V; ++k) { r.a[k] = qv[w].a[k] - y.a[k]; acc0 += (double)r.a[k] * (double)r.a[k]; }
             st_vec(A.y + o, r);
             if (A.s_out) st_vec(A.s_out + o, r);
+            if (P2P) {
+              if (i == A.row_lo && A.push_lo) st_vec(A.push_lo + j0[w], r);
+              if (i == A.row_hi - 1 && A.push_hi) st_vec(A.push_hi + j0[w], r);
+            }
           } else {
             st_vec(A.y + o, y);
+            if (P2P) {
+              if (i == A.row_lo && A.push_lo) st_vec(A.push_lo + j0[w], y);
+              if (i == A.row_hi - 1 && A.push_hi) st_vec(A.push_hi + j0[w], y);
+            }
             if ((EPI == EPI_ST && A.s_out) || EPI == EPI_DOT_Q_ST) st_vec(A.s_out + o, raw_c[w]);
 #pragma unroll
             for (int k = 0; k < V; ++k) {
@@ -303,8 +340,10 @@ __global__ void __launch_bounds__(256) k_dot(EwGeom g, const T* p, const T* q, R
 }
 
 // K0: r = b, (r_tld = b), x = 0, [p = r for CG]; dot (r,r).   bicgsolver.py:21-36 / cgsolver.py:31-39,90
-template <typename T, bool CG>
-__global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_tld, T* x, T* p, ReduceWs ws, int fin) {
+// P2P: the boundary rows of r (BiCGSTAB: the operand of the first t = A s) / of p (CG) also go to the neighbours (hp)
+template <typename T, bool CG, bool P2P = false>
+__global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_tld, T* x, T* p, ReduceWs ws, int fin,
+                                              HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
   double acc = 0.0;
@@ -312,6 +351,7 @@ __global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_t
     Pack<T> bb[U];
     KT_EW_FOR(U, u, o) bb[u] = ld_stream(b + o);
     KT_EW_FOR(U, u, o) {
+      if (P2P) ew_push(hp, o, bb[u]);
       st_vec(r + o, bb[u]);
       if (r_tld) st_vec(r_tld + o, bb[u]);
       if (CG) st_vec(p + o, bb[u]);
@@ -324,8 +364,9 @@ __global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_t
 }
 
 // K1: p = r + beta (p - omega v); first iteration p = r (bicgsolver.py:99-103)
-template <typename T>
-__global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, const T* v, const Scalars* sc) {
+template <typename T, bool P2P = false>
+__global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, const T* v, const Scalars* sc,
+                                                HaloPush<T> hp = HaloPush<T>(), ReduceWs ws = ReduceWs()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
   if (sc->done) return;
@@ -344,15 +385,18 @@ __global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, cons
         for (int k = 0; k < V; ++k) out.a[k] = rr[u].a[k] + beta * (pp[u].a[k] - omega * vv[u].a[k]);
       }
       st_vec(p + o, out);
+      if (P2P) ew_push(hp, o, out);
     }
   }
+  if (P2P) push_finalize(ws);
 }
 
 // K4: x += alpha p^ + omega s^ ; r = s - omega t ; dots (r,r), (r,r_tld)   (bicgsolver.py:120-123, 95)
-template <typename T, bool PRE>
+template <typename T, bool PRE, bool P2P = false>
 __global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* p, const T* s, const T* t,
                                                  const T* r_tld, const T* minv, double alpha_imm, double omega_imm,
-                                                 int from_sc, ReduceWs ws, int fin, const T* v_for_s = nullptr) {
+                                                 int from_sc, ReduceWs ws, int fin, const T* v_for_s = nullptr,
+                                                 HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = (kEwUnroll > 2) ? 2 : kEwUnroll;     // 5-6 operand planes: 2 strides already keep ~190 B in flight
   if (from_sc && ws.sc->done) return;
@@ -386,6 +430,7 @@ __global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* 
       }
       st_vec(x + o, xx[u]);
       st_vec(r + o, rn);
+      if (P2P) ew_push(hp, o, rn);
     }
   }
   block_reduce_finalize<2>(a0, a1, ws, fin);
@@ -418,8 +463,9 @@ __global__ void __launch_bounds__(256) k_cg_xr(EwGeom g, T* x, T* r, const T* p,
 }
 
 // C3: p = r + beta p   (cgsolver.py:78-81)
-template <typename T>
-__global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const Scalars* sc) {
+template <typename T, bool P2P = false>
+__global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const Scalars* sc, HaloPush<T> hp = HaloPush<T>(),
+                                              ReduceWs ws = ReduceWs()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
   if (sc->done) return;
@@ -431,8 +477,10 @@ __global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const 
 #pragma unroll
       for (int k = 0; k < V; ++k) pp[u].a[k] = rr[u].a[k] + beta * pp[u].a[k];
       st_vec(p + o, pp[u]);
+      if (P2P) ew_push(hp, o, pp[u]);
     }
   }
+  if (P2P) push_finalize(ws);
 }
 
 __global__ void k_sc_reset(Scalars* sc, double eps, long long max_iter, int flags) {
@@ -503,6 +551,7 @@ static Plan make_plan(const kt_handle_s* h) {
 
 static ReduceWs make_ws(kt_handle_s* h, double* history = nullptr, long long cap = 0, double* dots_out = nullptr) {
   ReduceWs ws;
+  memset(&ws, 0, sizeof(ws));
   ws.partials = h->partials; ws.ticket = h->ticket; ws.max_blocks = h->max_blocks; ws.sc = h->sc;
   ws.history = history; ws.history_cap = cap; ws.dots_out = dots_out;
   return ws;
@@ -527,13 +576,13 @@ constexpr int stencil_planes(int SRC, bool PRE, int EPI) {
 // planes the element-wise kernels with an inner product are sized by (the grid_for argument at their launch sites)
 enum { EWP_DOT = 2, EWP_INIT = 4, EWP_BICG_XR = 8, EWP_BICG_XR_UNIT = 7, EWP_CG_XR = 6 };
 
-template <typename T, int SRC, bool PRE, int EPI>
+template <typename T, int SRC, bool PRE, int EPI, bool P2P = false>
 static int launch_stencil(kt_handle_s* h, const Plan& P, const StencilArgs<T>& A) {
   constexpr int planes = stencil_planes(SRC, PRE, EPI);
   const StPlan S = stencil_plan(h, P.V, StencilCfg<SRC, PRE>::W, planes);
   StencilArgs<T> B = A;
   B.TI = S.TI; B.nCC = S.nCC; B.nTiles = S.nTiles;
-  k_stencil<T, SRC, PRE, EPI><<<S.grid, 256, 0, h->stream>>>(B);
+  k_stencil<T, SRC, PRE, EPI, P2P><<<S.grid, 256, 0, h->stream>>>(B);
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -935,31 +984,6 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
 // Solves use sum groups 0-2, 6-7 and halo slots 0-2 (p / v / r); the standalone calls (kt_p2p_exchange, kt_p2p_allreduce: the
 // SIMPLE kernels around the solves) rotate over their own sum groups 3-5 and halo slots 3-4, so that two consecutive
 // exchanges never meet in a slot a slow neighbour may still be reading.
-constexpr int P2P_GROUPS = 8, P2P_SLOTS = 5;
-struct P2PBlock {                     // layout of the comm block every rank allocates (zero-initialised)
-  double dots[P2P_GROUPS][16][2];
-  unsigned long long dot_flag[P2P_GROUPS][16];
-  unsigned long long halo_flag[P2P_SLOTS][2]; // [slot][0: from lower neighbour, 1: from upper neighbour]
-};
-
-__device__ __forceinline__ bool p2p_wait(const volatile unsigned long long* flag, unsigned long long seq, Scalars* sc, long long timeout_ns,
-                                         unsigned what) {
-  unsigned long long t0 = 0, seen;
-  while ((seen = *flag) < seq) {
-    __nanosleep(32);
-    unsigned long long now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-    if (t0 == 0) t0 = now;
-    if ((long long)(now - t0) > timeout_ns) {  // a peer died or the ranks disagree on the schedule -- fail, never hang
-      sc->wait_what = what; sc->wait_seq = seq; sc->wait_seen = seen;
-      *(volatile int*)&sc->status = 7; *(volatile int*)&sc->done = 1;
-      return false;
-    }
-  }
-  __threadfence_system();
-  return true;
-}
-
 // how long a wait may last (default 30 s; KT_P2P_TIMEOUT_MS: tests use a short one)
 static long long p2p_timeout_ns() {
   static long long ns = (long long)env_int("KT_P2P_TIMEOUT_MS", 30000) * 1000000LL;
@@ -1005,26 +1029,9 @@ struct P2PPeers { P2PBlock* blk[16]; };
 __global__ void k_p2p_reduce(P2PPeers peers, int rank, int nranks, int group, int ndot, const double* local, int fin,
                              unsigned long long seq, Scalars* sc, double* history, long long cap, int in_solve, int op_max,
                              long long timeout_ns) {
-  const int lane = threadIdx.x;
   if (in_solve && sc->done) return;
-  P2PBlock* mine = peers.blk[rank];
-  if (lane < nranks) {
-    P2PBlock* pb = peers.blk[lane];
-    pb->dots[group][rank][0] = local[0];
-    pb->dots[group][rank][1] = ndot > 1 ? local[1] : 0.0;
-    __threadfence_system();
-    *(volatile unsigned long long*)&pb->dot_flag[group][rank] = seq;
-    p2p_wait(&mine->dot_flag[group][lane], seq, sc, timeout_ns, 2u << 8 | (unsigned)group | (unsigned)lane << 16);
-  }
-  __syncwarp();
-  if (lane == 0 && (!in_solve || !sc->done)) {
-    double d0 = 0.0, d1 = 0.0;
-    for (int r = 0; r < nranks; ++r) {          // rank order: the same bits on every rank
-      const double a0 = *(volatile double*)&mine->dots[group][r][0], a1 = *(volatile double*)&mine->dots[group][r][1];
-      if (op_max) { d0 = fmax(d0, a0); d1 = fmax(d1, a1); } else { d0 += a0; d1 += a1; }
-    }
-    scalar_algebra(fin, sc, d0, d1, history, cap);
-  }
+  p2p_allreduce_warp(peers.blk, rank, nranks, group, ndot, local[0], ndot > 1 ? local[1] : 0.0, fin, seq, sc, history, cap, in_solve, op_max,
+                     timeout_ns);
 }
 
 // Sequence numbers: (solve epoch << 32) | exchange index within the solve.  The epoch advances once per solve on every
@@ -1097,7 +1104,7 @@ static int p2p_reduce(P2PCtx& c, int group, int ndot, int fin, double* history, 
 // BICGSolver.solve (bicgsolver.py:88-135) over x-slabs; with Minv != NULL / KT_FLAG_WARM_START the monolith's Jacobi
 // variant (karman_taichi.py:342-456: warm start needs ws->r_tld and the halo rows of x, exchanged through plane slot 0).
 template <typename T>
-static int t_p2p_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* w,
+static int t_p2p_bicgstab_unfused(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* w,
                           const kt_p2p_comm* cm, double eps, long long max_iter, int flags, bool fixed_iters, long* iters, double* rel_res,
                           int* status) {
   T* r = (T*)w->r; T* p = (T*)w->p; T* v = (T*)w->Ap; T* s = (T*)w->s; T* t = (T*)w->t; T* r_tld = (T*)w->r_tld;
@@ -1165,7 +1172,7 @@ static int t_p2p_bicgstab(kt_handle_s* h, const void* coef, const void* b, void*
 // CGSolver.solve (cgsolver.py:83-114) over x-slabs with the same two comm kernels: one halo exchange (p) and two
 // all-reduces ((p,Ap) and (r,r)) per iteration.
 template <typename T>
-static int t_p2p_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const kt_krylov_ws* w, const kt_p2p_comm* cm,
+static int t_p2p_cg_unfused(kt_handle_s* h, const void* coef, const void* b, void* x, const kt_krylov_ws* w, const kt_p2p_comm* cm,
                     double eps, long long max_iter, bool fixed_iters, long* iters, double* rel_res, int* status) {
   T* r = (T*)w->r; T* p = (T*)w->p; T* Ap = (T*)w->Ap;
   KT_CHECK_ARG(r && p && Ap, "kt_krylov_ws: r, p, Ap are required for CG");
@@ -1191,6 +1198,222 @@ static int t_p2p_cg(kt_handle_s* h, const void* coef, const void* b, void* x, co
   if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
   if (status) *status = S.status;
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same two solvers with the communication FUSED into the compute kernels (default; KT_P2P_FUSED=0 selects the
+// separate comm kernels above for comparison).  Per BiCGSTAB iteration the four compute kernels are all that is launched:
+//   K1  p-update      stores its first / last owned row of p straight into the neighbours' receive buffers; the last block
+//                     to finish raises the neighbours' flags (push_finalize)
+//   K2  v = A p^      boundary tiles wait for the neighbours' p flag and read the halo rows from the receive buffer; stores
+//                     the boundary rows of v to the neighbours; its finalising block raises the v flags, then IS the
+//                     all-reduce of (r~, v) (p2p_allreduce_warp) and computes alpha
+//   K3  t = A s^      waits for the r and v flags, halo rows of s = r - alpha v from the receive buffers; finalising block
+//                     all-reduces (t,s), (t,t) -> omega
+//   K4  x, r update   stores the boundary rows of the new r to the neighbours; finalising block raises the r flags,
+//                     all-reduces (r,r), (r,r~) -> test, rho, beta
+// Same grids, same per-thread work, same rank-ordered sums as the unfused path: bit-identical results.  Write-after-read
+// safety of a receive row: the neighbour overwrites it one iteration later, after an all-reduce that this rank only joins
+// from a kernel that runs (stream order) after the kernel that read the row.
+struct P2PRows {      // receive rows and flags of one halo slot, from this rank's point of view
+  void* push_lo; void* push_hi;                        // where my first / last owned row goes (neighbours' buffers)
+  unsigned long long* raise_lo; unsigned long long* raise_hi;   // the neighbours' flags for them
+  const void* in_lo; const void* in_hi;                // where the neighbours' rows land (my buffer)
+  const unsigned long long* wait_lo; const unsigned long long* wait_hi;   // my flags for them
+};
+
+static P2PRows p2p_rows(const P2PCtx& c, int slot, size_t esize) {
+  const kt_handle_s* h = c.h;
+  const size_t row = (size_t)h->pitch * esize;
+  P2PRows R;
+  memset(&R, 0, sizeof(R));
+  char* lo = (char*)c.cm->peer_halo_recv[0]; char* hi = (char*)c.cm->peer_halo_recv[1]; char* mine = (char*)c.cm->halo_recv;
+  if (lo) { R.push_lo = lo + (size_t)(slot * 2 + 1) * row; R.raise_lo = &c.blk_lo->halo_flag[slot][1];
+            R.in_lo = mine + (size_t)(slot * 2 + 0) * row; R.wait_lo = &c.mine->halo_flag[slot][0]; }
+  if (hi) { R.push_hi = hi + (size_t)(slot * 2 + 0) * row; R.raise_hi = &c.blk_hi->halo_flag[slot][0];
+            R.in_hi = mine + (size_t)(slot * 2 + 1) * row; R.wait_hi = &c.mine->halo_flag[slot][1]; }
+  return R;
+}
+
+// device copy of the ranks' comm-block pointers (uploaded when they change)
+static int p2p_upload_peers(kt_handle_s* h, const P2PCtx& c) {
+  if (!h->p2p_peers_dev) KT_CUDA(cudaMalloc(&h->p2p_peers_dev, 16 * sizeof(void*)));
+  if (memcmp(h->p2p_peers_host, c.peers.blk, sizeof(h->p2p_peers_host)) != 0) {
+    memcpy(h->p2p_peers_host, c.peers.blk, sizeof(h->p2p_peers_host));
+    KT_CUDA(cudaMemcpyAsync(h->p2p_peers_dev, h->p2p_peers_host, sizeof(h->p2p_peers_host), cudaMemcpyHostToDevice, h->stream));
+  }
+  return 0;
+}
+
+// ReduceWs of a kernel whose finalising block all-reduces over the ranks (group >= 0) and / or announces pushed rows (R)
+static ReduceWs p2p_ws(P2PCtx& c, const kt_krylov_ws* w, int group, const P2PRows* R, int slot) {
+  kt_handle_s* h = c.h;
+  ReduceWs ws = make_ws(h, w->history, w->history_cap, c.dots);
+  ws.timeout_ns = p2p_timeout_ns();
+  if (group >= 0 && c.cm->nranks > 1) {
+    ws.peers = (P2PBlock* const*)h->p2p_peers_dev; ws.rank = c.cm->rank; ws.nranks = c.cm->nranks; ws.group = group;
+    ws.rseq = c.base | ++h->p2p_dot_k[group];
+  }
+  if (R && c.cm->nranks > 1) { ws.hflag_lo = R->raise_lo; ws.hflag_hi = R->raise_hi; ws.hseq = c.base | ++h->p2p_halo_k[slot]; }
+  return ws;
+}
+
+template <typename T>
+static HaloPush<T> p2p_push(const kt_handle_s* h, const P2PRows& R) {
+  HaloPush<T> hp;
+  hp.lo = (T*)R.push_lo; hp.hi = (T*)R.push_hi;
+  hp.first_off = (long long)h->row_lo * h->pitch; hp.last_off = (long long)(h->row_hi - 1) * h->pitch; hp.pitch = h->pitch;
+  return hp;
+}
+
+template <typename T>
+static int t_p2p_bicgstab_fused(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* w,
+                                const kt_p2p_comm* cm, double eps, long long max_iter, int flags, bool fixed_iters, long* iters,
+                                double* rel_res, int* status) {
+  T* r = (T*)w->r; T* p = (T*)w->p; T* v = (T*)w->Ap; T* s = (T*)w->s; T* t = (T*)w->t; T* r_tld = (T*)w->r_tld;
+  KT_CHECK_ARG(r && p && v && t, "kt_krylov_ws: r, p, Ap, t are required (s optional: NULL = recomputed, not stored)");
+  const bool warm = (flags & KT_FLAG_WARM_START) != 0, pre = Minv != nullptr;
+  KT_CHECK_ARG(!(warm && !r_tld), "warm start needs a separate r_tld plane");
+  P2PCtx c;
+  KT_TRY(p2p_begin(h, cm, &c));
+  KT_TRY(p2p_upload_peers(h, c));
+  KT_TRY(sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, flags & KT_FLAG_OMEGA_ZERO_BREAK));
+  const T* r_tld_c = r_tld ? r_tld : (const T*)b;
+  Plan P = make_plan(h);
+  const P2PRows Rp = p2p_rows(c, 0, sizeof(T)), Rv = p2p_rows(c, 1, sizeof(T)), Rr = p2p_rows(c, 2, sizeof(T));
+  const int g_init = 6 + (int)(h->p2p_epoch & 1ull);
+  auto consume = [&](StencilArgs<T>& A, const P2PRows& Rx, unsigned long long seq_x, const P2PRows* Rv_, unsigned long long seq_v) {
+    A.hx_lo = (const T*)Rx.in_lo; A.hx_hi = (const T*)Rx.in_hi; A.fx_lo = Rx.wait_lo; A.fx_hi = Rx.wait_hi; A.seq_x = seq_x;
+    if (Rv_) { A.hv_lo = (const T*)Rv_->in_lo; A.hv_hi = (const T*)Rv_->in_hi; A.fv_lo = Rv_->wait_lo; A.fv_hi = Rv_->wait_hi; A.seq_v = seq_v; }
+  };
+  // K0: r (and r~) = b - A x0 or b; (r, r) -> rTr0, rho; the boundary rows of r go to the neighbours (operand of the first K3)
+  if (warm) {
+    KT_TRY(p2p_halo<T>(c, 0, (T*)x));                               // halo rows of x0 (a plane of the caller's: separate exchange)
+    StencilArgs<T> A = stencil_args<T>(h, P, coef);
+    A.ws = p2p_ws(c, w, g_init, &Rr, 2);
+    A.x = (const T*)x; A.q = (const T*)b; A.y = r; A.s_out = r_tld; A.fin = FIN_BICG_INIT;
+    A.push_lo = (T*)Rr.push_lo; A.push_hi = (T*)Rr.push_hi;
+    KT_TRY((launch_stencil<T, SRC_X, false, EPI_RESID, true>(h, P, A)));
+  } else {
+    ProfScope ps(h, KT_K_INIT);
+    const ReduceWs ws0 = p2p_ws(c, w, g_init, &Rr, 2);
+    k_init<T, false, true><<<grid_for(h, P.ew_blocks, EWP_INIT), 256, 0, h->stream>>>(P.g, (const T*)b, r, r_tld, (T*)x, nullptr, ws0, FIN_BICG_INIT,
+                                                                                      p2p_push<T>(h, Rr));
+    KT_LAUNCH_CHECK(h);
+  }
+  StencilArgs<T> A2 = stencil_args<T>(h, P, coef);
+  A2.x = p; A2.minv = (const T*)Minv; A2.q = r_tld_c; A2.y = v; A2.check_done = 1; A2.fin = FIN_BICG_ALPHA;
+  A2.push_lo = (T*)Rv.push_lo; A2.push_hi = (T*)Rv.push_hi;
+  StencilArgs<T> A3 = stencil_args<T>(h, P, coef);
+  A3.x = r; A3.v = v; A3.minv = (const T*)Minv; A3.y = t; A3.s_out = s; A3.alpha_from_sc = 1; A3.check_done = 1; A3.fin = FIN_BICG_OMEGA;
+  auto iter = [&]() -> int {
+    {
+      ProfScope ps(h, KT_K_BICG_P);
+      const ReduceWs ws1 = p2p_ws(c, w, -1, &Rp, 0);
+      k_bicg_p<T, true><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, p, r, v, h->sc, p2p_push<T>(h, Rp), ws1);
+      KT_LAUNCH_CHECK(h);
+    }
+    {
+      ProfScope ps(h, KT_K_BICG_V);
+      A2.ws = p2p_ws(c, w, 0, &Rv, 1);
+      consume(A2, Rp, c.base | h->p2p_halo_k[0], nullptr, 0);
+      KT_TRY(pre ? (launch_stencil<T, SRC_X, true, EPI_DOT_Q, true>(h, P, A2)) : (launch_stencil<T, SRC_X, false, EPI_DOT_Q, true>(h, P, A2)));
+    }
+    {
+      ProfScope ps(h, KT_K_BICG_ST);
+      A3.ws = p2p_ws(c, w, 1, nullptr, 0);
+      consume(A3, Rr, c.base | h->p2p_halo_k[2], &Rv, c.base | h->p2p_halo_k[1]);
+      KT_TRY(pre ? (launch_stencil<T, SRC_S, true, EPI_ST, true>(h, P, A3)) : (launch_stencil<T, SRC_S, false, EPI_ST, true>(h, P, A3)));
+    }
+    {
+      ProfScope ps(h, KT_K_BICG_XR);
+      const T* v_for_s = s ? nullptr : v;
+      const ReduceWs ws4 = p2p_ws(c, w, 2, &Rr, 2);
+      const HaloPush<T> hp = p2p_push<T>(h, Rr);
+      if (pre) k_bicg_xr<T, true, true><<<grid_for(h, P.ew_blocks, EWP_BICG_XR_UNIT), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws4, FIN_BICG_END, v_for_s, hp);
+      else k_bicg_xr<T, false, true><<<grid_for(h, P.ew_blocks, EWP_BICG_XR_UNIT), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, nullptr, 0, 0, 1, ws4, FIN_BICG_END, v_for_s, hp);
+      KT_LAUNCH_CHECK(h);
+    }
+    return 0;
+  };
+  int rc = run_chunks(h, max_iter, iter);
+  if (rc) return rc;
+  const Scalars& S = *h->sc_host;
+  if (iters) *iters = (long)S.iter;
+  if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
+  if (status) *status = S.status;
+  return 0;
+}
+
+// CG fused the same way: k_init / the p-update push the boundary rows of p, Ap = A p waits for them; the finalising blocks
+// of k_init, Ap = A p and the x / r update are the three all-reduces.
+template <typename T>
+static int t_p2p_cg_fused(kt_handle_s* h, const void* coef, const void* b, void* x, const kt_krylov_ws* w, const kt_p2p_comm* cm,
+                          double eps, long long max_iter, bool fixed_iters, long* iters, double* rel_res, int* status) {
+  T* r = (T*)w->r; T* p = (T*)w->p; T* Ap = (T*)w->Ap;
+  KT_CHECK_ARG(r && p && Ap, "kt_krylov_ws: r, p, Ap are required for CG");
+  P2PCtx c;
+  KT_TRY(p2p_begin(h, cm, &c));
+  KT_TRY(p2p_upload_peers(h, c));
+  KT_TRY(sc_reset(h, fixed_iters ? -1.0 : eps, max_iter, 0));
+  Plan P = make_plan(h);
+  const P2PRows Rp = p2p_rows(c, 0, sizeof(T));
+  {
+    const ReduceWs ws0 = p2p_ws(c, w, 6 + (int)(h->p2p_epoch & 1ull), &Rp, 0);
+    k_init<T, true, true><<<grid_for(h, P.ew_blocks, EWP_INIT), 256, 0, h->stream>>>(P.g, (const T*)b, r, nullptr, (T*)x, p, ws0, FIN_CG_INIT,
+                                                                                     p2p_push<T>(h, Rp));
+    KT_LAUNCH_CHECK(h);
+  }
+  StencilArgs<T> A1 = stencil_args<T>(h, P, coef);
+  A1.x = p; A1.y = Ap; A1.check_done = 1; A1.fin = FIN_CG_ALPHA;
+  auto iter = [&]() -> int {
+    {
+      ProfScope ps(h, KT_K_CG_AP);
+      A1.ws = p2p_ws(c, w, 0, nullptr, 0);
+      A1.hx_lo = (const T*)Rp.in_lo; A1.hx_hi = (const T*)Rp.in_hi; A1.fx_lo = Rp.wait_lo; A1.fx_hi = Rp.wait_hi; A1.seq_x = c.base | h->p2p_halo_k[0];
+      KT_TRY((launch_stencil<T, SRC_X, false, EPI_DOT_SRC, true>(h, P, A1)));
+    }
+    {
+      ProfScope ps(h, KT_K_CG_XR);
+      const ReduceWs ws2 = p2p_ws(c, w, 1, nullptr, 0);
+      k_cg_xr<T><<<grid_for(h, P.ew_blocks, EWP_CG_XR), 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws2, FIN_CG_END);
+      KT_LAUNCH_CHECK(h);
+    }
+    {
+      ProfScope ps(h, KT_K_CG_P);
+      const ReduceWs ws3 = p2p_ws(c, w, -1, &Rp, 0);
+      k_cg_p<T, true><<<grid_for(h, P.ew_blocks, 3), 256, 0, h->stream>>>(P.g, p, r, h->sc, p2p_push<T>(h, Rp), ws3);
+      KT_LAUNCH_CHECK(h);
+    }
+    return 0;
+  };
+  int rc = run_chunks(h, max_iter, iter);
+  if (rc) return rc;
+  const Scalars& S = *h->sc_host;
+  if (iters) *iters = (long)S.iter;
+  if (rel_res) *rel_res = sqrt(S.rTr / S.rTr0);
+  if (status) *status = S.status;
+  return 0;
+}
+
+static bool p2p_fused() {
+  static int on = env_int("KT_P2P_FUSED", 1);
+  return on != 0;
+}
+
+template <typename T>
+static int t_p2p_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, const void* Minv, const kt_krylov_ws* w,
+                          const kt_p2p_comm* cm, double eps, long long max_iter, int flags, bool fixed_iters, long* iters, double* rel_res,
+                          int* status) {
+  return p2p_fused() ? t_p2p_bicgstab_fused<T>(h, coef, b, x, Minv, w, cm, eps, max_iter, flags, fixed_iters, iters, rel_res, status)
+                     : t_p2p_bicgstab_unfused<T>(h, coef, b, x, Minv, w, cm, eps, max_iter, flags, fixed_iters, iters, rel_res, status);
+}
+
+template <typename T>
+static int t_p2p_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const kt_krylov_ws* w, const kt_p2p_comm* cm, double eps,
+                    long long max_iter, bool fixed_iters, long* iters, double* rel_res, int* status) {
+  return p2p_fused() ? t_p2p_cg_fused<T>(h, coef, b, x, w, cm, eps, max_iter, fixed_iters, iters, rel_res, status)
+                     : t_p2p_cg_unfused<T>(h, coef, b, x, w, cm, eps, max_iter, fixed_iters, iters, rel_res, status);
 }
 #undef KT_TRY
 
