@@ -225,7 +225,8 @@ int kt_p2p_bicgstab_solve(kt_handle_t h, const void* coef, const void* b, void* 
  * halo-receive buffer must hold (kt_p2p_halo_slots() x 2 x pitch reals). */
 int kt_p2p_halo_slots(void);
 int kt_p2p_exchange(kt_handle_t h, const kt_p2p_comm* comm, void* plane);
-int kt_p2p_allreduce(kt_handle_t h, const kt_p2p_comm* comm, const double* vals_dev2, int op, double* out_host2);
+/* the two values: vals_dev2 (device memory) or, when it is NULL, vals_host2 (host memory; they travel as kernel arguments) */
+int kt_p2p_allreduce(kt_handle_t h, const kt_p2p_comm* comm, const double* vals_dev2, const double* vals_host2, int op, double* out_host2);
 /* CGSolver.solve (cgsolver.py:83-114) over x-slabs, same comm kernels: one halo exchange (p) and two all-reduces per
  * iteration.  ws: r, p, Ap. */
 int kt_p2p_cg_solve(kt_handle_t h, const void* coef, const void* b, void* x, const kt_krylov_ws* ws,

@@ -130,7 +130,7 @@ SIGNATURES = {
     'kt_p2p_bicgstab_solve': (_I, [_P, _P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _I, _PL, _PD, _PI]),
     'kt_p2p_halo_slots': (_I, []),
     'kt_p2p_exchange': (_I, [_P, C.POINTER(P2PComm), _P]),
-    'kt_p2p_allreduce': (_I, [_P, C.POINTER(P2PComm), _P, _I, _PD]),
+    'kt_p2p_allreduce': (_I, [_P, C.POINTER(P2PComm), _P, _PD, _I, _PD]),
     'kt_p2p_cg_solve': (_I, [_P, _P, _P, _P, _WS, C.POINTER(P2PComm), _D, _L, _I, _PL, _PD, _PI]),
     'kt_reduce_plan': (_I, [C.POINTER(Geom), _I, _I, C.POINTER(C.c_longlong)]),
     'kt_resident_plan': (_I, [C.POINTER(Geom), _I, _I, _I, _I, C.POINTER(C.c_longlong)]),

@@ -51,6 +51,18 @@ static int coef_layout(kt_handle_s* h, void* soa, void* aos, int row0 = 0, int n
 
 static size_t esize(const kt_handle_s* h) { return h->dtype == KT_F64 ? 8 : 4; }
 
+// kt::publish (kt_handle.h): one warp moves n 8-byte words; dst may be pinned host memory (zero-copy stores)
+__global__ void k_publish(const unsigned long long* src, unsigned long long* dst, int n) {
+  for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+}
+
+int publish(kt_handle_s* h, const void* src_dev, void* dst, int n_words) {
+  k_publish<<<1, 32, 0, h->stream>>>((const unsigned long long*)src_dev, (unsigned long long*)dst, n_words);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_publish launch", __FILE__, __LINE__);
+  return 0;
+}
+
 }  // namespace kt
 
 using namespace kt;

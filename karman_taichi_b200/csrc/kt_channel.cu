@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) k_ch_correct(CP S, const int* __restrict_
 static unsigned ch_rows(const CP& S) { return (unsigned)std::max(1, std::min(S.ib - S.ia, 65535)); }
 
 static int ch_read(kt_handle_s* h, double* out, int n) {
-  KT_CUDA(cudaMemcpyAsync(h->red_host, h->red_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (int rc = publish(h, h->red_out, h->red_host, 4)) return rc;
   KT_CUDA(cudaStreamSynchronize(h->stream));
   for (int k = 0; k < n; ++k) out[k] = h->red_host[k];
   return 0;
@@ -368,7 +368,7 @@ int kt_outlet_sums(kt_handle_t h, const kt_channel_params* P, const void* u, dou
   if (h->dtype == KT_F64) k_ch_outlet_sums<double><<<1, 256, 0, h->stream>>>(S, (const double*)u, h->red_out);
   else k_ch_outlet_sums<float><<<1, 256, 0, h->stream>>>(S, (const float*)u, h->red_out);
   KT_LAUNCH_CHECK(h);
-  KT_CUDA(cudaMemcpyAsync(sums_dev, h->red_out, 2 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (int rc = publish(h, h->red_out, sums_dev, 2)) return rc;
   return 0;
 }
 

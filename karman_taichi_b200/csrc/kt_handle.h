@@ -80,6 +80,11 @@ int coop_try_solve(kt_handle_s* h, const void* coef, const void* b, void* x, con
 template <typename T> int cluster_plan(const kt_handle_s* h, bool pre, bool warm, bool is_cg, long long* out);
 template <typename T> int coop_plan(const kt_handle_s* h, bool pre, bool warm, bool is_cg, long long* out);
 void set_error(const std::string& s);
+// n 8-byte words from device memory to pinned host memory (or device memory) by a one-warp KERNEL on the handle's stream,
+// instead of cudaMemcpyAsync: copies of all streams queue up in the copy engines in submission order, so a copy that waits
+// for a kernel which in turn waits for ANOTHER stream's kernel (the x-slab comm kernels with all ranks on one device) can
+// block that other stream's copies for good.  Kernels of different streams have no such order.
+int publish(kt_handle_s* h, const void* src_dev, void* dst, int n_words);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 }  // namespace kt
 

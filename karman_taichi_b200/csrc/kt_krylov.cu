@@ -587,8 +587,9 @@ static int launch_stencil(kt_handle_s* h, const Plan& P, const StencilArgs<T>& A
   return 0;
 }
 
+static_assert(sizeof(Scalars) % 8 == 0, "Scalars is published in 8-byte words");
 static int read_dots(kt_handle_s* h, double* out, int n) {
-  KT_CUDA(cudaMemcpyAsync(h->sc_host, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+  if (int rc = publish(h, h->sc, h->sc_host, (int)(sizeof(Scalars) / 8))) return rc;
   KT_CUDA(cudaStreamSynchronize(h->stream));
   out[0] = h->sc_host->dot0;
   if (n > 1) out[1] = h->sc_host->dot1;
@@ -724,7 +725,7 @@ static int run_chunks(kt_handle_s* h, long long max_iter, EnqueueIter&& enqueue_
       for (long long k = 0; k < n; ++k) { int rc = enqueue_iter(); if (rc) return rc; }
     }
     enq += n;
-    KT_CUDA(cudaMemcpyAsync(h->sc_host + slot, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+    if (int rc = publish(h, h->sc, h->sc_host + slot, (int)(sizeof(Scalars) / 8))) return rc;   // (a kernel, not a copy: kt_handle.h)
     KT_CUDA(cudaEventRecord(h->ev[slot], h->stream));
     pending[slot] = true;
     const int other = slot ^ 1;
@@ -735,8 +736,8 @@ static int run_chunks(kt_handle_s* h, long long max_iter, EnqueueIter&& enqueue_
     }
     slot = other;
   }
+  if (int rc = publish(h, h->sc, h->sc_host, (int)(sizeof(Scalars) / 8))) return rc;
   KT_CUDA(cudaStreamSynchronize(h->stream));
-  KT_CUDA(cudaMemcpy(h->sc_host, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -1028,10 +1029,11 @@ struct P2PPeers { P2PBlock* blk[16]; };
 
 __global__ void k_p2p_reduce(P2PPeers peers, int rank, int nranks, int group, int ndot, const double* local, int fin,
                              unsigned long long seq, Scalars* sc, double* history, long long cap, int in_solve, int op_max,
-                             long long timeout_ns) {
+                             long long timeout_ns, double imm0 = 0.0, double imm1 = 0.0) {
   if (in_solve && sc->done) return;
-  p2p_allreduce_warp(peers.blk, rank, nranks, group, ndot, local[0], ndot > 1 ? local[1] : 0.0, fin, seq, sc, history, cap, in_solve, op_max,
-                     timeout_ns);
+  // local == NULL: the two values arrive as kernel arguments (kt_p2p_allreduce with host values: no host-to-device copy)
+  p2p_allreduce_warp(peers.blk, rank, nranks, group, ndot, local ? local[0] : imm0, local ? (ndot > 1 ? local[1] : 0.0) : imm1, fin, seq, sc,
+                     history, cap, in_solve, op_max, timeout_ns);
 }
 
 // Sequence numbers: (solve epoch << 32) | exchange index within the solve.  The epoch advances once per solve on every
@@ -1567,7 +1569,7 @@ int kt_dist_scalar(kt_handle_t h, int fin, const double* dots_dev, double* histo
 int kt_dist_poll(kt_handle_t h, int* done, long* iters, int* status, double* rel_res) {
   KT_CHECK_ARG(h, "kt_dist_poll: null handle");
   KT_DEV_GUARD(h);
-  KT_CUDA(cudaMemcpyAsync(h->sc_host, h->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+  if (int rc = publish(h, h->sc, h->sc_host, (int)(sizeof(Scalars) / 8))) return rc;
   KT_CUDA(cudaStreamSynchronize(h->stream));
   const Scalars& S = *h->sc_host;
   if (done) *done = S.done;
@@ -1610,15 +1612,16 @@ int kt_p2p_exchange(kt_handle_t h, const kt_p2p_comm* comm, void* plane) {
   return KT_DISPATCH(h, t_p2p_exchange<double>(h, comm, plane), t_p2p_exchange<float>(h, comm, plane));
 }
 
-int kt_p2p_allreduce(kt_handle_t h, const kt_p2p_comm* comm, const double* vals_dev2, int op, double* out_host2) {
-  KT_CHECK_ARG(h && comm && vals_dev2 && out_host2 && (op == 0 || op == 1), "kt_p2p_allreduce: bad argument");
+int kt_p2p_allreduce(kt_handle_t h, const kt_p2p_comm* comm, const double* vals_dev2, const double* vals_host2, int op, double* out_host2) {
+  KT_CHECK_ARG(h && comm && (vals_dev2 || vals_host2) && out_host2 && (op == 0 || op == 1), "kt_p2p_allreduce: bad argument");
   KT_DEV_GUARD(h);
   P2PCtx c;
   int rc = p2p_begin(h, comm, &c, false);
   if (rc) return rc;
   const unsigned long long seq = ++h->p2p_red_seq;
   const int group = 3 + (int)(seq % 3ull);
-  k_p2p_reduce<<<1, 32, 0, h->stream>>>(c.peers, comm->rank, comm->nranks, group, 2, vals_dev2, FIN_NONE, seq, h->sc, nullptr, 0, 0, op, p2p_timeout_ns());
+  k_p2p_reduce<<<1, 32, 0, h->stream>>>(c.peers, comm->rank, comm->nranks, group, 2, vals_dev2, FIN_NONE, seq, h->sc, nullptr, 0, 0, op, p2p_timeout_ns(),
+                                        vals_dev2 ? 0.0 : vals_host2[0], vals_dev2 ? 0.0 : vals_host2[1]);
   KT_LAUNCH_CHECK(h);
   rc = read_dots(h, out_host2, 2);
   if (rc) return rc;

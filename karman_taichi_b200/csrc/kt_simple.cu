@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) k_mdiv(SP S, const T* __restrict__ u, con
 }
 
 static int read_red(kt_handle_s* h, double* out, int n) {
-  KT_CUDA(cudaMemcpyAsync(h->red_host, h->red_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (int rc = publish(h, h->red_out, h->red_host, 2)) return rc;
   KT_CUDA(cudaStreamSynchronize(h->stream));
   for (int k = 0; k < n; ++k) out[k] = h->red_host[k];
   return 0;

@@ -444,11 +444,13 @@ class P2PSlabSolver:
     def allreduce(self, a, b=0.0, op='sum', device_pair=None):
         """Two doubles reduced over the ranks in rank order (``kt_p2p_allreduce``); returns the pair."""
         self._hd.use_current_stream()
-        if device_pair is None:
-            self.red_in.copy_(torch.tensor([a, b], dtype=torch.float64), non_blocking=False)
-            device_pair = self.red_in
         out = (C.c_double * 2)()
-        _lib.check(self.lib.kt_p2p_allreduce(self._hd.h, C.byref(self.comm), C.c_void_p(device_pair.data_ptr()), 1 if op == 'max' else 0, out))
+        if device_pair is None:       # host values travel as kernel arguments (no host-to-device copy in the stream)
+            vals = (C.c_double * 2)(float(a), float(b))
+            _lib.check(self.lib.kt_p2p_allreduce(self._hd.h, C.byref(self.comm), None, vals, 1 if op == 'max' else 0, out))
+        else:
+            _lib.check(self.lib.kt_p2p_allreduce(self._hd.h, C.byref(self.comm), C.c_void_p(device_pair.data_ptr()), None,
+                                                 1 if op == 'max' else 0, out))
         return out[0], out[1]
 
     def __del__(self):
