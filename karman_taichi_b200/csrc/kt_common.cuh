@@ -314,22 +314,25 @@ __device__ __forceinline__ void p2p_allreduce_warp(P2PBlock* const* peers, int r
 
 // Block-level deterministic reduction of up to two running sums + last-block finalisation.
 // Must be called by every thread of every block of the grid (blockDim.x multiple of 32, <= 1024).
+// `pushed`: this thread stored part of a boundary row into a neighbour GPU's receive buffer (P2P kernels only).
 template <int NDOT>
-__device__ __forceinline__ void block_reduce_finalize(double a0, double a1, const ReduceWs& ws, int fin) {
+__device__ __forceinline__ void block_reduce_finalize(double a0, double a1, const ReduceWs& ws, int fin, bool pushed = false) {
   __shared__ double sm[KT_MAX_DOTS][32];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   a0 = warp_sum(a0);
   if (NDOT > 1) a1 = warp_sum(a1);
   if (lane == 0) { sm[0][wid] = a0; if (NDOT > 1) sm[1][wid] = a1; }
-  __syncthreads();
+  // only the few blocks that really stored peer rows pay for a system-scope fence (it costs microseconds under full memory load)
+  int block_pushed = 0;
+  if (ws.hflag_lo || ws.hflag_hi) block_pushed = __syncthreads_or(pushed ? 1 : 0); else __syncthreads();
   if (threadIdx.x == 0) {
     double s0 = 0.0, s1 = 0.0;
     for (int w = 0; w < nw; ++w) { s0 += sm[0][w]; if (NDOT > 1) s1 += sm[1][w]; }
     ws.partials[blockIdx.x] = s0;
     if (NDOT > 1) ws.partials[ws.max_blocks + blockIdx.x] = s1;
     // (rows this block stored into a neighbour GPU's receive buffer are ordered before the ticket at system scope)
-    if (ws.hflag_lo || ws.hflag_hi) __threadfence_system(); else __threadfence();
+    if (block_pushed) __threadfence_system(); else __threadfence();
     unsigned int t = atomicAdd(ws.ticket, 1u);
     is_last = (t == gridDim.x - 1);
   }
@@ -379,11 +382,11 @@ __device__ __forceinline__ void block_reduce_finalize(double a0, double a1, cons
 
 // Kernels that push boundary rows but compute no inner product (p-updates): the last block to finish raises the flags.
 // Must be called by every thread of every block.
-__device__ __forceinline__ void push_finalize(const ReduceWs& ws) {
+__device__ __forceinline__ void push_finalize(const ReduceWs& ws, bool pushed) {
   if (!ws.hflag_lo && !ws.hflag_hi) return;
-  __syncthreads();
+  const int block_pushed = __syncthreads_or(pushed ? 1 : 0);
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    if (block_pushed) __threadfence_system(); else __threadfence();
     if (atomicAdd(ws.ticket, 1u) == gridDim.x - 1) {
       *ws.ticket = 0u;
       __threadfence_system();
@@ -398,9 +401,11 @@ template <typename T> struct HaloPush {
   long long first_off, last_off;    // element offsets of this rank's first / last owned row in the plane
   int pitch;
 };
-template <typename T> __device__ __forceinline__ void ew_push(const HaloPush<T>& hp, size_t o, const Pack<T>& v) {
-  if (hp.lo) { const long long d = (long long)o - hp.first_off; if (d >= 0 && d < hp.pitch) st_vec(hp.lo + d, v); }
-  if (hp.hi) { const long long d = (long long)o - hp.last_off; if (d >= 0 && d < hp.pitch) st_vec(hp.hi + d, v); }
+template <typename T> __device__ __forceinline__ bool ew_push(const HaloPush<T>& hp, size_t o, const Pack<T>& v) {
+  bool pushed = false;
+  if (hp.lo) { const long long d = (long long)o - hp.first_off; if (d >= 0 && d < hp.pitch) { st_vec(hp.lo + d, v); pushed = true; } }
+  if (hp.hi) { const long long d = (long long)o - hp.last_off; if (d >= 0 && d < hp.pitch) { st_vec(hp.hi + d, v); pushed = true; } }
+  return pushed;
 }
 
 // block max -> partials[block] -> last block takes the max (order-independent, exact)

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
   const long long gwarp = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * wpb;
   double acc0 = 0.0, acc1 = 0.0;
+  bool pushed = false;     // P2P: this thread stored part of a boundary row into a neighbour's receive buffer
 
   for (long long tile = gwarp; tile < A.nTiles; tile += nwarps) {
     const int rchunk = (int)(tile / A.nCC), cc = (int)(tile - (long long)rchunk * A.nCC);
@@ -247,14 +248,14 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
             st_vec(A.y + o, r);
             if (A.s_out) st_vec(A.s_out + o, r);
             if (P2P) {
-              if (i == A.row_lo && A.push_lo) st_vec(A.push_lo + j0[w], r);
-              if (i == A.row_hi - 1 && A.push_hi) st_vec(A.push_hi + j0[w], r);
+              if (i == A.row_lo && A.push_lo) { st_vec(A.push_lo + j0[w], r); pushed = true; }
+              if (i == A.row_hi - 1 && A.push_hi) { st_vec(A.push_hi + j0[w], r); pushed = true; }
             }
           } else {
             st_vec(A.y + o, y);
             if (P2P) {
-              if (i == A.row_lo && A.push_lo) st_vec(A.push_lo + j0[w], y);
-              if (i == A.row_hi - 1 && A.push_hi) st_vec(A.push_hi + j0[w], y);
+              if (i == A.row_lo && A.push_lo) { st_vec(A.push_lo + j0[w], y); pushed = true; }
+              if (i == A.row_hi - 1 && A.push_hi) { st_vec(A.push_hi + j0[w], y); pushed = true; }
             }
             if ((EPI == EPI_ST && A.s_out) || EPI == EPI_DOT_Q_ST) st_vec(A.s_out + o, raw_c[w]);
 #pragma unroll
@@ -270,8 +271,8 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
     }
   }
   if (EPI == EPI_Y) return;
-  if (EPI == EPI_ST) block_reduce_finalize<2>(acc0, acc1, A.ws, A.fin);
-  else block_reduce_finalize<1>(acc0, acc1, A.ws, A.fin);
+  if (EPI == EPI_ST) block_reduce_finalize<2>(acc0, acc1, A.ws, A.fin, P2P && pushed);
+  else block_reduce_finalize<1>(acc0, acc1, A.ws, A.fin, P2P && pushed);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -347,11 +348,12 @@ __global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_t
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
   double acc = 0.0;
+  bool pushed = false;
   KT_EW_OUTER(U) {
     Pack<T> bb[U];
     KT_EW_FOR(U, u, o) bb[u] = ld_stream(b + o);
     KT_EW_FOR(U, u, o) {
-      if (P2P) ew_push(hp, o, bb[u]);
+      if (P2P) pushed |= ew_push(hp, o, bb[u]);
       st_vec(r + o, bb[u]);
       if (r_tld) st_vec(r_tld + o, bb[u]);
       if (CG) st_vec(p + o, bb[u]);
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_t
       for (int k = 0; k < V; ++k) acc += (double)bb[u].a[k] * (double)bb[u].a[k];
     }
   }
-  block_reduce_finalize<1>(acc, 0.0, ws, fin);
+  block_reduce_finalize<1>(acc, 0.0, ws, fin, P2P && pushed);
 }
 
 // K1: p = r + beta (p - omega v); first iteration p = r (bicgsolver.py:99-103)
@@ -372,6 +374,7 @@ __global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, cons
   if (sc->done) return;
   const bool first = sc->iter == 0;
   const T beta = T(sc->beta), omega = T(sc->omega);
+  bool pushed = false;
   KT_EW_OUTER(U) {
     Pack<T> rr[U], pp[U], vv[U];
     KT_EW_FOR(U, u, o) {
@@ -385,10 +388,10 @@ __global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, cons
         for (int k = 0; k < V; ++k) out.a[k] = rr[u].a[k] + beta * (pp[u].a[k] - omega * vv[u].a[k]);
       }
       st_vec(p + o, out);
-      if (P2P) ew_push(hp, o, out);
+      if (P2P) pushed |= ew_push(hp, o, out);
     }
   }
-  if (P2P) push_finalize(ws);
+  if (P2P) push_finalize(ws, pushed);
 }
 
 // K4: x += alpha p^ + omega s^ ; r = s - omega t ; dots (r,r), (r,r_tld)   (bicgsolver.py:120-123, 95)
@@ -402,6 +405,7 @@ __global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* 
   if (from_sc && ws.sc->done) return;
   const T alpha = T(from_sc ? ws.sc->alpha : alpha_imm), omega = T(from_sc ? ws.sc->omega : omega_imm);
   double a0 = 0.0, a1 = 0.0;
+  bool pushed = false;
   KT_EW_OUTER(U) {
     Pack<T> xx[U], pp[U], ss[U], tt[U], rt[U], mm[U];
     KT_EW_FOR(U, u, o) {
@@ -430,10 +434,10 @@ __global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* 
       }
       st_vec(x + o, xx[u]);
       st_vec(r + o, rn);
-      if (P2P) ew_push(hp, o, rn);
+      if (P2P) pushed |= ew_push(hp, o, rn);
     }
   }
-  block_reduce_finalize<2>(a0, a1, ws, fin);
+  block_reduce_finalize<2>(a0, a1, ws, fin, P2P && pushed);
 }
 
 // C2: x += alpha p ; r -= alpha Ap ; dot (r,r)   (cgsolver.py:98-101)
@@ -470,6 +474,7 @@ __global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const 
   constexpr int U = kEwUnroll;
   if (sc->done) return;
   const T beta = T(sc->beta);
+  bool pushed = false;
   KT_EW_OUTER(U) {
     Pack<T> rr[U], pp[U];
     KT_EW_FOR(U, u, o) { rr[u] = ld_stream(r + o); pp[u] = ld_rw(p + o); }
@@ -477,10 +482,10 @@ __global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const 
 #pragma unroll
       for (int k = 0; k < V; ++k) pp[u].a[k] = rr[u].a[k] + beta * pp[u].a[k];
       st_vec(p + o, pp[u]);
-      if (P2P) ew_push(hp, o, pp[u]);
+      if (P2P) pushed |= ew_push(hp, o, pp[u]);
     }
   }
-  if (P2P) push_finalize(ws);
+  if (P2P) push_finalize(ws, pushed);
 }
 
 __global__ void k_sc_reset(Scalars* sc, double eps, long long max_iter, int flags) {
