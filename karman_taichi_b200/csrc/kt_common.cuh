@@ -380,21 +380,6 @@ __device__ __forceinline__ void block_reduce_finalize(double a0, double a1, cons
   }
 }
 
-// Kernels that push boundary rows but compute no inner product (p-updates): the last block to finish raises the flags.
-// Must be called by every thread of every block.
-__device__ __forceinline__ void push_finalize(const ReduceWs& ws, bool pushed) {
-  if (!ws.hflag_lo && !ws.hflag_hi) return;
-  const int block_pushed = __syncthreads_or(pushed ? 1 : 0);
-  if (threadIdx.x == 0) {
-    if (block_pushed) __threadfence_system(); else __threadfence();
-    if (atomicAdd(ws.ticket, 1u) == gridDim.x - 1) {
-      *ws.ticket = 0u;
-      __threadfence_system();
-      p2p_raise_halo_flags(ws);
-    }
-  }
-}
-
 // The neighbours' receive rows for the plane an element-wise kernel writes (flat vector index -> row test by offset).
 template <typename T> struct HaloPush {
   T* lo; T* hi;                     // null: no neighbour on that side / not pushing

@@ -58,6 +58,10 @@ template <typename T> struct StencilArgs {
   const unsigned long long* fx_lo; const unsigned long long* fx_hi; const unsigned long long* fv_lo; const unsigned long long* fv_hi;
   unsigned long long seq_x, seq_v;
   T* push_lo; T* push_hi;
+  // raise_*: the neighbours' flags for the rows of x that the PREVIOUS kernel of this stream (a p-update, which has no
+  // finalising block and no barrier to pay for one) stored into their receive buffers: this kernel's first thread raises them
+  // to seq_x before anything else -- stream order puts every store of that kernel before it
+  unsigned long long* raise_lo; unsigned long long* raise_hi;
 };
 
 // scalars of the on-the-fly operand: SRC_S: a = alpha; SRC_P: a = beta, b = omega, first = (iteration 0: p = r)
@@ -153,6 +157,11 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
   // class solvers (cgsolver.py / bicgsolver.py) have neither.  The two write the same five products in a different order.
   constexpr bool MONO = PRE || EPI == EPI_RESID;
   if (A.check_done && A.ws.sc->done) return;
+  if (P2P && blockIdx.x == 0 && threadIdx.x == 0 && (A.raise_lo || A.raise_hi)) {
+    __threadfence_system();
+    if (A.raise_lo) *(volatile unsigned long long*)A.raise_lo = A.seq_x;
+    if (A.raise_hi) *(volatile unsigned long long*)A.raise_hi = A.seq_x;
+  }
   SrcCoef<T> alpha;   // (named for its SRC_S role)
   alpha.a = T(0); alpha.b = T(0); alpha.first = false;
   if (SRC == SRC_S) alpha.a = T(A.alpha_from_sc ? A.ws.sc->alpha : A.alpha_imm);
@@ -366,15 +375,16 @@ __global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_t
 }
 
 // K1: p = r + beta (p - omega v); first iteration p = r (bicgsolver.py:99-103)
+// P2P: the boundary rows of the new p also go into the neighbours' receive buffers; the NEXT kernel of the stream (v = A p^)
+// announces them (StencilArgs::raise_*), so this one keeps running without a barrier or a last-block ticket
 template <typename T, bool P2P = false>
 __global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, const T* v, const Scalars* sc,
-                                                HaloPush<T> hp = HaloPush<T>(), ReduceWs ws = ReduceWs()) {
+                                                HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
   if (sc->done) return;
   const bool first = sc->iter == 0;
   const T beta = T(sc->beta), omega = T(sc->omega);
-  bool pushed = false;
   KT_EW_OUTER(U) {
     Pack<T> rr[U], pp[U], vv[U];
     KT_EW_FOR(U, u, o) {
@@ -388,10 +398,9 @@ __global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, cons
         for (int k = 0; k < V; ++k) out.a[k] = rr[u].a[k] + beta * (pp[u].a[k] - omega * vv[u].a[k]);
       }
       st_vec(p + o, out);
-      if (P2P) pushed |= ew_push(hp, o, out);
+      if (P2P) ew_push(hp, o, out);
     }
   }
-  if (P2P) push_finalize(ws, pushed);
 }
 
 // K4: x += alpha p^ + omega s^ ; r = s - omega t ; dots (r,r), (r,r_tld)   (bicgsolver.py:120-123, 95)
@@ -468,13 +477,11 @@ __global__ void __launch_bounds__(256) k_cg_xr(EwGeom g, T* x, T* r, const T* p,
 
 // C3: p = r + beta p   (cgsolver.py:78-81)
 template <typename T, bool P2P = false>
-__global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const Scalars* sc, HaloPush<T> hp = HaloPush<T>(),
-                                              ReduceWs ws = ReduceWs()) {
+__global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const Scalars* sc, HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
   if (sc->done) return;
   const T beta = T(sc->beta);
-  bool pushed = false;
   KT_EW_OUTER(U) {
     Pack<T> rr[U], pp[U];
     KT_EW_FOR(U, u, o) { rr[u] = ld_stream(r + o); pp[u] = ld_rw(p + o); }
@@ -482,10 +489,9 @@ __global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const 
 #pragma unroll
       for (int k = 0; k < V; ++k) pp[u].a[k] = rr[u].a[k] + beta * pp[u].a[k];
       st_vec(p + o, pp[u]);
-      if (P2P) pushed |= ew_push(hp, o, pp[u]);
+      if (P2P) ew_push(hp, o, pp[u]);
     }
   }
-  if (P2P) push_finalize(ws, pushed);
 }
 
 __global__ void k_sc_reset(Scalars* sc, double eps, long long max_iter, int flags) {
@@ -1210,9 +1216,9 @@ static int t_p2p_cg_unfused(kt_handle_s* h, const void* coef, const void* b, voi
 // ---------------------------------------------------------------------------------------------
 // The same two solvers with the communication FUSED into the compute kernels (default; KT_P2P_FUSED=0 selects the
 // separate comm kernels above for comparison).  Per BiCGSTAB iteration the four compute kernels are all that is launched:
-//   K1  p-update      stores its first / last owned row of p straight into the neighbours' receive buffers; the last block
-//                     to finish raises the neighbours' flags (push_finalize)
-//   K2  v = A p^      boundary tiles wait for the neighbours' p flag and read the halo rows from the receive buffer; stores
+//   K1  p-update      stores its first / last owned row of p straight into the neighbours' receive buffers
+//   K2  v = A p^      its first thread raises the neighbours' p flags (stream order: every store of K1 is behind it); boundary
+//                     tiles wait for the neighbours' p flag and read the halo rows from the receive buffer; stores
 //                     the boundary rows of v to the neighbours; its finalising block raises the v flags, then IS the
 //                     all-reduce of (r~, v) (p2p_allreduce_warp) and computes alpha
 //   K3  t = A s^      waits for the r and v flags, halo rows of s = r - alpha v from the receive buffers; finalising block
@@ -1316,14 +1322,15 @@ static int t_p2p_bicgstab_fused(kt_handle_s* h, const void* coef, const void* b,
   auto iter = [&]() -> int {
     {
       ProfScope ps(h, KT_K_BICG_P);
-      const ReduceWs ws1 = p2p_ws(c, w, -1, &Rp, 0);
-      k_bicg_p<T, true><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, p, r, v, h->sc, p2p_push<T>(h, Rp), ws1);
+      ++h->p2p_halo_k[0];                                           // the rows this launch pushes; announced by K2 below
+      k_bicg_p<T, true><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, p, r, v, h->sc, p2p_push<T>(h, Rp));
       KT_LAUNCH_CHECK(h);
     }
     {
       ProfScope ps(h, KT_K_BICG_V);
       A2.ws = p2p_ws(c, w, 0, &Rv, 1);
       consume(A2, Rp, c.base | h->p2p_halo_k[0], nullptr, 0);
+      A2.raise_lo = Rp.raise_lo; A2.raise_hi = Rp.raise_hi;
       KT_TRY(pre ? (launch_stencil<T, SRC_X, true, EPI_DOT_Q, true>(h, P, A2)) : (launch_stencil<T, SRC_X, false, EPI_DOT_Q, true>(h, P, A2)));
     }
     {
@@ -1378,6 +1385,7 @@ static int t_p2p_cg_fused(kt_handle_s* h, const void* coef, const void* b, void*
       ProfScope ps(h, KT_K_CG_AP);
       A1.ws = p2p_ws(c, w, 0, nullptr, 0);
       A1.hx_lo = (const T*)Rp.in_lo; A1.hx_hi = (const T*)Rp.in_hi; A1.fx_lo = Rp.wait_lo; A1.fx_hi = Rp.wait_hi; A1.seq_x = c.base | h->p2p_halo_k[0];
+      A1.raise_lo = Rp.raise_lo; A1.raise_hi = Rp.raise_hi;       // rows pushed by k_init / the last p-update (idempotent after k_init)
       KT_TRY((launch_stencil<T, SRC_X, false, EPI_DOT_SRC, true>(h, P, A1)));
     }
     {
@@ -1388,8 +1396,8 @@ static int t_p2p_cg_fused(kt_handle_s* h, const void* coef, const void* b, void*
     }
     {
       ProfScope ps(h, KT_K_CG_P);
-      const ReduceWs ws3 = p2p_ws(c, w, -1, &Rp, 0);
-      k_cg_p<T, true><<<grid_for(h, P.ew_blocks, 3), 256, 0, h->stream>>>(P.g, p, r, h->sc, p2p_push<T>(h, Rp), ws3);
+      ++h->p2p_halo_k[0];                                           // announced by the next Ap = A p
+      k_cg_p<T, true><<<grid_for(h, P.ew_blocks, 3), 256, 0, h->stream>>>(P.g, p, r, h->sc, p2p_push<T>(h, Rp));
       KT_LAUNCH_CHECK(h);
     }
     return 0;
