@@ -333,6 +333,15 @@ __global__ void __launch_bounds__(256) k_ew(EwGeom g, T* out, const T* x, const 
   }
 }
 
+// fill with a non-zero value: logical columns only -- the pad columns [NY, pitch) stay zero (every kernel multiplies and sums
+// over whole padded rows)
+template <typename T>
+__global__ void __launch_bounds__(256) k_fill_cols(T* dst, int pitch, int NY, int row_lo, int row_hi, T value) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= NY) return;
+  for (int i = row_lo + (int)blockIdx.y; i < row_hi; i += (int)gridDim.y) dst[(size_t)i * pitch + j] = value;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_dot(EwGeom g, const T* p, const T* q, ReduceWs ws) {
   constexpr int V = VT<T>::V;
@@ -1477,6 +1486,13 @@ int kt_copy(kt_handle_t h, void* dst, const void* src) {
 int kt_fill(kt_handle_t h, void* dst, double value) {
   KT_CHECK_ARG(h && dst, "kt_fill: null argument");
   KT_DEV_GUARD(h);
+  if (value != 0.0) {
+    const dim3 grid((h->NY + 255) / 256, std::max(1, std::min(h->row_hi - h->row_lo, 1024)));
+    if (h->dtype == KT_F64) k_fill_cols<double><<<grid, 256, 0, h->stream>>>((double*)dst, h->pitch, h->NY, h->row_lo, h->row_hi, value);
+    else k_fill_cols<float><<<grid, 256, 0, h->stream>>>((float*)dst, h->pitch, h->NY, h->row_lo, h->row_hi, (float)value);
+    KT_LAUNCH_CHECK(h);
+    return 0;
+  }
   return KT_DISPATCH(h, (t_ew<double, EW_FILL>(h, dst, nullptr, nullptr, nullptr, value, 0)),
                      (t_ew<float, EW_FILL>(h, dst, nullptr, nullptr, nullptr, value, 0)));
 }

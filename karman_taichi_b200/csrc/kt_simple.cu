@@ -7,6 +7,7 @@
 // Layout: u (nx+3, ny+2), v (nx+2, ny+3), p-type (nx+2, ny+2) pitched planes; coef_* five SoA planes.
 // Threads map to j (contiguous); these kernels run once per SIMPLE outer iteration (<0.5 % of the
 // traffic of the Krylov iterations they feed) and are written as straightforward coalesced passes.
+#include <algorithm>
 #include "kt_handle.h"
 
 namespace kt {
@@ -18,6 +19,7 @@ struct SP {   // device copy of kt_simple_params + derived plane strides
   int pin_p, east_wall_bug;
   int pu, pv, pp;           // pitches
   size_t plu, plv, plp;     // plane strides of coef_u/v/p
+  int ib;                   // first row of this launch (row = ib + blockIdx.y): grids taller than 65535 rows go in chunks
 };
 
 static SP make_sp(const kt_simple_params* P) {
@@ -29,8 +31,18 @@ static SP make_sp(const kt_simple_params* P) {
   s.pin_p = P->pin_p; s.east_wall_bug = P->east_wall_bug;
   s.pu = P->pitch_u; s.pv = P->pitch_v; s.pp = P->pitch_p;
   s.plu = (size_t)(P->nx + 3) * P->pitch_u; s.plv = (size_t)(P->nx + 2) * P->pitch_v; s.plp = (size_t)(P->nx + 2) * P->pitch_p;
+  s.ib = 0;
   return s;
 }
+
+// one launch per chunk of <= 32768 rows (gridDim.y <= 65535 whatever nx is); S.ib carries the chunk's first row
+#define KT_ROW_CHUNKS(S, rows, gx, gz, LAUNCH)                                      \
+  for (int _r0 = 0; _r0 < (rows); _r0 += 32768) {                                   \
+    (S).ib = _r0;                                                                   \
+    const dim3 grid((gx), std::min(32768, (rows) - _r0), (gz));                     \
+    LAUNCH;                                                                         \
+    KT_LAUNCH_CHECK(h);                                                             \
+  }
 
 #define U(i, j) u[(size_t)(i) * S.pu + (j)]
 #define Vv(i, j) v[(size_t)(i) * S.pv + (j)]
@@ -42,7 +54,7 @@ __global__ void __launch_bounds__(256) k_assemble_uv(SP S, const T* __restrict__
                                                      const T* __restrict__ p, const T* __restrict__ u0,
                                                      const T* __restrict__ v0, T* cu, T* bu, T* cv, T* bv) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y;
+  const int i = S.ib + (int)blockIdx.y;
   const T dx = T(S.dx), dy = T(S.dy), dt = T(S.dt), rho = T(S.rho), mu = T(S.mu);
   const T half = T(0.5);
   if (blockIdx.z == 0) {
@@ -147,7 +159,7 @@ __global__ void __launch_bounds__(256) k_assemble_p(SP S, const T* __restrict__ 
                                                     const T* __restrict__ cu, const T* __restrict__ cv, T* cp, T* bp,
                                                     T* mdiv) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y;
+  const int i = S.ib + (int)blockIdx.y;
   if (i < 1 || i > S.nx || j < 1 || j > S.ny) return;
   const T dx = T(S.dx), dy = T(S.dy), rho = T(S.rho);
   const T m = rho * (U(i, j) - U(i + 1, j)) * dy + rho * (Vv(i, j) - Vv(i, j + 1)) * dx;
@@ -195,7 +207,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_correct(SP S, T* p, T* u, T* v, const T* __restrict__ pc,
                                                  const T* __restrict__ cu, const T* __restrict__ cv, int do_p, int do_uv) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y;
+  const int i = S.ib + (int)blockIdx.y;
   if (i < 1 || i > S.nx || j < 1 || j > S.ny) return;
   const T dx = T(S.dx), dy = T(S.dy);
   const T pcc = pc[(size_t)i * S.pp + j];
@@ -257,14 +269,15 @@ int kt_assemble_uv(kt_handle_t h, const kt_simple_params* P, const void* u, cons
   KT_DEV_GUARD(h);
   KT_SIMPLE_ARGS_OK(P);
   SP S = make_sp(P);
-  dim3 grid((P->ny + 2 + 255) / 256, P->nx + 1, 2);
-  if (h->dtype == KT_F64)
-    k_assemble_uv<double><<<grid, 256, 0, h->stream>>>(S, (const double*)u, (const double*)v, (const double*)p, (const double*)u0,
-                                                      (const double*)v0, (double*)coef_u, (double*)b_u, (double*)coef_v, (double*)b_v);
-  else
-    k_assemble_uv<float><<<grid, 256, 0, h->stream>>>(S, (const float*)u, (const float*)v, (const float*)p, (const float*)u0,
-                                                     (const float*)v0, (float*)coef_u, (float*)b_u, (float*)coef_v, (float*)b_v);
-  KT_LAUNCH_CHECK(h);
+  if (h->dtype == KT_F64) {
+    KT_ROW_CHUNKS(S, P->nx + 1, (P->ny + 2 + 255) / 256, 2,
+                  (k_assemble_uv<double><<<grid, 256, 0, h->stream>>>(S, (const double*)u, (const double*)v, (const double*)p, (const double*)u0,
+                                                                     (const double*)v0, (double*)coef_u, (double*)b_u, (double*)coef_v, (double*)b_v)));
+  } else {
+    KT_ROW_CHUNKS(S, P->nx + 1, (P->ny + 2 + 255) / 256, 2,
+                  (k_assemble_uv<float><<<grid, 256, 0, h->stream>>>(S, (const float*)u, (const float*)v, (const float*)p, (const float*)u0,
+                                                                    (const float*)v0, (float*)coef_u, (float*)b_u, (float*)coef_v, (float*)b_v)));
+  }
   return 0;
 }
 
@@ -294,14 +307,15 @@ int kt_assemble_p(kt_handle_t h, const kt_simple_params* P, const void* u, const
   KT_DEV_GUARD(h);
   KT_SIMPLE_ARGS_OK(P);
   SP S = make_sp(P);
-  dim3 grid((P->ny + 2 + 255) / 256, P->nx + 1);
-  if (h->dtype == KT_F64)
-    k_assemble_p<double><<<grid, 256, 0, h->stream>>>(S, (const double*)u, (const double*)v, (const double*)coef_u, (const double*)coef_v,
-                                                     (double*)coef_p, (double*)b_p, (double*)mdiv);
-  else
-    k_assemble_p<float><<<grid, 256, 0, h->stream>>>(S, (const float*)u, (const float*)v, (const float*)coef_u, (const float*)coef_v,
-                                                    (float*)coef_p, (float*)b_p, (float*)mdiv);
-  KT_LAUNCH_CHECK(h);
+  if (h->dtype == KT_F64) {
+    KT_ROW_CHUNKS(S, P->nx + 1, (P->ny + 2 + 255) / 256, 1,
+                  (k_assemble_p<double><<<grid, 256, 0, h->stream>>>(S, (const double*)u, (const double*)v, (const double*)coef_u, (const double*)coef_v,
+                                                                    (double*)coef_p, (double*)b_p, (double*)mdiv)));
+  } else {
+    KT_ROW_CHUNKS(S, P->nx + 1, (P->ny + 2 + 255) / 256, 1,
+                  (k_assemble_p<float><<<grid, 256, 0, h->stream>>>(S, (const float*)u, (const float*)v, (const float*)coef_u, (const float*)coef_v,
+                                                                   (float*)coef_p, (float*)b_p, (float*)mdiv)));
+  }
   return 0;
 }
 
@@ -335,14 +349,15 @@ int kt_correct_puv(kt_handle_t h, const kt_simple_params* P, void* p, void* u, v
   KT_CHECK_ARG(!do_uv || (u && v && coef_u && coef_v), "kt_correct_puv: velocity correction needs u, v, coef_u, coef_v");
   KT_SIMPLE_ARGS_OK(P);
   SP S = make_sp(P);
-  dim3 grid((P->ny + 2 + 255) / 256, P->nx + 1);
-  if (h->dtype == KT_F64)
-    k_correct<double><<<grid, 256, 0, h->stream>>>(S, (double*)p, (double*)u, (double*)v, (const double*)pcor, (const double*)coef_u,
-                                                  (const double*)coef_v, do_p, do_uv);
-  else
-    k_correct<float><<<grid, 256, 0, h->stream>>>(S, (float*)p, (float*)u, (float*)v, (const float*)pcor, (const float*)coef_u,
-                                                 (const float*)coef_v, do_p, do_uv);
-  KT_LAUNCH_CHECK(h);
+  if (h->dtype == KT_F64) {
+    KT_ROW_CHUNKS(S, P->nx + 1, (P->ny + 2 + 255) / 256, 1,
+                  (k_correct<double><<<grid, 256, 0, h->stream>>>(S, (double*)p, (double*)u, (double*)v, (const double*)pcor, (const double*)coef_u,
+                                                                 (const double*)coef_v, do_p, do_uv)));
+  } else {
+    KT_ROW_CHUNKS(S, P->nx + 1, (P->ny + 2 + 255) / 256, 1,
+                  (k_correct<float><<<grid, 256, 0, h->stream>>>(S, (float*)p, (float*)u, (float*)v, (const float*)pcor, (const float*)coef_u,
+                                                                (const float*)coef_v, do_p, do_uv)));
+  }
   return 0;
 }
 

@@ -84,19 +84,32 @@ class Field:
             raise ValueError('copy_from: shape mismatch')
         self.data.copy_(other.data)
 
+    def _index(self, idx):
+        """(i, j[, k]) checked against the LOGICAL shape: the pad columns [NY, pitch) must stay zero (every kernel sums and
+        multiplies over whole padded rows), so they are not addressable."""
+        if not isinstance(idx, tuple) or len(idx) != len(self.shape):
+            raise IndexError(f'Field index must be {len(self.shape)} integers')
+        out = []
+        for v, n in zip(idx, self.shape):
+            v = int(v)
+            if not -n <= v < n:
+                raise IndexError(f'Field index {idx} out of range for shape {self.shape}')
+            out.append(v % n)
+        return out
+
     def __getitem__(self, idx):
         if self.is_coef:
-            i, j, k = idx
+            i, j, k = self._index(idx)
             return float(self.data[k, i, j])
-        i, j = idx
+        i, j = self._index(idx)
         return float(self.data[i, j])
 
     def __setitem__(self, idx, value):
         if self.is_coef:
-            i, j, k = idx
+            i, j, k = self._index(idx)
             self.data[k, i, j] = value
         else:
-            i, j = idx
+            i, j = self._index(idx)
             self.data[i, j] = value
 
 

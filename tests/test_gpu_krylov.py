@@ -488,6 +488,28 @@ def test_empty_and_mismatched_inputs_raise(cuda):
         kt.CGSolver(fb, fb, fb)                                         # coef without the 5-plane axis
 
 
+def test_pad_columns_stay_zero(cuda):
+    """The kernels sum and multiply over whole padded rows, so the pad columns [NY, pitch) must stay zero: kt_fill with a
+    non-zero value writes the logical columns only, Field indices are checked against the logical shape."""
+    import karman_taichi_b200 as kt
+    from karman_taichi_b200 import _lib
+    coef, b = krylov.random_dd_system(37, 53, seed=5)
+    s = make(cuda, coef, b, kt.BICGSolver)
+    f = s.r
+    _lib.check(s._lib.kt_fill(s._h, C.c_void_p(f.ptr), 2.5))
+    assert f.pitch > f.NY
+    assert float(f.data[:, f.NY:].abs().sum()) == 0.0 and float(f.data[:, :f.NY].min()) == 2.5 == float(f.data[:, :f.NY].max())
+    assert s.reduce(f, f) == 2.5 * 2.5 * f.NX * f.NY
+    f[3, 4] = 1.0
+    assert f[3, 4] == 1.0 and f[-1, -1] == 2.5
+    for bad in ((0, f.NY), (f.NX, 0), (0, f.pitch - 1), (-f.NX - 1, 0)):
+        with pytest.raises(IndexError):
+            f[bad] = 7.0
+        with pytest.raises(IndexError):
+            f[bad]
+    assert float(f.data[:, f.NY:].abs().sum()) == 0.0
+
+
 @pytest.mark.parametrize('shape,seed', [((37, 53), 3), ((258, 1030), 4)])
 def test_bicgstab_solve_host_parity(cuda, shape, seed):
     """kt_bicgstab_solve_host: the reference-facing call with HOST buffers in the reference layout (coef[i][j][k] AoS, dense
