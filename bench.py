@@ -645,8 +645,28 @@ def bind_host_memory_near_gpu(torch, dev):
             bus_id = (bus_id.decode() if isinstance(bus_id, bytes) else bus_id).lower()
             if len(bus_id.split(':')[0]) == 8:
                 bus_id = bus_id[4:]
-        node = int(open(f'/sys/bus/pci/devices/{bus_id}/numa_node').read().strip())
+        try:
+            node = int(open(f'/sys/bus/pci/devices/{bus_id}/numa_node').read().strip())
+        except Exception:
+            node = -1
+        if node < 0:
+            # virtualised PCI tree: ask the driver which NUMA node the GPU's memory traffic is closest to
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                hd = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+                mask = pynvml.nvmlDeviceGetMemoryAffinity(hd, 4, pynvml.NVML_AFFINITY_SCOPE_NODE)
+                bits = [64 * w + k for w, word in enumerate(mask) for k in range(64) if int(word) >> k & 1]
+                if len(bits) == 1:
+                    node = bits[0]
+                    info['source'] = 'nvmlDeviceGetMemoryAffinity'
+            except Exception as e:
+                info['nvml'] = repr(e)
         info['gpu_numa_node'] = node
+        try:
+            info['mems_allowed'] = [l.split(':')[1].strip() for l in open('/proc/self/status') if l.startswith('Mems_allowed_list')][0]
+        except Exception:
+            pass
         if node < 0:
             return info
         # set_mempolicy(MPOL_PREFERRED = 1, nodemask) -- x86_64 syscall 238
