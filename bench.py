@@ -877,12 +877,25 @@ def simple_line(a, torch, dist, world, rank, dev, workload, steps=None, light=Fa
                                  'working set resident in shared memory / L2 by design (reference-sized grid); inputs change every step')},
             'gpu_launches': launches, 'roofline': roofline}
     if case == 'karman':
-        # correctness evidence that travels with the number: what the timed sub-iterations returned (max |p'|, identical on every
-        # rank) and the Krylov counts -- the same sequence at every N up to the order of the partial sums
-        line['check'] = {'max_pcor_per_step': [float(v) for v in returned], 'krylov_iterations_last_step': its(),
-                         'krylov_status_last_step': dict(s.last_status),
-                         'note': 'same initial state, same number of warm-up + timed sub-iterations at every N: the values agree across '
-                                 '--gpus 1, 2, 4, 8 to the rounding of the rank-ordered partial sums'}
+        # correctness evidence that travels with the number.  (1) what the timed sub-iterations returned (max |p'|, identical on
+        # every rank).  With the p' solve CAPPED (status 1: stopped in the erratic phase of BiCGSTAB, far from converged) these
+        # agree across N only to 2-3 digits: the truncated iterate moves with the order of the partial sums.  (2) an N-independent
+        # figure: from a fresh init, the first momentum step (u and v solves converge to eps = 1e-8 in ~25 iterations) and
+        # correct_conserv -- inlet / outlet mass flux and max |div u| must agree across --gpus 1, 2, 4, 8 to ~1e-8.
+        chk = {'max_pcor_per_step': [float(v) for v in returned], 'krylov_iterations_last_step': its(),
+               'krylov_status_last_step': dict(s.last_status)}
+        if not light:
+            s.init()
+            s.solve_momentum_bicgstab(1e-8, 1)
+            inlet, outlet, ratio = s.correct_conserv()
+            l0_, l1_ = (s.part_p.local_owned(rank) if slab else (0, nx + 2))
+            chk['first_momentum_step'] = {'krylov_iterations': {k: v for k, v in its().items() if k != 'p'},
+                                          'krylov_status': {k: v for k, v in s.last_status.items() if k != 'p'},
+                                          'inlet_mass_flux': float(inlet), 'outlet_mass_flux_before_scaling': float(outlet),
+                                          'div_u_abs_max': cm.max(float(s.udiv.data[l0_:l1_].abs().max()))}
+        chk['note'] = ('max_pcor_per_step: capped p\' solves, agree across N to 2-3 digits only; first_momentum_step: converged solves, '
+                       'agrees across --gpus 1, 2, 4, 8 to ~1e-8 (only the order of the rank partial sums differs)')
+        line['check'] = chk
     if light:
         return line
     line['clocks'] = clocks

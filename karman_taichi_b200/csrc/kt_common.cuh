@@ -94,6 +94,17 @@ __device__ __forceinline__ void st_vec(float* p, const Pack<float>& v) {
                : "memory");
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------
+// First statements of every streaming Krylov kernel.  When the host launches the kernel with
+// cudaLaunchAttributeProgrammaticStreamSerialization (kt_krylov.cu: launch_k), its blocks may become resident while the
+// previous kernel of the stream is still draining its last wave / running its finalising block; they then sit in
+// griddepcontrol.wait until that kernel has completed and its writes are visible, so nothing of the previous kernel
+// (vectors, scalars, tickets, flags) is touched early.  Launched the ordinary way both instructions do nothing.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---- warp shuffles for double/float ------------------------------------------------------
 template <typename T> __device__ __forceinline__ T shfl_up1(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 template <typename T> __device__ __forceinline__ T shfl_down1(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }

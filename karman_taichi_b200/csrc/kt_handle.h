@@ -32,6 +32,7 @@ struct kt_handle_s {
   std::vector<GraphEntry> graphs;
   cudaStream_t gstream = nullptr;
   cudaEvent_t gev = nullptr;
+  bool capturing = false;            // inside cudaStreamBeginCapture / EndCapture (programmatic launches are left out of graphs)
   int graphs_state = 0;              // 0 untested, 1 usable, -1 unavailable (capture refused)
   unsigned long long graph_clock = 0;
   // x-slab peer-memory solves (kt_p2p_*): solve epoch and exchange counters behind the flag sequence numbers

@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(256, (StencilCfg<SRC, PRE>::MINB)) k_stencil(c
   // The Jacobi-preconditioned and the warm-start-residual products are the monolith's (karman_taichi.py:342-456); the
   // class solvers (cgsolver.py / bicgsolver.py) have neither.  The two write the same five products in a different order.
   constexpr bool MONO = PRE || EPI == EPI_RESID;
+  pdl_prologue();
   if (A.check_done && A.ws.sc->done) return;
   if (P2P && blockIdx.x == 0 && threadIdx.x == 0 && (A.raise_lo || A.raise_hi)) {
     __threadfence_system();
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_t
   constexpr int U = kEwUnroll;
   double acc = 0.0;
   bool pushed = false;
+  pdl_prologue();
   KT_EW_OUTER(U) {
     Pack<T> bb[U];
     KT_EW_FOR(U, u, o) bb[u] = ld_stream(b + o);
@@ -391,6 +393,7 @@ __global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, cons
                                                 HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
+  pdl_prologue();
   if (sc->done) return;
   const bool first = sc->iter == 0;
   const T beta = T(sc->beta), omega = T(sc->omega);
@@ -420,6 +423,7 @@ __global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* 
                                                  HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = (kEwUnroll > 2) ? 2 : kEwUnroll;     // 5-6 operand planes: 2 strides already keep ~190 B in flight
+  pdl_prologue();
   if (from_sc && ws.sc->done) return;
   const T alpha = T(from_sc ? ws.sc->alpha : alpha_imm), omega = T(from_sc ? ws.sc->omega : omega_imm);
   double a0 = 0.0, a1 = 0.0;
@@ -464,6 +468,7 @@ __global__ void __launch_bounds__(256) k_cg_xr(EwGeom g, T* x, T* r, const T* p,
                                                int from_sc, ReduceWs ws, int fin) {
   constexpr int V = VT<T>::V;
   constexpr int U = (kEwUnroll > 2) ? 2 : kEwUnroll;
+  pdl_prologue();
   if (from_sc && ws.sc->done) return;
   const T alpha = T(from_sc ? ws.sc->alpha : alpha_imm);
   double a0 = 0.0;
@@ -489,6 +494,7 @@ template <typename T, bool P2P = false>
 __global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const Scalars* sc, HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
+  pdl_prologue();
   if (sc->done) return;
   const T beta = T(sc->beta);
   KT_EW_OUTER(U) {
@@ -521,6 +527,28 @@ struct Plan {
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
+}
+
+// Launch of a streaming Krylov kernel (256 threads).  With KT_PDL != 0 (default on) the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization: the kernel may be scheduled while its predecessor in the stream drains
+// (every such kernel starts with pdl_prologue(), kt_common.cuh), which hides the launch latency and the block ramp-up between
+// the four dependent kernels of an iteration -- what is left of a 100-300 us kernel's fixed cost.
+static bool pdl_on(const kt_handle_s* h) {
+  static int on = env_int("KT_PDL", 1);
+  return on != 0 && !h->capturing;
+}
+
+template <typename... KArgs, typename... Args>
+static void launch_k(kt_handle_s* h, void (*kernel)(KArgs...), int grid, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at; cfg.numAttrs = pdl_on(h) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // Grid sizing.  Work is assigned statically (tile / vector index = f(blockIdx, threadIdx, stride)), so the
@@ -602,7 +630,7 @@ static int launch_stencil(kt_handle_s* h, const Plan& P, const StencilArgs<T>& A
   const StPlan S = stencil_plan(h, P.V, StencilCfg<SRC, PRE>::W, planes);
   StencilArgs<T> B = A;
   B.TI = S.TI; B.nCC = S.nCC; B.nTiles = S.nTiles;
-  k_stencil<T, SRC, PRE, EPI, P2P><<<S.grid, 256, 0, h->stream>>>(B);
+  launch_k(h, k_stencil<T, SRC, PRE, EPI, P2P>, S.grid, B);
   KT_LAUNCH_CHECK(h);
   return 0;
 }
@@ -684,7 +712,9 @@ static kt_handle_s::GraphEntry* graph_for(kt_handle_s* h, const std::vector<cons
   }
   const long long l0 = h->launches;
   int rc = 0;
+  h->capturing = true;
   for (int k = 0; k < chunk && rc == 0; ++k) rc = enqueue_iter();
+  h->capturing = false;
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   const long long per_chunk = h->launches - l0;
@@ -826,7 +856,7 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
     } else {
       {
         ProfScope ps(h, KT_K_BICG_P);
-        k_bicg_p<T><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, p_new, r, v_new, h->sc);
+        launch_k(h, k_bicg_p<T, false>, grid_for(h, P.ew_blocks, 4), P.g, p_new, r, v_new, h->sc, HaloPush<T>());
       }
       KT_LAUNCH_CHECK(h);
       ProfScope ps(h, KT_K_BICG_V);
@@ -842,8 +872,8 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
     if (e) return e;
     ProfScope ps(h, KT_K_BICG_XR);
     const T* v_for_s = s ? nullptr : v_new;
-    if (pre) k_bicg_xr<T, true><<<grid_for(h, P.ew_blocks, EWP_BICG_XR), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END, v_for_s);
-    else k_bicg_xr<T, false><<<grid_for(h, P.ew_blocks, EWP_BICG_XR), 256, 0, h->stream>>>(P.g, (T*)x, r, p_new, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END, v_for_s);
+    if (pre) launch_k(h, k_bicg_xr<T, true, false>, grid_for(h, P.ew_blocks, EWP_BICG_XR), P.g, (T*)x, r, p_new, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws, FIN_BICG_END, v_for_s, HaloPush<T>());
+    else launch_k(h, k_bicg_xr<T, false, false>, grid_for(h, P.ew_blocks, EWP_BICG_XR), P.g, (T*)x, r, p_new, s, t, r_tld_c, nullptr, 0, 0, 1, ws, FIN_BICG_END, v_for_s, HaloPush<T>());
     KT_LAUNCH_CHECK(h);
     return 0;
   };
@@ -894,12 +924,12 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
     if (e) return e;
     {
       ProfScope ps(h, KT_K_CG_XR);
-      k_cg_xr<T><<<grid_for(h, P.ew_blocks, EWP_CG_XR), 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws, FIN_CG_END);
+      launch_k(h, k_cg_xr<T>, grid_for(h, P.ew_blocks, EWP_CG_XR), P.g, (T*)x, r, p, Ap, 0.0, 1, ws, FIN_CG_END);
     }
     KT_LAUNCH_CHECK(h);
     {
       ProfScope ps(h, KT_K_CG_P);
-      k_cg_p<T><<<grid_for(h, P.ew_blocks, 3), 256, 0, h->stream>>>(P.g, p, r, h->sc);
+      launch_k(h, k_cg_p<T, false>, grid_for(h, P.ew_blocks, 3), P.g, p, r, h->sc, HaloPush<T>());
     }
     KT_LAUNCH_CHECK(h);
     return 0;
@@ -1332,7 +1362,7 @@ static int t_p2p_bicgstab_fused(kt_handle_s* h, const void* coef, const void* b,
     {
       ProfScope ps(h, KT_K_BICG_P);
       ++h->p2p_halo_k[0];                                           // the rows this launch pushes; announced by K2 below
-      k_bicg_p<T, true><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, p, r, v, h->sc, p2p_push<T>(h, Rp));
+      launch_k(h, k_bicg_p<T, true>, grid_for(h, P.ew_blocks, 4), P.g, p, r, v, h->sc, p2p_push<T>(h, Rp));
       KT_LAUNCH_CHECK(h);
     }
     {
@@ -1353,8 +1383,8 @@ static int t_p2p_bicgstab_fused(kt_handle_s* h, const void* coef, const void* b,
       const T* v_for_s = s ? nullptr : v;
       const ReduceWs ws4 = p2p_ws(c, w, 2, &Rr, 2);
       const HaloPush<T> hp = p2p_push<T>(h, Rr);
-      if (pre) k_bicg_xr<T, true, true><<<grid_for(h, P.ew_blocks, EWP_BICG_XR_UNIT), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws4, FIN_BICG_END, v_for_s, hp);
-      else k_bicg_xr<T, false, true><<<grid_for(h, P.ew_blocks, EWP_BICG_XR_UNIT), 256, 0, h->stream>>>(P.g, (T*)x, r, p, s, t, r_tld_c, nullptr, 0, 0, 1, ws4, FIN_BICG_END, v_for_s, hp);
+      if (pre) launch_k(h, k_bicg_xr<T, true, true>, grid_for(h, P.ew_blocks, EWP_BICG_XR_UNIT), P.g, (T*)x, r, p, s, t, r_tld_c, (const T*)Minv, 0, 0, 1, ws4, FIN_BICG_END, v_for_s, hp);
+      else launch_k(h, k_bicg_xr<T, false, true>, grid_for(h, P.ew_blocks, EWP_BICG_XR_UNIT), P.g, (T*)x, r, p, s, t, r_tld_c, nullptr, 0, 0, 1, ws4, FIN_BICG_END, v_for_s, hp);
       KT_LAUNCH_CHECK(h);
     }
     return 0;
@@ -1400,13 +1430,13 @@ static int t_p2p_cg_fused(kt_handle_s* h, const void* coef, const void* b, void*
     {
       ProfScope ps(h, KT_K_CG_XR);
       const ReduceWs ws2 = p2p_ws(c, w, 1, nullptr, 0);
-      k_cg_xr<T><<<grid_for(h, P.ew_blocks, EWP_CG_XR), 256, 0, h->stream>>>(P.g, (T*)x, r, p, Ap, 0.0, 1, ws2, FIN_CG_END);
+      launch_k(h, k_cg_xr<T>, grid_for(h, P.ew_blocks, EWP_CG_XR), P.g, (T*)x, r, p, Ap, 0.0, 1, ws2, FIN_CG_END);
       KT_LAUNCH_CHECK(h);
     }
     {
       ProfScope ps(h, KT_K_CG_P);
       ++h->p2p_halo_k[0];                                           // announced by the next Ap = A p
-      k_cg_p<T, true><<<grid_for(h, P.ew_blocks, 3), 256, 0, h->stream>>>(P.g, p, r, h->sc, p2p_push<T>(h, Rp));
+      launch_k(h, k_cg_p<T, true>, grid_for(h, P.ew_blocks, 3), P.g, p, r, h->sc, p2p_push<T>(h, Rp));
       KT_LAUNCH_CHECK(h);
     }
     return 0;
