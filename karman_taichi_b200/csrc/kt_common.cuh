@@ -156,8 +156,10 @@ enum Fin {
 // increasing sequence numbers, never reset.
 constexpr int P2P_GROUPS = 8, P2P_SLOTS = 5;
 struct P2PBlock {
-  double dots[P2P_GROUPS][16][2];
-  unsigned long long dot_flag[P2P_GROUPS][16];
+  // all-reduce slots, [group][sending rank]: two doubles as four 8-byte words, each = 32 data bits | 32-bit tag << 32.  An
+  // 8-byte store is atomic, so a word whose tag matches carries valid data: no fence on either side, no separate flag
+  // (the low-latency protocol of the collective libraries, for 16 bytes per rank)
+  unsigned long long ll[P2P_GROUPS][16][4];
   unsigned long long halo_flag[P2P_SLOTS][2]; // [slot][0: from lower neighbour, 1: from upper neighbour]
 };
 
@@ -297,30 +299,48 @@ __device__ __forceinline__ void scalar_algebra(int fin, Scalars* sc, double d0, 
 }
 
 // All-reduce of (up to) two sums over the ranks + the scalar algebra, by ONE WARP (all 32 lanes call it): lane r stores this
-// rank's sums into slot [rank] of rank r's comm block and raises its flag; the warp waits for all nranks flags of its own block,
-// lane 0 adds the slots in rank order (the same bits on every rank) and runs the algebra.  Slot groups: see kt_krylov.cu.
+// rank's sums into slot [rank] of rank r's comm block as four tagged 8-byte words, then polls slot [r] of its OWN block until
+// all four tags match; the values are added in rank order (the same bits on every rank) and lane 0 runs the algebra.
+// Tag = 12 bits of the solve epoch | 20 bits of the exchange index: it only has to differ from what the slot held before,
+// which is always the previous use of the same group.  Slot groups: see kt_krylov.cu.
 __device__ __forceinline__ void p2p_allreduce_warp(P2PBlock* const* peers, int rank, int nranks, int group, int ndot, double l0, double l1,
                                                    int fin, unsigned long long seq, Scalars* sc, double* history, long long cap,
                                                    int in_solve, int op_max, long long timeout_ns) {
   const int lane = threadIdx.x & 31;
-  P2PBlock* mine = peers[rank];
+  const unsigned long long tag = (((seq >> 32) & 0xfffull) << 20 | (seq & 0xfffffull)) << 32;
+  double a0 = 0.0, a1 = 0.0;
   if (lane < nranks) {
-    P2PBlock* pb = peers[lane];
-    *(volatile double*)&pb->dots[group][rank][0] = l0;
-    *(volatile double*)&pb->dots[group][rank][1] = ndot > 1 ? l1 : 0.0;
-    __threadfence_system();
-    *(volatile unsigned long long*)&pb->dot_flag[group][rank] = seq;
-    p2p_wait(&mine->dot_flag[group][lane], seq, sc, timeout_ns, 2u << 8 | (unsigned)group | (unsigned)lane << 16);
-  }
-  __syncwarp();
-  if (lane == 0 && (!in_solve || !*(volatile int*)&sc->done)) {
-    double d0 = 0.0, d1 = 0.0;
-    for (int r = 0; r < nranks; ++r) {          // rank order: the same bits on every rank
-      const double a0 = *(volatile double*)&mine->dots[group][r][0], a1 = *(volatile double*)&mine->dots[group][r][1];
-      if (op_max) { d0 = fmax(d0, a0); d1 = fmax(d1, a1); } else { d0 += a0; d1 += a1; }
+    const unsigned long long b0 = (unsigned long long)__double_as_longlong(l0);
+    const unsigned long long b1 = (unsigned long long)__double_as_longlong(ndot > 1 ? l1 : 0.0);
+    unsigned long long* dst = peers[lane]->ll[group][rank];
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"((b0 & 0xffffffffull) | tag), "l"((b0 >> 32) | tag) : "memory");
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2), "l"((b1 & 0xffffffffull) | tag), "l"((b1 >> 32) | tag) : "memory");
+    const unsigned long long* src = peers[rank]->ll[group][lane];
+    unsigned long long w0, w1, w2, w3, t0 = 0;
+    for (;;) {
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "l"(src + 2) : "memory");
+      const unsigned long long m = 0xffffffff00000000ull;
+      if ((w0 & m) == tag && (w1 & m) == tag && (w2 & m) == tag && (w3 & m) == tag) break;
+      __nanosleep(20);
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if ((long long)(now - t0) > timeout_ns) {   // a peer died or the ranks disagree on the schedule -- fail, never hang
+        sc->wait_what = 2u << 8 | (unsigned)group | (unsigned)lane << 16; sc->wait_seq = seq; sc->wait_seen = w0 >> 32;
+        *(volatile int*)&sc->status = 7; *(volatile int*)&sc->done = 1;
+        break;
+      }
     }
-    scalar_algebra(fin, sc, d0, d1, history, cap);
+    a0 = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    a1 = __longlong_as_double((long long)((w2 & 0xffffffffull) | (w3 << 32)));
   }
+  double d0 = 0.0, d1 = 0.0;
+  for (int r = 0; r < nranks; ++r) {            // rank order: the same bits on every rank
+    const double x0 = __shfl_sync(0xffffffffu, a0, r), x1 = __shfl_sync(0xffffffffu, a1, r);
+    if (op_max) { d0 = fmax(d0, x0); d1 = fmax(d1, x1); } else { d0 += x0; d1 += x1; }
+  }
+  if (lane == 0 && (!in_solve || !*(volatile int*)&sc->done)) scalar_algebra(fin, sc, d0, d1, history, cap);
 }
 
 // Block-level deterministic reduction of up to two running sums + last-block finalisation.

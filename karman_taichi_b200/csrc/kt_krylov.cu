@@ -1021,9 +1021,10 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
 //   k_p2p_halo  : one block per side stores this rank's boundary row straight into the neighbour's receive buffer over
 //                 NVLink (16-byte peer stores), fences system-wide, bumps the neighbour's flag, waits for the neighbour's
 //                 row to land in its own receive buffer (flag >= seq) and copies it into the halo row of the local plane.
-//   k_p2p_reduce: lane r stores this rank's local sums into slot [rank] of rank r's comm block and bumps its flag; the
-//                 warp then waits for all nranks flags of its own block, sums the slots in rank order (every rank gets
-//                 the same bits) and runs the step's scalar algebra -- all-reduce + k_scalar_step in one launch.
+//   k_p2p_reduce: lane r stores this rank's local sums into slot [rank] of rank r's comm block as tagged 8-byte words
+//                 (p2p_allreduce_warp, kt_common.cuh); the warp then polls its own block until all nranks slots carry the
+//                 tag, adds them in rank order (every rank gets the same bits) and runs the step's scalar algebra --
+//                 all-reduce + k_scalar_step in one launch.
 // Flags are monotonically increasing sequence numbers (never reset), so a late reader can never see a stale "ready".
 // Write-after-read safety: a neighbour can only overwrite a receive row of iteration k after it has seen this rank's
 // sums of a later kernel (the sums are published after the halo kernel that copied the row out, in stream order).
@@ -1645,10 +1646,15 @@ static void p2p_timeout_error(const char* where, const kt_handle_s* h, const kt_
   const Scalars& S = *h->sc_host;
   char buf[384];
   const unsigned w = (unsigned)S.wait_what;
-  snprintf(buf, sizeof buf, "%s: rank %d of %d gave up waiting for %s %u, %s %u: expected sequence number %llu (epoch %llu, index %llu), last saw %llu "
-           "(epoch %llu, index %llu)", where, cm->rank, cm->nranks, (w >> 8 & 0xff) == 1 ? "halo slot" : "sum group", w & 0xff,
-           (w >> 8 & 0xff) == 1 ? "side" : "peer rank", w >> 16, S.wait_seq, S.wait_seq >> 32, S.wait_seq & 0xffffffffull, S.wait_seen,
-           S.wait_seen >> 32, S.wait_seen & 0xffffffffull);
+  if ((w >> 8 & 0xff) == 1)
+    snprintf(buf, sizeof buf, "%s: rank %d of %d gave up waiting for halo slot %u, side %u: expected sequence number %llu (epoch %llu, index %llu), "
+             "last saw %llu (epoch %llu, index %llu)", where, cm->rank, cm->nranks, w & 0xff, w >> 16, S.wait_seq, S.wait_seq >> 32,
+             S.wait_seq & 0xffffffffull, S.wait_seen, S.wait_seen >> 32, S.wait_seen & 0xffffffffull);
+  else   // sums travel as tagged words: tag = 12 bits of the epoch | 20 bits of the index
+    snprintf(buf, sizeof buf, "%s: rank %d of %d gave up waiting for sum group %u of peer rank %u: expected epoch %llu, index %llu (tag 0x%llx), "
+             "last saw tag 0x%llx (epoch %llu, index %llu)", where, cm->rank, cm->nranks, w & 0xff, w >> 16, S.wait_seq >> 32,
+             S.wait_seq & 0xffffffffull, ((S.wait_seq >> 32) & 0xfffull) << 20 | (S.wait_seq & 0xfffffull), S.wait_seen, S.wait_seen >> 20,
+             S.wait_seen & 0xfffffull);
   set_error(buf);
 }
 
