@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) k_fill_cols(T* dst, int pitch, int NY, in
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_dot(EwGeom g, const T* p, const T* q, ReduceWs ws) {
+__global__ void __launch_bounds__(256, 4) k_dot(EwGeom g, const T* p, const T* q, ReduceWs ws) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
   double acc = 0.0;
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(256) k_dot(EwGeom g, const T* p, const T* q, R
 // K0: r = b, (r_tld = b), x = 0, [p = r for CG]; dot (r,r).   bicgsolver.py:21-36 / cgsolver.py:31-39,90
 // P2P: the boundary rows of r (BiCGSTAB: the operand of the first t = A s) / of p (CG) also go to the neighbours (hp)
 template <typename T, bool CG, bool P2P = false>
-__global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_tld, T* x, T* p, ReduceWs ws, int fin,
+__global__ void __launch_bounds__(256, 6) k_init(EwGeom g, const T* b, T* r, T* r_tld, T* x, T* p, ReduceWs ws, int fin,
                                               HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_t
 // P2P: the boundary rows of the new p also go into the neighbours' receive buffers; the NEXT kernel of the stream (v = A p^)
 // announces them (StencilArgs::raise_*), so this one keeps running without a barrier or a last-block ticket
 template <typename T, bool P2P = false>
-__global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, const T* v, const Scalars* sc,
+__global__ void __launch_bounds__(256, 3) k_bicg_p(EwGeom g, T* p, const T* r, const T* v, const Scalars* sc,
                                                 HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, cons
 
 // K4: x += alpha p^ + omega s^ ; r = s - omega t ; dots (r,r), (r,r_tld)   (bicgsolver.py:120-123, 95)
 template <typename T, bool PRE, bool P2P = false>
-__global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* p, const T* s, const T* t,
+__global__ void __launch_bounds__(256, 3) k_bicg_xr(EwGeom g, T* x, T* r, const T* p, const T* s, const T* t,
                                                  const T* r_tld, const T* minv, double alpha_imm, double omega_imm,
                                                  int from_sc, ReduceWs ws, int fin, const T* v_for_s = nullptr,
                                                  HaloPush<T> hp = HaloPush<T>()) {
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* 
 
 // C2: x += alpha p ; r -= alpha Ap ; dot (r,r)   (cgsolver.py:98-101)
 template <typename T>
-__global__ void __launch_bounds__(256) k_cg_xr(EwGeom g, T* x, T* r, const T* p, const T* Ap, double alpha_imm,
+__global__ void __launch_bounds__(256, 4) k_cg_xr(EwGeom g, T* x, T* r, const T* p, const T* Ap, double alpha_imm,
                                                int from_sc, ReduceWs ws, int fin) {
   constexpr int V = VT<T>::V;
   constexpr int U = (kEwUnroll > 2) ? 2 : kEwUnroll;
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(256) k_cg_xr(EwGeom g, T* x, T* r, const T* p,
 
 // C3: p = r + beta p   (cgsolver.py:78-81)
 template <typename T, bool P2P = false>
-__global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const Scalars* sc, HaloPush<T> hp = HaloPush<T>()) {
+__global__ void __launch_bounds__(256, 4) k_cg_p(EwGeom g, T* p, const T* r, const Scalars* sc, HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
   pdl_prologue();
@@ -558,12 +558,36 @@ static void launch_k(kt_handle_s* h, void (*kernel)(KArgs...), int grid, Args&&.
 // bandwidth; a static persistent split leaves the fast ones idle at the end), while too many blocks make the
 // last-block sum of the block partials visible.  256-512 KB of traffic per block is the measured sweet spot at
 // both 4096^2 and 16384^2, so: blocks = bytes moved / KT_BLOCK_BYTES (512 KB), clamped to [4, 128] blocks per SM.
-static int grid_for(const kt_handle_s* h, long long blocks_wanted, int planes_moved) {
+// Whole waves.  A kernel of a few waves (grid / resident blocks) that ends on a fraction of a wave idles the rest of that wave:
+// 3.5 waves run like 4 (the t = A s kernel at 4096^2 sat at 0.89 of the copy peak when its neighbours reached 0.95), 1.76 like
+// 2 (config 4 cut 8 ways).  Grids of up to 16 waves are therefore rounded to the nearest whole number of waves.  `occ` =
+// resident blocks per SM of the kernel: the min-blocks of its __launch_bounds__ (register counts checked with cuobjdump:
+// 64 -> 4, 65..80 -> 3, 106..128 -> 2, 40 -> 6).  Pure integer arithmetic on the geometry, so kt_reduce_plan (the summation
+// order the oracle follows) sees the same grid.
+enum { EWP_DOT = 2, EWP_INIT = 4, EWP_BICG_XR = 8, EWP_BICG_XR_UNIT = 7, EWP_CG_XR = 6 };   // planes the reducing element-wise kernels are sized by
+constexpr int OCC_BICG_P = 3, OCC_CG_P = 4;
+static int occ_of_planes(int planes_moved) {
+  switch (planes_moved) {
+    case EWP_DOT: return 4;            // k_dot
+    case EWP_INIT: return 6;           // k_init
+    case EWP_CG_XR: return 4;          // k_cg_xr
+    case EWP_BICG_XR_UNIT: case EWP_BICG_XR: return 3;   // k_bicg_xr
+    default: return 0;
+  }
+}
+
+static int grid_for(const kt_handle_s* h, long long blocks_wanted, int planes_moved, int occ = -1) {
   static long long block_bytes = env_int("KT_BLOCK_BYTES", 1 << 19);
+  static int wave_round = env_int("KT_WAVE_ROUND", 1);
   const long long bytes = (long long)planes_moved * (h->row_hi - h->row_lo) * h->pitch * (h->dtype == KT_F64 ? 8 : 4);
   long long g = bytes / block_bytes;
   g = std::max<long long>(g, (long long)h->num_sms * 4);
   g = std::min<long long>(g, (long long)h->num_sms * 128);
+  if (occ < 0) occ = occ_of_planes(planes_moved);
+  if (wave_round && occ > 0) {
+    const long long R = (long long)h->num_sms * occ;
+    if (g > R && g < 16 * R) g = (g + R / 2) / R * R;
+  }
   g = std::min<long long>(g, h->max_blocks);
   return (int)std::max<long long>(1, std::min<long long>(blocks_wanted, g));
 }
@@ -572,12 +596,12 @@ struct StPlan { int TI, nCC, grid; long long nTiles; };
 
 // Stencil launch geometry for W column chunks per warp: grid from the traffic, then the tallest row tile (<= 64 rows,
 // >= 8) that still leaves every warp of the grid >= 4 tiles to stride over.
-static StPlan stencil_plan(const kt_handle_s* h, int V, int W, int planes_moved) {
+static StPlan stencil_plan(const kt_handle_s* h, int V, int W, int planes_moved, int occ) {
   StPlan S;
   const int rows = h->row_hi - h->row_lo;
   S.nCC = (h->pitch / V + 32 * W - 1) / (32 * W);
   const long long max_tiles = (long long)((rows + 7) / 8) * S.nCC;
-  S.grid = grid_for(h, (max_tiles + 7) / 8, planes_moved);
+  S.grid = grid_for(h, (max_tiles + 7) / 8, planes_moved, occ);
   static int ti_env = env_int("KT_TI", 0);
   int TI = 64;
   while (TI > 8 && (long long)((rows + TI - 1) / TI) * S.nCC < 4LL * S.grid * 8) TI >>= 1;
@@ -621,13 +645,11 @@ constexpr int stencil_planes(int SRC, bool PRE, int EPI) {
   return 5 + (SRC == SRC_S ? 2 : SRC == SRC_P ? 3 : 1) + (PRE ? 1 : 0) + 1 +
          (EPI == EPI_DOT_Q || EPI == EPI_DOT_Q_ST || EPI == EPI_RESID ? 1 : 0) + (EPI == EPI_ST || EPI == EPI_DOT_Q_ST ? 1 : 0);
 }
-// planes the element-wise kernels with an inner product are sized by (the grid_for argument at their launch sites)
-enum { EWP_DOT = 2, EWP_INIT = 4, EWP_BICG_XR = 8, EWP_BICG_XR_UNIT = 7, EWP_CG_XR = 6 };
 
 template <typename T, int SRC, bool PRE, int EPI, bool P2P = false>
 static int launch_stencil(kt_handle_s* h, const Plan& P, const StencilArgs<T>& A) {
   constexpr int planes = stencil_planes(SRC, PRE, EPI);
-  const StPlan S = stencil_plan(h, P.V, StencilCfg<SRC, PRE>::W, planes);
+  const StPlan S = stencil_plan(h, P.V, StencilCfg<SRC, PRE>::W, planes, StencilCfg<SRC, PRE>::MINB);
   StencilArgs<T> B = A;
   B.TI = S.TI; B.nCC = S.nCC; B.nTiles = S.nTiles;
   launch_k(h, k_stencil<T, SRC, PRE, EPI, P2P>, S.grid, B);
@@ -856,7 +878,7 @@ static int t_bicgstab(kt_handle_s* h, const void* coef, const void* b, void* x, 
     } else {
       {
         ProfScope ps(h, KT_K_BICG_P);
-        launch_k(h, k_bicg_p<T, false>, grid_for(h, P.ew_blocks, 4), P.g, p_new, r, v_new, h->sc, HaloPush<T>());
+        launch_k(h, k_bicg_p<T, false>, grid_for(h, P.ew_blocks, 4, OCC_BICG_P), P.g, p_new, r, v_new, h->sc, HaloPush<T>());
       }
       KT_LAUNCH_CHECK(h);
       ProfScope ps(h, KT_K_BICG_V);
@@ -929,7 +951,7 @@ static int t_cg(kt_handle_s* h, const void* coef, const void* b, void* x, const 
     KT_LAUNCH_CHECK(h);
     {
       ProfScope ps(h, KT_K_CG_P);
-      launch_k(h, k_cg_p<T, false>, grid_for(h, P.ew_blocks, 3), P.g, p, r, h->sc, HaloPush<T>());
+      launch_k(h, k_cg_p<T, false>, grid_for(h, P.ew_blocks, 3, OCC_CG_P), P.g, p, r, h->sc, HaloPush<T>());
     }
     KT_LAUNCH_CHECK(h);
     return 0;
@@ -968,7 +990,7 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
       break;
     }
     case 1: {   // p (o0) = r (a0) + beta (p - omega v (a1))
-      k_bicg_p<T><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, (T*)o0, (const T*)a0, (const T*)a1, h->sc);
+      k_bicg_p<T><<<grid_for(h, P.ew_blocks, 4, OCC_BICG_P), 256, 0, h->stream>>>(P.g, (T*)o0, (const T*)a0, (const T*)a1, h->sc);
       break;
     }
     case 2: {   // v (o0) = A p (a0); local (r_tld (a1), v)
@@ -1002,7 +1024,7 @@ static int t_dist_phase(kt_handle_s* h, int phase, const void* coef, const void*
       break;
     }
     case 8: {   // p (o0) = r (a0) + beta p
-      k_cg_p<T><<<grid_for(h, P.ew_blocks, 3), 256, 0, h->stream>>>(P.g, (T*)o0, (const T*)a0, h->sc);
+      k_cg_p<T><<<grid_for(h, P.ew_blocks, 3, OCC_CG_P), 256, 0, h->stream>>>(P.g, (T*)o0, (const T*)a0, h->sc);
       break;
     }
     default: set_error("kt_dist_bicg_phase: unknown phase"); return -2;
@@ -1187,7 +1209,7 @@ static int t_p2p_bicgstab_unfused(kt_handle_s* h, const void* coef, const void* 
   auto iter = [&]() -> int {
     {
       ProfScope ps(h, KT_K_BICG_P);
-      k_bicg_p<T><<<grid_for(h, P.ew_blocks, 4), 256, 0, h->stream>>>(P.g, p, r, v, h->sc);
+      k_bicg_p<T><<<grid_for(h, P.ew_blocks, 4, OCC_BICG_P), 256, 0, h->stream>>>(P.g, p, r, v, h->sc);
       KT_LAUNCH_CHECK(h);
     }
     KT_TRY(p2p_halo<T>(c, 0, p));
@@ -1363,7 +1385,7 @@ static int t_p2p_bicgstab_fused(kt_handle_s* h, const void* coef, const void* b,
     {
       ProfScope ps(h, KT_K_BICG_P);
       ++h->p2p_halo_k[0];                                           // the rows this launch pushes; announced by K2 below
-      launch_k(h, k_bicg_p<T, true>, grid_for(h, P.ew_blocks, 4), P.g, p, r, v, h->sc, p2p_push<T>(h, Rp));
+      launch_k(h, k_bicg_p<T, true>, grid_for(h, P.ew_blocks, 4, OCC_BICG_P), P.g, p, r, v, h->sc, p2p_push<T>(h, Rp));
       KT_LAUNCH_CHECK(h);
     }
     {
@@ -1437,7 +1459,7 @@ static int t_p2p_cg_fused(kt_handle_s* h, const void* coef, const void* b, void*
     {
       ProfScope ps(h, KT_K_CG_P);
       ++h->p2p_halo_k[0];                                           // announced by the next Ap = A p
-      launch_k(h, k_cg_p<T, true>, grid_for(h, P.ew_blocks, 3), P.g, p, r, h->sc, p2p_push<T>(h, Rp));
+      launch_k(h, k_cg_p<T, true>, grid_for(h, P.ew_blocks, 3, OCC_CG_P), P.g, p, r, h->sc, p2p_push<T>(h, Rp));
       KT_LAUNCH_CHECK(h);
     }
     return 0;
@@ -1735,11 +1757,11 @@ int kt_reduce_plan(const kt_geom* g, int kind, int pre, long long* out12) {
     out12[0] = 0; out12[1] = grid_for(&tmp, P.ew_blocks, ew_planes); out12[4] = P.g.v_lo; out12[5] = P.g.v_hi;
     return 0;
   }
-  int W = 1;
-  if (SRC == SRC_X) W = pre ? StencilCfg<SRC_X, true>::W : StencilCfg<SRC_X, false>::W;
-  else if (SRC == SRC_S) W = pre ? StencilCfg<SRC_S, true>::W : StencilCfg<SRC_S, false>::W;
-  else W = pre ? StencilCfg<SRC_P, true>::W : StencilCfg<SRC_P, false>::W;
-  const StPlan S = stencil_plan(&tmp, P.V, W, stencil_planes(SRC, pre != 0, EPI));
+  int W = 1, occ = 0;
+  if (SRC == SRC_X) { W = pre ? StencilCfg<SRC_X, true>::W : StencilCfg<SRC_X, false>::W; occ = pre ? StencilCfg<SRC_X, true>::MINB : StencilCfg<SRC_X, false>::MINB; }
+  else if (SRC == SRC_S) { W = pre ? StencilCfg<SRC_S, true>::W : StencilCfg<SRC_S, false>::W; occ = pre ? StencilCfg<SRC_S, true>::MINB : StencilCfg<SRC_S, false>::MINB; }
+  else { W = pre ? StencilCfg<SRC_P, true>::W : StencilCfg<SRC_P, false>::W; occ = pre ? StencilCfg<SRC_P, true>::MINB : StencilCfg<SRC_P, false>::MINB; }
+  const StPlan S = stencil_plan(&tmp, P.V, W, stencil_planes(SRC, pre != 0, EPI), occ);
   out12[0] = 1; out12[1] = S.grid; out12[4] = W; out12[5] = S.TI; out12[6] = S.nCC; out12[7] = S.nTiles;
   out12[8] = g->row_lo; out12[9] = g->row_hi; out12[10] = g->pitch;
   return 0;
