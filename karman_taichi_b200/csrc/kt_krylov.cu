@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) k_fill_cols(T* dst, int pitch, int NY, in
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 4) k_dot(EwGeom g, const T* p, const T* q, ReduceWs ws) {
+__global__ void __launch_bounds__(256) k_dot(EwGeom g, const T* p, const T* q, ReduceWs ws) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
   double acc = 0.0;
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(256, 4) k_dot(EwGeom g, const T* p, const T* q
 // K0: r = b, (r_tld = b), x = 0, [p = r for CG]; dot (r,r).   bicgsolver.py:21-36 / cgsolver.py:31-39,90
 // P2P: the boundary rows of r (BiCGSTAB: the operand of the first t = A s) / of p (CG) also go to the neighbours (hp)
 template <typename T, bool CG, bool P2P = false>
-__global__ void __launch_bounds__(256, 6) k_init(EwGeom g, const T* b, T* r, T* r_tld, T* x, T* p, ReduceWs ws, int fin,
+__global__ void __launch_bounds__(256) k_init(EwGeom g, const T* b, T* r, T* r_tld, T* x, T* p, ReduceWs ws, int fin,
                                               HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256, 6) k_init(EwGeom g, const T* b, T* r, T* 
 // P2P: the boundary rows of the new p also go into the neighbours' receive buffers; the NEXT kernel of the stream (v = A p^)
 // announces them (StencilArgs::raise_*), so this one keeps running without a barrier or a last-block ticket
 template <typename T, bool P2P = false>
-__global__ void __launch_bounds__(256, 3) k_bicg_p(EwGeom g, T* p, const T* r, const T* v, const Scalars* sc,
+__global__ void __launch_bounds__(256) k_bicg_p(EwGeom g, T* p, const T* r, const T* v, const Scalars* sc,
                                                 HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(256, 3) k_bicg_p(EwGeom g, T* p, const T* r, c
 
 // K4: x += alpha p^ + omega s^ ; r = s - omega t ; dots (r,r), (r,r_tld)   (bicgsolver.py:120-123, 95)
 template <typename T, bool PRE, bool P2P = false>
-__global__ void __launch_bounds__(256, 3) k_bicg_xr(EwGeom g, T* x, T* r, const T* p, const T* s, const T* t,
+__global__ void __launch_bounds__(256) k_bicg_xr(EwGeom g, T* x, T* r, const T* p, const T* s, const T* t,
                                                  const T* r_tld, const T* minv, double alpha_imm, double omega_imm,
                                                  int from_sc, ReduceWs ws, int fin, const T* v_for_s = nullptr,
                                                  HaloPush<T> hp = HaloPush<T>()) {
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(256, 3) k_bicg_xr(EwGeom g, T* x, T* r, const 
 
 // C2: x += alpha p ; r -= alpha Ap ; dot (r,r)   (cgsolver.py:98-101)
 template <typename T>
-__global__ void __launch_bounds__(256, 4) k_cg_xr(EwGeom g, T* x, T* r, const T* p, const T* Ap, double alpha_imm,
+__global__ void __launch_bounds__(256) k_cg_xr(EwGeom g, T* x, T* r, const T* p, const T* Ap, double alpha_imm,
                                                int from_sc, ReduceWs ws, int fin) {
   constexpr int V = VT<T>::V;
   constexpr int U = (kEwUnroll > 2) ? 2 : kEwUnroll;
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(256, 4) k_cg_xr(EwGeom g, T* x, T* r, const T*
 
 // C3: p = r + beta p   (cgsolver.py:78-81)
 template <typename T, bool P2P = false>
-__global__ void __launch_bounds__(256, 4) k_cg_p(EwGeom g, T* p, const T* r, const Scalars* sc, HaloPush<T> hp = HaloPush<T>()) {
+__global__ void __launch_bounds__(256) k_cg_p(EwGeom g, T* p, const T* r, const Scalars* sc, HaloPush<T> hp = HaloPush<T>()) {
   constexpr int V = VT<T>::V;
   constexpr int U = kEwUnroll;
   pdl_prologue();
@@ -560,10 +560,12 @@ static void launch_k(kt_handle_s* h, void (*kernel)(KArgs...), int grid, Args&&.
 // both 4096^2 and 16384^2, so: blocks = bytes moved / KT_BLOCK_BYTES (512 KB), clamped to [4, 128] blocks per SM.
 // Whole waves.  A kernel of a few waves (grid / resident blocks) that ends on a fraction of a wave idles the rest of that wave:
 // 3.5 waves run like 4 (the t = A s kernel at 4096^2 sat at 0.89 of the copy peak when its neighbours reached 0.95), 1.76 like
-// 2 (config 4 cut 8 ways).  Grids of up to 16 waves are therefore rounded to the nearest whole number of waves.  `occ` =
-// resident blocks per SM of the kernel: the min-blocks of its __launch_bounds__ (register counts checked with cuobjdump:
-// 64 -> 4, 65..80 -> 3, 106..128 -> 2, 40 -> 6).  Pure integer arithmetic on the geometry, so kt_reduce_plan (the summation
-// order the oracle follows) sees the same grid.
+// 2 (config 4 cut 8 ways; measured on one GPU at 2600^2: 0.892 -> 0.940 of the copy peak, at 1300^2 0.907 -> 0.966).  Grids of
+// up to 16 waves are therefore rounded to the nearest whole number of waves.  `occ` = resident blocks per SM of the kernel,
+// from its register count (cuobjdump --dump-resource-usage: 57..64 registers -> 4 blocks of 256 threads, 65..80 -> 3,
+// 106..128 -> 2, 40 -> 6; the stencil kernels' __launch_bounds__ min-blocks).  Forcing the element-wise kernels into these
+// classes with __launch_bounds__(256, n) was tried and reverted: it changed their register allocation and cost the p-update
+// 7-15 %.  Pure integer arithmetic on the geometry, so kt_reduce_plan (the summation order the oracle follows) sees the same grid.
 enum { EWP_DOT = 2, EWP_INIT = 4, EWP_BICG_XR = 8, EWP_BICG_XR_UNIT = 7, EWP_CG_XR = 6 };   // planes the reducing element-wise kernels are sized by
 constexpr int OCC_BICG_P = 3, OCC_CG_P = 4;
 static int occ_of_planes(int planes_moved) {

