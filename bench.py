@@ -68,7 +68,8 @@ METRIC = 'bicgstab_mcell_iters_per_s'
 CG_METRIC = 'cg_mcell_iters_per_s'
 UNIT = 'Mcell-iters/s'
 WORDS_PER_CELL_ITER = {'bicgstab': 28, 'cg': 16}      # algorithmic traffic per cell and iteration, in words
-TRAFFIC_JSON = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+TRAFFIC_JSON = os.path.join(ROOT, 'profiles', 'r02_traffic.json')                  # ncu launch list of the default command
+TRAFFIC_JSON_KARMAN = os.path.join(ROOT, 'profiles', 'r02_traffic_karman.json')    # ... of --workload karman16384 (Jacobi-plane kernels)
 
 
 _JSON_OUT = sys.stdout
@@ -85,19 +86,23 @@ def measured_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of every kernel, as ncu measured them on the default command
     (tools/gpu_job.sh launches -> tools/ncu_summary.py --json), with the commit the capture was taken at.  Scaled by plane
     words when the profiled workload is not the one being run.  None when the file is missing (never a stale constant)."""
-    try:
-        return json.load(open(TRAFFIC_JSON))
-    except Exception:
-        return None
+    docs = []
+    for path in (TRAFFIC_JSON, TRAFFIC_JSON_KARMAN):
+        try:
+            d = json.load(open(path))
+            d['path'] = os.path.relpath(path, ROOT)
+            docs.append(d)
+        except Exception:
+            pass
+    return docs or None
 
 
 def traffic_of(doc, pattern, words_local):
     """bytes per launch of the kernel whose ncu name starts with `pattern`, scaled to `words_local` plane words"""
-    if not doc:
-        return None, None
-    for name, k in doc.get('kernels', {}).items():
-        if name.startswith(pattern) and k.get('dram_bytes_per_word'):
-            return k['dram_bytes_per_word'] * words_local, f"{os.path.relpath(TRAFFIC_JSON, ROOT)} (ncu launch list of `{doc.get('command', '?')}` at commit {doc.get('commit', '?')}: {name}, {k['dram_bytes_per_word']:.1f} B per plane word, scaled by this run's plane words)"
+    for d in doc or []:
+        for name, k in d.get('kernels', {}).items():
+            if name.startswith(pattern) and k.get('dram_bytes_per_word'):
+                return k['dram_bytes_per_word'] * words_local, f"{d['path']} (ncu launch list of `{d.get('command', '?')}` at commit {d.get('commit', '?')}: {name}, {k['dram_bytes_per_word']:.1f} B per plane word, scaled by this run's plane words)"
     return None, None
 
 
@@ -296,16 +301,16 @@ class Comm:
 # kernel classes of kt_prof_* -> (short name, description, algorithmic words, ncu kernel-name prefix for the traffic lookup)
 def kernel_classes(solver, fused, store_s):
     if solver == 'cg':
-        return {4: ('Ap+dot', 'k_stencil<SRC_X,EPI_DOT_SRC>: Ap = A p, (p, Ap)', 7, 'k_stencil<double, 0, 0, 2>'),
-                5: ('x,r+dot', 'k_cg_xr: x += alpha p, r -= alpha Ap, (r,r)', 6, 'k_cg_xr<double>'),
-                6: ('p_update', 'k_cg_p: p = r + beta p', 3, 'k_cg_p<double>')}
-    return {0: ('p_update', 'k_bicg_p: p = r + beta (p - omega v)', 4, 'k_bicg_p<double>'),
-            1: (('p_update+v=Ap+dot', 'k_stencil<SRC_P,EPI_DOT_Q_ST>: p = r + beta (p - omega v), v = A p, (r~, v)', 11, 'k_stencil<double, 2, 0, 5>')
-                if fused else ('v=Ap+dot', 'k_stencil<SRC_X,EPI_DOT_Q>: v = A p, (r~, v)', 8, 'k_stencil<double, 0, 0, 1>')),
+        return {4: ('Ap+dot', 'k_stencil<SRC_X,EPI_DOT_SRC>: Ap = A p, (p, Ap)', 7, 'k_stencil<double, 0, 0, 2'),
+                5: ('x,r+dot', 'k_cg_xr: x += alpha p, r -= alpha Ap, (r,r)', 6, 'k_cg_xr<double'),
+                6: ('p_update', 'k_cg_p: p = r + beta p', 3, 'k_cg_p<double')}
+    return {0: ('p_update', 'k_bicg_p: p = r + beta (p - omega v)', 4, 'k_bicg_p<double'),
+            1: (('p_update+v=Ap+dot', 'k_stencil<SRC_P,EPI_DOT_Q_ST>: p = r + beta (p - omega v), v = A p, (r~, v)', 11, 'k_stencil<double, 2, 0, 5')
+                if fused else ('v=Ap+dot', 'k_stencil<SRC_X,EPI_DOT_Q>: v = A p, (r~, v)', 8, 'k_stencil<double, 0, 0, 1')),
             2: (('s,t+2dots', 'k_stencil<SRC_S,EPI_ST>: s = r - alpha v, t = A s, (t,s), (t,t)', 9, None) if store_s else
-                ('t=As+2dots', 'k_stencil<SRC_S,EPI_ST>: t = A (r - alpha v) [s not stored], (t,s), (t,t)', 8, 'k_stencil<double, 1, 0, 3>')),
+                ('t=As+2dots', 'k_stencil<SRC_S,EPI_ST>: t = A (r - alpha v) [s not stored], (t,s), (t,t)', 8, 'k_stencil<double, 1, 0, 3')),
             3: (('x,r+2dots', 'k_bicg_xr: x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 7, None) if store_s else
-                ('x,r+2dots', 'k_bicg_xr: s = r - alpha v, x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 8, 'k_bicg_xr<double, 0>'))}
+                ('x,r+2dots', 'k_bicg_xr: s = r - alpha v, x += alpha p + omega s, r = s - omega t, (r,r), (r,r~)', 8, 'k_bicg_xr<double, 0'))}
 
 
 def krylov_line(a, torch, dist, world, rank, dev, light=False, fields=None, workload=None, solver_kind=None, steps=None):
@@ -848,8 +853,8 @@ def simple_line(a, torch, dist, world, rank, dev, workload, steps=None, light=Fa
                 'us_per_krylov_iteration': ms_total * 1e3 / n_krylov,
                 'krylov_mcell_iters_per_s': cells * sum(tot_its.values()) / (ms_total * 1e-3) / 1e6}
     if streamed:
-        names = {0: ('p_update', 4, 'k_bicg_p<double>'), 1: ('v=A M^-1 p + dot', 9, 'k_stencil<double, 0, 1, 1>'),
-                 2: ('t=A M^-1 s + 2 dots', 9, 'k_stencil<double, 1, 1, 3>'), 3: ('x,r + 2 dots', 9, 'k_bicg_xr<double, 1>')}
+        names = {0: ('p_update', 4, 'k_bicg_p<double'), 1: ('v=A M^-1 p + dot', 9, 'k_stencil<double, 0, 1, 1'),
+                 2: ('t=A M^-1 s + 2 dots', 9, 'k_stencil<double, 1, 1, 3'), 3: ('x,r + 2 dots', 9, 'k_bicg_xr<double, 1')}
         dom = max(range(4), key=lambda i: tot[i])
         d_ms = tot[dom] / max(cnt[dom], 1)
         if case == 'karman':
