@@ -56,6 +56,17 @@ def main():
     ap.add_argument('--command', default='')
     a = ap.parse_args()
     launches = load(a.csv)
+    # launches behind the solver's `done` flag return at once (the host enqueues whole chunks of 16 iterations): they move no
+    # bytes and would dilute the per-launch averages -- dropped when they last < 1/10 of the kernel's median launch
+    by_kernel = collections.defaultdict(list)
+    for d in launches:
+        by_kernel[(d['name'], d['grid'])].append(to_ns(d))
+    med = {k: sorted(v)[len(v) // 2] for k, v in by_kernel.items()}
+    kept = [d for d in launches if to_ns(d) >= 0.1 * med[(d['name'], d['grid'])]]
+    dropped = len(launches) - len(kept)
+    if dropped:
+        print(f'({dropped} of {len(launches)} launches were no-ops behind the done flag and are left out)\n')
+    launches = kept
     agg = collections.OrderedDict()
     for d in launches:
         g = agg.setdefault((d['name'], d['grid']), {'n': 0, 'ns': 0.0, 'rd': 0.0, 'wr': 0.0})
