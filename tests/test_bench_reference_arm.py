@@ -45,3 +45,26 @@ def test_reference_arm_other_ranks_stay_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'pcor1024', '--gpus', '2'],
                          capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK='1', WORLD_SIZE='2'), cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ''
+
+
+def test_roofline_traffic_comes_from_the_committed_ncu_captures():
+    """bench.py never carries a traffic constant: roofline.traffic is looked up, by kernel-name prefix, in the ncu launch lists
+    committed under profiles/ (with the commit they were taken at) and scaled by the run's plane words."""
+    sys.path.insert(0, ROOT)
+    import bench
+    docs = bench.measured_traffic()
+    assert docs and all(d.get('commit') and d.get('kernels') for d in docs)
+    words = 32770 * 32832
+    for solver in ('bicgstab', 'cg'):
+        for i, (name, desc, alg_words, pattern) in bench.kernel_classes(solver, fused=False, store_s=False).items():
+            if solver == 'cg':
+                continue                                      # the CG kernels are not in the default command's capture
+            t, src = bench.traffic_of(docs, pattern, words)
+            assert t is not None and 'profiles/' in src, (name, pattern)
+            assert 0.9 <= t / (alg_words * 8 * words) <= 1.1, (name, t / (alg_words * 8 * words))   # traffic ~ algorithmic bytes
+    # config 4: the Jacobi-plane kernels come from the second capture (9 words per plane word)
+    for pattern in ('k_stencil<double, 0, 1, 1', 'k_stencil<double, 1, 1, 3', 'k_bicg_xr<double, 1'):
+        t, src = bench.traffic_of(docs, pattern, 16386 * 3328)
+        assert t is not None and 'karman' in src
+        assert 0.9 <= t / (9 * 8 * 16386 * 3328) <= 1.1
+    assert bench.traffic_of(docs, 'k_no_such_kernel', words) == (None, None)
