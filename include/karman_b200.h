@@ -193,9 +193,15 @@ int kt_dist_poll(kt_handle_t h, int* done, long* iters, int* status, double* rel
  * kt_p2p_comm_block_bytes() bytes and a halo-receive buffer of kt_p2p_halo_slots() x 2 sides x pitch reals, and passes device
  * pointers, mapped into ITS address space (kt_ipc_open), of every rank's comm block and of its two neighbours'
  * halo-receive buffers: peer_halo_recv[0] = lower neighbour (rank-1) or NULL, [1] = upper neighbour or NULL.  The field
- * planes themselves are ordinary allocations that no other rank maps: a boundary row travels plane -> neighbour's receive
- * buffer (peer store over NVLink) -> neighbour's plane (local copy).  local_dots: 2 doubles of device scratch.  All
- * ranks must call this with the same eps / max_iter / flags, in lock step. */
+ * planes themselves are ordinary allocations that no other rank maps.  By default the communication is FUSED into the compute
+ * kernels: the kernel that produces p / v / r stores its boundary rows straight into the neighbour's receive buffer (peer
+ * stores over NVLink), the kernel that consumes them reads the halo rows from there behind a flag wait, and the finalising
+ * block of every reducing kernel is the all-reduce (sums as tagged 8-byte words in every rank's comm block, added in rank
+ * order).  KT_P2P_FUSED=0 in the environment selects separate one-block comm kernels instead (same results, bit for bit).
+ * local_dots: 2 doubles of device scratch.  All ranks must call this with the same eps / max_iter / flags, in lock step;
+ * a rank whose peer never signals returns *status = KT_STATUS_COMM_TIMEOUT after 30 s (KT_P2P_TIMEOUT_MS) with the flag and
+ * sequence number in kt_last_error.  With Minv, the plane must be valid on the halo rows too (kt_p2p_exchange it after
+ * assembling it). */
 typedef struct {
   int rank, nranks;
   void* peer_halo_recv[2];
