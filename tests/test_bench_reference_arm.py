@@ -68,3 +68,17 @@ def test_roofline_traffic_comes_from_the_committed_ncu_captures():
         assert t is not None and 'karman' in src
         assert 0.9 <= t / (9 * 8 * 16386 * 3328) <= 1.1
     assert bench.traffic_of(docs, 'k_no_such_kernel', words) == (None, None)
+
+
+def test_ncu_summary_leaves_out_noop_launches(tmp_path):
+    """tools/ncu_summary.py on the committed config-4 launch list: launches behind the solver's done flag (a few microseconds, no
+    bytes) must not dilute the per-launch traffic -- 9 words x 8 B per plane word for the Jacobi-plane kernels."""
+    out = tmp_path / 't.json'
+    res = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ncu_summary.py'), os.path.join(ROOT, 'profiles', 'r02_launches_karman16384.csv'),
+                          '--words', str(16386 * 3328), '--json', str(out), '--commit', 'test', '--command', 'test'],
+                         capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    assert 'no-ops behind the done flag' in res.stdout
+    doc = json.load(open(out))
+    k = [v for n, v in doc['kernels'].items() if n.startswith('k_stencil<double, 1, 1, 3')][0]
+    assert 68.0 <= k['dram_bytes_per_word'] <= 76.0          # 72 algorithmic; 63.8 with the no-ops averaged in
